@@ -1,0 +1,488 @@
+// extern "C" surface of libwavenet_b200.so: argument checking, the flat parameter layout,
+// workspace carving and the launch sequences of the training / forward graphs.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/wavenet_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wn {
+
+// ---------------------------------------------------------------------------------------
+// per-kernel timing: one CUDA event after every launch of the training sequence
+// ---------------------------------------------------------------------------------------
+namespace {
+constexpr int PROF_MAX = 4096;
+bool g_prof_on = false;
+int g_prof_n = 0;
+cudaEvent_t g_prof_ev[PROF_MAX];
+int g_prof_tag[PROF_MAX];
+bool g_prof_created = false;
+}  // namespace
+
+void prof_mark(cudaStream_t st, int tag) {
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  cudaEventRecord(g_prof_ev[g_prof_n], st);
+  g_prof_tag[g_prof_n] = tag;
+  ++g_prof_n;
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+static int check_cfg(const wn_config* c) {
+  if (!c) return -1;
+  if (c->n_layers < 1 || c->n_layers > WN_MAX_LAYERS) return -1;
+  if (c->residual_channels != c->dilation_channels) return -2;
+  if (c->residual_channels != 16 && c->residual_channels != 32) return -2;
+  if (c->skip_channels < 4 || (c->skip_channels & 3)) return -2;
+  if (c->quantization_channels < 4 || (c->quantization_channels & 3) || c->quantization_channels > 1024) return -2;
+  if (c->gc_channels < 0 || c->gc_channels > 1024) return -2;
+  if (c->gc_channels > 0 && c->gc_cardinality < 0) return -2;
+  for (int i = 0; i < c->n_layers; ++i)
+    if (c->dilations[i] < 1) return -1;
+  return 0;
+}
+
+static int make_layout(const wn_config* c, wn_layout* o) {
+  int rc = check_cfg(c);
+  if (rc) return rc;
+  const int64_t L = c->n_layers, R = c->residual_channels, D = c->dilation_channels, S = c->skip_channels,
+                Q = c->quantization_channels, G = c->gc_channels;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t r = off; off = align_up(off + n, 64); return r; };
+  o->causal = take(2 * Q * R);
+  o->filter = take(L * 2 * R * D);
+  o->gate = take(L * 2 * R * D);
+  o->dense = take(L * D * R);
+  o->skip = take(L * D * S);
+  o->gc_filter = G > 0 ? take(L * G * D) : -1;
+  o->gc_gate = G > 0 ? take(L * G * D) : -1;
+  o->filter_bias = c->use_biases ? take(L * D) : -1;
+  o->gate_bias = c->use_biases ? take(L * D) : -1;
+  o->dense_bias = c->use_biases ? take(L * R) : -1;
+  o->skip_bias = c->use_biases ? take(L * S) : -1;
+  o->post1 = take(S * S);
+  o->post2 = take(S * Q);
+  o->post1_bias = c->use_biases ? take(S) : -1;
+  o->post2_bias = c->use_biases ? take(Q) : -1;
+  o->gc_embedding = (G > 0 && c->gc_cardinality > 0) ? take((int64_t)c->gc_cardinality * G) : -1;
+  o->total = off;
+  return 0;
+}
+
+struct Workspace {
+  int32_t* ids;
+  float* X;        // training: L buffers [M,R]; forward: 2 buffers
+  float* Zcat;     // [M, L*D]
+  float* A1;       // [M,S] tf32(relu(skip sum))
+  float* A2;       // [M,S] tf32(relu(post1))
+  float* S0;       // [M,S] raw skip sum            (residual_postproc only)
+  float* T2;       // [M,S] tf32(A2 + S0)           (residual_postproc only)
+  float* logits;   // [M,Q]                         (training only; forward writes to caller's)
+  float* G1;       // [M,S]
+  float* G2;       // [M,S]
+  float* G3;       // [M,S]                         (residual_postproc only)
+  float* dZcat;    // [M, L*D]
+  float* dX;       // 2 x [M,R]
+  float* dpre;     // [M,2D]
+  float* prebias;  // [L,B,2D]
+  float* gprebias; // [L,B,2D]
+  float* bsum;     // [S]
+  float* gtmp;     // [S]
+  float* partials; // [4096]
+  int64_t bytes;
+};
+
+static void carve(const wn_config* c, int B, int T, bool training, void* base, Workspace* w) {
+  const int64_t M = (int64_t)B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
+                S = c->skip_channels, Q = c->quantization_channels;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    int64_t r = off;
+    off = align_up(off + bytes, 256);
+    return base ? (void*)((char*)base + r) : (void*)nullptr;
+  };
+  const int64_t f = sizeof(float);
+  w->ids = (int32_t*)take(M * 4 + 16);
+  w->X = (float*)take((training ? L : 2) * M * R * f);
+  w->Zcat = (float*)take(M * L * D * f);
+  w->A1 = (float*)take(M * S * f);
+  w->A2 = (float*)take(M * S * f);
+  w->S0 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
+  w->T2 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
+  w->prebias = (float*)take(L * B * 2 * D * f);
+  w->bsum = (float*)take(S * f);
+  w->partials = (float*)take(4096 * f);
+  if (training) {
+    w->logits = (float*)take(M * Q * f);
+    w->G1 = (float*)take(M * S * f);
+    w->G2 = (float*)take(M * S * f);
+    w->G3 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
+    w->dZcat = (float*)take(M * L * D * f);
+    w->dX = (float*)take(2 * M * R * f);
+    w->dpre = (float*)take(M * 2 * D * f);
+    w->gprebias = (float*)take(L * B * 2 * D * f);
+    w->gtmp = (float*)take(S * f);
+  } else {
+    w->logits = w->G1 = w->G2 = w->G3 = w->dZcat = w->dX = w->dpre = w->gprebias = w->gtmp = nullptr;
+  }
+  w->bytes = off;
+}
+
+static inline const float* P(const float* base, int64_t off) { return off >= 0 ? base + off : nullptr; }
+static inline float* P(float* base, int64_t off) { return off >= 0 ? base + off : nullptr; }
+
+static GemmParams gp(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
+  return p;
+}
+
+static int split_for(int m_out, int n_out, int k) {
+  const int tiles = ((m_out + 127) / 128) * ((n_out + 127) / 128);
+  const int nkb = (k + 31) / 32;
+  int s = (4 * sm_count() + tiles - 1) / tiles;
+  if (s > nkb / 4) s = nkb / 4;
+  if (s < 1) s = 1;
+  if (s > 65535) s = 65535;
+  return s;
+}
+
+#define RC(x)            \
+  do {                   \
+    int rc__ = (x);      \
+    if (rc__) return rc__; \
+  } while (0)
+
+// network forward from ids: X (all layers when training), Zcat, A1, A2 and logits
+static int run_forward(const wn_config* c, const wn_layout& lo, const float* params, Workspace& w,
+                       const int32_t* ids, const int32_t* gc_ids, int B, int T, bool training, float* logits,
+                       cudaStream_t st) {
+  const int M = B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
+            S = c->skip_channels, Q = c->quantization_channels, G = c->gc_channels;
+  const int ldz = L * D;
+  if (G > 0 && !gc_ids) return -1;
+  RC(cond_bias_fwd(w.prebias, P(params, lo.filter_bias), P(params, lo.gate_bias), P(params, lo.gc_filter),
+                   P(params, lo.gc_gate), P(params, lo.gc_embedding), gc_ids, L, B, D, gc_ids ? G : 0, st));
+  prof_mark(st, PT_COND_BIAS);
+  RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, st));
+  prof_mark(st, PT_FRONTEND_FWD);
+  const int64_t xs = (int64_t)M * R;
+  for (int l = 0; l < L; ++l) {
+    const float* xin = training ? w.X + l * xs : w.X + (l & 1) * xs;
+    float* xout = training ? w.X + (l + 1) * xs : w.X + ((l + 1) & 1) * xs;
+    const int last = (l == L - 1);
+    RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz, params + lo.filter + (int64_t)l * 2 * R * D,
+                 params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
+                 w.prebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr,
+                 M, T, c->dilations[l], R, last, st));
+  }
+  const float* bsum = nullptr;
+  if (c->use_biases) {
+    RC(skip_bias_sum(params + lo.skip_bias, L, S, w.bsum, st));
+    prof_mark(st, PT_SKIP_BIAS_SUM);
+    bsum = w.bsum;
+  }
+  {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
+    GemmParams p = gp(w.Zcat, ldz, params + lo.skip, S, w.A1, S, M, S, ldz);
+    p.bias = bsum;
+    p.flags = GEMM_RELU | GEMM_ROUND;
+    if (c->residual_postproc) { p.C2 = w.S0; p.ldc2 = S; }
+    RC(gemm_tf32(0, p, 1, st));
+    prof_mark(st, PT_GEMM_SKIP_FWD);
+  }
+  {  // conv1 -> relu                             (model.py:432-435)
+    GemmParams p = gp(w.A1, S, params + lo.post1, S, w.A2, S, M, S, S);
+    p.bias = P(params, lo.post1_bias);
+    p.flags = GEMM_RELU | GEMM_ROUND;
+    RC(gemm_tf32(0, p, 1, st));
+    prof_mark(st, PT_GEMM_POST1_FWD);
+  }
+  const float* x2 = w.A2;
+  if (c->residual_postproc) {  // transformed2 += total   (model.py:436-437)
+    RC((int)cudaMemcpyAsync(w.T2, w.A2, (size_t)M * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    RC(add_inplace(w.T2, w.S0, (int64_t)M * S, 1, st));
+    x2 = w.T2;
+  }
+  {  // conv2                                      (model.py:438-440)
+    GemmParams p = gp(x2, S, params + lo.post2, Q, logits, Q, M, Q, S);
+    p.bias = P(params, lo.post2_bias);
+    RC(gemm_tf32(0, p, 1, st));
+    prof_mark(st, PT_GEMM_POST2_FWD);
+  }
+  return 0;
+}
+
+}  // namespace wn
+
+using namespace wn;
+
+extern "C" {
+
+int wn_abi_version(void) { return WN_ABI_VERSION; }
+
+int wn_profile_begin(void) {
+  if (!g_prof_created) {
+    for (int i = 0; i < PROF_MAX; ++i)
+      if (cudaEventCreate(&g_prof_ev[i]) != cudaSuccess) return (int)cudaGetLastError();
+    g_prof_created = true;
+  }
+  g_prof_n = 0;
+  g_prof_on = true;
+  return 0;
+}
+
+int wn_profile_end(float* ms_per_tag, int32_t* launches_per_tag, int32_t n_tags) {
+  g_prof_on = false;
+  if (!ms_per_tag || !launches_per_tag || n_tags < PT_COUNT) return -1;
+  for (int i = 0; i < n_tags; ++i) { ms_per_tag[i] = 0.f; launches_per_tag[i] = 0; }
+  if (g_prof_n == 0) return 0;
+  cudaError_t e = cudaEventSynchronize(g_prof_ev[g_prof_n - 1]);
+  if (e != cudaSuccess) return (int)e;
+  for (int i = 1; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g_prof_ev[i - 1], g_prof_ev[i]);
+    if (e != cudaSuccess) return (int)e;
+    ms_per_tag[g_prof_tag[i]] += ms;
+    launches_per_tag[g_prof_tag[i]] += 1;
+  }
+  return 0;
+}
+
+int wn_profile_tag_name(int32_t tag, char* out, int32_t n) {
+  static const char* names[PT_COUNT] = {
+      "misc", "mulaw_encode", "cond_bias_fwd", "frontend_fwd", "block_fwd", "skip_bias_sum", "gemm_skip_fwd",
+      "gemm_post1_fwd", "gemm_post2_fwd", "softmax_xent", "gemm_post2_wgrad", "colsum", "gemm_post2_dgrad",
+      "gemm_post1_wgrad", "gemm_post1_dgrad", "gemm_skip_wgrad", "gemm_skip_dgrad", "block_bwd_dx",
+      "block_wgrad", "frontend_bwd", "cond_bias_bwd"};
+  if (tag < 0 || tag >= PT_COUNT || !out || n < 1) return -1;
+  snprintf(out, n, "%s", names[tag]);
+  return 0;
+}
+
+int wn_param_layout(const wn_config* cfg, wn_layout* out) {
+  if (!out) return -1;
+  return make_layout(cfg, out);
+}
+
+int wn_mulaw_encode(const float* audio, int64_t n, const float* thresholds, int32_t q, int32_t* ids,
+                    wn_stream_t stream) {
+  if (n > 0 && (!audio || !thresholds || !ids)) return -1;
+  return mulaw_encode(audio, n, thresholds, q, ids, (cudaStream_t)stream);
+}
+int wn_mulaw_decode(const int32_t* ids, int64_t n, const float* lut, int32_t q, float* out, wn_stream_t stream) {
+  if (n > 0 && (!ids || !lut || !out)) return -1;
+  return mulaw_decode(ids, n, lut, q, out, (cudaStream_t)stream);
+}
+
+int wn_frontend_fwd(const int32_t* ids, const float* causal_filter, float* x0, int32_t batch, int32_t time,
+                    int32_t q, int32_t r, wn_stream_t stream) {
+  if (!ids || !causal_filter || !x0 || batch < 1 || time < 1) return -1;
+  return frontend_fwd(ids, causal_filter, x0, batch * time, time, q, r, (cudaStream_t)stream);
+}
+int wn_frontend_bwd(const int32_t* ids, const float* dx0, float* grad_causal_filter, int32_t batch, int32_t time,
+                    int32_t q, int32_t r, wn_stream_t stream) {
+  if (!ids || !dx0 || !grad_causal_filter || batch < 1 || time < 1) return -1;
+  return frontend_bwd(ids, dx0, grad_causal_filter, batch * time, time, q, r, (cudaStream_t)stream);
+}
+
+int wn_causal_conv(const float* x, const float* w, float* y, int32_t batch, int32_t time, int32_t cin, int32_t cout,
+                   int32_t width, int32_t dilation, wn_stream_t stream) {
+  if (!x || !w || !y || batch < 1 || time < 1) return -1;
+  return causal_conv(x, w, y, batch * time, time, cin, cout, width, dilation, (cudaStream_t)stream);
+}
+
+int wn_block_fwd(const float* x, float* x_out, float* zcat, int32_t ldz, const float* filter, const float* gate,
+                 const float* dense, const float* prebias, const float* dense_bias, int32_t batch, int32_t time,
+                 int32_t dilation, int32_t channels, int32_t is_last, wn_stream_t stream) {
+  if (!x || !zcat || !filter || !gate || !prebias || batch < 1 || time < 1 || dilation < 1) return -1;
+  if (!is_last && (!x_out || !dense)) return -1;
+  if ((ldz & 1) || ldz < channels) return -3;
+  return block_fwd(x, x_out, zcat, ldz, filter, gate, dense, prebias, dense_bias, batch * time, time, dilation,
+                   channels, is_last, (cudaStream_t)stream);
+}
+
+int wn_block_bwd(const float* x, const float* dx_out, const float* dz_skip, int32_t ldz, float* dx,
+                 float* dpre_scratch, const float* zcat, const float* filter, const float* gate, const float* dense,
+                 const float* prebias, float* grad_filter, float* grad_gate, float* grad_dense, float* grad_prebias,
+                 float* grad_dense_bias, int32_t batch, int32_t time, int32_t dilation, int32_t channels,
+                 int32_t is_last, wn_stream_t stream) {
+  if (!x || !dz_skip || !dx || !dpre_scratch || !zcat || !filter || !gate || !prebias || !grad_filter ||
+      !grad_gate || !grad_prebias || batch < 1 || time < 1 || dilation < 1)
+    return -1;
+  if (!is_last && (!dx_out || !dense || !grad_dense)) return -1;
+  if ((ldz & 3) || ldz < channels) return -3;
+  return block_bwd(x, dx_out, dz_skip, ldz, dx, dpre_scratch, zcat, filter, gate, dense, prebias, grad_filter,
+                   grad_gate, grad_dense, grad_prebias, grad_dense_bias, batch * time, time, dilation, channels,
+                   is_last, (cudaStream_t)stream);
+}
+
+int wn_gemm_tf32(int32_t mode, const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc,
+                 int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask, int32_t ldmask,
+                 int32_t flags, int32_t split_k, wn_stream_t stream) {
+  if (!a || !b || !c) return -1;
+  GemmParams p = gp(a, lda, b, ldb, c, ldc, m, n, k);
+  p.bias = bias;
+  p.aux = relu_mask;
+  p.ldaux = ldmask;
+  p.flags = flags;
+  if (mode == 2) p.flags |= GEMM_ATOMIC;
+  return gemm_tf32(mode, p, split_k, (cudaStream_t)stream);
+}
+
+int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t time, int32_t q, float* partials,
+                    int32_t n_partials, float* loss_out, int32_t write_grad, wn_stream_t stream) {
+  if (!logits || !ids || !partials || !loss_out || batch < 1 || time < 1) return -1;
+  const int M = batch * time;
+  return softmax_xent(logits, ids, M, time, q, 1.0f / (float)M, partials, n_partials, loss_out, write_grad,
+                      (cudaStream_t)stream);
+}
+
+int64_t wn_train_workspace_bytes(const wn_config* cfg, int32_t batch, int32_t time) {
+  if (check_cfg(cfg) || batch < 1 || time < 1 || (int64_t)batch * time > (1 << 30)) return -1;
+  Workspace w;
+  carve(cfg, batch, time, true, nullptr, &w);
+  return w.bytes;
+}
+int64_t wn_forward_workspace_bytes(const wn_config* cfg, int32_t batch, int32_t time) {
+  if (check_cfg(cfg) || batch < 1 || time < 1 || (int64_t)batch * time > (1 << 30)) return -1;
+  Workspace w;
+  carve(cfg, batch, time, false, nullptr, &w);
+  return w.bytes;
+}
+
+int wn_forward_logits(const wn_config* cfg, const float* params, void* workspace, int64_t workspace_bytes,
+                      const int32_t* ids, const int32_t* gc_ids, int32_t batch, int32_t time, float* logits,
+                      wn_stream_t stream) {
+  wn_layout lo;
+  RC(make_layout(cfg, &lo));
+  if (!params || !workspace || !ids || !logits || batch < 1 || time < 1) return -1;
+  if ((uintptr_t)workspace & 255) return -4;
+  Workspace w;
+  carve(cfg, batch, time, false, workspace, &w);
+  if (w.bytes > workspace_bytes) return -5;
+  return run_forward(cfg, lo, params, w, ids, gc_ids, batch, time, false, logits, (cudaStream_t)stream);
+}
+
+int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* workspace, int64_t workspace_bytes,
+                 const float* audio, const int32_t* gc_ids, const float* mulaw_thresholds, int32_t batch,
+                 int32_t time, float* loss_out, wn_stream_t stream) {
+  wn_layout lo;
+  RC(make_layout(cfg, &lo));
+  if (!params || !grads || !workspace || !audio || !mulaw_thresholds || !loss_out || batch < 1 || time < 1) return -1;
+  if ((uintptr_t)workspace & 255) return -4;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve(cfg, batch, time, true, workspace, &w);
+  if (w.bytes > workspace_bytes) return -5;
+  const int B = batch, T = time, M = B * T, L = cfg->n_layers, R = cfg->residual_channels,
+            D = cfg->dilation_channels, S = cfg->skip_channels, Q = cfg->quantization_channels,
+            G = cfg->gc_channels;
+  const int ldz = L * D;
+  const bool rp = cfg->residual_postproc != 0;
+
+  RC((int)cudaMemsetAsync(grads, 0, (size_t)lo.total * sizeof(float), st));
+  RC((int)cudaMemsetAsync(w.gprebias, 0, (size_t)L * B * 2 * D * sizeof(float), st));
+  prof_mark(st, PT_MISC);
+  RC(mulaw_encode(audio, M, mulaw_thresholds, Q, w.ids, st));            // model.py:639
+  prof_mark(st, PT_MULAW);
+  RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, w.logits, st));
+  RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, st));
+  prof_mark(st, PT_XENT);
+
+  const float* x2 = rp ? w.T2 : w.A2;
+  {  // postprocess2 gradients
+    GemmParams p = gp(x2, S, w.logits, Q, grads + lo.post2, Q, S, Q, M);
+    p.flags = GEMM_ATOMIC;
+    RC(gemm_tf32(2, p, split_for(S, Q, M), st));
+    prof_mark(st, PT_GEMM_POST2_WGRAD);
+    if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, st)); prof_mark(st, PT_COLSUM); }
+  }
+  {  // d transformed2 -> d conv1 (relu mask from A2)
+    GemmParams p = gp(w.logits, Q, params + lo.post2, Q, w.G1, S, M, S, Q);
+    p.aux = w.A2; p.ldaux = S;
+    p.flags = GEMM_ROUND;
+    if (rp) { p.C2 = w.G3; p.ldc2 = S; }
+    RC(gemm_tf32(1, p, 1, st));
+    prof_mark(st, PT_GEMM_POST2_DGRAD);
+  }
+  {  // postprocess1 gradients
+    GemmParams p = gp(w.A1, S, w.G1, S, grads + lo.post1, S, S, S, M);
+    p.flags = GEMM_ATOMIC;
+    RC(gemm_tf32(2, p, split_for(S, S, M), st));
+    prof_mark(st, PT_GEMM_POST1_WGRAD);
+    if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, st)); prof_mark(st, PT_COLSUM); }
+  }
+  {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
+    GemmParams p = gp(w.G1, S, params + lo.post1, S, w.G2, S, M, S, S);
+    p.aux = w.A1; p.ldaux = S;
+    p.flags = rp ? 0 : GEMM_ROUND;
+    RC(gemm_tf32(1, p, 1, st));
+    prof_mark(st, PT_GEMM_POST1_DGRAD);
+    if (rp) { RC(add_inplace(w.G2, w.G3, (int64_t)M * S, 1, st)); prof_mark(st, PT_MISC); }
+  }
+  {  // skip weights / biases
+    GemmParams p = gp(w.Zcat, ldz, w.G2, S, grads + lo.skip, S, ldz, S, M);
+    p.flags = GEMM_ATOMIC;
+    RC(gemm_tf32(2, p, split_for(ldz, S, M), st));
+    prof_mark(st, PT_GEMM_SKIP_WGRAD);
+    if (lo.skip_bias >= 0) {
+      RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), st));
+      RC(colsum(w.G2, S, M, S, w.gtmp, st));
+      prof_mark(st, PT_COLSUM);
+      RC(bcast_rows(w.gtmp, S, grads + lo.skip_bias, L, st));
+      prof_mark(st, PT_MISC);
+    }
+  }
+  {  // d z (skip path) for every layer at once
+    GemmParams p = gp(w.G2, S, params + lo.skip, S, w.dZcat, ldz, M, ldz, S);
+    RC(gemm_tf32(1, p, 1, st));
+    prof_mark(st, PT_GEMM_SKIP_DGRAD);
+  }
+  const int64_t xs = (int64_t)M * R;
+  float* dcur = w.dX;        // gradient wrt the output of the layer being processed
+  float* dnext = w.dX + xs;  // gradient wrt its input
+  for (int l = L - 1; l >= 0; --l) {
+    const int last = (l == L - 1);
+    RC(block_bwd(w.X + l * xs, last ? nullptr : dcur, w.dZcat + (int64_t)l * D, ldz, dnext, w.dpre,
+                 w.Zcat + (int64_t)l * D, params + lo.filter + (int64_t)l * 2 * R * D,
+                 params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
+                 w.prebias + (int64_t)l * B * 2 * D, grads + lo.filter + (int64_t)l * 2 * R * D,
+                 grads + lo.gate + (int64_t)l * 2 * R * D, grads + lo.dense + (int64_t)l * D * R,
+                 w.gprebias + (int64_t)l * B * 2 * D,
+                 lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, M, T, cfg->dilations[l], R,
+                 last, st));
+    float* tmp = dcur; dcur = dnext; dnext = tmp;
+  }
+  RC(frontend_bwd(w.ids, dcur, grads + lo.causal, M, T, Q, R, st));
+  prof_mark(st, PT_FRONTEND_BWD);
+  if (lo.filter_bias >= 0 || G > 0) {
+    RC(cond_bias_bwd(w.gprebias, P(grads, lo.filter_bias), P(grads, lo.gate_bias), P(params, lo.gc_filter),
+                     P(params, lo.gc_gate), P(grads, lo.gc_filter), P(grads, lo.gc_gate),
+                     P(params, lo.gc_embedding), P(grads, lo.gc_embedding), gc_ids, L, B, D, gc_ids ? G : 0,
+                     cfg->gc_cardinality, st));
+    prof_mark(st, PT_COND_BIAS_BWD);
+  }
+  return 0;
+}
+
+int wn_optim_adam(float* w, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                  double eps, int64_t step, float l2, float grad_scale, wn_stream_t stream) {
+  if (!w || !g || !m || !v || step < 1) return -1;
+  const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
+  return optim_adam(w, g, m, v, n, lr_t, beta1, beta2, eps, l2, grad_scale, (cudaStream_t)stream);
+}
+int wn_optim_momentum(float* w, const float* g, float* accum, int64_t n, double lr, double momentum, float l2,
+                      float grad_scale, wn_stream_t stream) {
+  if (!w || !g || !accum) return -1;
+  return optim_momentum(w, g, accum, n, lr, momentum, l2, grad_scale, (cudaStream_t)stream);
+}
+int wn_optim_rmsprop(float* w, const float* g, float* ms, float* mom, int64_t n, double lr, double decay,
+                     double momentum, double eps, float l2, float grad_scale, wn_stream_t stream) {
+  if (!w || !g || !ms || !mom) return -1;
+  return optim_rmsprop(w, g, ms, mom, n, lr, decay, momentum, eps, l2, grad_scale, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Internal launcher declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wn {
+
+// ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream ----
+enum ProfTag {
+  PT_MISC = 0, PT_MULAW, PT_COND_BIAS, PT_FRONTEND_FWD, PT_BLOCK_FWD, PT_SKIP_BIAS_SUM, PT_GEMM_SKIP_FWD,
+  PT_GEMM_POST1_FWD, PT_GEMM_POST2_FWD, PT_XENT, PT_GEMM_POST2_WGRAD, PT_COLSUM, PT_GEMM_POST2_DGRAD,
+  PT_GEMM_POST1_WGRAD, PT_GEMM_POST1_DGRAD, PT_GEMM_SKIP_WGRAD, PT_GEMM_SKIP_DGRAD, PT_BLOCK_BWD_DX,
+  PT_BLOCK_WGRAD, PT_FRONTEND_BWD, PT_COND_BIAS_BWD, PT_COUNT
+};
+void prof_mark(cudaStream_t st, int tag);   // no-op unless wn_profile_begin() was called
+
+enum { GEMM_RELU = 1, GEMM_ROUND = 2, GEMM_ATOMIC = 4 };
+
+struct GemmParams {
+  const float* A; int lda;
+  const float* B; int ldb;
+  float* C; int ldc;
+  int M, N, K;
+  const float* bias;            // per output column, nullable
+  const float* aux; int ldaux;  // relu-gradient mask source (keep where aux > 0), nullable
+  float* C2; int ldc2;          // optional second output: acc + bias before relu/mask, nullable
+  int flags;
+};
+
+int gemm_tf32(int mode, const GemmParams& p, int split_k, cudaStream_t st);
+int colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
+
+int block_fwd(const float* x, float* xout, float* zc, int ldz, const float* wf, const float* wg,
+              const float* dense, const float* prebias, const float* dense_bias, int M, int T, int d,
+              int C, int is_last, cudaStream_t st);
+int block_bwd(const float* x, const float* dxn, const float* dzs, int ldz, float* dx, float* dpre,
+              const float* zc, const float* wf, const float* wg, const float* dense, const float* prebias,
+              float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int M, int T,
+              int d, int C, int is_last, cudaStream_t st);
+
+int mulaw_encode(const float* audio, int64_t n, const float* thresholds, int Q, int32_t* ids, cudaStream_t st);
+int mulaw_decode(const int32_t* ids, int64_t n, const float* lut, int Q, float* out, cudaStream_t st);
+
+int frontend_fwd(const int32_t* ids, const float* wc, float* x0, int M, int T, int Q, int R, cudaStream_t st);
+int frontend_bwd(const int32_t* ids, const float* dx0, float* gwc, int M, int T, int Q, int R, cudaStream_t st);
+
+int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float scale, float* row_loss_partials,
+                 int n_partials, float* loss_out, int write_grad, cudaStream_t st);
+
+// prebias[l][b][2D] = [filter_bias_l | gate_bias_l] + emb[b] . [gc_filter_l | gc_gate_l]
+int cond_bias_fwd(float* prebias, const float* filter_bias, const float* gate_bias, const float* gc_filter,
+                  const float* gc_gate, const float* emb_table, const int32_t* gc_ids, int L, int B, int D,
+                  int G, cudaStream_t st);
+int cond_bias_bwd(const float* gprebias, float* gfilter_bias, float* ggate_bias, const float* gc_filter,
+                  const float* gc_gate, float* ggc_filter, float* ggc_gate, const float* emb_table,
+                  float* gemb_table, const int32_t* gc_ids, int L, int B, int D, int G, int card,
+                  cudaStream_t st);
+int causal_conv(const float* x, const float* w, float* y, int M, int T, int cin, int cout, int width, int d,
+                cudaStream_t st);
+int skip_bias_sum(const float* skip_bias, int L, int S, float* out, cudaStream_t st);
+int bcast_rows(const float* src, int n, float* dst, int rows, cudaStream_t st);
+int add_inplace(float* dst, const float* src, int64_t n, int round_out, cudaStream_t st);
+int relu_mask_add(float* dst, const float* grad, const float* act, int64_t n, int round_out, cudaStream_t st);
+
+int optim_adam(float* w, const float* g, float* m, float* v, int64_t n, double lr_t, double beta1, double beta2,
+               double eps, float l2, float gscale, cudaStream_t st);
+int optim_momentum(float* w, const float* g, float* a, int64_t n, double lr, double mu, float l2, float gscale,
+                   cudaStream_t st);
+int optim_rmsprop(float* w, const float* g, float* ms, float* mom, int64_t n, double lr, double decay, double mu,
+                  double eps, float l2, float gscale, cudaStream_t st);
+
+}  // namespace wn

@@ -1,0 +1,77 @@
+"""One data-parallel training step (reference: the `sess.run([loss, optim])` of train.py:287-306).
+
+Every rank runs the full model on its own [B_local, T] windows (the reference is single-device;
+data parallelism is this build's addition).  The only exchange is a sum
+all-reduce of the flat fp32 gradient buffer over NCCL, followed by the same optimizer update on
+every rank (weights stay replicated).  The loss/gradient launch sequence (~170 kernels for the
+default network) is captured once into a CUDA graph and replayed.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .ops import as_cuda, device_tables
+
+
+class TrainStep(object):
+    def __init__(self, net, optimizer, batch, time, l2_regularization_strength=None, process_group=None,
+                 use_cuda_graph=True):
+        net._require_native()
+        self.net, self.opt = net, optimizer
+        self.batch, self.time = int(batch), int(time)
+        self.l2 = 0.0 if l2_regularization_strength is None else float(l2_regularization_strength)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        dev = net.device
+        self.audio = torch.zeros((self.batch, self.time), dtype=torch.float32, device=dev)   # static inputs
+        self.gc = (torch.zeros((self.batch,), dtype=torch.int32, device=dev)
+                   if net.global_condition_channels is not None else None)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self._ws = net._workspace('train', self.batch, self.time)
+        self._thr, _ = device_tables(net.quantization_channels)
+        self._graph = None
+        self.kernel_launches = None
+        if use_cuda_graph:
+            self._capture()
+
+    def _launch(self):
+        n = self.net
+        rc = n._lib.wn_loss_grad(C.byref(n._cfg), _lib.ptr(n.flat_params), _lib.ptr(n.flat_grads),
+                                 _lib.ptr(self._ws), self._ws.numel(), _lib.ptr(self.audio), _lib.ptr(self.gc),
+                                 _lib.ptr(self._thr), self.batch, self.time, _lib.ptr(self.loss), _lib.stream_ptr())
+        _lib.check(rc, 'wn_loss_grad')
+
+    def _capture(self):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._launch()          # warm-up: function attributes, lazy module load
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch()
+        self._graph = g
+
+    def __call__(self, audio=None, gc_ids=None):
+        """Runs one step on `audio` [B,T] (host or device; copied into the static input buffer)
+        and returns the (device) loss of this rank."""
+        if audio is not None:
+            src = audio if isinstance(audio, torch.Tensor) else torch.as_tensor(audio)
+            self.audio.copy_(src.reshape(self.batch, self.time), non_blocking=True)
+        if gc_ids is not None and self.gc is not None:
+            src = gc_ids if isinstance(gc_ids, torch.Tensor) else torch.as_tensor(gc_ids)
+            self.gc.copy_(src.reshape(-1).to(torch.int32), non_blocking=True)
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._launch()
+        scale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(self.net.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            scale = 1.0 / self.world
+        self.opt.apply(self.net.flat_params, self.net.flat_grads, l2=self.l2, grad_scale=scale)
+        return self.loss

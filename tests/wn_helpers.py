@@ -1,0 +1,41 @@
+"""Shared helpers for the GPU parity tests."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+# Tolerances (BASELINE.json north_star): integer / index work is bit exact; logits and loss of the
+# TF32-tensor-core path must be within 1e-3 relative of the fp32 reference arithmetic.  "Relative"
+# for a tensor means max|a-b| / max|b| (error against the scale of the tensor); for the scalar loss
+# it is |a-b| / |b|.
+LOGIT_RTOL = 1e-3
+LOSS_RTOL = 1e-3
+# Gradients are not covered by north_star; they go through one more TF32 GEMM level each way.
+GRAD_RTOL = 4e-3
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    return float(np.abs(a - b).max() / scale)
+
+
+def dev(x, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x), device='cuda').to(dtype).contiguous()
+
+
+def p(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_pair(O, wavenet, seed=0, bias_scale=0.1, dtype=torch.float64, **kw):
+    """(oracle net, product net) holding identical weights (biases non-zero to exercise them)."""
+    onet = O.OracleWaveNet(dtype=dtype, seed=seed, bias_scale=bias_scale, faithful=False, **kw)
+    net = wavenet.WaveNetModel(**kw)
+    net.load_state_dict(onet.state_dict())
+    return onet, net
