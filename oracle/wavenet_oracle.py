@@ -194,6 +194,44 @@ def init_variables(specs, seed=0, bias_scale=0.0):
 
 
 # --------------------------------------------------------------------------- #
+# TF32 operand-rounding emulation (arithmetic-matched variant of the oracle)
+# --------------------------------------------------------------------------- #
+# The sm_100a kernels feed the tensor cores TF32 operands (fp32 rounded to a 10-bit mantissa,
+# round-to-nearest ties-away = PTX cvt.rna.tf32.f32) and accumulate in fp32.  `emulate='tf32'`
+# makes the oracle apply the same rounding at the same operand positions, so that kernel LOGIC
+# can be checked tightly; parity against the un-rounded oracle is asserted separately at the
+# tolerance BASELINE.json states.
+
+
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    x32 = x.detach().to(torch.float32).contiguous()
+    i = x32.view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    return r.to(x.dtype)
+
+
+class _RoundedMatmul(torch.autograd.Function):
+    """y = a @ b with TF32-rounded operands.  fwd_round=False keeps the forward product exact
+    (the forward block kernel uses a 3-term split that is fp32-grade) while the backward
+    products still see rounded operands (single-pass TF32 gradient kernels)."""
+
+    @staticmethod
+    def forward(ctx, a, b, fwd_round):
+        ctx.save_for_backward(a, b)
+        if fwd_round:
+            return round_tf32(a) @ round_tf32(b)
+        return a @ b
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        gr = round_tf32(g)
+        ga = gr @ round_tf32(b).transpose(-1, -2)
+        gb = round_tf32(a).reshape(-1, a.shape[-1]).t() @ gr.reshape(-1, g.shape[-1])
+        return ga, gb, None
+
+
+# --------------------------------------------------------------------------- #
 # softmax cross entropy with TF-0.10 forward AND backward semantics
 # --------------------------------------------------------------------------- #
 
@@ -231,7 +269,7 @@ class OracleWaveNet(object):
                  skip_channels, quantization_channels=2 ** 8, use_biases=False, scalar_input=False,
                  initial_filter_width=32, histograms=False, global_condition_channels=None,
                  global_condition_cardinality=None, residual_postproc=False,
-                 dtype=torch.float32, seed=0, bias_scale=0.0, faithful=True):
+                 dtype=torch.float32, seed=0, bias_scale=0.0, faithful=True, emulate=None):
         self.batch_size = batch_size
         self.dilations = list(dilations)
         self.filter_width = filter_width
@@ -247,6 +285,8 @@ class OracleWaveNet(object):
         self.residual_postproc = residual_postproc
         self.dtype = dtype
         self.faithful = faithful  # True: reshape-chain causal_conv; False: closed form
+        self.emulate = emulate    # None | 'tf32' (closed-form path only): see round_tf32 above
+        assert emulate in (None, 'tf32') and not (emulate and faithful)
         self.specs = variable_specs(dilations, filter_width, residual_channels, dilation_channels,
                                     skip_channels, quantization_channels, use_biases, scalar_input,
                                     initial_filter_width, global_condition_channels,
@@ -271,7 +311,16 @@ class OracleWaveNet(object):
     def _cc(self, x, w, d):
         if self.faithful or w.shape[0] != 2:
             return causal_conv(x, w, d)
+        if self.emulate:
+            past = F.pad(x, (0, 0, d, 0))[:, :x.shape[1], :]
+            return _RoundedMatmul.apply(past, w[0], False) + _RoundedMatmul.apply(x, w[1], False)
         return causal_conv_closed_form(x, w, d)
+
+    def _conv1x1(self, x, w, kind):
+        """tf.nn.conv1d with a width-1 filter; kind: 'block' (dense) or 'gemm' (skip/post)."""
+        if self.emulate:
+            return _RoundedMatmul.apply(x, w[0], kind == 'gemm')
+        return _conv1d_same(x, w)
 
     # -- pieces ----------------------------------------------------------------
     def _one_hot(self, ids):
@@ -305,10 +354,13 @@ class OracleWaveNet(object):
             conv_filter = conv_filter + self._lv(i, 'filter_bias')
             conv_gate = conv_gate + self._lv(i, 'gate_bias')
         out = torch.tanh(conv_filter) * torch.sigmoid(conv_gate)
+        if self.emulate:
+            # the kernel stores z tf32-rounded (straight-through for the gradient)
+            out = out + (round_tf32(out) - out).detach()
         transformed = None
         if not is_last:
-            transformed = _conv1d_same(out, self._lv(i, 'dense'))
-        skip = _conv1d_same(out, self._lv(i, 'skip'))
+            transformed = self._conv1x1(out, self._lv(i, 'dense'), 'block')
+        skip = self._conv1x1(out, self._lv(i, 'skip'), 'gemm')
         if self.use_biases:
             if not is_last:
                 transformed = transformed + self._lv(i, 'dense_bias')
@@ -331,13 +383,13 @@ class OracleWaveNet(object):
         p = 'wavenet/postprocessing/'
         total = sum(outputs)
         t1 = torch.relu(total)
-        conv1 = _conv1d_same(t1, self.vars[p + 'postprocess1'])
+        conv1 = self._conv1x1(t1, self.vars[p + 'postprocess1'], 'gemm')
         if self.use_biases:
             conv1 = conv1 + self.vars[p + 'postprocess1_bias']
         t2 = torch.relu(conv1)
         if self.residual_postproc:
             t2 = t2 + total
-        conv2 = _conv1d_same(t2, self.vars[p + 'postprocess2'])
+        conv2 = self._conv1x1(t2, self.vars[p + 'postprocess2'], 'gemm')
         if self.use_biases:
             conv2 = conv2 + self.vars[p + 'postprocess2_bias']
         if return_intermediates:

@@ -220,6 +220,176 @@ block_fwd_kernel(const float* __restrict__ x, float* __restrict__ xout, float* _
   }
 }
 
+
+// ---- split-precision ("3xTF32") forward ---------------------------------------------------
+// A single TF32 pass rounds both operands to 11 bits; through 50 residual layers that error
+// accumulates in the residual stream and alone pushes the logits ~2e-3 away from the fp32
+// reference (measured).  The forward block therefore splits every operand
+// into hi + lo TF32 parts and issues a.lo*b.hi + a.hi*b.lo + a.hi*b.hi (fp32-grade products).
+template <int C>
+__device__ __forceinline__ void load_chunk3(uint32_t (&hi)[C / 4], uint32_t (&lo)[C / 4],
+                                            const float* __restrict__ row, int t, bool valid) {
+  if (valid) {
+    const float4* p = reinterpret_cast<const float4*>(row + (C / 4) * t);
+#pragma unroll
+    for (int i = 0; i < C / 16; ++i) {
+      float4 q = __ldg(p + i);
+      const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t h = f2tf32(v[e]);
+        hi[4 * i + e] = h;
+        lo[4 * i + e] = f2tf32(v[e] - __uint_as_float(h));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) hi[i] = lo[i] = 0u;
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void split_tile(float2* hi, float2* lo, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float2 w = lo[i];   // staged as raw fp32 in `lo`
+    const float hx = round_tf32(w.x), hy = round_tf32(w.y);
+    hi[i] = make_float2(hx, hy);
+    lo[i] = make_float2(round_tf32(w.x - hx), round_tf32(w.y - hy));
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256, 2)
+block_fwd3_kernel(const float* __restrict__ x, float* __restrict__ xout, float* __restrict__ zc, int ldz,
+                  const float* __restrict__ wf, const float* __restrict__ wg,
+                  const float* __restrict__ dense, const float* __restrict__ prebias,
+                  const float* __restrict__ dense_bias, int M, int T, int d, int is_last) {
+  using K = BlockCfg<C>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* wcat_hi = reinterpret_cast<float2*>(smem_raw);
+  float2* wcat_lo = wcat_hi + C * K::NTP;
+  float2* wd_hi = wcat_lo + C * K::NTP;
+  float2* wd_lo = wd_hi + (C / 2) * K::NDP;
+  // stage raw fp32 pairs into the *_lo tiles, then split in place
+  for (int i = threadIdx.x; i < C * K::NT; i += blockDim.x) {
+    const int kp = i / K::NT, n = i % K::NT;
+    const float* w = (n < C) ? wf : wg;
+    const int col = (n < C) ? n : n - C;
+    wcat_lo[kp * K::NTP + n] = make_float2(w[(2 * kp) * C + col], w[(2 * kp + 1) * C + col]);
+  }
+  if (!is_last)
+    for (int i = threadIdx.x; i < (C / 2) * C; i += blockDim.x) {
+      const int kp = i / C, n = i % C;
+      wd_lo[kp * K::NDP + n] = make_float2(dense[(2 * kp) * C + n], dense[(2 * kp + 1) * C + n]);
+    }
+  __syncthreads();
+  split_tile<C>(wcat_hi, wcat_lo, C * K::NTP);
+  if (!is_last) split_tile<C>(wd_hi, wd_lo, (C / 2) * K::NDP);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int n_tiles = (M + 15) >> 4;
+  for (int tile = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); tile < n_tiles;
+       tile += gridDim.x * warps_per_cta) {
+    const int r0 = tile * 16 + g, r1 = r0 + 8;
+    const bool v0 = r0 < M, v1 = r1 < M;
+    const int b0 = v0 ? r0 / T : 0, b1 = v1 ? r1 / T : 0;
+    const int t0 = r0 - b0 * T, t1 = r1 - b1 * T;
+    float acc[K::NT / 8][4];
+#pragma unroll
+    for (int j = 0; j < K::NT / 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      uint32_t h0[K::CH], l0[K::CH], h1[K::CH], l1[K::CH];
+      if (part == 0) {
+        load_chunk3<C>(h0, l0, x + (size_t)(r0 - d) * C, t, v0 && t0 >= d);
+        load_chunk3<C>(h1, l1, x + (size_t)(r1 - d) * C, t, v1 && t1 >= d);
+      } else {
+        load_chunk3<C>(h0, l0, x + (size_t)r0 * C, t, v0);
+        load_chunk3<C>(h1, l1, x + (size_t)r1 * C, t, v1);
+      }
+#pragma unroll
+      for (int s = 0; s < K::KS; ++s) {
+        const int kp = part * (C / 2) + K::KS * t + s;
+        const float2* whi = wcat_hi + kp * K::NTP + g;
+        const float2* wlo = wcat_lo + kp * K::NTP + g;
+#pragma unroll
+        for (int j = 0; j < K::NT / 8; ++j) {
+          const float2 bh = whi[8 * j], bl = wlo[8 * j];
+          mma_tf32(acc[j], l0[2 * s], l1[2 * s], l0[2 * s + 1], l1[2 * s + 1], __float_as_uint(bh.x),
+                   __float_as_uint(bh.y));
+          mma_tf32(acc[j], h0[2 * s], h1[2 * s], h0[2 * s + 1], h1[2 * s + 1], __float_as_uint(bl.x),
+                   __float_as_uint(bl.y));
+          mma_tf32(acc[j], h0[2 * s], h1[2 * s], h0[2 * s + 1], h1[2 * s + 1], __float_as_uint(bh.x),
+                   __float_as_uint(bh.y));
+        }
+      }
+    }
+    const float* pb0 = prebias + (size_t)b0 * K::NT;
+    const float* pb1 = prebias + (size_t)b1 * K::NT;
+    uint32_t zh[K::KS][4], zl[K::KS][4];
+#pragma unroll
+    for (int j = 0; j < K::KS; ++j) {
+      const int col = 8 * j + 2 * t;
+      float2 bf0 = __ldg(reinterpret_cast<const float2*>(pb0 + col));
+      float2 bg0 = __ldg(reinterpret_cast<const float2*>(pb0 + C + col));
+      float2 bf1 = __ldg(reinterpret_cast<const float2*>(pb1 + col));
+      float2 bg1 = __ldg(reinterpret_cast<const float2*>(pb1 + C + col));
+      float z[4];
+      z[0] = tanhf(acc[j][0] + bf0.x) * (1.0f / (1.0f + expf(-(acc[j + K::KS][0] + bg0.x))));
+      z[1] = tanhf(acc[j][1] + bf0.y) * (1.0f / (1.0f + expf(-(acc[j + K::KS][1] + bg0.y))));
+      z[2] = tanhf(acc[j][2] + bf1.x) * (1.0f / (1.0f + expf(-(acc[j + K::KS][2] + bg1.x))));
+      z[3] = tanhf(acc[j][3] + bf1.y) * (1.0f / (1.0f + expf(-(acc[j + K::KS][3] + bg1.y))));
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = f2tf32(z[e]);
+        l[e] = f2tf32(z[e] - __uint_as_float(h[e]));
+      }
+      // Zcat feeds the single-pass TF32 skip GEMM: store the tf32-rounded value
+      if (v0) *reinterpret_cast<float2*>(zc + (size_t)r0 * ldz + col) =
+          make_float2(__uint_as_float(h[0]), __uint_as_float(h[1]));
+      if (v1) *reinterpret_cast<float2*>(zc + (size_t)r1 * ldz + col) =
+          make_float2(__uint_as_float(h[2]), __uint_as_float(h[3]));
+      zh[j][0] = h[0]; zh[j][1] = h[2]; zh[j][2] = h[1]; zh[j][3] = h[3];
+      zl[j][0] = l[0]; zl[j][1] = l[2]; zl[j][2] = l[1]; zl[j][3] = l[3];
+    }
+    if (is_last) continue;
+    float o[K::KS][4];
+#pragma unroll
+    for (int i = 0; i < K::KS; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < K::KS; ++j) {
+      const float2* whi = wd_hi + (4 * j + t) * K::NDP + g;
+      const float2* wlo = wd_lo + (4 * j + t) * K::NDP + g;
+#pragma unroll
+      for (int i = 0; i < K::KS; ++i) {
+        const float2 bh = whi[8 * i], bl = wlo[8 * i];
+        mma_tf32(o[i], zl[j][0], zl[j][1], zl[j][2], zl[j][3], __float_as_uint(bh.x), __float_as_uint(bh.y));
+        mma_tf32(o[i], zh[j][0], zh[j][1], zh[j][2], zh[j][3], __float_as_uint(bl.x), __float_as_uint(bl.y));
+        mma_tf32(o[i], zh[j][0], zh[j][1], zh[j][2], zh[j][3], __float_as_uint(bh.x), __float_as_uint(bh.y));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < K::KS; ++i) {
+      const int col = 8 * i + 2 * t;
+      float2 bd = make_float2(0.f, 0.f);
+      if (dense_bias) bd = __ldg(reinterpret_cast<const float2*>(dense_bias + col));
+      if (v0) {
+        float2 xi = __ldg(reinterpret_cast<const float2*>(x + (size_t)r0 * C + col));
+        *reinterpret_cast<float2*>(xout + (size_t)r0 * C + col) =
+            make_float2(xi.x + o[i][0] + bd.x, xi.y + o[i][1] + bd.y);
+      }
+      if (v1) {
+        float2 xi = __ldg(reinterpret_cast<const float2*>(x + (size_t)r1 * C + col));
+        *reinterpret_cast<float2*>(xout + (size_t)r1 * C + col) =
+            make_float2(xi.x + o[i][2] + bd.x, xi.y + o[i][3] + bd.y);
+      }
+    }
+  }
+}
+
 // =========================================================================================
 // backward, input gradient:  dx[m] = dxn[m] + dpre[m].Wcur^T + dpre[m+d].Wpast^T
 // dpre = [df | dg] is recomputed for both row sets from x (no activations besides x and
@@ -559,18 +729,18 @@ static int launch_fwd(const float* x, float* xout, float* zc, int ldz, const flo
                       const float* dense, const float* prebias, const float* dense_bias, int M, int T,
                       int d, int is_last, cudaStream_t st) {
   using K = BlockCfg<C>;
-  const size_t smem = sizeof(float2) * (C * K::NTP + (C / 2) * K::NDP);
+  const size_t smem = 2 * sizeof(float2) * (C * K::NTP + (C / 2) * K::NDP);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(block_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(block_fwd3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
   const int n_tiles = (M + 15) / 16;
   int grid = (n_tiles + 7) / 8;
   const int cap = 2 * sm_count();
   if (grid > cap) grid = cap;
-  block_fwd_kernel<C><<<grid, 256, smem, st>>>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T,
-                                               d, is_last);
+  block_fwd3_kernel<C><<<grid, 256, smem, st>>>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T,
+                                                d, is_last);
   WN_CHECK_LAUNCH();
   prof_mark(st, PT_BLOCK_FWD);
   return 0;

@@ -184,10 +184,11 @@ def test_block_fwd_bwd(lib, C_, B, T, d, is_last):
                           p(dpb_), p(dbd_), B, T, d, C_, is_last, stream())
     assert rc == 0
     z = zc[:, C_:2 * C_].cpu().numpy().reshape(B, T, C_)
-    assert rel_err(z, ref['z']) < LOGIT_RTOL
+    # forward block = split-precision (3xTF32) products; only the stored z is tf32-rounded (2^-11)
+    assert rel_err(z, ref['z']) < 6e-4
     assert float(zc[:, :C_].abs().max()) == 0.0 and float(zc[:, 2 * C_:].abs().max()) == 0.0
     if not is_last:
-        assert rel_err(xo.cpu().numpy().reshape(B, T, C_), ref['xo']) < LOGIT_RTOL
+        assert rel_err(xo.cpu().numpy().reshape(B, T, C_), ref['xo']) < 2e-5
 
     dzs = torch.zeros(M, ldz, device='cuda')
     dzs[:, C_:2 * C_] = dev(gz).reshape(M, C_)
@@ -292,6 +293,7 @@ def test_sampler_bit_exact(lib):
     rows, Q = 4000, 256
     pr = rng.dirichlet(np.ones(Q) * 0.3, size=rows).astype(np.float32)
     pr[5, 10:200] = 0.0
+    pr[5] /= pr[5].sum()
     u = rng.random_sample(rows)
     u[:4] = [0.0, 1.0 - 2 ** -53, 0.5, 1e-300]
     out = torch.zeros(rows, dtype=torch.int32, device='cuda')

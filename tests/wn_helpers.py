@@ -10,8 +10,14 @@ import torch
 # it is |a-b| / |b|.
 LOGIT_RTOL = 1e-3
 LOSS_RTOL = 1e-3
-# Gradients are not covered by north_star; they go through one more TF32 GEMM level each way.
+# Gradients are not covered by north_star.  They are checked (a) tightly against the oracle run with
+# the same TF32 operand rounding the kernels use (emulate='tf32': verifies the kernel logic), and
+# (b) loosely, norm-wise, against the exact oracle: rounding the forward GEMM operands to TF32 moves the
+# logits by ~5e-4, and at random initialisation the back-propagated signal is a small residual of
+# large cancelling terms, so that perturbation is amplified to a few percent of the gradient norm
+# (reproduced on the CPU by the emulation itself).
 GRAD_RTOL = 4e-3
+GRAD_L2_VS_EXACT = 0.1
 
 
 def rel_err(a, b):
@@ -19,6 +25,12 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-30)
     return float(np.abs(a - b).max() / scale)
+
+
+def l2_rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
 def dev(x, dtype=torch.float32):
@@ -39,3 +51,10 @@ def make_pair(O, wavenet, seed=0, bias_scale=0.1, dtype=torch.float64, **kw):
     net = wavenet.WaveNetModel(**kw)
     net.load_state_dict(onet.state_dict())
     return onet, net
+
+
+def matched_oracle(O, onet, **kw):
+    """The same network with the kernels' TF32 operand rounding emulated (see oracle round_tf32)."""
+    m = O.OracleWaveNet(dtype=onet.dtype, seed=0, faithful=False, emulate='tf32', **kw)
+    m.load_state_dict(onet.state_dict())
+    return m
