@@ -112,6 +112,13 @@ int wn_gemm_tf32(int32_t mode, const float* a, int32_t lda, const float* b, int3
                  int32_t ldc, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
                  int32_t ldmask, int32_t flags, int32_t split_k, wn_stream_t stream);
 
+/* The production GEMM: C[M,N] (+)= A[M,K] . B[N,K]^T, both operands K-major, on tcgen05 (TMA +
+ * tcgen05.mma.kind::tf32 + TMEM).  ct (nullable) receives a transposed copy [N][M] (row pitch ldct).
+ * flags as above; flag 4 (atomic) enables split-K over `split_k` CTAs along K. */
+int wn_gemm_nt_umma(const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc, float* ct,
+                    int32_t ldct, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
+                    int32_t ldmask, int32_t flags, int32_t split_k, wn_stream_t stream);
+
 /* ---- softmax cross entropy vs the next sample: model.py:654-666 ---------------------------
  * logits [B*T, Q] are overwritten by d loss / d logits (TF backprop semantics) when write_grad. */
 int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t time, int32_t q,
@@ -165,7 +172,7 @@ int wn_sample(const float* proba, const double* uniforms, int32_t rows, int32_t 
 
 /* ---- measurement aid (bench.py roofline): CUDA events on the launching stream after every kernel
  * of wn_loss_grad between begin/end; results are summed per kernel kind (wn_profile_tag_name). */
-#define WN_PROFILE_TAGS 21
+#define WN_PROFILE_TAGS 22
 int wn_profile_begin(void);
 int wn_profile_end(float* ms_per_tag /*host*/, int32_t* launches_per_tag /*host*/, int32_t n_tags);
 int wn_profile_tag_name(int32_t tag, char* out /*host*/, int32_t n);

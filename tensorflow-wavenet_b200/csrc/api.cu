@@ -2,6 +2,7 @@
 // workspace carving and the launch sequences of the training / forward graphs.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/wavenet_b200.h"
 #include "common.cuh"
@@ -91,6 +92,17 @@ struct Workspace {
   float* bsum;     // [S]
   float* gtmp;     // [S]
   float* partials; // [4096]
+  // K-major operand copies for the tcgen05 "NT" GEMM form (ldm = M rounded up to 4)
+  float* WskipT;   // [S, L*D]
+  float* W1T;      // [S, S]
+  float* W2T;      // [Q, S]
+  float* ZcatT;    // [L*D, ldm]   (training)
+  float* A1T;      // [S, ldm]
+  float* X2T;      // [S, ldm]     transposed input of postprocess2 (A2, or A2 + S0)
+  float* dlogT;    // [Q, ldm]
+  float* G1T;      // [S, ldm]
+  float* G2T;      // [S, ldm]
+  int ldm;
   int64_t bytes;
 };
 
@@ -114,6 +126,21 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->prebias = (float*)take(L * B * 2 * D * f);
   w->bsum = (float*)take(S * f);
   w->partials = (float*)take(4096 * f);
+  w->WskipT = (float*)take(S * L * D * f);
+  w->W1T = (float*)take(S * S * f);
+  w->W2T = (float*)take(Q * S * f);
+  const int64_t ldm = (M + 3) & ~(int64_t)3;
+  w->ldm = (int)ldm;
+  if (training) {
+    w->ZcatT = (float*)take(L * D * ldm * f);
+    w->A1T = (float*)take(S * ldm * f);
+    w->X2T = (float*)take(S * ldm * f);
+    w->dlogT = (float*)take(Q * ldm * f);
+    w->G1T = (float*)take(S * ldm * f);
+    w->G2T = (float*)take(S * ldm * f);
+  } else {
+    w->ZcatT = w->A1T = w->X2T = w->dlogT = w->G1T = w->G2T = nullptr;
+  }
   if (training) {
     w->logits = (float*)take(M * Q * f);
     w->G1 = (float*)take(M * S * f);
@@ -148,6 +175,24 @@ static int split_for(int m_out, int n_out, int k) {
   if (s < 1) s = 1;
   if (s > 65535) s = 65535;
   return s;
+}
+
+// C[M,N] (+)= A[M,K] . B[N,K]^T with optional transposed copy CT[N][M].  tcgen05 by default;
+// WN_GEMM_IMPL=mma selects the mma.sync kernel (validation of one implementation against the other).
+static bool use_mma_gemm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WN_GEMM_IMPL");
+    v = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+static int gemm_nt(const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st) {
+  if (!use_mma_gemm()) return gemm_nt_umma(p, CT, ldct, split_k, st);
+  int rc = gemm_tf32(1, p, split_k, st);
+  if (rc) return rc;
+  if (CT) return transpose(p.C, p.ldc, CT, ldct, p.M, p.N, st);
+  return 0;
 }
 
 #define RC(x)            \
@@ -185,31 +230,41 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     prof_mark(st, PT_SKIP_BIAS_SUM);
     bsum = w.bsum;
   }
+  // K-major weight copies for the forward products (weights change every step; 1.2 M elements)
+  RC(transpose(params + lo.skip, S, w.WskipT, ldz, ldz, S, st));
+  RC(transpose(params + lo.post1, S, w.W1T, S, S, S, st));
+  RC(transpose(params + lo.post2, Q, w.W2T, S, S, Q, st));
+  prof_mark(st, PT_MISC);
+  if (training) {
+    RC(transpose(w.Zcat, ldz, w.ZcatT, w.ldm, M, ldz, st));
+    prof_mark(st, PT_TRANSPOSE);
+  }
   {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
-    GemmParams p = gp(w.Zcat, ldz, params + lo.skip, S, w.A1, S, M, S, ldz);
+    GemmParams p = gp(w.Zcat, ldz, w.WskipT, ldz, w.A1, S, M, S, ldz);
     p.bias = bsum;
     p.flags = GEMM_RELU | GEMM_ROUND;
     if (c->residual_postproc) { p.C2 = w.S0; p.ldc2 = S; }
-    RC(gemm_tf32(0, p, 1, st));
+    RC(gemm_nt(p, training ? w.A1T : nullptr, w.ldm, 1, st));
     prof_mark(st, PT_GEMM_SKIP_FWD);
   }
   {  // conv1 -> relu                             (model.py:432-435)
-    GemmParams p = gp(w.A1, S, params + lo.post1, S, w.A2, S, M, S, S);
+    GemmParams p = gp(w.A1, S, w.W1T, S, w.A2, S, M, S, S);
     p.bias = P(params, lo.post1_bias);
     p.flags = GEMM_RELU | GEMM_ROUND;
-    RC(gemm_tf32(0, p, 1, st));
+    RC(gemm_nt(p, (training && !c->residual_postproc) ? w.X2T : nullptr, w.ldm, 1, st));
     prof_mark(st, PT_GEMM_POST1_FWD);
   }
   const float* x2 = w.A2;
   if (c->residual_postproc) {  // transformed2 += total   (model.py:436-437)
     RC((int)cudaMemcpyAsync(w.T2, w.A2, (size_t)M * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
     RC(add_inplace(w.T2, w.S0, (int64_t)M * S, 1, st));
+    if (training) RC(transpose(w.T2, S, w.X2T, w.ldm, M, S, st));
     x2 = w.T2;
   }
   {  // conv2                                      (model.py:438-440)
-    GemmParams p = gp(x2, S, params + lo.post2, Q, logits, Q, M, Q, S);
+    GemmParams p = gp(x2, S, w.W2T, S, logits, Q, M, Q, S);
     p.bias = P(params, lo.post2_bias);
-    RC(gemm_tf32(0, p, 1, st));
+    RC(gemm_nt(p, nullptr, 0, 1, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
   }
   return 0;
@@ -256,7 +311,7 @@ int wn_profile_tag_name(int32_t tag, char* out, int32_t n) {
       "misc", "mulaw_encode", "cond_bias_fwd", "frontend_fwd", "block_fwd", "skip_bias_sum", "gemm_skip_fwd",
       "gemm_post1_fwd", "gemm_post2_fwd", "softmax_xent", "gemm_post2_wgrad", "colsum", "gemm_post2_dgrad",
       "gemm_post1_wgrad", "gemm_post1_dgrad", "gemm_skip_wgrad", "gemm_skip_dgrad", "block_bwd_dx",
-      "block_wgrad", "frontend_bwd", "cond_bias_bwd"};
+      "block_wgrad", "frontend_bwd", "cond_bias_bwd", "transpose"};
   if (tag < 0 || tag >= PT_COUNT || !out || n < 1) return -1;
   snprintf(out, n, "%s", names[tag]);
   return 0;
@@ -332,6 +387,18 @@ int wn_gemm_tf32(int32_t mode, const float* a, int32_t lda, const float* b, int3
   return gemm_tf32(mode, p, split_k, (cudaStream_t)stream);
 }
 
+int wn_gemm_nt_umma(const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc, float* ct,
+                    int32_t ldct, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
+                    int32_t ldmask, int32_t flags, int32_t split_k, wn_stream_t stream) {
+  if (!a || !b || (!c && !ct)) return -1;
+  GemmParams p = gp(a, lda, b, ldb, c, ldc, m, n, k);
+  p.bias = bias;
+  p.aux = relu_mask;
+  p.ldaux = ldmask;
+  p.flags = flags;
+  return gemm_nt_umma(p, ct, ldct, split_k, (cudaStream_t)stream);
+}
+
 int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t time, int32_t q, float* partials,
                     int32_t n_partials, float* loss_out, int32_t write_grad, wn_stream_t stream) {
   if (!logits || !ids || !partials || !loss_out || batch < 1 || time < 1) return -1;
@@ -392,26 +459,27 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, st));
   prof_mark(st, PT_XENT);
 
-  const float* x2 = rp ? w.T2 : w.A2;
-  {  // postprocess2 gradients
-    GemmParams p = gp(x2, S, w.logits, Q, grads + lo.post2, Q, S, Q, M);
+  RC(transpose(w.logits, Q, w.dlogT, w.ldm, M, Q, st));
+  prof_mark(st, PT_TRANSPOSE);
+  {  // postprocess2 gradients:  dW2[S,Q] = X2^T . dlogits
+    GemmParams p = gp(w.X2T, w.ldm, w.dlogT, w.ldm, grads + lo.post2, Q, S, Q, M);
     p.flags = GEMM_ATOMIC;
-    RC(gemm_tf32(2, p, split_for(S, Q, M), st));
+    RC(gemm_nt(p, nullptr, 0, split_for(S, Q, M), st));
     prof_mark(st, PT_GEMM_POST2_WGRAD);
     if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, st)); prof_mark(st, PT_COLSUM); }
   }
-  {  // d transformed2 -> d conv1 (relu mask from A2)
+  {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
     GemmParams p = gp(w.logits, Q, params + lo.post2, Q, w.G1, S, M, S, Q);
     p.aux = w.A2; p.ldaux = S;
     p.flags = GEMM_ROUND;
     if (rp) { p.C2 = w.G3; p.ldc2 = S; }
-    RC(gemm_tf32(1, p, 1, st));
+    RC(gemm_nt(p, w.G1T, w.ldm, 1, st));
     prof_mark(st, PT_GEMM_POST2_DGRAD);
   }
-  {  // postprocess1 gradients
-    GemmParams p = gp(w.A1, S, w.G1, S, grads + lo.post1, S, S, S, M);
+  {  // postprocess1 gradients:  dW1[S,S] = A1^T . G1
+    GemmParams p = gp(w.A1T, w.ldm, w.G1T, w.ldm, grads + lo.post1, S, S, S, M);
     p.flags = GEMM_ATOMIC;
-    RC(gemm_tf32(2, p, split_for(S, S, M), st));
+    RC(gemm_nt(p, nullptr, 0, split_for(S, S, M), st));
     prof_mark(st, PT_GEMM_POST1_WGRAD);
     if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, st)); prof_mark(st, PT_COLSUM); }
   }
@@ -419,14 +487,18 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     GemmParams p = gp(w.G1, S, params + lo.post1, S, w.G2, S, M, S, S);
     p.aux = w.A1; p.ldaux = S;
     p.flags = rp ? 0 : GEMM_ROUND;
-    RC(gemm_tf32(1, p, 1, st));
+    RC(gemm_nt(p, rp ? nullptr : w.G2T, w.ldm, 1, st));
     prof_mark(st, PT_GEMM_POST1_DGRAD);
-    if (rp) { RC(add_inplace(w.G2, w.G3, (int64_t)M * S, 1, st)); prof_mark(st, PT_MISC); }
+    if (rp) {
+      RC(add_inplace(w.G2, w.G3, (int64_t)M * S, 1, st));
+      RC(transpose(w.G2, S, w.G2T, w.ldm, M, S, st));
+      prof_mark(st, PT_MISC);
+    }
   }
-  {  // skip weights / biases
-    GemmParams p = gp(w.Zcat, ldz, w.G2, S, grads + lo.skip, S, ldz, S, M);
+  {  // skip weights / biases:  dWskip[L*D,S] = Zcat^T . G2
+    GemmParams p = gp(w.ZcatT, w.ldm, w.G2T, w.ldm, grads + lo.skip, S, ldz, S, M);
     p.flags = GEMM_ATOMIC;
-    RC(gemm_tf32(2, p, split_for(ldz, S, M), st));
+    RC(gemm_nt(p, nullptr, 0, split_for(ldz, S, M), st));
     prof_mark(st, PT_GEMM_SKIP_WGRAD);
     if (lo.skip_bias >= 0) {
       RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), st));
@@ -436,9 +508,9 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       prof_mark(st, PT_MISC);
     }
   }
-  {  // d z (skip path) for every layer at once
+  {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
     GemmParams p = gp(w.G2, S, params + lo.skip, S, w.dZcat, ldz, M, ldz, S);
-    RC(gemm_tf32(1, p, 1, st));
+    RC(gemm_nt(p, nullptr, 0, 1, st));
     prof_mark(st, PT_GEMM_SKIP_DGRAD);
   }
   const int64_t xs = (int64_t)M * R;

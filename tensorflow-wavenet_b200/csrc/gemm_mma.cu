@@ -181,7 +181,7 @@ int gemm_tf32(int mode, const GemmParams& p, int split_k, cudaStream_t st) {
   if (((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15) || ((uintptr_t)p.C & 7)) return -4;
   const size_t smem = sizeof(float) * STAGES * STAGE_FLOATS;
   static bool attr[3] = {false, false, false};
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, mode == 2 ? (split_k > 0 ? split_k : 1) : 1);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, (p.flags & GEMM_ATOMIC) ? (split_k > 0 ? split_k : 1) : 1);
   if (mode == 0) {
     if (!attr[0]) { cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr[0] = true; }
     gemm_tf32_kernel<0><<<grid, 256, smem, st>>>(p);

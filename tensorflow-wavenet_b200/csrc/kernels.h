@@ -10,7 +10,7 @@ enum ProfTag {
   PT_MISC = 0, PT_MULAW, PT_COND_BIAS, PT_FRONTEND_FWD, PT_BLOCK_FWD, PT_SKIP_BIAS_SUM, PT_GEMM_SKIP_FWD,
   PT_GEMM_POST1_FWD, PT_GEMM_POST2_FWD, PT_XENT, PT_GEMM_POST2_WGRAD, PT_COLSUM, PT_GEMM_POST2_DGRAD,
   PT_GEMM_POST1_WGRAD, PT_GEMM_POST1_DGRAD, PT_GEMM_SKIP_WGRAD, PT_GEMM_SKIP_DGRAD, PT_BLOCK_BWD_DX,
-  PT_BLOCK_WGRAD, PT_FRONTEND_BWD, PT_COND_BIAS_BWD, PT_COUNT
+  PT_BLOCK_WGRAD, PT_FRONTEND_BWD, PT_COND_BIAS_BWD, PT_TRANSPOSE, PT_COUNT
 };
 void prof_mark(cudaStream_t st, int tag);   // no-op unless wn_profile_begin() was called
 
@@ -29,6 +29,9 @@ struct GemmParams {
 
 int gemm_tf32(int mode, const GemmParams& p, int split_k, cudaStream_t st);
 int colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
+// tcgen05 path: C[M,N] (+)= A[M,K] . B[N,K]^T (p.B is the [N,K] operand), optional transposed copy CT[N][M]
+int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st);
+int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, cudaStream_t st);
 
 int block_fwd(const float* x, float* xout, float* zc, int ldz, const float* wf, const float* wg,
               const float* dense, const float* prebias, const float* dense_bias, int M, int T, int d,

@@ -247,6 +247,42 @@ def test_gemm_epilogues(lib):
     assert rel_err(c.cpu().numpy(), (a @ b) * (mask > 0)) < LOGIT_RTOL
 
 
+@pytest.mark.parametrize('M,N,K,split', [(1000, 512, 1600, 0), (333, 32, 32, 0), (4096, 256, 512, 0), (517, 1600, 512, 0),
+                                         (1600, 512, 3001, 9), (32, 256, 1000, 4), (512, 512, 777, 3), (130, 132, 40, 0)])
+def test_gemm_nt_umma(lib, M, N, K, split):
+    """tcgen05 GEMM: C = A[M,K] . B[N,K]^T (+ transposed copy, split-K atomics) vs float64."""
+    rng = np.random.default_rng(M + N + K)
+    a, b = rng.standard_normal((M, K)), rng.standard_normal((N, K))
+    ref = a @ b.T
+    lda = (K + 3) // 4 * 4
+    da = torch.zeros(M, lda, device='cuda'); da[:, :K] = dev(a)
+    db = torch.zeros(N, lda, device='cuda'); db[:, :K] = dev(b)
+    c = torch.zeros(M, N, device='cuda')
+    ldct = (M + 3) // 4 * 4
+    ct = torch.zeros(N, ldct, device='cuda')
+    flags = 4 if split else 0
+    rc = lib.wn_gemm_nt_umma(p(da), lda, p(db), lda, p(c), N, None if split else p(ct), ldct, M, N, K, None, None, 0,
+                             flags, split, stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert rel_err(c.cpu().numpy(), ref) < LOGIT_RTOL
+    if not split:
+        np.testing.assert_array_equal(ct[:, :M].cpu().numpy(), c.cpu().numpy().T)
+
+
+def test_gemm_nt_umma_epilogues(lib):
+    rng = np.random.default_rng(5)
+    M, N, K = 300, 200, 96
+    a, b, bias = rng.standard_normal((M, K)), rng.standard_normal((N, K)), rng.standard_normal(N)
+    mask = rng.standard_normal((M, N))
+    da, db, dbias, dmask = dev(a), dev(b), dev(bias), dev(mask)
+    c = torch.zeros(M, N, device='cuda')
+    assert lib.wn_gemm_nt_umma(p(da), K, p(db), K, p(c), N, None, 0, M, N, K, p(dbias), None, 0, 1 | 2, 1, stream()) == 0
+    assert rel_err(c.cpu().numpy(), np.maximum(a @ b.T + bias, 0)) < LOGIT_RTOL
+    assert lib.wn_gemm_nt_umma(p(da), K, p(db), K, p(c), N, None, 0, M, N, K, None, p(dmask), N, 2, 1, stream()) == 0
+    assert rel_err(c.cpu().numpy(), (a @ b.T) * (mask > 0)) < LOGIT_RTOL
+
+
 # ----------------------------------------------------------------------------- softmax cross entropy
 @pytest.mark.parametrize('B,T,Q', [(1, 1000, 256), (3, 50, 128), (2, 7, 512), (1, 1, 256)])
 def test_softmax_xent(lib, B, T, Q):

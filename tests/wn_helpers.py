@@ -10,14 +10,15 @@ import torch
 # it is |a-b| / |b|.
 LOGIT_RTOL = 1e-3
 LOSS_RTOL = 1e-3
-# Gradients are not covered by north_star.  They are checked (a) tightly against the oracle run with
-# the same TF32 operand rounding the kernels use (emulate='tf32': verifies the kernel logic), and
-# (b) loosely, norm-wise, against the exact oracle: rounding the forward GEMM operands to TF32 moves the
-# logits by ~5e-4, and at random initialisation the back-propagated signal is a small residual of
-# large cancelling terms, so that perturbation is amplified to a few percent of the gradient norm
-# (reproduced on the CPU by the emulation itself).
+# Gradients are not covered by north_star.  Every gradient KERNEL is checked on its own at GRAD_RTOL
+# (max-norm relative, test_gpu_kernels.py).  End to end, against the exact oracle, they are checked
+# norm-wise: rounding the forward GEMM operands to TF32 moves the logits by ~5e-4, and at random
+# initialisation the back-propagated signal is a small residual of large cancelling terms, so any
+# 1e-3-level perturbation is amplified to ~1-3 % of the gradient norm.  The CPU emulation of the
+# same operand rounding (oracle emulate='tf32') shows the same deviation from the exact oracle
+# (tests/test_oracle_network.py::test_tf32_rounding_explains_gradient_deviation).
 GRAD_RTOL = 4e-3
-GRAD_L2_VS_EXACT = 0.1
+GRAD_L2_VS_EXACT = 5e-2
 
 
 def rel_err(a, b):
