@@ -96,6 +96,9 @@ struct Workspace {
   float* WskipT;   // [S, L*D]
   float* W1T;      // [S, S]
   float* W2T;      // [Q, S]
+  float* WskipR;   // [L*D, S]  tf32-rounded copies (B operands of the input-gradient GEMMs; training)
+  float* W1R;      // [S, S]
+  float* W2R;      // [S, Q]
   float* ZcatT;    // [L*D, ldm]   (training)
   float* A1T;      // [S, ldm]
   float* X2T;      // [S, ldm]     transposed input of postprocess2 (A2, or A2 + S0)
@@ -132,6 +135,9 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   const int64_t ldm = (M + 3) & ~(int64_t)3;
   w->ldm = (int)ldm;
   if (training) {
+    w->WskipR = (float*)take(S * L * D * f);
+    w->W1R = (float*)take(S * S * f);
+    w->W2R = (float*)take(Q * S * f);
     w->ZcatT = (float*)take(L * D * ldm * f);
     w->A1T = (float*)take(S * ldm * f);
     w->X2T = (float*)take(S * ldm * f);
@@ -139,7 +145,7 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->G1T = (float*)take(S * ldm * f);
     w->G2T = (float*)take(S * ldm * f);
   } else {
-    w->ZcatT = w->A1T = w->X2T = w->dlogT = w->G1T = w->G2T = nullptr;
+    w->ZcatT = w->A1T = w->X2T = w->dlogT = w->G1T = w->G2T = w->WskipR = w->W1R = w->W2R = nullptr;
   }
   if (training) {
     w->logits = (float*)take(M * Q * f);
@@ -191,7 +197,7 @@ static int gemm_nt(const GemmParams& p, float* CT, int ldct, int split_k, cudaSt
   if (!use_mma_gemm()) return gemm_nt_umma(p, CT, ldct, split_k, st);
   int rc = gemm_tf32(1, p, split_k, st);
   if (rc) return rc;
-  if (CT) return transpose(p.C, p.ldc, CT, ldct, p.M, p.N, st);
+  if (CT) return transpose(p.C, p.ldc, CT, ldct, p.M, p.N, 0, st);
   return 0;
 }
 
@@ -231,12 +237,17 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     bsum = w.bsum;
   }
   // K-major weight copies for the forward products (weights change every step; 1.2 M elements)
-  RC(transpose(params + lo.skip, S, w.WskipT, ldz, ldz, S, st));
-  RC(transpose(params + lo.post1, S, w.W1T, S, S, S, st));
-  RC(transpose(params + lo.post2, Q, w.W2T, S, S, Q, st));
+  RC(transpose(params + lo.skip, S, w.WskipT, ldz, ldz, S, 1, st));
+  RC(transpose(params + lo.post1, S, w.W1T, S, S, S, 1, st));
+  RC(transpose(params + lo.post2, Q, w.W2T, S, S, Q, 1, st));
+  if (training) {
+    RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, st));
+    RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, st));
+    RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
+  }
   prof_mark(st, PT_MISC);
   if (training) {
-    RC(transpose(w.Zcat, ldz, w.ZcatT, w.ldm, M, ldz, st));
+    RC(transpose(w.Zcat, ldz, w.ZcatT, w.ldm, M, ldz, 0, st));
     prof_mark(st, PT_TRANSPOSE);
   }
   {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
@@ -258,7 +269,7 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   if (c->residual_postproc) {  // transformed2 += total   (model.py:436-437)
     RC((int)cudaMemcpyAsync(w.T2, w.A2, (size_t)M * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
     RC(add_inplace(w.T2, w.S0, (int64_t)M * S, 1, st));
-    if (training) RC(transpose(w.T2, S, w.X2T, w.ldm, M, S, st));
+    if (training) RC(transpose(w.T2, S, w.X2T, w.ldm, M, S, 0, st));
     x2 = w.T2;
   }
   {  // conv2                                      (model.py:438-440)
@@ -459,7 +470,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, st));
   prof_mark(st, PT_XENT);
 
-  RC(transpose(w.logits, Q, w.dlogT, w.ldm, M, Q, st));
+  RC(transpose(w.logits, Q, w.dlogT, w.ldm, M, Q, 0, st));
   prof_mark(st, PT_TRANSPOSE);
   {  // postprocess2 gradients:  dW2[S,Q] = X2^T . dlogits
     GemmParams p = gp(w.X2T, w.ldm, w.dlogT, w.ldm, grads + lo.post2, Q, S, Q, M);
@@ -469,7 +480,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, st)); prof_mark(st, PT_COLSUM); }
   }
   {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
-    GemmParams p = gp(w.logits, Q, params + lo.post2, Q, w.G1, S, M, S, Q);
+    GemmParams p = gp(w.logits, Q, w.W2R, Q, w.G1, S, M, S, Q);
     p.aux = w.A2; p.ldaux = S;
     p.flags = GEMM_ROUND;
     if (rp) { p.C2 = w.G3; p.ldc2 = S; }
@@ -484,14 +495,14 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, st)); prof_mark(st, PT_COLSUM); }
   }
   {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
-    GemmParams p = gp(w.G1, S, params + lo.post1, S, w.G2, S, M, S, S);
+    GemmParams p = gp(w.G1, S, w.W1R, S, w.G2, S, M, S, S);
     p.aux = w.A1; p.ldaux = S;
     p.flags = rp ? 0 : GEMM_ROUND;
     RC(gemm_nt(p, rp ? nullptr : w.G2T, w.ldm, 1, st));
     prof_mark(st, PT_GEMM_POST1_DGRAD);
     if (rp) {
       RC(add_inplace(w.G2, w.G3, (int64_t)M * S, 1, st));
-      RC(transpose(w.G2, S, w.G2T, w.ldm, M, S, st));
+      RC(transpose(w.G2, S, w.G2T, w.ldm, M, S, 0, st));
       prof_mark(st, PT_MISC);
     }
   }
@@ -509,7 +520,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
   }
   {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
-    GemmParams p = gp(w.G2, S, params + lo.skip, S, w.dZcat, ldz, M, ldz, S);
+    GemmParams p = gp(w.G2, S, w.WskipR, S, w.dZcat, ldz, M, ldz, S);
     RC(gemm_nt(p, nullptr, 0, 1, st));
     prof_mark(st, PT_GEMM_SKIP_DGRAD);
   }

@@ -306,7 +306,7 @@ int gemm_nt_umma(const GemmParams& g, float* CT, int ldct, int split_k, cudaStre
 
 // out[c][r] = in[r][c]  (32x32 tiles through shared memory, both sides coalesced)
 __global__ void transpose_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int rows,
-                                 int cols) {
+                                 int cols, int round_out) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -316,15 +316,30 @@ __global__ void transpose_kernel(const float* __restrict__ in, int ldi, float* _
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < cols && r < rows) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
+    if (c < cols && r < rows) out[(size_t)c * ldo + r] = round_out ? round_tf32(tile[threadIdx.x][i]) : tile[threadIdx.x][i];
   }
 }
 
-int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, cudaStream_t st) {
+int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return -1;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
   if (grid.y > 65535) return -1;
-  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ldi, out, ldo, rows, cols);
+  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ldi, out, ldo, rows, cols, round_out);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+// out = tf32-rounded copy of in (tcgen05 kind::tf32 truncates raw fp32 operands; pre-rounding to
+// nearest halves the error and removes its bias)
+__global__ void round_copy_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = round_tf32(in[i]);
+}
+int round_copy(const float* in, float* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 2048) blocks = 2048;
+  round_copy_kernel<<<(int)blocks, 256, 0, st>>>(in, out, n);
   WN_CHECK_LAUNCH();
   return 0;
 }

@@ -31,7 +31,8 @@ int gemm_tf32(int mode, const GemmParams& p, int split_k, cudaStream_t st);
 int colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
 // tcgen05 path: C[M,N] (+)= A[M,K] . B[N,K]^T (p.B is the [N,K] operand), optional transposed copy CT[N][M]
 int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st);
-int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, cudaStream_t st);
+int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st);
+int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
 
 int block_fwd(const float* x, float* xout, float* zc, int ldz, const float* wf, const float* wg,
               const float* dense, const float* prebias, const float* dense_bias, int M, int T, int d,
