@@ -225,7 +225,8 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     const float* xin = training ? w.X + l * xs : w.X + (l & 1) * xs;
     float* xout = training ? w.X + (l + 1) * xs : w.X + ((l + 1) & 1) * xs;
     const int last = (l == L - 1);
-    RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz, params + lo.filter + (int64_t)l * 2 * R * D,
+    RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz,
+                 training ? w.ZcatT + (int64_t)l * D * w.ldm : nullptr, w.ldm, params + lo.filter + (int64_t)l * 2 * R * D,
                  params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
                  w.prebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr,
                  M, T, c->dilations[l], R, last, st));
@@ -246,10 +247,6 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
   }
   prof_mark(st, PT_MISC);
-  if (training) {
-    RC(transpose(w.Zcat, ldz, w.ZcatT, w.ldm, M, ldz, 0, st));
-    prof_mark(st, PT_TRANSPOSE);
-  }
   {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
     GemmParams p = gp(w.Zcat, ldz, w.WskipT, ldz, w.A1, S, M, S, ldz);
     p.bias = bsum;
@@ -366,8 +363,8 @@ int wn_block_fwd(const float* x, float* x_out, float* zcat, int32_t ldz, const f
   if (!x || !zcat || !filter || !gate || !prebias || batch < 1 || time < 1 || dilation < 1) return -1;
   if (!is_last && (!x_out || !dense)) return -1;
   if ((ldz & 1) || ldz < channels) return -3;
-  return block_fwd(x, x_out, zcat, ldz, filter, gate, dense, prebias, dense_bias, batch * time, time, dilation,
-                   channels, is_last, (cudaStream_t)stream);
+  return block_fwd(x, x_out, zcat, ldz, nullptr, 0, filter, gate, dense, prebias, dense_bias, batch * time, time,
+                   dilation, channels, is_last, (cudaStream_t)stream);
 }
 
 int wn_block_bwd(const float* x, const float* dx_out, const float* dz_skip, int32_t ldz, float* dx,

@@ -15,6 +15,9 @@
 // permuted (slot t <-> column (C/4)*t+2s, slot t+4 <-> the next column) so that each lane
 // owns a contiguous chunk of its row; the weight tiles in shared memory are packed with the
 // same permutation as float2 k-pairs with bank-conflict-free pitches.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -787,12 +790,35 @@ static int launch_bwd(const float* x, const float* dxn, const float* dzs, int ld
   return 0;
 }
 
-int block_fwd(const float* x, float* xout, float* zc, int ldz, const float* wf, const float* wg,
+static bool use_mma_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WN_BLOCK_IMPL");
+    v = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// zcT (nullable): transposed copy of z, [C][ldm] starting at this layer's row block of ZcatT
+__global__ void zct_kernel(const float* __restrict__ zc, int ldz, float* __restrict__ zcT, int ldm, int M, int C) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  for (int c = 0; c < C; ++c) zcT[(size_t)c * ldm + m] = zc[(size_t)m * ldz + c];
+}
+
+int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, int ldm, const float* wf, const float* wg,
               const float* dense, const float* prebias, const float* dense_bias, int M, int T, int d,
               int C, int is_last, cudaStream_t st) {
-  if (C == 32) return launch_fwd<32>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
-  if (C == 16) return launch_fwd<16>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
-  return -2;
+  if (C == 32 && !use_mma_blocks())
+    return block_fwd_umma(x, xout, zc, ldz, zcT, ldm, wf, wg, dense, prebias, dense_bias, M / T, T, d, is_last, st);
+  int rc = -2;
+  if (C == 32) rc = launch_fwd<32>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
+  if (C == 16) rc = launch_fwd<16>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
+  if (rc == 0 && zcT) {
+    zct_kernel<<<(M + 127) / 128, 128, 0, st>>>(zc, ldz, zcT, ldm, M, C);
+    WN_CHECK_LAUNCH();
+  }
+  return rc;
 }
 
 int block_bwd(const float* x, const float* dxn, const float* dzs, int ldz, float* dx, float* dpre,

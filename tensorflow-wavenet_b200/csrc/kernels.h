@@ -34,9 +34,12 @@ int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStre
 int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st);
 int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
 
-int block_fwd(const float* x, float* xout, float* zc, int ldz, const float* wf, const float* wg,
+int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, int ldm, const float* wf, const float* wg,
               const float* dense, const float* prebias, const float* dense_bias, int M, int T, int d,
               int C, int is_last, cudaStream_t st);
+int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, int ldm, const float* wf,
+                   const float* wg, const float* dense, const float* prebias, const float* dense_bias, int B, int T,
+                   int d, int is_last, cudaStream_t st);
 int block_bwd(const float* x, const float* dxn, const float* dzs, int ldz, float* dx, float* dpre,
               const float* zc, const float* wf, const float* wg, const float* dense, const float* prebias,
               float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int M, int T,
