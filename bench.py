@@ -255,7 +255,7 @@ def main():
     e2e_value = world * B * T * K / float(e2e_s)
 
     # ---------------- per-kernel durations (CUDA events after every launch, eager pass) ----------------
-    n_tags = 22
+    n_tags = 23
     ms_tag = (C.c_float * n_tags)()
     n_tag = (C.c_int32 * n_tags)()
     prof_steps = 3

@@ -172,7 +172,11 @@ int wn_sample(const float* proba, const double* uniforms, int32_t rows, int32_t 
 
 /* ---- measurement aid (bench.py roofline): CUDA events on the launching stream after every kernel
  * of wn_loss_grad between begin/end; results are summed per kernel kind (wn_profile_tag_name). */
-#define WN_PROFILE_TAGS 22
+/* Validation switch: run the GEMMs / residual blocks on the legacy mma.sync kernels instead of tcgen05
+ * (same arithmetic contract) so that one implementation can be checked against the other.  Workspace
+ * sizes depend on the choice: query them again after switching. */
+int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma);
+#define WN_PROFILE_TAGS 23
 int wn_profile_begin(void);
 int wn_profile_end(float* ms_per_tag /*host*/, int32_t* launches_per_tag /*host*/, int32_t n_tags);
 int wn_profile_tag_name(int32_t tag, char* out /*host*/, int32_t n);

@@ -105,6 +105,12 @@ struct Workspace {
   float* dlogT;    // [Q, ldm]
   float* G1T;      // [S, ldm]
   float* G2T;      // [S, ldm]
+  // tcgen05 block kernels (C == 32)
+  unsigned char* Wimg;  // per-layer weight images
+  float* XT;       // [L][32][ldm] transposed layer inputs   (training, T % 4 == 0)
+  float* dpreT;    // [64][ldm]
+  float* dXT;      // 2 x [32][ldm]
+  int umma_bwd;    // 1 when the tcgen05 backward path is used for this (cfg, B, T)
   int ldm;
   int64_t bytes;
 };
@@ -134,6 +140,16 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->W2T = (float*)take(Q * S * f);
   const int64_t ldm = (M + 3) & ~(int64_t)3;
   w->ldm = (int)ldm;
+  const bool umma_blocks = (R == 32) && block_umma_enabled();
+  w->Wimg = umma_blocks ? (unsigned char*)take(block_images_bytes((int)L)) : nullptr;
+  w->umma_bwd = (training && umma_blocks && (T % 4 == 0)) ? 1 : 0;
+  if (w->umma_bwd) {
+    w->XT = (float*)take(L * 32 * ldm * f);
+    w->dpreT = (float*)take(64 * ldm * f);
+    w->dXT = (float*)take(2 * 32 * ldm * f);
+  } else {
+    w->XT = w->dpreT = w->dXT = nullptr;
+  }
   if (training) {
     w->WskipR = (float*)take(S * L * D * f);
     w->W1R = (float*)take(S * S * f);
@@ -185,13 +201,13 @@ static int split_for(int m_out, int n_out, int k) {
 
 // C[M,N] (+)= A[M,K] . B[N,K]^T with optional transposed copy CT[N][M].  tcgen05 by default;
 // WN_GEMM_IMPL=mma selects the mma.sync kernel (validation of one implementation against the other).
+static int g_gemm_impl = -1;   // -1 unset, 0 tcgen05, 1 mma.sync
 static bool use_mma_gemm() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_gemm_impl < 0) {
     const char* e = getenv("WN_GEMM_IMPL");
-    v = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+    g_gemm_impl = (e && strcmp(e, "mma") == 0) ? 1 : 0;
   }
-  return v == 1;
+  return g_gemm_impl == 1;
 }
 static int gemm_nt(const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st) {
   if (!use_mma_gemm()) return gemm_nt_umma(p, CT, ldct, split_k, st);
@@ -221,12 +237,18 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, st));
   prof_mark(st, PT_FRONTEND_FWD);
   const int64_t xs = (int64_t)M * R;
+  if (w.Wimg) {
+    RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
+    prof_mark(st, PT_MISC);
+  }
   for (int l = 0; l < L; ++l) {
     const float* xin = training ? w.X + l * xs : w.X + (l & 1) * xs;
     float* xout = training ? w.X + (l + 1) * xs : w.X + ((l + 1) & 1) * xs;
     const int last = (l == L - 1);
     RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz,
-                 training ? w.ZcatT + (int64_t)l * D * w.ldm : nullptr, w.ldm, params + lo.filter + (int64_t)l * 2 * R * D,
+                 training ? w.ZcatT + (int64_t)l * D * w.ldm : nullptr,
+                 w.umma_bwd ? w.XT + (int64_t)l * 32 * w.ldm : nullptr, w.ldm,
+                 w.Wimg ? w.Wimg + (size_t)l * block_img_stride() : nullptr, params + lo.filter + (int64_t)l * 2 * R * D,
                  params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
                  w.prebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr,
                  M, T, c->dilations[l], R, last, st));
@@ -286,6 +308,12 @@ extern "C" {
 
 int wn_abi_version(void) { return WN_ABI_VERSION; }
 
+int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma) {
+  g_gemm_impl = gemm_mma ? 1 : 0;
+  set_block_impl(block_mma);
+  return 0;
+}
+
 int wn_profile_begin(void) {
   if (!g_prof_created) {
     for (int i = 0; i < PROF_MAX; ++i)
@@ -319,7 +347,7 @@ int wn_profile_tag_name(int32_t tag, char* out, int32_t n) {
       "misc", "mulaw_encode", "cond_bias_fwd", "frontend_fwd", "block_fwd", "skip_bias_sum", "gemm_skip_fwd",
       "gemm_post1_fwd", "gemm_post2_fwd", "softmax_xent", "gemm_post2_wgrad", "colsum", "gemm_post2_dgrad",
       "gemm_post1_wgrad", "gemm_post1_dgrad", "gemm_skip_wgrad", "gemm_skip_dgrad", "block_bwd_dx",
-      "block_wgrad", "frontend_bwd", "cond_bias_bwd", "transpose"};
+      "block_wgrad", "frontend_bwd", "cond_bias_bwd", "transpose", "block_bwd_pre"};
   if (tag < 0 || tag >= PT_COUNT || !out || n < 1) return -1;
   snprintf(out, n, "%s", names[tag]);
   return 0;
@@ -363,8 +391,8 @@ int wn_block_fwd(const float* x, float* x_out, float* zcat, int32_t ldz, const f
   if (!x || !zcat || !filter || !gate || !prebias || batch < 1 || time < 1 || dilation < 1) return -1;
   if (!is_last && (!x_out || !dense)) return -1;
   if ((ldz & 1) || ldz < channels) return -3;
-  return block_fwd(x, x_out, zcat, ldz, nullptr, 0, filter, gate, dense, prebias, dense_bias, batch * time, time,
-                   dilation, channels, is_last, (cudaStream_t)stream);
+  return block_fwd(x, x_out, zcat, ldz, nullptr, nullptr, 0, nullptr, filter, gate, dense, prebias, dense_bias,
+                   batch * time, time, dilation, channels, is_last, (cudaStream_t)stream);
 }
 
 int wn_block_bwd(const float* x, const float* dx_out, const float* dz_skip, int32_t ldz, float* dx,
@@ -524,8 +552,23 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   const int64_t xs = (int64_t)M * R;
   float* dcur = w.dX;        // gradient wrt the output of the layer being processed
   float* dnext = w.dX + xs;  // gradient wrt its input
+  float* dcurT = w.dXT;
+  float* dnextT = w.dXT ? w.dXT + (int64_t)32 * w.ldm : nullptr;
   for (int l = L - 1; l >= 0; --l) {
     const int last = (l == L - 1);
+    if (w.umma_bwd) {
+      const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
+      RC(block_bwd_umma(w.X + l * xs, w.XT + (int64_t)l * 32 * w.ldm, last ? nullptr : dcur, last ? nullptr : dcurT,
+                        w.dZcat, ldz, l * D, w.ZcatT, dnext, dnextT, w.dpre, w.dpreT, w.ldm, img + block_img_off_pre(),
+                        img + block_img_off_dx(), w.prebias + (int64_t)l * B * 2 * D,
+                        grads + lo.filter + (int64_t)l * 2 * R * D, grads + lo.gate + (int64_t)l * 2 * R * D,
+                        grads + lo.dense + (int64_t)l * D * R, w.gprebias + (int64_t)l * B * 2 * D,
+                        lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, B, T, cfg->dilations[l],
+                        last, st));
+      float* tmp = dcur; dcur = dnext; dnext = tmp;
+      tmp = dcurT; dcurT = dnextT; dnextT = tmp;
+      continue;
+    }
     RC(block_bwd(w.X + l * xs, last ? nullptr : dcur, w.dZcat + (int64_t)l * D, ldz, dnext, w.dpre,
                  w.Zcat + (int64_t)l * D, params + lo.filter + (int64_t)l * 2 * R * D,
                  params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,

@@ -790,13 +790,14 @@ static int launch_bwd(const float* x, const float* dxn, const float* dzs, int ld
   return 0;
 }
 
+static int g_block_impl = -1;   // -1 unset, 0 tcgen05, 1 mma.sync
+void set_block_impl(int mma) { g_block_impl = mma ? 1 : 0; }
 static bool use_mma_blocks() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_block_impl < 0) {
     const char* e = getenv("WN_BLOCK_IMPL");
-    v = (e && strcmp(e, "mma") == 0) ? 1 : 0;
+    g_block_impl = (e && strcmp(e, "mma") == 0) ? 1 : 0;
   }
-  return v == 1;
+  return g_block_impl == 1;
 }
 
 // zcT (nullable): transposed copy of z, [C][ldm] starting at this layer's row block of ZcatT
@@ -806,11 +807,15 @@ __global__ void zct_kernel(const float* __restrict__ zc, int ldz, float* __restr
   for (int c = 0; c < C; ++c) zcT[(size_t)c * ldm + m] = zc[(size_t)m * ldz + c];
 }
 
-int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, int ldm, const float* wf, const float* wg,
-              const float* dense, const float* prebias, const float* dense_bias, int M, int T, int d,
-              int C, int is_last, cudaStream_t st) {
+bool block_umma_enabled() { return !use_mma_blocks(); }
+
+int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm, const unsigned char* img,
+              const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
+              int M, int T, int d, int C, int is_last, cudaStream_t st) {
   if (C == 32 && !use_mma_blocks())
-    return block_fwd_umma(x, xout, zc, ldz, zcT, ldm, wf, wg, dense, prebias, dense_bias, M / T, T, d, is_last, st);
+    return block_fwd_umma(x, xout, zc, ldz, zcT, xT, ldm, img, wf, wg, dense, prebias, dense_bias, M / T, T, d,
+                          is_last, st);
+  if (xT) return -2;   // x^T is only produced by the tcgen05 path
   int rc = -2;
   if (C == 32) rc = launch_fwd<32>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
   if (C == 16) rc = launch_fwd<16>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);

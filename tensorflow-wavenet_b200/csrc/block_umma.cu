@@ -11,8 +11,16 @@
 //   * accumulators live in TMEM, thread r of the CTA owns time step t0 + r (TMEM lane r);
 //   * intermediate operands (z, lo parts, gradients) are written back to shared memory in the same
 //     swizzled layout by the threads (fence.proxy.async) and fed to the next MMA: nothing but x, z and
-//     x' touches HBM.
+//     x' touches HBM;
+//   * the weights of a layer are pre-arranged once per step into the exact shared-memory image
+//     (swizzled K-major B operands, hi/lo split) and arrive with one cp.async.bulk.
 // Forward products are split-precision (hi + lo TF32 terms, 3 MMAs per product): DESIGN.md section 6.
+//
+// Backward of a layer is three kernels:
+//   bwd_pre  : recompute pre-activations, dz = dz_skip + dx'.Wd^T, dpre = [df|dg]  -> dpre, dpre^T
+//   wgrad    : one GEMM over time (K = T) on the transposed copies gives every weight / bias gradient
+//              of the layer: [x^T ; x[t-d]^T ; z^T ; 1] . [dpre^T ; dx'^T]^T  (block rows/cols selected)
+//   bwd_dx   : dx = dx' + dpre[t].Wcur^T + dpre[t+d].Wpast^T                       -> dx, dx^T
 #include "common.cuh"
 #include "kernels.h"
 #include "umma_common.cuh"
@@ -24,26 +32,81 @@ namespace {
 constexpr int C = 32;
 constexpr int TM = 128;                 // time steps per tile
 constexpr uint32_t TILE = TM * 128;     // bytes of a [128][32] fp32 tile
+constexpr uint32_t IMG_FWD = 4 * 8192 + 2 * 4096;    // W0h W0l W1h W1l | Wdh Wdl
+constexpr uint32_t IMG_PRE = 2 * 8192 + 4096;        // W0h W1h | WdB
+constexpr uint32_t IMG_DX = 4 * 4096;                // Bcf Bcg Bpf Bpg
+constexpr uint32_t IMG_ALL = IMG_FWD + IMG_PRE + IMG_DX;
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// stage a weight matrix as a K-major B operand: rows n (output channel), cols k (input channel), hi/lo split
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// K-major B operand image: rows n (output channel), cols k (input channel), hi (and lo) split
 template <typename F>
 __device__ __forceinline__ void stage_b(unsigned char* hi, unsigned char* lo, int n_rows, F&& w_of) {
   for (int i = threadIdx.x; i < n_rows * 32; i += blockDim.x) {
-    const int n = i >> 5, k = i & 31;
+    const int k = i / n_rows, n = i % n_rows;     // n fastest: coalesced reads of [k][n] weights
     const float w = w_of(n, k);
     const float h = round_tf32(w);
     *reinterpret_cast<float*>(hi + swz(n, k)) = h;
     if (lo) *reinterpret_cast<float*>(lo + swz(n, k)) = round_tf32(w - h);
   }
 }
+
+// the three weight images of one layer (pointers may be shared or global memory)
+__device__ __forceinline__ void build_images(unsigned char* fwd, unsigned char* pre, unsigned char* dx,
+                                             const float* __restrict__ wf, const float* __restrict__ wg,
+                                             const float* __restrict__ dense, bool have_dense) {
+  auto w0 = [&](int n, int k) { return n < C ? wf[k * C + n] : wg[k * C + (n - C)]; };
+  auto w1 = [&](int n, int k) { return n < C ? wf[(C + k) * C + n] : wg[(C + k) * C + (n - C)]; };
+  if (fwd) {
+    stage_b(fwd, fwd + 8192, 64, w0);
+    stage_b(fwd + 16384, fwd + 24576, 64, w1);
+    if (have_dense) stage_b(fwd + 32768, fwd + 36864, 32, [&](int n, int k) { return dense[k * C + n]; });   // n = r, k = d
+  }
+  if (pre) {
+    stage_b(pre, nullptr, 64, w0);
+    stage_b(pre + 8192, nullptr, 64, w1);
+    if (have_dense) stage_b(pre + 16384, nullptr, 32, [&](int n, int k) { return dense[n * C + k]; });      // n = d, k = r
+  }
+  if (dx) {   // n = residual channel r, k = dilation channel d
+    stage_b(dx, nullptr, 32, [&](int n, int k) { return wf[(C + n) * C + k]; });
+    stage_b(dx + 4096, nullptr, 32, [&](int n, int k) { return wg[(C + n) * C + k]; });
+    stage_b(dx + 8192, nullptr, 32, [&](int n, int k) { return wf[n * C + k]; });
+    stage_b(dx + 12288, nullptr, 32, [&](int n, int k) { return wg[n * C + k]; });
+  }
+}
 }  // namespace
 
+__global__ void block_images_kernel(unsigned char* __restrict__ img, const float* __restrict__ filter,
+                                    const float* __restrict__ gate, const float* __restrict__ dense) {
+  const int l = blockIdx.x;
+  unsigned char* base = img + (size_t)l * IMG_ALL;
+  build_images(base, base + IMG_FWD, base + IMG_FWD + IMG_PRE, filter + (size_t)l * 2 * C * C,
+               gate + (size_t)l * 2 * C * C, dense + (size_t)l * C * C, true);
+}
+
+int64_t block_images_bytes(int L) { return (int64_t)L * IMG_ALL; }
+uint32_t block_img_off_pre() { return IMG_FWD; }
+uint32_t block_img_off_dx() { return IMG_FWD + IMG_PRE; }
+uint32_t block_img_stride() { return IMG_ALL; }
+int block_images(unsigned char* img, const float* filter, const float* gate, const float* dense, int L, cudaStream_t st) {
+  block_images_kernel<<<L, 256, 0, st>>>(img, filter, gate, dense);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+// =========================================================================================
+// forward
+// =========================================================================================
 struct FwdArgs {
   float* xout;
-  float* zc; int ldz;          // Zcat + l*C, row pitch ldz
-  float* zcT; int ldm;         // ZcatT + l*C*ldm (nullable): transposed copy for the skip weight-gradient GEMM
+  float* zc; int ldz;               // Zcat + l*C, row pitch ldz
+  float* zcT; float* xT; int ldm;   // transposed copies [32][ldm] of z and of the layer input x (nullable)
+  const unsigned char* img;         // IMG_FWD bytes (nullable -> built in the kernel from wf/wg/dense)
   const float *wf, *wg, *dense, *prebias, *dense_bias;
   int B, T, d, is_last;
 };
@@ -51,7 +114,7 @@ struct FwdArgs {
 __global__ void __launch_bounds__(128, 2)
 block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared provenance
   unsigned char* Xc = smem;
   unsigned char* Xp = smem + TILE;
   unsigned char* L0 = smem + 2 * TILE;     // lo(x_past), later hi(z)
@@ -62,21 +125,42 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   unsigned char* W1l = W1h + 8192;
   unsigned char* Wdh = W1l + 8192;         // [32][32] dense^T
   unsigned char* Wdl = Wdh + 4096;
-  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_m2;
+  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_m2, bar_w;
   __shared__ uint32_t tmem_slot;
+  __shared__ float pb_s[64];
+  __shared__ float bd_s[32];
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     mbar_init(&bar_tma, 1);
     mbar_init(&bar_m1, 1);
     mbar_init(&bar_m2, 1);
+    mbar_init(&bar_w, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 128);
-  stage_b(W0h, W0l, 64, [&](int n, int k) { return n < C ? a.wf[k * C + n] : a.wg[k * C + (n - C)]; });
-  stage_b(W1h, W1l, 64, [&](int n, int k) { return n < C ? a.wf[(C + k) * C + n] : a.wg[(C + k) * C + (n - C)]; });
-  if (!a.is_last) stage_b(Wdh, Wdl, 32, [&](int n, int k) { return a.dense[k * C + n]; });
-  fence_async_smem();
+  if (tid < 32) bd_s[tid] = a.dense_bias ? a.dense_bias[tid] : 0.f;
+  __syncthreads();
+  if (a.img) {
+    if (tid == 0) {
+      mbar_expect_tx(&bar_w, IMG_FWD);
+      bulk_g2s(W0h, a.img, IMG_FWD, &bar_w);
+    }
+  } else {
+    build_images(W0h, nullptr, nullptr, a.wf, a.wg, a.dense, !a.is_last);
+    fence_async_smem();
+  }
+
+  const int n_tt = (a.T + TM - 1) / TM;
+  const int n_tiles = a.B * n_tt;
+  auto issue_loads = [&](int tile) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    mbar_expect_tx(&bar_tma, 2 * TILE);
+    tma_load_3d(Xc, &mapX, &bar_tma, 0, t0, b);
+    tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);
+  };
+  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+  if (a.img) mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -89,17 +173,16 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   const uint64_t dW1h = kmajor_desc(smem_u32(W1h)), dW1l = kmajor_desc(smem_u32(W1l));
   const uint64_t dWdh = kmajor_desc(smem_u32(Wdh)), dWdl = kmajor_desc(smem_u32(Wdl));
 
-  const int n_tt = (a.T + TM - 1) / TM;
-  const int n_tiles = a.B * n_tt;
   const int r = tid;
   int it = 0;
+  int pb_batch = -1;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
     const uint32_t par = it & 1;
-    if (tid == 0) {
-      mbar_expect_tx(&bar_tma, 2 * TILE);
-      tma_load_3d(Xc, &mapX, &bar_tma, 0, t0, b);
-      tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);
+    if (b != pb_batch) {   // block-uniform: conditioning + bias row of this batch element
+      __syncthreads();
+      if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
+      pb_batch = b;
     }
     mbar_wait(&bar_tma, par);
     if (tid == 0) {   // hi*hi terms: the tensor core reads the upper 19 bits of the raw fp32 tile
@@ -109,11 +192,13 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1h + 2 * k, ID64, 1);
     }
-    // lo parts of this thread's rows: x - trunc_tf32(x), same swizzled position
+    // lo parts of this thread's rows: x - trunc_tf32(x), same swizzled position; x_cur stays in registers
+    float4 xr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t off = (uint32_t)r * 128 + ((uint32_t)(j ^ (r & 7)) << 4);
       float4 v = *reinterpret_cast<const float4*>(Xc + off);
+      xr[j] = v;
       *reinterpret_cast<float4*>(L1 + off) =
           make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
       v = *reinterpret_cast<const float4*>(Xp + off);
@@ -134,20 +219,30 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1l + 2 * k, ID64, 1);
       mma_commit(&bar_m1);
     }
-    mbar_wait(&bar_m1, par);
-    tc_fence_after();
-
     const bool valid = (t0 + r) < a.T;
     const size_t m = (size_t)b * a.T + t0 + r;
+    if (a.xT && valid) {   // x^T for the weight-gradient GEMM: lanes hold consecutive time steps (coalesced)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a.xT[(size_t)(4 * j + 0) * a.ldm + m] = round_tf32(xr[j].x);
+        a.xT[(size_t)(4 * j + 1) * a.ldm + m] = round_tf32(xr[j].y);
+        a.xT[(size_t)(4 * j + 2) * a.ldm + m] = round_tf32(xr[j].z);
+        a.xT[(size_t)(4 * j + 3) * a.ldm + m] = round_tf32(xr[j].w);
+      }
+    }
+    mbar_wait(&bar_m1, par);
+    tc_fence_after();
+    // both input tiles are consumed: prefetch the next tile of this CTA behind the epilogue
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
+
     float z[32];
     {
       uint32_t fv[32], gv[32];
       tmem_ld32(lane_addr + 0, fv);
       tmem_ld32(lane_addr + 32, gv);
-      const float* pb = a.prebias + (size_t)b * 64;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        z[j] = tanh_f(__uint_as_float(fv[j]) + __ldg(pb + j)) * sigmoid_f(__uint_as_float(gv[j]) + __ldg(pb + 32 + j));
+        z[j] = tanh_f(__uint_as_float(fv[j]) + pb_s[j]) * sigmoid_f(__uint_as_float(gv[j]) + pb_s[32 + j]);
     }
     // z -> Zcat (tf32-rounded: it feeds the single-pass skip GEMM), its transposed copy, and the
     // hi/lo A operand of the dense product
@@ -190,10 +285,8 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
       tmem_ld32(lane_addr + 64, ov);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t off = (uint32_t)r * 128 + ((uint32_t)(j ^ (r & 7)) << 4);
-        const float4 xv = *reinterpret_cast<const float4*>(Xc + off);
-        float4 bd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.dense_bias) bd = __ldg(reinterpret_cast<const float4*>(a.dense_bias + 4 * j));
+        const float4 xv = xr[j];
+        const float4 bd = make_float4(bd_s[4 * j], bd_s[4 * j + 1], bd_s[4 * j + 2], bd_s[4 * j + 3]);
         if (valid)
           *reinterpret_cast<float4*>(a.xout + m * C + 4 * j) =
               make_float4(xv.x + __uint_as_float(ov[4 * j]) + bd.x, xv.y + __uint_as_float(ov[4 * j + 1]) + bd.y,
@@ -206,16 +299,16 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, int ldm, const float* wf,
-                   const float* wg, const float* dense, const float* prebias, const float* dense_bias, int B, int T,
-                   int d, int is_last, cudaStream_t st) {
+int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm,
+                   const unsigned char* img, const float* wf, const float* wg, const float* dense,
+                   const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st) {
   CUtensorMap mapX;
   int rc = make_map_3d(&mapX, x, B, T, C, C, TM);
   if (rc) return rc;
   FwdArgs a;
-  a.xout = xout; a.zc = zc; a.ldz = ldz; a.zcT = zcT; a.ldm = ldm; a.wf = wf; a.wg = wg; a.dense = dense;
-  a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
-  const size_t smem = 1024 + 4 * TILE + 4 * 8192 + 2 * 4096;
+  a.xout = xout; a.zc = zc; a.ldz = ldz; a.zcT = zcT; a.xT = xT; a.ldm = ldm; a.img = img; a.wf = wf; a.wg = wg;
+  a.dense = dense; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
+  const size_t smem = 1024 + 4 * TILE + IMG_FWD;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(block_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -227,6 +320,436 @@ int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, 
   if (grid > cap) grid = cap;
   block_fwd_umma_kernel<<<grid, 128, smem, st>>>(mapX, a);
   WN_CHECK_LAUNCH();
+  prof_mark(st, PT_BLOCK_FWD);
+  return 0;
+}
+
+// =========================================================================================
+// backward 1/3: dpre = [df | dg]
+// =========================================================================================
+struct PreArgs {
+  float* dpre;                 // [M][64]
+  float* dpreT; int ldm;       // [64][ldm]
+  const unsigned char* img;    // IMG_PRE bytes
+  const float* prebias;
+  int B, T, d, is_last, zcol;  // zcol: column of this layer inside dZcat
+};
+
+__global__ void __launch_bounds__(128, 2)
+block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDn,
+                          const __grid_constant__ CUtensorMap mapDz, PreArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* Xc = smem;
+  unsigned char* Xp = smem + TILE;
+  unsigned char* Dn = smem + 2 * TILE;
+  unsigned char* Dz = smem + 3 * TILE;
+  unsigned char* W0 = smem + 4 * TILE;
+  unsigned char* W1 = W0 + 8192;
+  unsigned char* Wd = W1 + 8192;
+  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_w;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float pb_s[64];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_m1, 1);
+    mbar_init(&bar_w, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 128);
+  __syncthreads();
+  const int n_tt = (a.T + TM - 1) / TM;
+  const int n_tiles = a.B * n_tt;
+  const uint32_t tile_bytes = (a.is_last ? 3 : 4) * TILE;
+  auto issue_loads = [&](int tile) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    mbar_expect_tx(&bar_tma, tile_bytes);
+    tma_load_3d(Xc, &mapX, &bar_tma, 0, t0, b);
+    tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);
+    tma_load_3d(Dz, &mapDz, &bar_tma, a.zcol, t0, b);
+    if (!a.is_last) tma_load_3d(Dn, &mapDn, &bar_tma, 0, t0, b);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&bar_w, IMG_PRE);
+    bulk_g2s(W0, a.img, IMG_PRE, &bar_w);
+    if ((int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+  }
+  mbar_wait(&bar_w, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t ID64 = idesc_tf32(128, 64), ID32 = idesc_tf32(128, 32);
+  const uint64_t dXc = kmajor_desc(smem_u32(Xc)), dXp = kmajor_desc(smem_u32(Xp)), dDn = kmajor_desc(smem_u32(Dn));
+  const uint64_t dW0 = kmajor_desc(smem_u32(W0)), dW1 = kmajor_desc(smem_u32(W1)), dWd = kmajor_desc(smem_u32(Wd));
+
+  const int r = tid;
+  int it = 0, pb_batch = -1;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    const uint32_t par = it & 1;
+    if (b != pb_batch) {
+      __syncthreads();
+      if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
+      pb_batch = b;
+    }
+    mbar_wait(&bar_tma, par);
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXp + 2 * k, dW0 + 2 * k, ID64, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1 + 2 * k, ID64, 1);
+      if (!a.is_last) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem + 64, dDn + 2 * k, dWd + 2 * k, ID32, k > 0);   // dx' . Wd^T
+      }
+      mma_commit(&bar_m1);
+    }
+    // gradient coming from the skip path (this thread's row of the dZcat tile)
+    float dz[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t off = (uint32_t)r * 128 + ((uint32_t)(j ^ (r & 7)) << 4);
+      const float4 v = *reinterpret_cast<const float4*>(Dz + off);
+      dz[4 * j] = v.x; dz[4 * j + 1] = v.y; dz[4 * j + 2] = v.z; dz[4 * j + 3] = v.w;
+    }
+    mbar_wait(&bar_m1, par);
+    tc_fence_after();
+    __syncthreads();   // every thread has read its Dz row and the MMAs are done: the tiles are free
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
+
+    const bool valid = (t0 + r) < a.T;
+    const size_t m = (size_t)b * a.T + t0 + r;
+    if (!a.is_last) {
+      uint32_t av[32];
+      tmem_ld32(lane_addr + 64, av);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dz[j] += __uint_as_float(av[j]);
+    }
+    uint32_t fv[32], gv[32];
+    tmem_ld32(lane_addr + 0, fv);
+    tmem_ld32(lane_addr + 32, gv);
+    float df[32], dg[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float tf = tanh_f(__uint_as_float(fv[j]) + pb_s[j]);
+      const float sg = sigmoid_f(__uint_as_float(gv[j]) + pb_s[32 + j]);
+      const float dzv = valid ? dz[j] : 0.f;
+      df[j] = round_tf32(dzv * sg * (1.f - tf * tf));
+      dg[j] = round_tf32(dzv * tf * sg * (1.f - sg));
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<float4*>(a.dpre + m * 64 + 4 * j) = make_float4(df[4 * j], df[4 * j + 1], df[4 * j + 2], df[4 * j + 3]);
+        *reinterpret_cast<float4*>(a.dpre + m * 64 + 32 + 4 * j) = make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        a.dpreT[(size_t)j * a.ldm + m] = df[j];
+        a.dpreT[(size_t)(32 + j) * a.ldm + m] = dg[j];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// =========================================================================================
+// backward 2/3: dx = dx' + dpre[t] . Wcur^T + dpre[t+d] . Wpast^T
+// =========================================================================================
+struct DxArgs {
+  const float* dxn;            // gradient wrt the layer output (nullable for the last layer)
+  float* dx;                   // [M][32]
+  float* dxT; int ldm;         // [32][ldm]
+  const unsigned char* img;    // IMG_DX bytes
+  int B, T, d;
+};
+
+__global__ void __launch_bounds__(128, 2)
+block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* P0f = smem;
+  unsigned char* P0g = smem + TILE;
+  unsigned char* P1f = smem + 2 * TILE;
+  unsigned char* P1g = smem + 3 * TILE;
+  unsigned char* Wb = smem + 4 * TILE;     // Bcf Bcg Bpf Bpg
+  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_w;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_m1, 1);
+    mbar_init(&bar_w, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  __syncthreads();
+  const int n_tt = (a.T + TM - 1) / TM;
+  const int n_tiles = a.B * n_tt;
+  auto issue_loads = [&](int tile) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    mbar_expect_tx(&bar_tma, 4 * TILE);
+    tma_load_3d(P0f, &mapP, &bar_tma, 0, t0, b);
+    tma_load_3d(P0g, &mapP, &bar_tma, 32, t0, b);
+    tma_load_3d(P1f, &mapP, &bar_tma, 0, t0 + a.d, b);     // rows with t + d >= T arrive as zeros
+    tma_load_3d(P1g, &mapP, &bar_tma, 32, t0 + a.d, b);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&bar_w, IMG_DX);
+    bulk_g2s(Wb, a.img, IMG_DX, &bar_w);
+    if ((int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+  }
+  mbar_wait(&bar_w, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t ID32 = idesc_tf32(128, 32);
+  const int r = tid;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    const uint32_t par = it & 1;
+    mbar_wait(&bar_tma, par);
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint64_t dp = kmajor_desc(smem_u32(smem + q * TILE)), db = kmajor_desc(smem_u32(Wb + q * 4096));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dp + 2 * k, db + 2 * k, ID32, (q | k) > 0);
+      }
+      mma_commit(&bar_m1);
+    }
+    const bool valid = (t0 + r) < a.T;
+    const size_t m = (size_t)b * a.T + t0 + r;
+    float4 xn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      xn[j] = (a.dxn && valid) ? __ldg(reinterpret_cast<const float4*>(a.dxn + m * C) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    mbar_wait(&bar_m1, par);
+    tc_fence_after();
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
+    uint32_t ov[32];
+    tmem_ld32(lane_addr, ov);
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 o = make_float4(xn[j].x + __uint_as_float(ov[4 * j]), xn[j].y + __uint_as_float(ov[4 * j + 1]),
+                                     xn[j].z + __uint_as_float(ov[4 * j + 2]), xn[j].w + __uint_as_float(ov[4 * j + 3]));
+        *reinterpret_cast<float4*>(a.dx + m * C + 4 * j) = o;
+        a.dxT[(size_t)(4 * j + 0) * a.ldm + m] = round_tf32(o.x);
+        a.dxT[(size_t)(4 * j + 1) * a.ldm + m] = round_tf32(o.y);
+        a.dxT[(size_t)(4 * j + 2) * a.ldm + m] = round_tf32(o.z);
+        a.dxT[(size_t)(4 * j + 3) * a.ldm + m] = round_tf32(o.w);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+// =========================================================================================
+// backward 3/3: every weight / bias gradient of the layer as ONE GEMM over time
+//   A rows (M = 128):  0-31 x^T | 32-63 x[t-d]^T | 64-95 z^T | 96 ones | 97-127 zero
+//   B rows (N = 96) :  0-63 dpre^T = [df ; dg]^T | 64-95 dx'^T
+//   D[0:32 ,0:64] -> filter[1],gate[1]   D[32:64,0:64] -> filter[0],gate[0]   D[64:96,64:96] -> dense
+//   D[96,0:64]    -> prebias gradient (per batch element)      D[96,64:96] -> dense_bias
+// grid = (splits, B): a CTA reduces a contiguous range of 32-step blocks of one batch element.
+// =========================================================================================
+struct WgArgs {
+  float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;
+  int B, T, d, is_last, zrow;   // zrow: first row of this layer inside ZcatT
+};
+
+__global__ void __launch_bounds__(192, 1)
+block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ CUtensorMap mapZT,
+                        const __grid_constant__ CUtensorMap mapPT, const __grid_constant__ CUtensorMap mapDT, WgArgs a) {
+  constexpr int STG = 4;
+  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = 96 * 128, STAGE = A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full_bar[STG], empty_bar[STG], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int nkb_total = (a.T + 31) / 32;
+  const int per = (nkb_total + gridDim.x - 1) / gridDim.x;
+  const int kb0 = blockIdx.x * per;
+  int kb1 = kb0 + per;
+  if (kb1 > nkb_total) kb1 = nkb_total;
+  const int nk = kb1 - kb0;
+  if (nk <= 0) return;
+
+  // constant rows of every stage: row 96 = 1, rows 97..127 = 0; dx'^T rows of B are zero for the last layer
+  for (int i = tid; i < STG * 32 * 32; i += blockDim.x) {
+    const int s = i / 1024, rr = (i / 32) % 32, cc = i % 32;
+    *reinterpret_cast<float*>(smem + s * STAGE + 96 * 128 + swz(rr, cc)) = (rr == 0) ? 1.0f : 0.0f;
+    if (a.is_last) *reinterpret_cast<float*>(smem + s * STAGE + A_BYTES + 64 * 128 + swz(rr, cc)) = 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STG; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = 3 * 4096 + 8192 + (a.is_last ? 0 : 4096);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STG;
+        const uint32_t ph = (i / STG) & 1;
+        const int t = (kb0 + i) * 32;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], bytes);
+        unsigned char* sa = smem + s * STAGE;
+        tma_load_3d(sa, &mapXT, &full_bar[s], t, b, 0);                 // x^T      rows 0-31
+        tma_load_3d(sa + 4096, &mapXT, &full_bar[s], t - a.d, b, 0);    // x[t-d]^T rows 32-63 (zero for t < d)
+        tma_load_3d(sa + 8192, &mapZT, &full_bar[s], t, b, a.zrow);     // z^T      rows 64-95
+        tma_load_3d(sa + A_BYTES, &mapPT, &full_bar[s], t, b, 0);       // dpre^T   B rows 0-63
+        if (!a.is_last) tma_load_3d(sa + A_BYTES + 8192, &mapDT, &full_bar[s], t, b, 0);   // dx'^T B rows 64-95
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t ID = idesc_tf32(128, 96);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STG;
+        const uint32_t ph = (i / STG) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE);
+        const uint64_t da = kmajor_desc(sa), db = kmajor_desc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, da + 2 * k, db + 2 * k, ID, (i | k) > 0);
+        mma_commit(&empty_bar[s]);
+      }
+      mma_commit(&done_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < 96; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + c0, v);   // warp-collective: every lane issues it
+      float* dst = nullptr;
+      if (row < 64) {
+        if (c0 < 64) dst = (c0 == 0 ? a.gwf : a.gwg) + ((row < 32 ? 1 : 0) * C + (row & 31)) * C;
+      } else if (row < 96) {
+        if (c0 == 64 && !a.is_last) dst = a.gdense + (row - 64) * C;
+      } else if (row == 96) {
+        if (c0 < 64) dst = a.gprebias + (size_t)b * 64 + c0;
+        else if (!a.is_last) dst = a.gdense_bias;   // may be null (no biases)
+      }
+      if (dst) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// transposed activations [rows][B][T] with row pitch ldm (T % 4 == 0 keeps the batch stride 16-byte aligned)
+static int make_map_T(CUtensorMap* m, const float* ptr, int64_t rows, int64_t B, int64_t T, int64_t ldm, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {(cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)rows};
+  cuuint64_t gstr[2] = {(cuuint64_t)T * 4, (cuuint64_t)ldm * 4};
+  cuuint32_t box[3] = {32, 1, (cuuint32_t)box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+
+int block_bwd_umma(const float* x, const float* xT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
+                   int zcol, const float* ZcatT, float* dx, float* dxT, float* dpre, float* dpreT, int ldm,
+                   const unsigned char* img_pre, const unsigned char* img_dx, const float* prebias, float* gwf,
+                   float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d, int is_last,
+                   cudaStream_t st) {
+  if (T & 3) return -3;
+  const int n_tiles = B * ((T + TM - 1) / TM);
+  int grid = n_tiles;
+  const int cap = 2 * sm_count();
+  if (grid > cap) grid = cap;
+  {
+    CUtensorMap mX, mDn, mDz;
+    int rc = make_map_3d(&mX, x, B, T, C, C, TM);
+    if (rc) return rc;
+    rc = make_map_3d(&mDn, is_last ? x : dxn, B, T, C, C, TM);
+    if (rc) return rc;
+    rc = make_map_3d(&mDz, dZcat, B, T, ldz, ldz, TM);
+    if (rc) return rc;
+    PreArgs a;
+    a.dpre = dpre; a.dpreT = dpreT; a.ldm = ldm; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
+    a.is_last = is_last; a.zcol = zcol;
+    const size_t smem = 1024 + 4 * TILE + IMG_PRE;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(block_bwd_pre_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    block_bwd_pre_umma_kernel<<<grid, 128, smem, st>>>(mX, mDn, mDz, a);
+    WN_CHECK_LAUNCH();
+    prof_mark(st, PT_BLOCK_BWD_PRE);
+  }
+  {
+    CUtensorMap mXT, mZT, mPT, mDT;
+    int rc = make_map_T(&mXT, xT, C, B, T, ldm, 32);
+    if (rc) return rc;
+    rc = make_map_T(&mZT, ZcatT, (int64_t)(zcol + C), B, T, ldm, 32);
+    if (rc) return rc;
+    rc = make_map_T(&mPT, dpreT, 64, B, T, ldm, 64);
+    if (rc) return rc;
+    rc = make_map_T(&mDT, is_last ? xT : dxnT, C, B, T, ldm, 32);
+    if (rc) return rc;
+    WgArgs a;
+    a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias; a.B = B; a.T = T;
+    a.d = d; a.is_last = is_last; a.zrow = zcol;
+    const size_t smem = 1024 + 4 * (128 * 128 + 96 * 128);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(block_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    const int nkb = (T + 31) / 32;
+    int splits = sm_count() / (B > 0 ? B : 1);
+    if (splits < 1) splits = 1;
+    if (splits > nkb) splits = nkb;
+    block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mXT, mZT, mPT, mDT, a);
+    WN_CHECK_LAUNCH();
+    prof_mark(st, PT_BLOCK_WGRAD);
+  }
+  {
+    CUtensorMap mP;
+    int rc = make_map_3d(&mP, dpre, B, T, 64, 64, TM);
+    if (rc) return rc;
+    DxArgs a;
+    a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.dxT = dxT; a.ldm = ldm; a.img = img_dx; a.B = B; a.T = T; a.d = d;
+    const size_t smem = 1024 + 4 * TILE + IMG_DX;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    block_bwd_dx_umma_kernel<<<grid, 128, smem, st>>>(mP, a);
+    WN_CHECK_LAUNCH();
+    prof_mark(st, PT_BLOCK_BWD_DX);
+  }
   return 0;
 }
 

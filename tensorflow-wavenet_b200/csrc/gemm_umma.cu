@@ -109,7 +109,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr uint32_t B_BYTES = BN * UK * 4;       // 16 / 32 KB
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
 

@@ -10,7 +10,7 @@ enum ProfTag {
   PT_MISC = 0, PT_MULAW, PT_COND_BIAS, PT_FRONTEND_FWD, PT_BLOCK_FWD, PT_SKIP_BIAS_SUM, PT_GEMM_SKIP_FWD,
   PT_GEMM_POST1_FWD, PT_GEMM_POST2_FWD, PT_XENT, PT_GEMM_POST2_WGRAD, PT_COLSUM, PT_GEMM_POST2_DGRAD,
   PT_GEMM_POST1_WGRAD, PT_GEMM_POST1_DGRAD, PT_GEMM_SKIP_WGRAD, PT_GEMM_SKIP_DGRAD, PT_BLOCK_BWD_DX,
-  PT_BLOCK_WGRAD, PT_FRONTEND_BWD, PT_COND_BIAS_BWD, PT_TRANSPOSE, PT_COUNT
+  PT_BLOCK_WGRAD, PT_FRONTEND_BWD, PT_COND_BIAS_BWD, PT_TRANSPOSE, PT_BLOCK_BWD_PRE, PT_COUNT
 };
 void prof_mark(cudaStream_t st, int tag);   // no-op unless wn_profile_begin() was called
 
@@ -34,12 +34,25 @@ int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStre
 int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st);
 int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
 
-int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, int ldm, const float* wf, const float* wg,
-              const float* dense, const float* prebias, const float* dense_bias, int M, int T, int d,
-              int C, int is_last, cudaStream_t st);
-int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, int ldm, const float* wf,
-                   const float* wg, const float* dense, const float* prebias, const float* dense_bias, int B, int T,
-                   int d, int is_last, cudaStream_t st);
+// zcT / xT (nullable): transposed copies [C][ldm] of z and of the layer input; img (nullable): pre-built weight image
+int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm, const unsigned char* img,
+              const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
+              int M, int T, int d, int C, int is_last, cudaStream_t st);
+bool block_umma_enabled();
+void set_block_impl(int mma);
+int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm,
+                   const unsigned char* img, const float* wf, const float* wg, const float* dense,
+                   const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
+int block_bwd_umma(const float* x, const float* xT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
+                   int zcol, const float* ZcatT, float* dx, float* dxT, float* dpre, float* dpreT, int ldm,
+                   const unsigned char* img_pre, const unsigned char* img_dx, const float* prebias, float* gwf,
+                   float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d, int is_last,
+                   cudaStream_t st);
+int64_t block_images_bytes(int L);
+uint32_t block_img_off_pre();
+uint32_t block_img_off_dx();
+uint32_t block_img_stride();
+int block_images(unsigned char* img, const float* filter, const float* gate, const float* dense, int L, cudaStream_t st);
 int block_bwd(const float* x, const float* dxn, const float* dzs, int ldz, float* dx, float* dpre,
               const float* zc, const float* wf, const float* wg, const float* dense, const float* prebias,
               float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int M, int T,

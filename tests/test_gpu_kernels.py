@@ -268,7 +268,7 @@ def test_gemm_nt_umma(lib, M, N, K, split):
                              flags, split, stream())
     assert rc == 0
     torch.cuda.synchronize()
-    assert rel_err(c.cpu().numpy(), ref) < 2e-6
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5      # fp32 accumulation order only
     if not split:
         np.testing.assert_array_equal(ct[:, :M].cpu().numpy(), c.cpu().numpy().T)
 

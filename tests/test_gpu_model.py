@@ -274,6 +274,34 @@ def test_train_step_graph_matches_eager():
     np.testing.assert_allclose(nets[0].flat_params.cpu().numpy(), nets[1].flat_params.cpu().numpy(), atol=2e-4)
 
 
+@pytest.mark.parametrize('case', ['test_net_biases', 'gc_batch3', 'residual_postproc', 'default_params_short'])
+def test_tcgen05_path_matches_mma_sync_path(case):
+    """The tcgen05 kernels (TMA + UMMA + TMEM GEMMs and residual blocks) against the independent mma.sync
+    implementation of the same arithmetic: loss, logits and every gradient."""
+    import wavenet
+    from wavenet import _lib
+    lib = _lib.load()
+    kw, T, gc = CASES[case]
+    audio = _audio(np.random.default_rng(3), kw['batch_size'], T)
+    ids = O.mu_law_encode(audio, kw['quantization_channels'])
+    out = {}
+    try:
+        for name, flag in (('umma', 0), ('mma', 1)):
+            assert lib.wn_debug_set_impl(flag, flag) == 0
+            net = wavenet.WaveNetModel(**kw, seed=11)
+            out[name] = (float(net.loss(audio, gc)), net.logits(ids, gc).cpu().numpy(), net.gradients())
+    finally:
+        lib.wn_debug_set_impl(0, 0)
+    assert abs(out['umma'][0] - out['mma'][0]) < 2e-4 * abs(out['mma'][0])
+    assert rel_err(out['umma'][1], out['mma'][1]) < LOGIT_RTOL
+    worst = 0.0
+    for k, g in out['mma'][2].items():
+        e = l2_rel(out['umma'][2][k], g) if np.abs(g).max() > 0 else float(np.abs(out['umma'][2][k]).max())
+        worst = max(worst, e)
+        assert e < 2e-2, (k, e)
+    print('case {}: tcgen05 vs mma.sync worst gradient l2-rel {:.2e}'.format(case, worst))
+
+
 def test_default_params_full_size_properties():
     """BASELINE config (default wavenet_params.json, T = 100000): size-independent checks."""
     import wavenet
