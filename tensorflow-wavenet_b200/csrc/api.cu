@@ -23,6 +23,12 @@ bool g_prof_created = false;
 }  // namespace
 
 void prof_mark(cudaStream_t st, int tag) {
+  static int dbg = -1;
+  if (dbg < 0) dbg = getenv("WN_DEBUG_SYNC") ? 1 : 0;
+  if (dbg) {   // debugging aid: synchronise after every launch and report the first failing kernel kind
+    cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, "[wn debug] after tag %d: %s\n", tag, cudaGetErrorString(e));
+  }
   if (!g_prof_on || g_prof_n >= PROF_MAX) return;
   cudaEventRecord(g_prof_ev[g_prof_n], st);
   g_prof_tag[g_prof_n] = tag;
@@ -108,6 +114,8 @@ struct Workspace {
   // tcgen05 block kernels (C == 32)
   unsigned char* Wimg;  // per-layer weight images
   float* XT;       // [L][32][ldm] transposed layer inputs   (training, T % 4 == 0)
+  float* XpT;      // [n][32][ldm] transposed x[t-d] of the n layers with d % 4 != 0 (TMA alignment)
+  int xpt_slot[WN_MAX_LAYERS];   // layer -> slot in XpT, or -1
   float* dpreT;    // [64][ldm]
   float* dXT;      // 2 x [32][ldm]
   int umma_bwd;    // 1 when the tcgen05 backward path is used for this (cfg, B, T)
@@ -145,10 +153,14 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->umma_bwd = (training && umma_blocks && (T % 4 == 0)) ? 1 : 0;
   if (w->umma_bwd) {
     w->XT = (float*)take(L * 32 * ldm * f);
+    int n_un = 0;
+    for (int l = 0; l < L; ++l) w->xpt_slot[l] = (c->dilations[l] % 4 != 0) ? n_un++ : -1;
+    w->XpT = n_un ? (float*)take((int64_t)n_un * 32 * ldm * f) : nullptr;
     w->dpreT = (float*)take(64 * ldm * f);
     w->dXT = (float*)take(2 * 32 * ldm * f);
   } else {
-    w->XT = w->dpreT = w->dXT = nullptr;
+    w->XT = w->XpT = w->dpreT = w->dXT = nullptr;
+    for (int l = 0; l < L; ++l) w->xpt_slot[l] = -1;
   }
   if (training) {
     w->WskipR = (float*)take(S * L * D * f);
@@ -247,7 +259,8 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     const int last = (l == L - 1);
     RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz,
                  training ? w.ZcatT + (int64_t)l * D * w.ldm : nullptr,
-                 w.umma_bwd ? w.XT + (int64_t)l * 32 * w.ldm : nullptr, w.ldm,
+                 w.umma_bwd ? w.XT + (int64_t)l * 32 * w.ldm : nullptr,
+                 (w.umma_bwd && w.xpt_slot[l] >= 0) ? w.XpT + (int64_t)w.xpt_slot[l] * 32 * w.ldm : nullptr, w.ldm,
                  w.Wimg ? w.Wimg + (size_t)l * block_img_stride() : nullptr, params + lo.filter + (int64_t)l * 2 * R * D,
                  params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
                  w.prebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr,
@@ -391,7 +404,7 @@ int wn_block_fwd(const float* x, float* x_out, float* zcat, int32_t ldz, const f
   if (!x || !zcat || !filter || !gate || !prebias || batch < 1 || time < 1 || dilation < 1) return -1;
   if (!is_last && (!x_out || !dense)) return -1;
   if ((ldz & 1) || ldz < channels) return -3;
-  return block_fwd(x, x_out, zcat, ldz, nullptr, nullptr, 0, nullptr, filter, gate, dense, prebias, dense_bias,
+  return block_fwd(x, x_out, zcat, ldz, nullptr, nullptr, nullptr, 0, nullptr, filter, gate, dense, prebias, dense_bias,
                    batch * time, time, dilation, channels, is_last, (cudaStream_t)stream);
 }
 
@@ -558,7 +571,8 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     const int last = (l == L - 1);
     if (w.umma_bwd) {
       const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
-      RC(block_bwd_umma(w.X + l * xs, w.XT + (int64_t)l * 32 * w.ldm, last ? nullptr : dcur, last ? nullptr : dcurT,
+      RC(block_bwd_umma(w.X + l * xs, w.XT + (int64_t)l * 32 * w.ldm,
+                        w.xpt_slot[l] >= 0 ? w.XpT + (int64_t)w.xpt_slot[l] * 32 * w.ldm : nullptr, last ? nullptr : dcur, last ? nullptr : dcurT,
                         w.dZcat, ldz, l * D, w.ZcatT, dnext, dnextT, w.dpre, w.dpreT, w.ldm, img + block_img_off_pre(),
                         img + block_img_off_dx(), w.prebias + (int64_t)l * B * 2 * D,
                         grads + lo.filter + (int64_t)l * 2 * R * D, grads + lo.gate + (int64_t)l * 2 * R * D,

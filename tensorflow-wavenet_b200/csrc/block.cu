@@ -809,13 +809,14 @@ __global__ void zct_kernel(const float* __restrict__ zc, int ldz, float* __restr
 
 bool block_umma_enabled() { return !use_mma_blocks(); }
 
-int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm, const unsigned char* img,
+int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
+              const unsigned char* img,
               const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
               int M, int T, int d, int C, int is_last, cudaStream_t st) {
   if (C == 32 && !use_mma_blocks())
-    return block_fwd_umma(x, xout, zc, ldz, zcT, xT, ldm, img, wf, wg, dense, prebias, dense_bias, M / T, T, d,
+    return block_fwd_umma(x, xout, zc, ldz, zcT, xT, xpT, ldm, img, wf, wg, dense, prebias, dense_bias, M / T, T, d,
                           is_last, st);
-  if (xT) return -2;   // x^T is only produced by the tcgen05 path
+  if (xT || xpT) return -2;   // x^T is only produced by the tcgen05 path
   int rc = -2;
   if (C == 32) rc = launch_fwd<32>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
   if (C == 16) rc = launch_fwd<16>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);

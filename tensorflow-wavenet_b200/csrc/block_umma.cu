@@ -106,6 +106,7 @@ struct FwdArgs {
   float* xout;
   float* zc; int ldz;               // Zcat + l*C, row pitch ldz
   float* zcT; float* xT; int ldm;   // transposed copies [32][ldm] of z and of the layer input x (nullable)
+  float* xpT;                       // transposed copy of the dilated past x[t-d] (nullable; see block_bwd_umma)
   const unsigned char* img;         // IMG_FWD bytes (nullable -> built in the kernel from wf/wg/dense)
   const float *wf, *wg, *dense, *prebias, *dense_bias;
   int B, T, d, is_last;
@@ -204,6 +205,13 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
       v = *reinterpret_cast<const float4*>(Xp + off);
       *reinterpret_cast<float4*>(L0 + off) =
           make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
+      if (a.xpT && t0 + r < a.T) {
+        const size_t mm = (size_t)b * a.T + t0 + r;
+        a.xpT[(size_t)(4 * j + 0) * a.ldm + mm] = round_tf32(v.x);
+        a.xpT[(size_t)(4 * j + 1) * a.ldm + mm] = round_tf32(v.y);
+        a.xpT[(size_t)(4 * j + 2) * a.ldm + mm] = round_tf32(v.z);
+        a.xpT[(size_t)(4 * j + 3) * a.ldm + mm] = round_tf32(v.w);
+      }
     }
     fence_async_smem();
     __syncthreads();
@@ -299,14 +307,14 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm,
+int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
                    const unsigned char* img, const float* wf, const float* wg, const float* dense,
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st) {
   CUtensorMap mapX;
   int rc = make_map_3d(&mapX, x, B, T, C, C, TM);
   if (rc) return rc;
   FwdArgs a;
-  a.xout = xout; a.zc = zc; a.ldz = ldz; a.zcT = zcT; a.xT = xT; a.ldm = ldm; a.img = img; a.wf = wf; a.wg = wg;
+  a.xout = xout; a.zc = zc; a.ldz = ldz; a.zcT = zcT; a.xT = xT; a.xpT = xpT; a.ldm = ldm; a.img = img; a.wf = wf; a.wg = wg;
   a.dense = dense; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
   const size_t smem = 1024 + 4 * TILE + IMG_FWD;
   static bool attr = false;
@@ -570,11 +578,13 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
 struct WgArgs {
   float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;
   int B, T, d, is_last, zrow;   // zrow: first row of this layer inside ZcatT
+  int past_shift;               // 1: x[t-d]^T is read from x^T at coordinate t-d (d % 4 == 0)
 };
 
 __global__ void __launch_bounds__(192, 1)
-block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ CUtensorMap mapZT,
-                        const __grid_constant__ CUtensorMap mapPT, const __grid_constant__ CUtensorMap mapDT, WgArgs a) {
+block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ CUtensorMap mapXpT,
+                        const __grid_constant__ CUtensorMap mapZT, const __grid_constant__ CUtensorMap mapPT,
+                        const __grid_constant__ CUtensorMap mapDT, WgArgs a) {
   constexpr int STG = 4;
   constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = 96 * 128, STAGE = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
@@ -620,7 +630,10 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_
         mbar_expect_tx(&full_bar[s], bytes);
         unsigned char* sa = smem + s * STAGE;
         tma_load_3d(sa, &mapXT, &full_bar[s], t, b, 0);                 // x^T      rows 0-31
-        tma_load_3d(sa + 4096, &mapXT, &full_bar[s], t - a.d, b, 0);    // x[t-d]^T rows 32-63 (zero for t < d)
+        // x[t-d]^T rows 32-63 (zero for t < d).  TMA needs the innermost coordinate 16-byte aligned
+        // (measured: d = 1, 2 never complete), so d % 4 != 0 reads the pre-shifted copy the forward wrote.
+        if (a.past_shift) tma_load_3d(sa + 4096, &mapXT, &full_bar[s], t - a.d, b, 0);
+        else tma_load_3d(sa + 4096, &mapXpT, &full_bar[s], t, b, 0);
         tma_load_3d(sa + 8192, &mapZT, &full_bar[s], t, b, a.zrow);     // z^T      rows 64-95
         tma_load_3d(sa + A_BYTES, &mapPT, &full_bar[s], t, b, 0);       // dpre^T   B rows 0-63
         if (!a.is_last) tma_load_3d(sa + A_BYTES + 8192, &mapDT, &full_bar[s], t, b, 0);   // dx'^T B rows 64-95
@@ -685,7 +698,7 @@ static int make_map_T(CUtensorMap* m, const float* ptr, int64_t rows, int64_t B,
   return r == CUDA_SUCCESS ? 0 : -9;
 }
 
-int block_bwd_umma(const float* x, const float* xT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
+int block_bwd_umma(const float* x, const float* xT, const float* xpT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
                    int zcol, const float* ZcatT, float* dx, float* dxT, float* dpre, float* dpreT, int ldm,
                    const unsigned char* img_pre, const unsigned char* img_dx, const float* prebias, float* gwf,
                    float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d, int is_last,
@@ -717,6 +730,11 @@ int block_bwd_umma(const float* x, const float* xT, const float* dxn, const floa
     CUtensorMap mXT, mZT, mPT, mDT;
     int rc = make_map_T(&mXT, xT, C, B, T, ldm, 32);
     if (rc) return rc;
+    CUtensorMap mXpT;
+    const bool past_shift = (d % 4 == 0);
+    if (!past_shift && !xpT) return -3;
+    rc = make_map_T(&mXpT, past_shift ? xT : xpT, C, B, T, ldm, 32);
+    if (rc) return rc;
     rc = make_map_T(&mZT, ZcatT, (int64_t)(zcol + C), B, T, ldm, 32);
     if (rc) return rc;
     rc = make_map_T(&mPT, dpreT, 64, B, T, ldm, 64);
@@ -725,7 +743,7 @@ int block_bwd_umma(const float* x, const float* xT, const float* dxn, const floa
     if (rc) return rc;
     WgArgs a;
     a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias; a.B = B; a.T = T;
-    a.d = d; a.is_last = is_last; a.zrow = zcol;
+    a.d = d; a.is_last = is_last; a.zrow = zcol; a.past_shift = past_shift ? 1 : 0;
     const size_t smem = 1024 + 4 * (128 * 128 + 96 * 128);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(block_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
@@ -733,7 +751,7 @@ int block_bwd_umma(const float* x, const float* xT, const float* dxn, const floa
     int splits = sm_count() / (B > 0 ? B : 1);
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
-    block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mXT, mZT, mPT, mDT, a);
+    block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mXT, mXpT, mZT, mPT, mDT, a);
     WN_CHECK_LAUNCH();
     prof_mark(st, PT_BLOCK_WGRAD);
   }

@@ -34,16 +34,17 @@ int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStre
 int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st);
 int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
 
-// zcT / xT (nullable): transposed copies [C][ldm] of z and of the layer input; img (nullable): pre-built weight image
-int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm, const unsigned char* img,
+// zcT / xT / xpT (nullable): transposed copies [C][ldm] of z, of the layer input and of x[t-d]; img (nullable): pre-built weight image
+int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
+              const unsigned char* img,
               const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
               int M, int T, int d, int C, int is_last, cudaStream_t st);
 bool block_umma_enabled();
 void set_block_impl(int mma);
-int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, int ldm,
+int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
                    const unsigned char* img, const float* wf, const float* wg, const float* dense,
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
-int block_bwd_umma(const float* x, const float* xT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
+int block_bwd_umma(const float* x, const float* xT, const float* xpT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
                    int zcol, const float* ZcatT, float* dx, float* dxT, float* dpre, float* dpreT, int ldm,
                    const unsigned char* img_pre, const unsigned char* img_dx, const float* prebias, float* gwf,
                    float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d, int is_last,
