@@ -26,14 +26,15 @@ static EncodeTiledFn get_encode() {
   return (EncodeTiledFn)fn;
 }
 // 2-D fp32 row-major [rows][cols] tensor, box = [box_rows][32 floats], 128B swizzle
-static CUtensorMap make_map(EncodeTiledFn enc, const float* ptr, int rows, int cols, int box_rows) {
+static CUtensorMap make_map(EncodeTiledFn enc, const float* ptr, int rows, int cols, int box_rows,
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
   cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed %d\n", (int)r); exit(2); }
   return m;
@@ -59,13 +60,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -76,6 +77,7 @@ struct Case {
   uint32_t a_lbo, a_sbo, a_kstep;                // descriptor fields (bytes) and start-address step per k-step
   uint32_t b_lbo, b_sbo, b_kstep;
   int N, ksteps, manual_a;
+  int a_lt, b_lt;            // descriptor layout types (0 -> default 2)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -130,8 +132,8 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)c.a_mn << 15) | ((uint32_t)c.b_mn << 16) |
                        ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int k = 0; k < c.ksteps; ++k) {
-        const uint64_t da = make_desc(smem_u32(sA) + k * c.a_kstep, c.a_lbo, c.a_sbo);
-        const uint64_t db = make_desc(smem_u32(sB) + k * c.b_kstep, c.b_lbo, c.b_sbo);
+        const uint64_t da = make_desc(smem_u32(sA) + k * c.a_kstep, c.a_lbo, c.a_sbo, c.a_lt ? c.a_lt : 2);
+        const uint64_t db = make_desc(smem_u32(sB) + k * c.b_kstep, c.b_lbo, c.b_sbo, c.b_lt ? c.b_lt : 2);
         const uint32_t accum = k > 0 ? 1u : 0u;
         asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                      ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
@@ -176,7 +178,7 @@ int main() {
   EncodeTiledFn enc = get_encode();
   const int M = 128, K = 32;
   int n_fail = 0;
-  for (int variant = 0; variant < 8; ++variant) {
+  for (int variant = 0; variant < 20; ++variant) {
     Case c;
     memset(&c, 0, sizeof(c));
     const char* name = "";
@@ -200,6 +202,18 @@ int main() {
       case 7: name = "A MN-major, B MN-major (N=128)"; N = 128; c.a_mn = 1; c.a_boxes = 4; c.a_box_rows = 32; c.a_box_dc = 32;
               c.a_lbo = 4096; c.a_sbo = 1024; c.a_kstep = 1024;
               c.b_mn = 1; c.b_boxes = 4; c.b_box_rows = 32; c.b_box_dc = 32; c.b_lbo = 4096; c.b_sbo = 1024; c.b_kstep = 1024; break;
+    }
+    // ---- tf32 MN-major operands: 128B swizzle with 32-byte atoms (TMA SWIZZLE_128B_ATOM_32B, descriptor layout 1)
+    char namebuf[160];
+    if (variant >= 8) {
+      static const uint32_t cand[6][2] = {{4096, 512}, {512, 4096}, {4096, 1024}, {1024, 4096}, {4096, 256}, {256, 4096}};
+      const int which = (variant - 8) / 6;        // 0: B MN-major, 1: A MN-major
+      const int ci = (variant - 8) % 6;
+      if (which > 1) break;
+      if (which == 0) { c.b_mn = 1; c.b_lt = 1; c.b_boxes = 2; c.b_box_rows = 32; c.b_box_dc = 32; c.b_lbo = cand[ci][0]; c.b_sbo = cand[ci][1]; c.b_kstep = 1024; }
+      else { c.a_mn = 1; c.a_lt = 1; c.a_boxes = 4; c.a_box_rows = 32; c.a_box_dc = 32; c.a_lbo = cand[ci][0]; c.a_sbo = cand[ci][1]; c.a_kstep = 1024; }
+      snprintf(namebuf, sizeof(namebuf), "%s MN-major SW128_ATOM_32B layout=1 LBO=%u SBO=%u", which ? "A" : "B", cand[ci][0], cand[ci][1]);
+      name = namebuf;
     }
     c.N = N;
     // logical matrices
@@ -226,8 +240,8 @@ int main() {
     CK(cudaMemcpy(dB, Bs.data(), Bs.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dC, Cout.data(), Cout.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(dS, 0, 4));
-    CUtensorMap mA = c.a_mn ? make_map(enc, dA, K, M, c.a_box_rows) : make_map(enc, dA, M, K, c.a_box_rows);
-    CUtensorMap mB = c.b_mn ? make_map(enc, dB, K, N, c.b_box_rows) : make_map(enc, dB, N, K, c.b_box_rows);
+    CUtensorMap mA = c.a_mn ? make_map(enc, dA, K, M, c.a_box_rows, c.a_lt == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B) : make_map(enc, dA, M, K, c.a_box_rows);
+    CUtensorMap mB = c.b_mn ? make_map(enc, dB, K, N, c.b_box_rows, c.b_lt == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B) : make_map(enc, dB, N, K, c.b_box_rows);
     CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 1024));
     probe_kernel<<<1, 128, 16384 + 32768 + 1024>>>(mA, mB, c, dA, dC, dS);
     cudaError_t e = cudaDeviceSynchronize();
