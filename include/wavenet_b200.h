@@ -119,6 +119,13 @@ int wn_gemm_nt_umma(const float* a, int32_t lda, const float* b, int32_t ldb, fl
                     int32_t ldct, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
                     int32_t ldmask, int32_t flags, int32_t split_k, wn_stream_t stream);
 
+/* The same tcgen05 kernel in all three operand forms of wn_gemm_tf32 (mode 0 NN / 1 NT / 2 TN), every
+ * operand read as it lies in HBM (MN-major operands through the 32-byte-atom 128B swizzle).  Returns -3
+ * for shapes it does not take (N % 32 for modes 0/2, M % 32 for mode 2, leading dimensions % 4). */
+int wn_gemm_umma(int32_t mode, const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc,
+                 int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask, int32_t ldmask,
+                 int32_t flags, int32_t split_k, wn_stream_t stream);
+
 /* ---- softmax cross entropy vs the next sample: model.py:654-666 ---------------------------
  * logits [B*T, Q] are overwritten by d loss / d logits (TF backprop semantics) when write_grad. */
 int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t time, int32_t q,

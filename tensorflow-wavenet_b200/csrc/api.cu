@@ -98,28 +98,11 @@ struct Workspace {
   float* bsum;     // [S]
   float* gtmp;     // [S]
   float* partials; // [4096]
-  // K-major operand copies for the tcgen05 "NT" GEMM form (ldm = M rounded up to 4)
-  float* WskipT;   // [S, L*D]
-  float* W1T;      // [S, S]
-  float* W2T;      // [Q, S]
-  float* WskipR;   // [L*D, S]  tf32-rounded copies (B operands of the input-gradient GEMMs; training)
+  float* WskipR;   // [L*D, S]  tf32-rounded weight copies (tcgen05 truncates raw fp32 operands)
   float* W1R;      // [S, S]
   float* W2R;      // [S, Q]
-  float* ZcatT;    // [L*D, ldm]   (training)
-  float* A1T;      // [S, ldm]
-  float* X2T;      // [S, ldm]     transposed input of postprocess2 (A2, or A2 + S0)
-  float* dlogT;    // [Q, ldm]
-  float* G1T;      // [S, ldm]
-  float* G2T;      // [S, ldm]
-  // tcgen05 block kernels (C == 32)
-  unsigned char* Wimg;  // per-layer weight images
-  float* XT;       // [L][32][ldm] transposed layer inputs   (training, T % 4 == 0)
-  float* XpT;      // [n][32][ldm] transposed x[t-d] of the n layers with d % 4 != 0 (TMA alignment)
-  int xpt_slot[WN_MAX_LAYERS];   // layer -> slot in XpT, or -1
-  float* dpreT;    // [64][ldm]
-  float* dXT;      // 2 x [32][ldm]
-  int umma_bwd;    // 1 when the tcgen05 backward path is used for this (cfg, B, T)
-  int ldm;
+  unsigned char* Wimg;  // per-layer weight images of the tcgen05 block kernels (C == 32)
+  int umma_bwd;    // 1 when the tcgen05 backward path is used
   int64_t bytes;
 };
 
@@ -143,38 +126,12 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->prebias = (float*)take(L * B * 2 * D * f);
   w->bsum = (float*)take(S * f);
   w->partials = (float*)take(4096 * f);
-  w->WskipT = (float*)take(S * L * D * f);
-  w->W1T = (float*)take(S * S * f);
-  w->W2T = (float*)take(Q * S * f);
-  const int64_t ldm = (M + 3) & ~(int64_t)3;
-  w->ldm = (int)ldm;
+  w->WskipR = (float*)take(S * L * D * f);
+  w->W1R = (float*)take(S * S * f);
+  w->W2R = (float*)take(Q * S * f);
   const bool umma_blocks = (R == 32) && block_umma_enabled();
   w->Wimg = umma_blocks ? (unsigned char*)take(block_images_bytes((int)L)) : nullptr;
-  w->umma_bwd = (training && umma_blocks && (T % 4 == 0)) ? 1 : 0;
-  if (w->umma_bwd) {
-    w->XT = (float*)take(L * 32 * ldm * f);
-    int n_un = 0;
-    for (int l = 0; l < L; ++l) w->xpt_slot[l] = (c->dilations[l] % 4 != 0) ? n_un++ : -1;
-    w->XpT = n_un ? (float*)take((int64_t)n_un * 32 * ldm * f) : nullptr;
-    w->dpreT = (float*)take(64 * ldm * f);
-    w->dXT = (float*)take(2 * 32 * ldm * f);
-  } else {
-    w->XT = w->XpT = w->dpreT = w->dXT = nullptr;
-    for (int l = 0; l < L; ++l) w->xpt_slot[l] = -1;
-  }
-  if (training) {
-    w->WskipR = (float*)take(S * L * D * f);
-    w->W1R = (float*)take(S * S * f);
-    w->W2R = (float*)take(Q * S * f);
-    w->ZcatT = (float*)take(L * D * ldm * f);
-    w->A1T = (float*)take(S * ldm * f);
-    w->X2T = (float*)take(S * ldm * f);
-    w->dlogT = (float*)take(Q * ldm * f);
-    w->G1T = (float*)take(S * ldm * f);
-    w->G2T = (float*)take(S * ldm * f);
-  } else {
-    w->ZcatT = w->A1T = w->X2T = w->dlogT = w->G1T = w->G2T = w->WskipR = w->W1R = w->W2R = nullptr;
-  }
+  w->umma_bwd = (training && umma_blocks) ? 1 : 0;
   if (training) {
     w->logits = (float*)take(M * Q * f);
     w->G1 = (float*)take(M * S * f);
@@ -211,8 +168,9 @@ static int split_for(int m_out, int n_out, int k) {
   return s;
 }
 
-// C[M,N] (+)= A[M,K] . B[N,K]^T with optional transposed copy CT[N][M].  tcgen05 by default;
-// WN_GEMM_IMPL=mma selects the mma.sync kernel (validation of one implementation against the other).
+// mode 0 NN: C = A[M,K].B[K,N]   1 NT: C = A[M,K].B[N,K]^T   2 TN: C += A[K,M]^T.B[K,N] (split-K, atomics).
+// tcgen05 by default; WN_GEMM_IMPL=mma (or a shape the tcgen05 kernel does not take) selects the mma.sync
+// kernel -- also how one implementation is validated against the other.
 static int g_gemm_impl = -1;   // -1 unset, 0 tcgen05, 1 mma.sync
 static bool use_mma_gemm() {
   if (g_gemm_impl < 0) {
@@ -221,12 +179,10 @@ static bool use_mma_gemm() {
   }
   return g_gemm_impl == 1;
 }
-static int gemm_nt(const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st) {
-  if (!use_mma_gemm()) return gemm_nt_umma(p, CT, ldct, split_k, st);
-  int rc = gemm_tf32(1, p, split_k, st);
-  if (rc) return rc;
-  if (CT) return transpose(p.C, p.ldc, CT, ldct, p.M, p.N, 0, st);
-  return 0;
+static int gemm(int mode, GemmParams p, int split_k, cudaStream_t st) {
+  if (mode == 2) p.flags |= GEMM_ATOMIC;
+  if (!use_mma_gemm() && gemm_umma_supported(mode, p)) return gemm_umma(mode, p, nullptr, 0, split_k, st);
+  return gemm_tf32(mode, p, split_k, st);
 }
 
 #define RC(x)            \
@@ -258,9 +214,6 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     float* xout = training ? w.X + (l + 1) * xs : w.X + ((l + 1) & 1) * xs;
     const int last = (l == L - 1);
     RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz,
-                 training ? w.ZcatT + (int64_t)l * D * w.ldm : nullptr,
-                 w.umma_bwd ? w.XT + (int64_t)l * 32 * w.ldm : nullptr,
-                 (w.umma_bwd && w.xpt_slot[l] >= 0) ? w.XpT + (int64_t)w.xpt_slot[l] * 32 * w.ldm : nullptr, w.ldm,
                  w.Wimg ? w.Wimg + (size_t)l * block_img_stride() : nullptr, params + lo.filter + (int64_t)l * 2 * R * D,
                  params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
                  w.prebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr,
@@ -272,42 +225,36 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     prof_mark(st, PT_SKIP_BIAS_SUM);
     bsum = w.bsum;
   }
-  // K-major weight copies for the forward products (weights change every step; 1.2 M elements)
-  RC(transpose(params + lo.skip, S, w.WskipT, ldz, ldz, S, 1, st));
-  RC(transpose(params + lo.post1, S, w.W1T, S, S, S, 1, st));
-  RC(transpose(params + lo.post2, Q, w.W2T, S, S, Q, 1, st));
-  if (training) {
-    RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, st));
-    RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, st));
-    RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
-  }
+  // tf32-rounded weight copies: B operands of the forward products and of the input-gradient products
+  RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, st));
+  RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, st));
+  RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
   prof_mark(st, PT_MISC);
   {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
-    GemmParams p = gp(w.Zcat, ldz, w.WskipT, ldz, w.A1, S, M, S, ldz);
+    GemmParams p = gp(w.Zcat, ldz, w.WskipR, S, w.A1, S, M, S, ldz);
     p.bias = bsum;
     p.flags = GEMM_RELU | GEMM_ROUND;
     if (c->residual_postproc) { p.C2 = w.S0; p.ldc2 = S; }
-    RC(gemm_nt(p, training ? w.A1T : nullptr, w.ldm, 1, st));
+    RC(gemm(0, p, 1, st));
     prof_mark(st, PT_GEMM_SKIP_FWD);
   }
   {  // conv1 -> relu                             (model.py:432-435)
-    GemmParams p = gp(w.A1, S, w.W1T, S, w.A2, S, M, S, S);
+    GemmParams p = gp(w.A1, S, w.W1R, S, w.A2, S, M, S, S);
     p.bias = P(params, lo.post1_bias);
     p.flags = GEMM_RELU | GEMM_ROUND;
-    RC(gemm_nt(p, (training && !c->residual_postproc) ? w.X2T : nullptr, w.ldm, 1, st));
+    RC(gemm(0, p, 1, st));
     prof_mark(st, PT_GEMM_POST1_FWD);
   }
   const float* x2 = w.A2;
   if (c->residual_postproc) {  // transformed2 += total   (model.py:436-437)
     RC((int)cudaMemcpyAsync(w.T2, w.A2, (size_t)M * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
     RC(add_inplace(w.T2, w.S0, (int64_t)M * S, 1, st));
-    if (training) RC(transpose(w.T2, S, w.X2T, w.ldm, M, S, 0, st));
     x2 = w.T2;
   }
   {  // conv2                                      (model.py:438-440)
-    GemmParams p = gp(x2, S, w.W2T, S, logits, Q, M, Q, S);
+    GemmParams p = gp(x2, S, w.W2R, Q, logits, Q, M, Q, S);
     p.bias = P(params, lo.post2_bias);
-    RC(gemm_nt(p, nullptr, 0, 1, st));
+    RC(gemm(0, p, 1, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
   }
   return 0;
@@ -404,7 +351,7 @@ int wn_block_fwd(const float* x, float* x_out, float* zcat, int32_t ldz, const f
   if (!x || !zcat || !filter || !gate || !prebias || batch < 1 || time < 1 || dilation < 1) return -1;
   if (!is_last && (!x_out || !dense)) return -1;
   if ((ldz & 1) || ldz < channels) return -3;
-  return block_fwd(x, x_out, zcat, ldz, nullptr, nullptr, nullptr, 0, nullptr, filter, gate, dense, prebias, dense_bias,
+  return block_fwd(x, x_out, zcat, ldz, nullptr, filter, gate, dense, prebias, dense_bias,
                    batch * time, time, dilation, channels, is_last, (cudaStream_t)stream);
 }
 
@@ -446,6 +393,19 @@ int wn_gemm_nt_umma(const float* a, int32_t lda, const float* b, int32_t ldb, fl
   p.ldaux = ldmask;
   p.flags = flags;
   return gemm_nt_umma(p, ct, ldct, split_k, (cudaStream_t)stream);
+}
+
+int wn_gemm_umma(int32_t mode, const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc,
+                 int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask, int32_t ldmask,
+                 int32_t flags, int32_t split_k, wn_stream_t stream) {
+  if (!a || !b || !c) return -1;
+  GemmParams p = gp(a, lda, b, ldb, c, ldc, m, n, k);
+  p.bias = bias;
+  p.aux = relu_mask;
+  p.ldaux = ldmask;
+  p.flags = flags;
+  if (mode == 2) p.flags |= GEMM_ATOMIC;
+  return gemm_umma(mode, p, nullptr, 0, split_k, (cudaStream_t)stream);
 }
 
 int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t time, int32_t q, float* partials,
@@ -508,12 +468,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, st));
   prof_mark(st, PT_XENT);
 
-  RC(transpose(w.logits, Q, w.dlogT, w.ldm, M, Q, 0, st));
-  prof_mark(st, PT_TRANSPOSE);
+  const float* x2 = rp ? w.T2 : w.A2;   // input of postprocess2
   {  // postprocess2 gradients:  dW2[S,Q] = X2^T . dlogits
-    GemmParams p = gp(w.X2T, w.ldm, w.dlogT, w.ldm, grads + lo.post2, Q, S, Q, M);
-    p.flags = GEMM_ATOMIC;
-    RC(gemm_nt(p, nullptr, 0, split_for(S, Q, M), st));
+    GemmParams p = gp(x2, S, w.logits, Q, grads + lo.post2, Q, S, Q, M);
+    RC(gemm(2, p, split_for(S, Q, M), st));
     prof_mark(st, PT_GEMM_POST2_WGRAD);
     if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, st)); prof_mark(st, PT_COLSUM); }
   }
@@ -522,13 +480,12 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     p.aux = w.A2; p.ldaux = S;
     p.flags = GEMM_ROUND;
     if (rp) { p.C2 = w.G3; p.ldc2 = S; }
-    RC(gemm_nt(p, w.G1T, w.ldm, 1, st));
+    RC(gemm(1, p, 1, st));
     prof_mark(st, PT_GEMM_POST2_DGRAD);
   }
   {  // postprocess1 gradients:  dW1[S,S] = A1^T . G1
-    GemmParams p = gp(w.A1T, w.ldm, w.G1T, w.ldm, grads + lo.post1, S, S, S, M);
-    p.flags = GEMM_ATOMIC;
-    RC(gemm_nt(p, nullptr, 0, split_for(S, S, M), st));
+    GemmParams p = gp(w.A1, S, w.G1, S, grads + lo.post1, S, S, S, M);
+    RC(gemm(2, p, split_for(S, S, M), st));
     prof_mark(st, PT_GEMM_POST1_WGRAD);
     if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, st)); prof_mark(st, PT_COLSUM); }
   }
@@ -536,18 +493,16 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     GemmParams p = gp(w.G1, S, w.W1R, S, w.G2, S, M, S, S);
     p.aux = w.A1; p.ldaux = S;
     p.flags = rp ? 0 : GEMM_ROUND;
-    RC(gemm_nt(p, rp ? nullptr : w.G2T, w.ldm, 1, st));
+    RC(gemm(1, p, 1, st));
     prof_mark(st, PT_GEMM_POST1_DGRAD);
     if (rp) {
       RC(add_inplace(w.G2, w.G3, (int64_t)M * S, 1, st));
-      RC(transpose(w.G2, S, w.G2T, w.ldm, M, S, 0, st));
       prof_mark(st, PT_MISC);
     }
   }
   {  // skip weights / biases:  dWskip[L*D,S] = Zcat^T . G2
-    GemmParams p = gp(w.ZcatT, w.ldm, w.G2T, w.ldm, grads + lo.skip, S, ldz, S, M);
-    p.flags = GEMM_ATOMIC;
-    RC(gemm_nt(p, nullptr, 0, split_for(ldz, S, M), st));
+    GemmParams p = gp(w.Zcat, ldz, w.G2, S, grads + lo.skip, S, ldz, S, M);
+    RC(gemm(2, p, split_for(ldz, S, M), st));
     prof_mark(st, PT_GEMM_SKIP_WGRAD);
     if (lo.skip_bias >= 0) {
       RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), st));
@@ -559,28 +514,23 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   }
   {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
     GemmParams p = gp(w.G2, S, w.WskipR, S, w.dZcat, ldz, M, ldz, S);
-    RC(gemm_nt(p, nullptr, 0, 1, st));
+    RC(gemm(1, p, 1, st));
     prof_mark(st, PT_GEMM_SKIP_DGRAD);
   }
   const int64_t xs = (int64_t)M * R;
   float* dcur = w.dX;        // gradient wrt the output of the layer being processed
   float* dnext = w.dX + xs;  // gradient wrt its input
-  float* dcurT = w.dXT;
-  float* dnextT = w.dXT ? w.dXT + (int64_t)32 * w.ldm : nullptr;
   for (int l = L - 1; l >= 0; --l) {
     const int last = (l == L - 1);
     if (w.umma_bwd) {
       const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
-      RC(block_bwd_umma(w.X + l * xs, w.XT + (int64_t)l * 32 * w.ldm,
-                        w.xpt_slot[l] >= 0 ? w.XpT + (int64_t)w.xpt_slot[l] * 32 * w.ldm : nullptr, last ? nullptr : dcur, last ? nullptr : dcurT,
-                        w.dZcat, ldz, l * D, w.ZcatT, dnext, dnextT, w.dpre, w.dpreT, w.ldm, img + block_img_off_pre(),
-                        img + block_img_off_dx(), w.prebias + (int64_t)l * B * 2 * D,
+      RC(block_bwd_umma(w.X + l * xs, last ? nullptr : dcur, w.dZcat, w.Zcat, ldz, l * D, dnext, w.dpre,
+                        img + block_img_off_pre(), img + block_img_off_dx(), w.prebias + (int64_t)l * B * 2 * D,
                         grads + lo.filter + (int64_t)l * 2 * R * D, grads + lo.gate + (int64_t)l * 2 * R * D,
                         grads + lo.dense + (int64_t)l * D * R, w.gprebias + (int64_t)l * B * 2 * D,
                         lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, B, T, cfg->dilations[l],
                         last, st));
       float* tmp = dcur; dcur = dnext; dnext = tmp;
-      tmp = dcurT; dcurT = dnextT; dnextT = tmp;
       continue;
     }
     RC(block_bwd(w.X + l * xs, last ? nullptr : dcur, w.dZcat + (int64_t)l * D, ldz, dnext, w.dpre,

@@ -800,30 +800,17 @@ static bool use_mma_blocks() {
   return g_block_impl == 1;
 }
 
-// zcT (nullable): transposed copy of z, [C][ldm] starting at this layer's row block of ZcatT
-__global__ void zct_kernel(const float* __restrict__ zc, int ldz, float* __restrict__ zcT, int ldm, int M, int C) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  for (int c = 0; c < C; ++c) zcT[(size_t)c * ldm + m] = zc[(size_t)m * ldz + c];
-}
-
 bool block_umma_enabled() { return !use_mma_blocks(); }
 
-int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
-              const unsigned char* img,
+int block_fwd(const float* x, float* xout, float* zc, int ldz, const unsigned char* img,
               const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
               int M, int T, int d, int C, int is_last, cudaStream_t st) {
   if (C == 32 && !use_mma_blocks())
-    return block_fwd_umma(x, xout, zc, ldz, zcT, xT, xpT, ldm, img, wf, wg, dense, prebias, dense_bias, M / T, T, d,
+    return block_fwd_umma(x, xout, zc, ldz, img, wf, wg, dense, prebias, dense_bias, M / T, T, d,
                           is_last, st);
-  if (xT || xpT) return -2;   // x^T is only produced by the tcgen05 path
   int rc = -2;
   if (C == 32) rc = launch_fwd<32>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
   if (C == 16) rc = launch_fwd<16>(x, xout, zc, ldz, wf, wg, dense, prebias, dense_bias, M, T, d, is_last, st);
-  if (rc == 0 && zcT) {
-    zct_kernel<<<(M + 127) / 128, 128, 0, st>>>(zc, ldz, zcT, ldm, M, C);
-    WN_CHECK_LAUNCH();
-  }
   return rc;
 }
 

@@ -17,10 +17,11 @@
 // Forward products are split-precision (hi + lo TF32 terms, 3 MMAs per product): DESIGN.md section 6.
 //
 // Backward of a layer is three kernels:
-//   bwd_pre  : recompute pre-activations, dz = dz_skip + dx'.Wd^T, dpre = [df|dg]  -> dpre, dpre^T
-//   wgrad    : one GEMM over time (K = T) on the transposed copies gives every weight / bias gradient
-//              of the layer: [x^T ; x[t-d]^T ; z^T ; 1] . [dpre^T ; dx'^T]^T  (block rows/cols selected)
-//   bwd_dx   : dx = dx' + dpre[t].Wcur^T + dpre[t+d].Wpast^T                       -> dx, dx^T
+//   bwd_pre  : recompute pre-activations, dz = dz_skip + dx'.Wd^T, dpre = [df|dg]  -> dpre
+//   wgrad    : one GEMM over time (K = T) gives every weight / bias gradient of the layer:
+//              [x ; x[t-d] ; z ; 1]^T . [dpre ; dx']  with both operands read MN-major straight from the
+//              [time][channel] activations (no transposed copies)
+//   bwd_dx   : dx = dx' + dpre[t].Wcur^T + dpre[t+d].Wpast^T                       -> dx
 #include "common.cuh"
 #include "kernels.h"
 #include "umma_common.cuh"
@@ -105,8 +106,6 @@ int block_images(unsigned char* img, const float* filter, const float* gate, con
 struct FwdArgs {
   float* xout;
   float* zc; int ldz;               // Zcat + l*C, row pitch ldz
-  float* zcT; float* xT; int ldm;   // transposed copies [32][ldm] of z and of the layer input x (nullable)
-  float* xpT;                       // transposed copy of the dilated past x[t-d] (nullable; see block_bwd_umma)
   const unsigned char* img;         // IMG_FWD bytes (nullable -> built in the kernel from wf/wg/dense)
   const float *wf, *wg, *dense, *prebias, *dense_bias;
   int B, T, d, is_last;
@@ -205,13 +204,6 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
       v = *reinterpret_cast<const float4*>(Xp + off);
       *reinterpret_cast<float4*>(L0 + off) =
           make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
-      if (a.xpT && t0 + r < a.T) {
-        const size_t mm = (size_t)b * a.T + t0 + r;
-        a.xpT[(size_t)(4 * j + 0) * a.ldm + mm] = round_tf32(v.x);
-        a.xpT[(size_t)(4 * j + 1) * a.ldm + mm] = round_tf32(v.y);
-        a.xpT[(size_t)(4 * j + 2) * a.ldm + mm] = round_tf32(v.z);
-        a.xpT[(size_t)(4 * j + 3) * a.ldm + mm] = round_tf32(v.w);
-      }
     }
     fence_async_smem();
     __syncthreads();
@@ -229,15 +221,6 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
     }
     const bool valid = (t0 + r) < a.T;
     const size_t m = (size_t)b * a.T + t0 + r;
-    if (a.xT && valid) {   // x^T for the weight-gradient GEMM: lanes hold consecutive time steps (coalesced)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a.xT[(size_t)(4 * j + 0) * a.ldm + m] = round_tf32(xr[j].x);
-        a.xT[(size_t)(4 * j + 1) * a.ldm + m] = round_tf32(xr[j].y);
-        a.xT[(size_t)(4 * j + 2) * a.ldm + m] = round_tf32(xr[j].z);
-        a.xT[(size_t)(4 * j + 3) * a.ldm + m] = round_tf32(xr[j].w);
-      }
-    }
     mbar_wait(&bar_m1, par);
     tc_fence_after();
     // both input tiles are consumed: prefetch the next tile of this CTA behind the epilogue
@@ -263,10 +246,6 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
         l[e] = round_tf32(z[4 * j + e] - h[e]);
       }
       if (valid) *reinterpret_cast<float4*>(a.zc + m * a.ldz + 4 * j) = make_float4(h[0], h[1], h[2], h[3]);
-      if (a.zcT && valid) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) a.zcT[(size_t)(4 * j + e) * a.ldm + m] = h[e];
-      }
       if (!a.is_last) {
         const uint32_t off = (uint32_t)r * 128 + ((uint32_t)(j ^ (r & 7)) << 4);
         *reinterpret_cast<float4*>(L0 + off) = make_float4(h[0], h[1], h[2], h[3]);
@@ -307,14 +286,13 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
-                   const unsigned char* img, const float* wf, const float* wg, const float* dense,
+int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsigned char* img, const float* wf, const float* wg, const float* dense,
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st) {
   CUtensorMap mapX;
   int rc = make_map_3d(&mapX, x, B, T, C, C, TM);
   if (rc) return rc;
   FwdArgs a;
-  a.xout = xout; a.zc = zc; a.ldz = ldz; a.zcT = zcT; a.xT = xT; a.xpT = xpT; a.ldm = ldm; a.img = img; a.wf = wf; a.wg = wg;
+  a.xout = xout; a.zc = zc; a.ldz = ldz; a.img = img; a.wf = wf; a.wg = wg;
   a.dense = dense; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
   const size_t smem = 1024 + 4 * TILE + IMG_FWD;
   static bool attr = false;
@@ -337,7 +315,6 @@ int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, 
 // =========================================================================================
 struct PreArgs {
   float* dpre;                 // [M][64]
-  float* dpreT; int ldm;       // [64][ldm]
   const unsigned char* img;    // IMG_PRE bytes
   const float* prebias;
   int B, T, d, is_last, zcol;  // zcol: column of this layer inside dZcat
@@ -456,11 +433,6 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
         *reinterpret_cast<float4*>(a.dpre + m * 64 + 4 * j) = make_float4(df[4 * j], df[4 * j + 1], df[4 * j + 2], df[4 * j + 3]);
         *reinterpret_cast<float4*>(a.dpre + m * 64 + 32 + 4 * j) = make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]);
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        a.dpreT[(size_t)j * a.ldm + m] = df[j];
-        a.dpreT[(size_t)(32 + j) * a.ldm + m] = dg[j];
-      }
     }
     tc_fence_before();
     __syncthreads();
@@ -474,7 +446,6 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
 struct DxArgs {
   const float* dxn;            // gradient wrt the layer output (nullable for the last layer)
   float* dx;                   // [M][32]
-  float* dxT; int ldm;         // [32][ldm]
   const unsigned char* img;    // IMG_DX bytes
   int B, T, d;
 };
@@ -555,10 +526,6 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
         const float4 o = make_float4(xn[j].x + __uint_as_float(ov[4 * j]), xn[j].y + __uint_as_float(ov[4 * j + 1]),
                                      xn[j].z + __uint_as_float(ov[4 * j + 2]), xn[j].w + __uint_as_float(ov[4 * j + 3]));
         *reinterpret_cast<float4*>(a.dx + m * C + 4 * j) = o;
-        a.dxT[(size_t)(4 * j + 0) * a.ldm + m] = round_tf32(o.x);
-        a.dxT[(size_t)(4 * j + 1) * a.ldm + m] = round_tf32(o.y);
-        a.dxT[(size_t)(4 * j + 2) * a.ldm + m] = round_tf32(o.z);
-        a.dxT[(size_t)(4 * j + 3) * a.ldm + m] = round_tf32(o.w);
       }
     }
     tc_fence_before();
@@ -569,24 +536,31 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
 
 // =========================================================================================
 // backward 3/3: every weight / bias gradient of the layer as ONE GEMM over time
-//   A rows (M = 128):  0-31 x^T | 32-63 x[t-d]^T | 64-95 z^T | 96 ones | 97-127 zero
-//   B rows (N = 96) :  0-63 dpre^T = [df ; dg]^T | 64-95 dx'^T
+//   D[i][j] = sum_t A[t][i] * B[t][j]          (contraction over time steps)
+//   A columns (M = 128): 0-31 x[t] | 32-63 x[t-d] | 64-95 z[t] | 96 ones | 97-127 zero
+//   B columns (N = 96) : 0-31 df | 32-63 dg | 64-95 dx'
 //   D[0:32 ,0:64] -> filter[1],gate[1]   D[32:64,0:64] -> filter[0],gate[0]   D[64:96,64:96] -> dense
 //   D[96,0:64]    -> prebias gradient (per batch element)      D[96,64:96] -> dense_bias
+// Both operands are read exactly as the activations lie in HBM ([time][channel], channel contiguous =
+// "MN-major"): TMA boxes of [32 steps][32 channels] in the 32-byte-atom swizzle, no transposed copies.
+// The dilated past x[t-d] is the same tensor at time coordinate t-d (zero filled for t < d).
 // grid = (splits, B): a CTA reduces a contiguous range of 32-step blocks of one batch element.
 // =========================================================================================
 struct WgArgs {
   float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;
-  int B, T, d, is_last, zrow;   // zrow: first row of this layer inside ZcatT
-  int past_shift;               // 1: x[t-d]^T is read from x^T at coordinate t-d (d % 4 == 0)
+  int B, T, d, is_last, zcol;   // zcol: first column of this layer inside Zcat
 };
 
-__global__ void __launch_bounds__(192, 1)
-block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ CUtensorMap mapXpT,
-                        const __grid_constant__ CUtensorMap mapZT, const __grid_constant__ CUtensorMap mapPT,
-                        const __grid_constant__ CUtensorMap mapDT, WgArgs a) {
-  constexpr int STG = 4;
-  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = 96 * 128, STAGE = A_BYTES + B_BYTES;
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 2)
+block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
+                        const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapDn, WgArgs a) {
+  constexpr int STG = 3;
+  constexpr uint32_t BLK = 32 * 128;                       // one [32 steps][32 channels] block
+  constexpr uint32_t A_BYTES = 4 * BLK, B_BYTES = 3 * BLK, STAGE = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full_bar[STG], empty_bar[STG], done_bar;
@@ -601,11 +575,11 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_
   const int nk = kb1 - kb0;
   if (nk <= 0) return;
 
-  // constant rows of every stage: row 96 = 1, rows 97..127 = 0; dx'^T rows of B are zero for the last layer
+  // constant block of every stage: column 96 = 1, columns 97..127 = 0; dx' block is zero for the last layer
   for (int i = tid; i < STG * 32 * 32; i += blockDim.x) {
     const int s = i / 1024, rr = (i / 32) % 32, cc = i % 32;
-    *reinterpret_cast<float*>(smem + s * STAGE + 96 * 128 + swz(rr, cc)) = (rr == 0) ? 1.0f : 0.0f;
-    if (a.is_last) *reinterpret_cast<float*>(smem + s * STAGE + A_BYTES + 64 * 128 + swz(rr, cc)) = 0.f;
+    *reinterpret_cast<float*>(smem + s * STAGE + 3 * BLK + swz32(rr, cc)) = (cc == 0) ? 1.0f : 0.0f;
+    if (a.is_last) *reinterpret_cast<float*>(smem + s * STAGE + A_BYTES + 2 * BLK + swz32(rr, cc)) = 0.f;
   }
   if (tid == 0) {
     for (int s = 0; s < STG; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -621,7 +595,7 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t bytes = 3 * 4096 + 8192 + (a.is_last ? 0 : 4096);
+      const uint32_t bytes = (a.is_last ? 5 : 6) * BLK;
       for (int i = 0; i < nk; ++i) {
         const int s = i % STG;
         const uint32_t ph = (i / STG) & 1;
@@ -629,28 +603,26 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], bytes);
         unsigned char* sa = smem + s * STAGE;
-        tma_load_3d(sa, &mapXT, &full_bar[s], t, b, 0);                 // x^T      rows 0-31
-        // x[t-d]^T rows 32-63 (zero for t < d).  TMA needs the innermost coordinate 16-byte aligned
-        // (measured: d = 1, 2 never complete), so d % 4 != 0 reads the pre-shifted copy the forward wrote.
-        if (a.past_shift) tma_load_3d(sa + 4096, &mapXT, &full_bar[s], t - a.d, b, 0);
-        else tma_load_3d(sa + 4096, &mapXpT, &full_bar[s], t, b, 0);
-        tma_load_3d(sa + 8192, &mapZT, &full_bar[s], t, b, a.zrow);     // z^T      rows 64-95
-        tma_load_3d(sa + A_BYTES, &mapPT, &full_bar[s], t, b, 0);       // dpre^T   B rows 0-63
-        if (!a.is_last) tma_load_3d(sa + A_BYTES + 8192, &mapDT, &full_bar[s], t, b, 0);   // dx'^T B rows 64-95
+        tma_load_3d(sa, &mapX, &full_bar[s], 0, t, b);                      // x[t]
+        tma_load_3d(sa + BLK, &mapX, &full_bar[s], 0, t - a.d, b);          // x[t-d]  (zeros for t < d)
+        tma_load_3d(sa + 2 * BLK, &mapZ, &full_bar[s], a.zcol, t, b);       // z[t]
+        tma_load_3d(sa + A_BYTES, &mapP, &full_bar[s], 0, t, b);            // df
+        tma_load_3d(sa + A_BYTES + BLK, &mapP, &full_bar[s], 32, t, b);     // dg
+        if (!a.is_last) tma_load_3d(sa + A_BYTES + 2 * BLK, &mapDn, &full_bar[s], 0, t, b);   // dx'
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t ID = idesc_tf32(128, 96);
+      constexpr uint32_t ID = idesc_tf32(128, 96, 1, 1);
       for (int i = 0; i < nk; ++i) {
         const int s = i % STG;
         const uint32_t ph = (i / STG) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE);
-        const uint64_t da = kmajor_desc(sa), db = kmajor_desc(sa + A_BYTES);
+        const uint64_t da = mnmajor_desc(sa, BLK), db = mnmajor_desc(sa + A_BYTES, BLK);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, da + 2 * k, db + 2 * k, ID, (i | k) > 0);
+        for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, da + 64 * k, db + 64 * k, ID, (i | k) > 0);   // +1024 B per K=8
         mma_commit(&empty_bar[s]);
       }
       mma_commit(&done_bar);
@@ -675,7 +647,9 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_
       }
       if (dst) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                     __uint_as_float(v[j + 3]));
       }
     }
   }
@@ -684,26 +658,10 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapXT, const __grid_
   if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
-// transposed activations [rows][B][T] with row pitch ldm (T % 4 == 0 keeps the batch stride 16-byte aligned)
-static int make_map_T(CUtensorMap* m, const float* ptr, int64_t rows, int64_t B, int64_t T, int64_t ldm, int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return -8;
-  cuuint64_t gdim[3] = {(cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)rows};
-  cuuint64_t gstr[2] = {(cuuint64_t)T * 4, (cuuint64_t)ldm * 4};
-  cuuint32_t box[3] = {32, 1, (cuuint32_t)box_rows};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -9;
-}
-
-int block_bwd_umma(const float* x, const float* xT, const float* xpT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
-                   int zcol, const float* ZcatT, float* dx, float* dxT, float* dpre, float* dpreT, int ldm,
-                   const unsigned char* img_pre, const unsigned char* img_dx, const float* prebias, float* gwf,
-                   float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d, int is_last,
-                   cudaStream_t st) {
-  if (T & 3) return -3;
+int block_bwd_umma(const float* x, const float* dxn, const float* dZcat, const float* Zcat, int ldz, int zcol,
+                   float* dx, float* dpre, const unsigned char* img_pre, const unsigned char* img_dx,
+                   const float* prebias, float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias,
+                   int B, int T, int d, int is_last, cudaStream_t st) {
   const int n_tiles = B * ((T + TM - 1) / TM);
   int grid = n_tiles;
   const int cap = 2 * sm_count();
@@ -717,7 +675,7 @@ int block_bwd_umma(const float* x, const float* xT, const float* xpT, const floa
     rc = make_map_3d(&mDz, dZcat, B, T, ldz, ldz, TM);
     if (rc) return rc;
     PreArgs a;
-    a.dpre = dpre; a.dpreT = dpreT; a.ldm = ldm; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
+    a.dpre = dpre; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
     a.is_last = is_last; a.zcol = zcol;
     const size_t smem = 1024 + 4 * TILE + IMG_PRE;
     static bool attr = false;
@@ -727,31 +685,26 @@ int block_bwd_umma(const float* x, const float* xT, const float* xpT, const floa
     prof_mark(st, PT_BLOCK_BWD_PRE);
   }
   {
-    CUtensorMap mXT, mZT, mPT, mDT;
-    int rc = make_map_T(&mXT, xT, C, B, T, ldm, 32);
+    CUtensorMap mX, mZ, mP, mDn;
+    int rc = make_map_3d_mn(&mX, x, B, T, C, C, 32);
     if (rc) return rc;
-    CUtensorMap mXpT;
-    const bool past_shift = (d % 4 == 0);
-    if (!past_shift && !xpT) return -3;
-    rc = make_map_T(&mXpT, past_shift ? xT : xpT, C, B, T, ldm, 32);
+    rc = make_map_3d_mn(&mZ, Zcat, B, T, ldz, ldz, 32);
     if (rc) return rc;
-    rc = make_map_T(&mZT, ZcatT, (int64_t)(zcol + C), B, T, ldm, 32);
+    rc = make_map_3d_mn(&mP, dpre, B, T, 64, 64, 32);
     if (rc) return rc;
-    rc = make_map_T(&mPT, dpreT, 64, B, T, ldm, 64);
-    if (rc) return rc;
-    rc = make_map_T(&mDT, is_last ? xT : dxnT, C, B, T, ldm, 32);
+    rc = make_map_3d_mn(&mDn, is_last ? x : dxn, B, T, C, C, 32);
     if (rc) return rc;
     WgArgs a;
     a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias; a.B = B; a.T = T;
-    a.d = d; a.is_last = is_last; a.zrow = zcol; a.past_shift = past_shift ? 1 : 0;
-    const size_t smem = 1024 + 4 * (128 * 128 + 96 * 128);
+    a.d = d; a.is_last = is_last; a.zcol = zcol;
+    const size_t smem = 1024 + 3 * (7 * 4096);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(block_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     const int nkb = (T + 31) / 32;
-    int splits = sm_count() / (B > 0 ? B : 1);
+    int splits = 2 * sm_count() / (B > 0 ? B : 1);
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
-    block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mXT, mXpT, mZT, mPT, mDT, a);
+    block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mX, mZ, mP, mDn, a);
     WN_CHECK_LAUNCH();
     prof_mark(st, PT_BLOCK_WGRAD);
   }
@@ -760,7 +713,7 @@ int block_bwd_umma(const float* x, const float* xT, const float* xpT, const floa
     int rc = make_map_3d(&mP, dpre, B, T, 64, 64, TM);
     if (rc) return rc;
     DxArgs a;
-    a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.dxT = dxT; a.ldm = ldm; a.img = img_dx; a.B = B; a.T = T; a.d = d;
+    a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.img = img_dx; a.B = B; a.T = T; a.d = d;
     const size_t smem = 1024 + 4 * TILE + IMG_DX;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }

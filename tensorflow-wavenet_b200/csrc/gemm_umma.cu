@@ -1,10 +1,12 @@
-// tcgen05 (5th-generation tensor core) TF32 GEMM for the skip / post-processing path:
-//     C[M,N] (+)= A[M,K] . B[N,K]^T      A, B row-major with K contiguous ("K-major"), fp32
+// tcgen05 (5th-generation tensor core) TF32 GEMM for the skip / post-processing path, fp32 row-major
+// storage, three operand forms (the same three the TF graph and its autodiff need):
+//     NN: C[M,N]   = A[M,K] . B[K,N]          forward 1x1 convolutions      (A K-major, B MN-major)
+//     NT: C[M,N]   = A[M,K] . B[N,K]^T        input gradients               (A, B K-major)
+//     TN: C[M,N]  += A[Kr,M]^T . B[Kr,N]      weight gradients, Kr = B*T    (A, B MN-major, split-K + red.add)
 // Reference call sites: wavenet/model.py:304-305,430-440 (1x1 convolutions = matmuls) and the
-// TF autodiff of them (train.py:252).  All nine GEMMs of a training step are expressed in this
-// one form: forward uses transposed weight copies, input gradients use the weights as stored,
-// weight gradients use transposed activation copies (written coalesced by the producers), so
-// both operands are always K-major and TMA's 128-byte swizzle matches the UMMA descriptors.
+// TF autodiff of them (train.py:252).  Every operand is read as it lies in HBM: K-major tiles use
+// TMA's 128-byte swizzle, MN-major tiles the 32-byte-atom flavour (the only one kind::tf32 accepts,
+// probe/umma_probe.cu) -- no transposed copies of activations or weights exist.
 //
 // Structure (one 128 x BN output tile per CTA, BN in {128, 256}):
 //   warp 0 : TMA producer   -- cp.async.bulk.tensor 2D boxes [128|BN rows x 32 floats] into a
@@ -19,6 +21,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "umma_common.cuh"
 
 namespace wn {
 
@@ -100,6 +103,7 @@ struct UmmaParams {
   int M, N, K;
   int flags;                      // GEMM_RELU | GEMM_ROUND | GEMM_ATOMIC
   int k_per_split;                // K range per blockIdx.z (multiple of UK)
+  int a_mn, b_mn;                 // operand majors: 0 = K contiguous, 1 = M / N contiguous
 };
 
 template <int BN>
@@ -142,25 +146,30 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         unsigned char* sa = smem + s * STAGE_BYTES;
-        tma_load_2d(sa, &mapA, &full_bar[s], k_begin + i * UK, m0);
-        tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], k_begin + i * UK, n0);
+        const int kc = k_begin + i * UK;
+        if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> 5);     // [UM/32 blocks][32 k][32 m]
+        else tma_load_2d(sa, &mapA, &full_bar[s], kc, m0);
+        if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> 5);
+        else tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kc, n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && nk > 0) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+      const uint32_t idesc = umma::idesc_tf32(UM, BN, p.a_mn, p.b_mn);
+      const uint32_t astep = p.a_mn ? 64 : 2, bstep = p.b_mn ? 64 : 2;   // descriptor start-address step per K=8
       for (int i = 0; i < nk; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t da = kmajor_desc(sa), db = kmajor_desc(sa + A_BYTES);
+        const uint64_t da = p.a_mn ? umma::mnmajor_desc(sa, 4096) : kmajor_desc(sa);
+        const uint64_t db = p.b_mn ? umma::mnmajor_desc(sa + A_BYTES, 4096) : kmajor_desc(sa + A_BYTES);
 #pragma unroll
         for (int k = 0; k < UK / 8; ++k) {
           const uint32_t accum = (i > 0 || k > 0) ? 1u : 0u;
           asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                       ::"r"(tmem), "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(accum) : "memory");
+                       ::"r"(tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
       }
@@ -197,9 +206,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const bool full = (nb + 32 <= p.N);
       if (p.flags & GEMM_ATOMIC) {
         if (row_ok) {
+          float* dst = p.C + (size_t)row * p.ldc + nb;
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || nb + j < p.N) atomicAdd(p.C + (size_t)row * p.ldc + nb + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
         }
         continue;
       }
@@ -269,22 +286,34 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
 }
 
-// C[M,N] (+)= A[M,K] . B[N,K]^T on tcgen05.  GemmParams.B is the [N,K] (K-major) operand here.
-int gemm_nt_umma(const GemmParams& g, float* CT, int ldct, int split_k, cudaStream_t st) {
+// mode 0 NN / 1 NT / 2 TN (see the file header).  Returns -3 for shapes the tcgen05 path does not take
+// (MN-major dimensions must be multiples of 32, leading dimensions multiples of 4, 16-byte aligned bases);
+// callers fall back to the mma.sync kernel (gemm_mma.cu) for those.
+bool gemm_umma_supported(int mode, const GemmParams& g) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
+  if ((g.lda & 3) || (g.ldb & 3) || ((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) return false;
+  if (g.C && ((g.ldc & 3) || ((uintptr_t)g.C & 15))) return false;
+  if (g.C2 && ((g.ldc2 & 3) || ((uintptr_t)g.C2 & 15))) return false;
+  if (g.aux && ((g.ldaux & 3) || ((uintptr_t)g.aux & 15))) return false;
+  if (mode == 2 && (g.M & 31)) return false;
+  if (mode != 1 && (g.N & 31)) return false;
+  return mode >= 0 && mode <= 2;
+}
+
+int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return -1;
-  if ((g.lda & 3) || (g.ldb & 3) || ((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) return -3;
-  if (g.C && ((g.ldc & 3) || ((uintptr_t)g.C & 15))) return -3;
-  if (g.C2 && ((g.ldc2 & 3) || ((uintptr_t)g.C2 & 15))) return -3;
-  if (g.aux && ((g.ldaux & 3) || ((uintptr_t)g.aux & 15))) return -3;
+  if (!gemm_umma_supported(mode, g)) return -3;
+  const int a_mn = (mode == 2), b_mn = (mode != 1);
   const int BN = g.N > 128 ? 256 : 128;
   CUtensorMap mA, mB;
-  int rc = make_map(&mA, g.A, g.M, g.K, g.lda, UM);
+  int rc = a_mn ? umma::make_map_blocks_mn(&mA, g.A, g.K, g.M, g.lda, UK, UM / 32) : make_map(&mA, g.A, g.M, g.K, g.lda, UM);
   if (rc) return rc;
-  rc = make_map(&mB, g.B, g.N, g.K, g.ldb, BN);
+  rc = b_mn ? umma::make_map_blocks_mn(&mB, g.B, g.K, g.N, g.ldb, UK, BN / 32) : make_map(&mB, g.B, g.N, g.K, g.ldb, BN);
   if (rc) return rc;
   UmmaParams p;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
+  p.a_mn = a_mn; p.b_mn = b_mn;
   int splits = (g.flags & GEMM_ATOMIC) ? (split_k > 0 ? split_k : 1) : 1;
   int kps = ((g.K + splits - 1) / splits + UK - 1) / UK * UK;
   splits = (g.K + kps - 1) / kps;
@@ -302,6 +331,11 @@ int gemm_nt_umma(const GemmParams& g, float* CT, int ldct, int split_k, cudaStre
   }
   WN_CHECK_LAUNCH();
   return 0;
+}
+
+// C[M,N] (+)= A[M,K] . B[N,K]^T on tcgen05 (kept for the C ABI / tests).  GemmParams.B is the [N,K] operand here.
+int gemm_nt_umma(const GemmParams& g, float* CT, int ldct, int split_k, cudaStream_t st) {
+  return gemm_umma(1, g, CT, ldct, split_k, st);
 }
 
 // out[c][r] = in[r][c]  (32x32 tiles through shared memory, both sides coalesced)

@@ -31,24 +31,24 @@ int gemm_tf32(int mode, const GemmParams& p, int split_k, cudaStream_t st);
 int colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
 // tcgen05 path: C[M,N] (+)= A[M,K] . B[N,K]^T (p.B is the [N,K] operand), optional transposed copy CT[N][M]
 int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st);
+// tcgen05 path, mode 0 NN (p.B = [K,N]) / 1 NT (p.B = [N,K]) / 2 TN (p.A = [K,M], p.B = [K,N]; GEMM_ATOMIC)
+int gemm_umma(int mode, const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st);
+bool gemm_umma_supported(int mode, const GemmParams& p);
 int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st);
 int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
 
-// zcT / xT / xpT (nullable): transposed copies [C][ldm] of z, of the layer input and of x[t-d]; img (nullable): pre-built weight image
-int block_fwd(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
-              const unsigned char* img,
+// img (nullable): pre-built weight image of the layer (block_images)
+int block_fwd(const float* x, float* xout, float* zc, int ldz, const unsigned char* img,
               const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
               int M, int T, int d, int C, int is_last, cudaStream_t st);
 bool block_umma_enabled();
 void set_block_impl(int mma);
-int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, float* zcT, float* xT, float* xpT, int ldm,
-                   const unsigned char* img, const float* wf, const float* wg, const float* dense,
+int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsigned char* img, const float* wf, const float* wg, const float* dense,
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
-int block_bwd_umma(const float* x, const float* xT, const float* xpT, const float* dxn, const float* dxnT, const float* dZcat, int ldz,
-                   int zcol, const float* ZcatT, float* dx, float* dxT, float* dpre, float* dpreT, int ldm,
-                   const unsigned char* img_pre, const unsigned char* img_dx, const float* prebias, float* gwf,
-                   float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d, int is_last,
-                   cudaStream_t st);
+int block_bwd_umma(const float* x, const float* dxn, const float* dZcat, const float* Zcat, int ldz, int zcol,
+                   float* dx, float* dpre, const unsigned char* img_pre, const unsigned char* img_dx,
+                   const float* prebias, float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias,
+                   int B, int T, int d, int is_last, cudaStream_t st);
 int64_t block_images_bytes(int L);
 uint32_t block_img_off_pre();
 uint32_t block_img_off_dx();

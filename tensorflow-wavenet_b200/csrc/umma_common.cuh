@@ -54,6 +54,56 @@ static inline int make_map_3d(CUtensorMap* m, const float* ptr, int64_t B, int64
   return r == CUDA_SUCCESS ? 0 : -9;
 }
 
+// ---- MN-major TF32 operands (probe/umma_probe.cu variants 8, 14) ----
+// tcgen05 kind::tf32 reads an operand whose NON-contracted dimension is contiguous in memory only
+// from the 32-byte-atom flavour of the 128B swizzle: TMA mode SWIZZLE_128B_ATOM_32B, descriptor
+// layout type 1.  A block is [K rows][32 floats]: 128-byte rows, the 32-byte chunk index XORed with
+// (row & 3); 4-row groups are 512 B apart (SBO), blocks of 32 MN elements are LBO bytes apart, one
+// K=8 MMA step advances the start address by 1024 B.
+// fp32 row-major [rows][cols]; box = [box_rows][32 floats] at (col, row)
+static inline int make_map_2d_mn(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+// fp32 row-major [rows][cols] with cols % 32 == 0, viewed as [cols/32][rows][32]: one box
+// {32, box_rows, n_blocks} lands as n_blocks consecutive [box_rows][32] blocks (LBO = box_rows * 128).
+// Coordinates: (0, row, col / 32).
+static inline int make_map_blocks_mn(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld,
+                                     int box_rows, int n_blocks) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)n_blocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+// activations [B][T][cols] (row pitch ld): box = [1][box_rows][32 floats] at (col, t, b); rows outside [0,T) are zeros
+static inline int make_map_3d_mn(CUtensorMap* m, const float* ptr, int64_t B, int64_t T, int64_t cols, int64_t ld,
+                                 int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)T * ld * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int n) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n));
@@ -96,13 +146,28 @@ __device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand descriptor (layout type 1 = SWIZZLE_128B_BASE32B): lbo = bytes between 32-element MN blocks
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// byte offset of element (row, col) inside a [rows][32 floats] MN-major block (32-byte-atom swizzle)
+__device__ __forceinline__ uint32_t swz32(int row, int col) {
+  return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 3))) << 5) + ((col & 7) << 2));
+}
 // byte offset of element (row, col) inside a [rows][32 floats] 128B-swizzled K-major tile (1024-aligned base)
 __device__ __forceinline__ uint32_t swz(int row, int col) {
   return (uint32_t)(row * 128 + ((((col >> 2) ^ (row & 7))) << 4) + ((col & 3) << 2));
 }
 // instruction descriptor: kind::tf32, fp32 accumulate, both operands K-major, M x N tile
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"

@@ -273,6 +273,43 @@ def test_gemm_nt_umma(lib, M, N, K, split):
         np.testing.assert_array_equal(ct[:, :M].cpu().numpy(), c.cpu().numpy().T)
 
 
+@pytest.mark.parametrize('mode,M,N,K,split', [(0, 1000, 512, 1600, 0), (0, 333, 32, 448, 0), (0, 4096, 256, 512, 0),
+                                              (0, 130, 64, 40, 0), (1, 517, 1600, 512, 0),
+                                              (2, 1600, 512, 3001, 9), (2, 32, 256, 1000, 4), (2, 512, 512, 777, 3),
+                                              (2, 64, 32, 100000, 148)])
+def test_gemm_umma_modes(lib, mode, M, N, K, split):
+    """tcgen05 GEMM with MN-major operands (32-byte-atom swizzle): NN / NT / TN vs float64 on tf32-exact inputs."""
+    rng = np.random.default_rng(mode + M + N + K)
+    r = lambda *s: O.round_tf32(torch.tensor(rng.standard_normal(s))).numpy()
+    if mode == 0:
+        a, b = r(M, K), r(K, N)
+        ref = a @ b
+    elif mode == 1:
+        a, b = r(M, K), r(N, K)
+        ref = a @ b.T
+    else:
+        a, b = r(K, M), r(K, N)
+        ref = a.T @ b
+    def padded(x):
+        ld = (x.shape[1] + 3) // 4 * 4
+        t = torch.zeros(x.shape[0], ld, device='cuda')
+        t[:, :x.shape[1]] = dev(x)
+        return t, ld
+    da, lda = padded(a)
+    db, ldb = padded(b)
+    c = torch.zeros(M, N, device='cuda')
+    rc = lib.wn_gemm_umma(mode, p(da), lda, p(db), ldb, p(c), N, M, N, K, None, None, 0, 0, split, stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5      # fp32 accumulation order only
+
+
+def test_gemm_umma_rejects_unaligned_mn(lib):
+    a = torch.zeros(64, 48, device='cuda')
+    c = torch.zeros(64, 48, device='cuda')
+    assert lib.wn_gemm_umma(0, p(a), 48, p(a), 48, p(c), 48, 64, 48, 48, None, None, 0, 0, 0, stream()) == -3
+
+
 def test_gemm_nt_umma_epilogues(lib):
     rng = np.random.default_rng(5)
     M, N, K = 300, 200, 96
