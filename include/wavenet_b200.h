@@ -183,6 +183,10 @@ int wn_sample(const float* proba, const double* uniforms, int32_t rows, int32_t 
  * (same arithmetic contract) so that one implementation can be checked against the other.  Workspace
  * sizes depend on the choice: query them again after switching. */
 int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma);
+/* debug: device buffer of 48 int64 receiving clock64() stamps (4 tiles x 8 phases) of CTA 0, then
+ * %globaltimer entry / first-tile / exit stamps of the first, middle and last CTA, of the next
+ * wn_block_fwd launches on the tcgen05 path; null disables. */
+int wn_debug_timeline(long long* stamps);
 #define WN_PROFILE_TAGS 23
 int wn_profile_begin(void);
 int wn_profile_end(float* ms_per_tag /*host*/, int32_t* launches_per_tag /*host*/, int32_t n_tags);

@@ -109,9 +109,17 @@ struct FwdArgs {
   const unsigned char* img;         // IMG_FWD bytes (nullable -> built in the kernel from wf/wg/dense)
   const float *wf, *wg, *dense, *prebias, *dense_bias;
   int B, T, d, is_last;
+  long long* timeline;              // debug: per-phase clock64 stamps of CTA 0 (wn_debug_timeline), else null
 };
 
-__global__ void __launch_bounds__(128, 2)
+static long long* g_timeline = nullptr;
+void set_block_timeline(long long* p) { g_timeline = p; }
+#define TL(i)                                                                          \
+  do {                                                                                 \
+    if (a.timeline && blockIdx.x == 0 && tid == 0 && it < 4) a.timeline[it * 8 + (i)] = clock64(); \
+  } while (0)
+
+__global__ void __launch_bounds__(256, 2)
 block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared provenance
@@ -130,7 +138,16 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   __shared__ float pb_s[64];
   __shared__ float bd_s[32];
 
+  // 256 threads: thread (r, half) owns time step t0 + r and channels [16*half, 16*half + 16) of every
+  // 32-channel quantity of that step (TMEM lane r is reachable from warps r/32 and r/32 + 4).
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;
+  const int tl_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
+  if (a.timeline && tid == 0 && tl_slot >= 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    a.timeline[32 + 3 * tl_slot] = (long long)g;
+  }
   if (tid == 0) {
     mbar_init(&bar_tma, 1);
     mbar_init(&bar_m1, 1);
@@ -159,13 +176,15 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
     tma_load_3d(Xc, &mapX, &bar_tma, 0, t0, b);
     tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);
   };
+  pdl_wait();      // x (previous layer's output) is complete and visible from here on
+  pdl_trigger();
   if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   if (a.img) mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
   constexpr uint32_t ID64 = idesc_tf32(128, 64), ID32 = idesc_tf32(128, 32);
   const uint64_t dXc = kmajor_desc(smem_u32(Xc)), dXp = kmajor_desc(smem_u32(Xp));
   const uint64_t dL0 = kmajor_desc(smem_u32(L0)), dL1 = kmajor_desc(smem_u32(L1));
@@ -173,7 +192,6 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
   const uint64_t dW1h = kmajor_desc(smem_u32(W1h)), dW1l = kmajor_desc(smem_u32(W1l));
   const uint64_t dWdh = kmajor_desc(smem_u32(Wdh)), dWdl = kmajor_desc(smem_u32(Wdl));
 
-  const int r = tid;
   int it = 0;
   int pb_batch = -1;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -184,7 +202,9 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
       if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
       pb_batch = b;
     }
+    TL(0);
     mbar_wait(&bar_tma, par);
+    TL(1);
     if (tid == 0) {   // hi*hi terms: the tensor core reads the upper 19 bits of the raw fp32 tile
       tc_fence_after();
 #pragma unroll
@@ -192,13 +212,14 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1h + 2 * k, ID64, 1);
     }
-    // lo parts of this thread's rows: x - trunc_tf32(x), same swizzled position; x_cur stays in registers
-    float4 xr[8];
+    // lo parts of this thread's half rows: x - trunc_tf32(x), same swizzled position; x_cur stays in registers
+    float4 xr[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * half + jj;
       const uint32_t off = (uint32_t)r * 128 + ((uint32_t)(j ^ (r & 7)) << 4);
       float4 v = *reinterpret_cast<const float4*>(Xc + off);
-      xr[j] = v;
+      xr[jj] = v;
       *reinterpret_cast<float4*>(L1 + off) =
           make_float4(v.x - trunc_tf32(v.x), v.y - trunc_tf32(v.y), v.z - trunc_tf32(v.z), v.w - trunc_tf32(v.w));
       v = *reinterpret_cast<const float4*>(Xp + off);
@@ -221,29 +242,32 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
     }
     const bool valid = (t0 + r) < a.T;
     const size_t m = (size_t)b * a.T + t0 + r;
+    TL(2);
     mbar_wait(&bar_m1, par);
+    TL(3);
     tc_fence_after();
     // both input tiles are consumed: prefetch the next tile of this CTA behind the epilogue
     if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
 
-    float z[32];
+    float z[16];
     {
-      uint32_t fv[32], gv[32];
-      tmem_ld32(lane_addr + 0, fv);
-      tmem_ld32(lane_addr + 32, gv);
+      uint32_t fv[16], gv[16];
+      tmem_ld16(lane_addr + 0, fv);
+      tmem_ld16(lane_addr + 32, gv);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        z[j] = tanh_f(__uint_as_float(fv[j]) + pb_s[j]) * sigmoid_f(__uint_as_float(gv[j]) + pb_s[32 + j]);
+      for (int j = 0; j < 16; ++j)
+        z[j] = tanh_fast(__uint_as_float(fv[j]) + pb_s[16 * half + j]) *
+               sigmoid_fast(__uint_as_float(gv[j]) + pb_s[32 + 16 * half + j]);
     }
-    // z -> Zcat (tf32-rounded: it feeds the single-pass skip GEMM), its transposed copy, and the
-    // hi/lo A operand of the dense product
+    // z -> Zcat (tf32-rounded: it feeds the single-pass skip GEMM) and the hi/lo A operand of the dense product
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * half + jj;
       float h[4], l[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        h[e] = round_tf32(z[4 * j + e]);
-        l[e] = round_tf32(z[4 * j + e] - h[e]);
+        h[e] = round_tf32(z[4 * jj + e]);
+        l[e] = round_tf32(z[4 * jj + e] - h[e]);
       }
       if (valid) *reinterpret_cast<float4*>(a.zc + m * a.ldz + 4 * j) = make_float4(h[0], h[1], h[2], h[3]);
       if (!a.is_last) {
@@ -252,10 +276,12 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
         *reinterpret_cast<float4*>(L1 + off) = make_float4(l[0], l[1], l[2], l[3]);
       }
     }
+    TL(4);
     if (!a.is_last) {
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
+      TL(5);
       if (tid == 0) {
         tc_fence_after();
 #pragma unroll
@@ -267,21 +293,33 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
         mma_commit(&bar_m2);
       }
       mbar_wait(&bar_m2, par);
+      TL(6);
       tc_fence_after();
-      uint32_t ov[32];
-      tmem_ld32(lane_addr + 64, ov);
+      uint32_t ov[16];
+      tmem_ld16(lane_addr + 64, ov);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 xv = xr[j];
-        const float4 bd = make_float4(bd_s[4 * j], bd_s[4 * j + 1], bd_s[4 * j + 2], bd_s[4 * j + 3]);
+      for (int jj = 0; jj < 4; ++jj) {
+        const int c = 16 * half + 4 * jj;
+        const float4 xv = xr[jj];
         if (valid)
-          *reinterpret_cast<float4*>(a.xout + m * C + 4 * j) =
-              make_float4(xv.x + __uint_as_float(ov[4 * j]) + bd.x, xv.y + __uint_as_float(ov[4 * j + 1]) + bd.y,
-                          xv.z + __uint_as_float(ov[4 * j + 2]) + bd.z, xv.w + __uint_as_float(ov[4 * j + 3]) + bd.w);
+          *reinterpret_cast<float4*>(a.xout + m * C + c) =
+              make_float4(xv.x + __uint_as_float(ov[4 * jj]) + bd_s[c], xv.y + __uint_as_float(ov[4 * jj + 1]) + bd_s[c + 1],
+                          xv.z + __uint_as_float(ov[4 * jj + 2]) + bd_s[c + 2], xv.w + __uint_as_float(ov[4 * jj + 3]) + bd_s[c + 3]);
       }
     }
     tc_fence_before();
     __syncthreads();   // shared tiles and TMEM columns are free for the next tile
+    TL(7);
+    if (a.timeline && tid == 0 && tl_slot >= 0 && it == 0) {
+      unsigned long long g;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+      a.timeline[32 + 3 * tl_slot + 1] = (long long)g;   // end of the first tile
+    }
+  }
+  if (a.timeline && tid == 0 && tl_slot >= 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    a.timeline[32 + 3 * tl_slot + 2] = (long long)g;
   }
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
@@ -294,6 +332,7 @@ int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsign
   FwdArgs a;
   a.xout = xout; a.zc = zc; a.ldz = ldz; a.img = img; a.wf = wf; a.wg = wg;
   a.dense = dense; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
+  a.timeline = g_timeline;
   const size_t smem = 1024 + 4 * TILE + IMG_FWD;
   static bool attr = false;
   if (!attr) {
@@ -304,7 +343,7 @@ int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsign
   int grid = n_tiles;
   const int cap = 2 * sm_count();
   if (grid > cap) grid = cap;
-  block_fwd_umma_kernel<<<grid, 128, smem, st>>>(mapX, a);
+  { cudaError_t e = launch_pdl(block_fwd_umma_kernel, dim3(grid), dim3(256), smem, st, mapX, a); if (e != cudaSuccess) return (int)e; }
   WN_CHECK_LAUNCH();
   prof_mark(st, PT_BLOCK_FWD);
   return 0;
@@ -320,7 +359,7 @@ struct PreArgs {
   int B, T, d, is_last, zcol;  // zcol: column of this layer inside dZcat
 };
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDn,
                           const __grid_constant__ CUtensorMap mapDz, PreArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -337,6 +376,7 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
   __shared__ float pb_s[64];
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;   // thread = (time step, 16-channel half), see block_fwd_umma_kernel
   if (tid == 0) {
     mbar_init(&bar_tma, 1);
     mbar_init(&bar_m1, 1);
@@ -359,19 +399,20 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
   if (tid == 0) {
     mbar_expect_tx(&bar_w, IMG_PRE);
     bulk_g2s(W0, a.img, IMG_PRE, &bar_w);
-    if ((int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   }
+  pdl_wait();
+  pdl_trigger();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
   constexpr uint32_t ID64 = idesc_tf32(128, 64), ID32 = idesc_tf32(128, 32);
   const uint64_t dXc = kmajor_desc(smem_u32(Xc)), dXp = kmajor_desc(smem_u32(Xp)), dDn = kmajor_desc(smem_u32(Dn));
   const uint64_t dW0 = kmajor_desc(smem_u32(W0)), dW1 = kmajor_desc(smem_u32(W1)), dWd = kmajor_desc(smem_u32(Wd));
 
-  const int r = tid;
   int it = 0, pb_batch = -1;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
@@ -394,13 +435,14 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
       }
       mma_commit(&bar_m1);
     }
-    // gradient coming from the skip path (this thread's row of the dZcat tile)
-    float dz[32];
+    // gradient coming from the skip path (this thread's half row of the dZcat tile)
+    float dz[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * half + jj;
       const uint32_t off = (uint32_t)r * 128 + ((uint32_t)(j ^ (r & 7)) << 4);
       const float4 v = *reinterpret_cast<const float4*>(Dz + off);
-      dz[4 * j] = v.x; dz[4 * j + 1] = v.y; dz[4 * j + 2] = v.z; dz[4 * j + 3] = v.w;
+      dz[4 * jj] = v.x; dz[4 * jj + 1] = v.y; dz[4 * jj + 2] = v.z; dz[4 * jj + 3] = v.w;
     }
     mbar_wait(&bar_m1, par);
     tc_fence_after();
@@ -410,28 +452,29 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     const bool valid = (t0 + r) < a.T;
     const size_t m = (size_t)b * a.T + t0 + r;
     if (!a.is_last) {
-      uint32_t av[32];
-      tmem_ld32(lane_addr + 64, av);
+      uint32_t av[16];
+      tmem_ld16(lane_addr + 64, av);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) dz[j] += __uint_as_float(av[j]);
+      for (int j = 0; j < 16; ++j) dz[j] += __uint_as_float(av[j]);
     }
-    uint32_t fv[32], gv[32];
-    tmem_ld32(lane_addr + 0, fv);
-    tmem_ld32(lane_addr + 32, gv);
-    float df[32], dg[32];
+    uint32_t fv[16], gv[16];
+    tmem_ld16(lane_addr + 0, fv);
+    tmem_ld16(lane_addr + 32, gv);
+    float df[16], dg[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float tf = tanh_f(__uint_as_float(fv[j]) + pb_s[j]);
-      const float sg = sigmoid_f(__uint_as_float(gv[j]) + pb_s[32 + j]);
+    for (int j = 0; j < 16; ++j) {
+      const float tf = tanh_fast(__uint_as_float(fv[j]) + pb_s[16 * half + j]);
+      const float sg = sigmoid_fast(__uint_as_float(gv[j]) + pb_s[32 + 16 * half + j]);
       const float dzv = valid ? dz[j] : 0.f;
       df[j] = round_tf32(dzv * sg * (1.f - tf * tf));
       dg[j] = round_tf32(dzv * tf * sg * (1.f - sg));
     }
     if (valid) {
+      float* row = a.dpre + m * 64 + 16 * half;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        *reinterpret_cast<float4*>(a.dpre + m * 64 + 4 * j) = make_float4(df[4 * j], df[4 * j + 1], df[4 * j + 2], df[4 * j + 3]);
-        *reinterpret_cast<float4*>(a.dpre + m * 64 + 32 + 4 * j) = make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]);
+      for (int jj = 0; jj < 4; ++jj) {
+        *reinterpret_cast<float4*>(row + 4 * jj) = make_float4(df[4 * jj], df[4 * jj + 1], df[4 * jj + 2], df[4 * jj + 3]);
+        *reinterpret_cast<float4*>(row + 32 + 4 * jj) = make_float4(dg[4 * jj], dg[4 * jj + 1], dg[4 * jj + 2], dg[4 * jj + 3]);
       }
     }
     tc_fence_before();
@@ -450,7 +493,7 @@ struct DxArgs {
   int B, T, d;
 };
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -463,6 +506,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;   // thread = (time step, 16-channel half)
   if (tid == 0) {
     mbar_init(&bar_tma, 1);
     mbar_init(&bar_m1, 1);
@@ -484,16 +528,17 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
   if (tid == 0) {
     mbar_expect_tx(&bar_w, IMG_DX);
     bulk_g2s(Wb, a.img, IMG_DX, &bar_w);
-    if ((int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   }
+  pdl_wait();
+  pdl_trigger();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
   constexpr uint32_t ID32 = idesc_tf32(128, 32);
-  const int r = tid;
   int it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
@@ -511,21 +556,22 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
     }
     const bool valid = (t0 + r) < a.T;
     const size_t m = (size_t)b * a.T + t0 + r;
-    float4 xn[8];
+    float4 xn[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      xn[j] = (a.dxn && valid) ? __ldg(reinterpret_cast<const float4*>(a.dxn + m * C) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jj = 0; jj < 4; ++jj)
+      xn[jj] = (a.dxn && valid) ? __ldg(reinterpret_cast<const float4*>(a.dxn + m * C + 16 * half) + jj)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(&bar_m1, par);
     tc_fence_after();
     if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
-    uint32_t ov[32];
-    tmem_ld32(lane_addr, ov);
+    uint32_t ov[16];
+    tmem_ld16(lane_addr, ov);
     if (valid) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 o = make_float4(xn[j].x + __uint_as_float(ov[4 * j]), xn[j].y + __uint_as_float(ov[4 * j + 1]),
-                                     xn[j].z + __uint_as_float(ov[4 * j + 2]), xn[j].w + __uint_as_float(ov[4 * j + 3]));
-        *reinterpret_cast<float4*>(a.dx + m * C + 4 * j) = o;
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 o = make_float4(xn[jj].x + __uint_as_float(ov[4 * jj]), xn[jj].y + __uint_as_float(ov[4 * jj + 1]),
+                                     xn[jj].z + __uint_as_float(ov[4 * jj + 2]), xn[jj].w + __uint_as_float(ov[4 * jj + 3]));
+        *reinterpret_cast<float4*>(a.dx + m * C + 16 * half + 4 * jj) = o;
       }
     }
     tc_fence_before();
@@ -573,7 +619,9 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   int kb1 = kb0 + per;
   if (kb1 > nkb_total) kb1 = nkb_total;
   const int nk = kb1 - kb0;
-  if (nk <= 0) return;
+  if (nk <= 0) {   // (exiting counts as the trigger; nothing of the predecessor is touched)
+    return;
+  }
 
   // constant block of every stage: column 96 = 1, columns 97..127 = 0; dx' block is zero for the last layer
   for (int i = tid; i < STG * 32 * 32; i += blockDim.x) {
@@ -592,6 +640,8 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -680,7 +730,7 @@ int block_bwd_umma(const float* x, const float* dxn, const float* dZcat, const f
     const size_t smem = 1024 + 4 * TILE + IMG_PRE;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(block_bwd_pre_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    block_bwd_pre_umma_kernel<<<grid, 128, smem, st>>>(mX, mDn, mDz, a);
+    { cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, a); if (e != cudaSuccess) return (int)e; }
     WN_CHECK_LAUNCH();
     prof_mark(st, PT_BLOCK_BWD_PRE);
   }
@@ -704,7 +754,7 @@ int block_bwd_umma(const float* x, const float* dxn, const float* dZcat, const f
     int splits = 2 * sm_count() / (B > 0 ? B : 1);
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
-    block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mX, mZ, mP, mDn, a);
+    { cudaError_t e = launch_pdl(block_wgrad_umma_kernel, dim3(splits, B), dim3(192), smem, st, mX, mZ, mP, mDn, a); if (e != cudaSuccess) return (int)e; }
     WN_CHECK_LAUNCH();
     prof_mark(st, PT_BLOCK_WGRAD);
   }
@@ -717,7 +767,7 @@ int block_bwd_umma(const float* x, const float* dxn, const float* dZcat, const f
     const size_t smem = 1024 + 4 * TILE + IMG_DX;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    block_bwd_dx_umma_kernel<<<grid, 128, smem, st>>>(mP, a);
+    { cudaError_t e = launch_pdl(block_bwd_dx_umma_kernel, dim3(grid), dim3(256), smem, st, mP, a); if (e != cudaSuccess) return (int)e; }
     WN_CHECK_LAUNCH();
     prof_mark(st, PT_BLOCK_BWD_DX);
   }

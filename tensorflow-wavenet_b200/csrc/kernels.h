@@ -42,6 +42,7 @@ int block_fwd(const float* x, float* xout, float* zc, int ldz, const unsigned ch
               const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
               int M, int T, int d, int C, int is_last, cudaStream_t st);
 bool block_umma_enabled();
+void set_block_timeline(long long* p);   // debug: clock64 stamps of block_fwd_umma CTA 0 (4 tiles x 8 phases)
 void set_block_impl(int mma);
 int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsigned char* img, const float* wf, const float* wg, const float* dense,
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
