@@ -8,11 +8,11 @@
 // TMA's 128-byte swizzle, MN-major tiles the 32-byte-atom flavour (the only one kind::tf32 accepts,
 // probe/umma_probe.cu) -- no transposed copies of activations or weights exist.
 //
-// Structure (one 128 x BN output tile per CTA, BN in {128, 256}):
+// Structure (persistent CTAs, one per SM, looping over 128 x BN output tiles x K splits, BN in {128, 256}):
 //   warp 0 : TMA producer   -- cp.async.bulk.tensor 2D boxes [128|BN rows x 32 floats] into a
 //            4-stage ring of 128B-swizzled tiles, completion on "full" mbarriers
-//   warp 1 : MMA issuer     -- one lane issues 4 x tcgen05.mma.kind::tf32 (K=8 each) per stage into a
-//            128 x BN fp32 accumulator in TMEM; tcgen05.commit releases the stage ("empty" mbarrier)
+//   warp 1 : MMA issuer     -- one lane issues 4 x tcgen05.mma.kind::tf32 (K=8 each) per stage into one of
+//            TWO 128 x BN fp32 accumulators in TMEM; tcgen05.commit releases the stage ("empty" mbarrier)
 //   warps 2-5 : epilogue    -- tcgen05.ld the accumulator (each warp its TMEM lane quadrant), apply
 //            bias / relu / relu-gradient mask / tf32 rounding, store row-major and (optionally) a
 //            transposed copy (coalesced: lanes hold consecutive rows), or red.add for split-K.
@@ -29,7 +29,8 @@ namespace {
 
 constexpr int UM = 128;        // UMMA M (rows of A per tile)
 constexpr int UK = 32;         // floats per stage along K (= one 128-byte swizzle row)
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
+constexpr uint32_t STG_BYTES = 4096;   // one [32 rows][32 floats] epilogue staging block (128B-swizzled)
 constexpr int THREADS = 192;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -102,35 +103,42 @@ struct UmmaParams {
   const float* aux; int ldaux;    // relu-gradient mask source (nullable)
   int M, N, K;
   int flags;                      // GEMM_RELU | GEMM_ROUND | GEMM_ATOMIC
-  int k_per_split;                // K range per blockIdx.z (multiple of UK)
+  int k_per_split;                // K range per split (multiple of UK)
+  int splits;
   int a_mn, b_mn;                 // operand majors: 0 = K contiguous, 1 = M / N contiguous
 };
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, UmmaParams p) {
+gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapAux, UmmaParams p) {
   constexpr uint32_t A_BYTES = UM * UK * 4;       // 16 KB
   constexpr uint32_t B_BYTES = BN * UK * 4;       // 16 / 32 KB
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[4][2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[BN];
+  // epilogue staging (per epilogue warp, double buffered): output chunks leave through TMA stores, the
+  // relu-gradient mask chunks arrive through TMA loads -- no scattered 16-byte global accesses
+  unsigned char* out_stage = smem + STAGES * STAGE_BYTES;
+  unsigned char* aux_stage = out_stage + 4 * 2 * STG_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * UM, n0 = blockIdx.x * BN;
-  const int k_begin = blockIdx.z * p.k_per_split;
-  int k_end = k_begin + p.k_per_split;
-  if (k_end > p.K) k_end = p.K;
-  const int nk = (k_end - k_begin + UK - 1) / UK;
+  // Persistent CTA: work items (output tile x K split), N tile fastest so that CTAs running side by side share
+  // the A tile in L2.  Two accumulators in TMEM: the epilogue of item i overlaps the main loop of item i+1.
+  const int n_nt = (p.N + BN - 1) / BN, n_mt = (p.M + UM - 1) / UM;
+  const int n_items = n_nt * n_mt * p.splits;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+    for (int s = 0; s < 8; ++s) mbar_init(&aux_bar[s >> 1][s & 1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -138,152 +146,208 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
+  auto decode = [&](int item, int& m0, int& n0, int& k_begin, int& nk) {
+    const int nt = item % n_nt;
+    const int rest = item / n_nt;
+    const int mt = rest % n_mt, sp = rest / n_mt;
+    m0 = mt * UM;
+    n0 = nt * BN;
+    k_begin = sp * p.k_per_split;
+    int k_end = k_begin + p.k_per_split;
+    if (k_end > p.K) k_end = p.K;
+    nk = (k_end - k_begin + UK - 1) / UK;
+  };
+
   if (warp == 0) {
-    if (lane == 0 && nk > 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        unsigned char* sa = smem + s * STAGE_BYTES;
-        const int kc = k_begin + i * UK;
-        if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> 5);     // [UM/32 blocks][32 k][32 m]
-        else tma_load_2d(sa, &mapA, &full_bar[s], kc, m0);
-        if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> 5);
-        else tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kc, n0);
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int m0, n0, k_begin, nk;
+        decode(item, m0, n0, k_begin, nk);
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          unsigned char* sa = smem + s * STAGE_BYTES;
+          const int kc = k_begin + i * UK;
+          if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> 5);     // [UM/32 blocks][32 k][32 m]
+          else tma_load_2d(sa, &mapA, &full_bar[s], kc, m0);
+          if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> 5);
+          else tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kc, n0);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nk > 0) {
+    if (lane == 0) {
       const uint32_t idesc = umma::idesc_tf32(UM, BN, p.a_mn, p.b_mn);
       const uint32_t astep = p.a_mn ? 64 : 2, bstep = p.b_mn ? 64 : 2;   // descriptor start-address step per K=8
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, local = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        int m0, n0, k_begin, nk;
+        decode(item, m0, n0, k_begin, nk);
+        const uint32_t acc = local & 1, aph = (local >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1);      // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t da = p.a_mn ? umma::mnmajor_desc(sa, 4096) : kmajor_desc(sa);
-        const uint64_t db = p.b_mn ? umma::mnmajor_desc(sa + A_BYTES, 4096) : kmajor_desc(sa + A_BYTES);
+        const uint32_t d_tmem = tmem + acc * BN;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = p.a_mn ? umma::mnmajor_desc(sa, 4096) : kmajor_desc(sa);
+          const uint64_t db = p.b_mn ? umma::mnmajor_desc(sa + A_BYTES, 4096) : kmajor_desc(sa + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < UK / 8; ++k) {
-          const uint32_t accum = (i > 0 || k > 0) ? 1u : 0u;
-          asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                       ::"r"(tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
+          for (int k = 0; k < UK / 8; ++k) {
+            const uint32_t accum = (i > 0 || k > 0) ? 1u : 0u;
+            asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                         ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tmem_full_bar[acc])) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tmem_full_bar)) : "memory");
     }
   } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ----------------
     const int quad = warp & 3;
-    const int row = m0 + quad * 32 + lane;
-    if (nk > 0) {
-      mbar_wait(&tmem_full_bar, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.N) break;                      // warp-uniform
-      uint32_t v[32];
-      if (nk > 0) {
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      const int nb = n0 + c0;
+    const int etid = threadIdx.x - 64;                       // 0..127 among the epilogue warps
+    unsigned char* my_out = out_stage + quad * 2 * STG_BYTES;
+    unsigned char* my_aux = aux_stage + quad * 2 * STG_BYTES;
+    const bool staged = !(p.flags & GEMM_ATOMIC) && p.C != nullptr;
+    uint32_t local = 0, out_cnt = 0, aux_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+      int m0, n0, k_begin, nk;
+      decode(item, m0, n0, k_begin, nk);
+      const uint32_t acc = local & 1, aph = (local >> 1) & 1;
+      const int row0 = m0 + quad * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const bool full = (nb + 32 <= p.N);
-      if (p.flags & GEMM_ATOMIC) {
-        if (row_ok) {
-          float* dst = p.C + (size_t)row * p.ldc + nb;
+      if (p.bias) {   // bias of this tile's columns -> shared memory (all four epilogue warps)
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
+        for (int i = etid; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      auto issue_aux = [&](int c0) {   // lane 0: mask chunk [32 rows][32 cols] -> staging buffer (aux_cnt parity)
+        const uint32_t buf = (aux_cnt + (c0 > 0 ? 1u : 0u)) & 1u;
+        mbar_expect_tx(&aux_bar[quad][buf], STG_BYTES);
+        tma_load_2d(my_aux + buf * STG_BYTES, &mapAux, &aux_bar[quad][buf], n0 + c0, row0);
+      };
+      if (p.aux && lane == 0) issue_aux(0);
+      mbar_wait(&tmem_full_bar[acc], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;                      // warp-uniform
+        uint32_t v[32];
+        {
+          const uint32_t taddr = tmem + acc * BN + ((uint32_t)(quad * 32) << 16) + c0;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        const int nb = n0 + c0;
+        const bool full = (nb + 32 <= p.N);
+        if (p.flags & GEMM_ATOMIC) {
+          if (row_ok) {
+            float* dst = p.C + (size_t)row * p.ldc + nb;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) atomicAdd(dst + j, __uint_as_float(v[j]));
+            }
+          }
+          continue;
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          }
+        }
+        if (p.C2 && row_ok) {
+          float* dst = p.C2 + (size_t)row * p.ldc2 + nb;
           if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
-                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) atomicAdd(dst + j, __uint_as_float(v[j]));
+              if (nb + j < p.N) dst[j] = f[j];
           }
         }
-        continue;
-      }
-      float f[32];
+        if (p.flags & GEMM_RELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (p.bias && (full || nb + j < p.N)) x += __ldg(p.bias + nb + j);
-        f[j] = x;
-      }
-      if (p.C2 && row_ok) {
-        float* dst = p.C2 + (size_t)row * p.ldc2 + nb;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) dst[j] = f[j];
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-      }
-      if (p.flags & GEMM_RELU) {
+        if (p.aux) {
+          const uint32_t buf = aux_cnt & 1u;
+          if (lane == 0 && c0 + 32 < BN && nb + 32 < p.N) issue_aux(c0 + 32);   // next chunk, other buffer
+          mbar_wait(&aux_bar[quad][buf], (aux_cnt >> 1) & 1u);
+          const unsigned char* ms = my_aux + buf * STG_BYTES + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-      }
-      if (p.aux && row_ok) {
-        const float* a = p.aux + (size_t)row * p.ldaux + nb;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 m = __ldg(reinterpret_cast<const float4*>(a + j));
-            f[j] = m.x > 0.f ? f[j] : 0.f;
-            f[j + 1] = m.y > 0.f ? f[j + 1] : 0.f;
-            f[j + 2] = m.z > 0.f ? f[j + 2] : 0.f;
-            f[j + 3] = m.w > 0.f ? f[j + 3] : 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const float4 mk = *reinterpret_cast<const float4*>(ms + ((uint32_t)(j ^ (lane & 7)) << 4));
+            f[4 * j] = mk.x > 0.f ? f[4 * j] : 0.f;
+            f[4 * j + 1] = mk.y > 0.f ? f[4 * j + 1] : 0.f;
+            f[4 * j + 2] = mk.z > 0.f ? f[4 * j + 2] : 0.f;
+            f[4 * j + 3] = mk.w > 0.f ? f[4 * j + 3] : 0.f;
           }
-        } else {
+          __syncwarp();      // every lane has read the buffer before a later load re-targets it
+          ++aux_cnt;
+        }
+        if (p.flags & GEMM_ROUND) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
+        }
+        if (staged) {   // row chunk -> swizzled staging block -> one TMA store (clipped to [M, N] by the tensor map)
+          const uint32_t buf = out_cnt & 1u;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store of 2 chunks ago left the buffer
+          __syncwarp();
+          unsigned char* os = my_out + buf * STG_BYTES + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(os + ((uint32_t)(j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&mapC), "r"(smem_u32(my_out + buf * STG_BYTES)), "r"(nb), "r"(row0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++out_cnt;
+        }
+        if (p.CT && row_ok) {   // transposed copy: for a fixed column the 32 lanes write 32 consecutive floats
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) f[j] = __ldg(a + j) > 0.f ? f[j] : 0.f;
+            if (full || nb + j < p.N) p.CT[(size_t)(nb + j) * p.ldct + row] = f[j];
         }
       }
-      if (p.flags & GEMM_ROUND) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
-      }
-      if (p.C && row_ok) {
-        float* dst = p.C + (size_t)row * p.ldc + nb;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) dst[j] = f[j];
-        }
-      }
-      if (p.CT && row_ok) {   // transposed copy: for a fixed column the 32 lanes write 32 consecutive floats
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || nb + j < p.N) p.CT[(size_t)(nb + j) * p.ldct + row] = f[j];
-      }
+      // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN));
 }
 
 // mode 0 NN / 1 NT / 2 TN (see the file header).  Returns -3 for shapes the tcgen05 path does not take
@@ -310,6 +374,15 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   if (rc) return rc;
   rc = b_mn ? umma::make_map_blocks_mn(&mB, g.B, g.K, g.N, g.ldb, UK, BN / 32) : make_map(&mB, g.B, g.N, g.K, g.ldb, BN);
   if (rc) return rc;
+  CUtensorMap mC = mA, mAux = mA;   // (unused maps must still be valid objects)
+  if (g.C && !(g.flags & GEMM_ATOMIC)) {
+    rc = make_map(&mC, g.C, g.M, g.N, g.ldc, 32);
+    if (rc) return rc;
+  }
+  if (g.aux) {
+    rc = make_map(&mAux, g.aux, g.M, g.N, g.ldaux, 32);
+    if (rc) return rc;
+  }
   UmmaParams p;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
@@ -318,16 +391,19 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   int kps = ((g.K + splits - 1) / splits + UK - 1) / UK * UK;
   splits = (g.K + kps - 1) / kps;
   p.k_per_split = kps;
-  dim3 grid((g.N + BN - 1) / BN, (g.M + UM - 1) / UM, splits);
-  const size_t smem = 1024 + (size_t)STAGES * (UM * UK * 4 + BN * UK * 4);
+  p.splits = splits;
+  const int64_t items = (int64_t)((g.N + BN - 1) / BN) * ((g.M + UM - 1) / UM) * splits;
+  if (items > (1 << 30)) return -1;
+  dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
+  const size_t smem = 1024 + (size_t)STAGES * (UM * UK * 4 + BN * UK * 4) + 2 * 4 * 2 * STG_BYTES;
   if (BN == 256) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, p);
+    gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
   } else {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, p);
+    gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
   }
   WN_CHECK_LAUNCH();
   return 0;
