@@ -183,6 +183,9 @@ int wn_sample(const float* proba, const double* uniforms, int32_t rows, int32_t 
  * (same arithmetic contract) so that one implementation can be checked against the other.  Workspace
  * sizes depend on the choice: query them again after switching. */
 int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma);
+/* fast generation: 1 = allow the latency-mode kernel (one stream over the whole GPU, default), 0 = always the
+ * throughput-mode kernel (validation of one against the other). */
+int wn_debug_set_gen_impl(int32_t latency_kernel);
 /* debug: device buffer of 48 int64 receiving clock64() stamps (4 tiles x 8 phases) of CTA 0, then
  * %globaltimer entry / first-tile / exit stamps of the first, middle and last CTA, of the next
  * wn_block_fwd launches on the tcgen05 path; null disables. */

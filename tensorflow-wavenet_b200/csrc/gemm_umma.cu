@@ -29,7 +29,7 @@ namespace {
 
 constexpr int UM = 128;        // UMMA M (rows of A per tile)
 constexpr int UK = 32;         // floats per stage along K (= one 128-byte swizzle row)
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 4;        // 4 for the split-K weight-gradient form (no staging buffers), else 3
 constexpr uint32_t STG_BYTES = 4096;   // one [32 rows][32 floats] epilogue staging block (128B-swizzled)
 constexpr int THREADS = 192;
 
@@ -105,6 +105,7 @@ struct UmmaParams {
   int flags;                      // GEMM_RELU | GEMM_ROUND | GEMM_ATOMIC
   int k_per_split;                // K range per split (multiple of UK)
   int splits;
+  int stages;                     // depth of the TMA -> MMA ring
   int a_mn, b_mn;                 // operand majors: 0 = K contiguous, 1 = M / N contiguous
 };
 
@@ -117,11 +118,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[4][2];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[4][2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[BN];
   // epilogue staging (per epilogue warp, double buffered): output chunks leave through TMA stores, the
   // relu-gradient mask chunks arrive through TMA loads -- no scattered 16-byte global accesses
+  const int STAGES = p.stages;
   unsigned char* out_stage = smem + STAGES * STAGE_BYTES;
   unsigned char* aux_stage = out_stage + 4 * 2 * STG_BYTES;
 
@@ -132,7 +134,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int n_items = n_nt * n_mt * p.splits;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
     for (int s = 0; s < 8; ++s) mbar_init(&aux_bar[s >> 1][s & 1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -395,14 +397,16 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   const int64_t items = (int64_t)((g.N + BN - 1) / BN) * ((g.M + UM - 1) / UM) * splits;
   if (items > (1 << 30)) return -1;
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-  const size_t smem = 1024 + (size_t)STAGES * (UM * UK * 4 + BN * UK * 4) + 2 * 4 * 2 * STG_BYTES;
+  const bool atomic = (g.flags & GEMM_ATOMIC) != 0;
+  p.stages = atomic ? 4 : 3;
+  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + (atomic ? 0 : 2 * 4 * 2 * STG_BYTES);
   if (BN == 256) {
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 3 * (UM + 256) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
     gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
   } else {
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 4 * (UM + 128) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
     gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
   }
   WN_CHECK_LAUNCH();

@@ -9,29 +9,16 @@
 // layer chain with the weights of layer l+1 prefetched (cp.async) into shared memory while
 // layer l computes, every weight element fetched once per step is reused for all SPB streams,
 // matvecs are k-split over thread groups and reduced through shared memory.
+#include <cstdlib>
+#include <cstring>
+
 #include "../../include/wavenet_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "gen_common.h"
 
 namespace wn {
 
-struct GenArgs {
-  int L, C, S, Q, G, use_biases;
-  int sum_d;                       // sum of dilations (ring rows per stream)
-  int streams, n_steps, commit;
-  float temperature;
-  const float *causal, *filter, *gate, *dense, *skip, *gc_filter, *gc_gate, *filter_bias, *gate_bias,
-      *dense_bias, *skip_bias, *post1, *post2, *post1_bias, *post2_bias, *gc_embedding;
-  int32_t* hdr;                    // [streams][4]: prev_id, step, pending_id, pending_valid
-  float* pending;                  // [streams][L][C] layer inputs of an uncommitted single step
-  float* rings;                    // [streams][sum_d][C]
-  const int32_t *inputs, *forced, *gc_ids;
-  const double* uniforms;
-  int32_t* samples_out;
-  float* proba_out;
-  int dil[WN_MAX_LAYERS];
-  int ring_off[WN_MAX_LAYERS];     // row offset of each layer's ring
-};
 
 // out[s][n] (+)= sum_k in[s][k] * W[k][n], W row-major [K][N] in GLOBAL memory, coalesced over n.
 // Threads: column group cg = tid % NC4 (4 columns), k-slice kg = tid / NC4.  Result is left as
@@ -427,6 +414,9 @@ static int64_t gen_hdr_bytes(const wn_config* c, int streams) {
 static int64_t gen_pending_bytes(const wn_config* c, int streams) {
   return ((int64_t)streams * c->n_layers * c->residual_channels * 4 + 255) / 256 * 256;
 }
+static int64_t gen_rings_bytes(const wn_config* c, int streams) {
+  return ((int64_t)streams * sum_dil(c) * c->residual_channels * (int64_t)sizeof(float) + 255) / 256 * 256;
+}
 
 template <int SPB, int C>
 static int launch_gen(const GenArgs& a, cudaStream_t st) {
@@ -453,13 +443,20 @@ static int launch_gen(const GenArgs& a, cudaStream_t st) {
 
 using namespace wn;
 
+static int g_gen_lat_enabled = 1;
+
 extern "C" {
+
+int wn_debug_set_gen_impl(int32_t latency_kernel) {
+  g_gen_lat_enabled = latency_kernel ? 1 : 0;
+  return 0;
+}
 
 int64_t wn_gen_state_bytes(const wn_config* cfg, int32_t streams) {
   wn_layout lo;
   if (wn_param_layout(cfg, &lo) || streams < 1) return -1;
-  return gen_hdr_bytes(cfg, streams) + gen_pending_bytes(cfg, streams) +
-         (int64_t)streams * sum_dil(cfg) * cfg->residual_channels * (int64_t)sizeof(float);
+  return gen_hdr_bytes(cfg, streams) + gen_pending_bytes(cfg, streams) + gen_rings_bytes(cfg, streams) +
+         gen_lat_comm_bytes(cfg);      // tagged-word scratch of the latency-mode kernel (generator_lat.cu)
 }
 
 int wn_gen_reset(const wn_config* cfg, void* state, int32_t streams, wn_stream_t stream) {
@@ -524,6 +521,18 @@ int wn_gen_run(const wn_config* cfg, const float* params, void* state, int32_t s
   int off = 0;
   for (int i = 0; i < a.L; ++i) { a.dil[i] = cfg->dilations[i]; a.ring_off[i] = off; off += cfg->dilations[i]; }
   cudaStream_t st = (cudaStream_t)stream;
+  {   // one stream: latency-mode kernel (the whole GPU works on the sample chain); WN_GEN_IMPL=v1 disables it
+    static int use_lat = -1;
+    if (use_lat < 0) {
+      const char* e = getenv("WN_GEN_IMPL");
+      use_lat = (e && strcmp(e, "v1") == 0) ? 0 : 1;
+    }
+    if (use_lat && g_gen_lat_enabled && gen_lat_eligible(a)) {
+      static uint32_t launch_seq = 0;
+      void* comm = (char*)state + gen_hdr_bytes(cfg, streams) + gen_pending_bytes(cfg, streams) + gen_rings_bytes(cfg, streams);
+      return gen_lat_run(a, comm, ++launch_seq, st);
+    }
+  }
   const int nsm = sm_count();
   int spb = 1;
   if (streams > nsm) spb = 2;

@@ -1,0 +1,556 @@
+// Fast generation, latency mode: ONE stream spread over the whole GPU by a persistent cooperative kernel.
+// Reference: wavenet/model.py:332-387 (_generator_conv / _generator_dilation_layer), :444-516
+// (_create_generator, one tf.FIFOQueue per layer), :592-626 (predict_proba_incremental) and the sampling
+// loop of generate.py:213-241 (one sess.run per sample there; here the sample loop never leaves the device).
+//
+// A sample is a dependent chain of L+3 stages, so the design minimises the latency of each hop:
+//   * chain CTAs   : LPC = 8 layers per CTA, ONE WARP PER LAYER with that layer's weights held in registers
+//                    (2*32*64 filter/gate + 32*32 dense floats = 160 registers per lane, packed-FMA pairs).
+//                    The half of the gated pre-activation that multiplies the delay-line output (x[t-d]) is
+//                    computed while the warp waits for its input; a layer then costs one 32x64 and one
+//                    32x32 register-resident mat-vec.  Warps hand the 32-float residual to the next layer
+//                    through shared memory (next CTA: through L2) as 64-bit words {value, tag}: a word is valid
+//                    when its tag names the current launch and step, so no fences or flags are needed.
+//                    Delay lines stay where the reference's queues semantics put them (ring slot = t mod d)
+//                    in the generator state; the slot to read is known a step ahead and is prefetched.
+//   * post CTAs    : 128 CTAs, each owning 4 columns of the skip / postprocess1 matrices and 2 of
+//                    postprocess2 RESIDENT in shared memory; z (all layers), relu(skip sum) and relu(post1) travel
+//                    as tagged words through L2, every stage is one block-wide dot product.
+//   * sampler CTA  : float64 softmax (model.py:619-621), temperature scaling (generate.py:229-233), np.cumsum /
+//                    searchsorted('right') draw (np.random.choice), feeds the drawn id back to the chain head.
+// wn_gen_run selects this kernel for streams == 1, commit, C == 32; everything else runs generator.cu.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "gen_common.h"
+#include "kernels.h"
+
+namespace wn {
+
+namespace {
+constexpr int C = 32;
+constexpr int LPC = 8;          // layers (= warps) per chain CTA
+constexpr int THREADS = 256;
+constexpr int CS = 4;           // skip / post1 columns per post CTA
+typedef unsigned long long u64;
+
+struct LatArgs {
+  GenArgs g;
+  u64* comm;
+  uint32_t tag_base;             // (launch_seq << 20); word tag = tag_base + step + 1
+  int NC, NP, cq;                // chain CTAs, post CTAs, post2 columns per post CTA
+  int causal_in_smem;
+};
+
+// comm layout (u64 words)
+__host__ __device__ inline int off_xg() { return 0; }                                   // [NC+1][32]
+__host__ __device__ inline int off_zt(int NC) { return (NC + 1) * 32; }                 // [L*32]
+__host__ __device__ inline int off_v0(int NC, int L) { return off_zt(NC) + L * 32; }    // [S]
+__host__ __device__ inline int off_v1(int NC, int L, int S) { return off_v0(NC, L) + S; }
+__host__ __device__ inline int off_lg(int NC, int L, int S) { return off_v1(NC, L, S) + S; }   // [Q]
+__host__ __device__ inline int off_misc(int NC, int L, int S, int Q) { return off_lg(NC, L, S) + Q; }   // id, zdone, chain_done
+
+__device__ __forceinline__ u64 pack(float v, uint32_t tag) { return ((u64)tag << 32) | (u64)__float_as_uint(v); }
+__device__ __forceinline__ void st_gpu(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_gpu(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_gpu_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_gpu_f32(float* p, float v) { asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// spin until the word carries `tag` (bounded: a protocol bug must trap, not hang the GPU)
+__device__ __forceinline__ float wait_gpu(const u64* p, uint32_t tag) {
+  for (uint32_t i = 0; i < (1u << 26); ++i) {
+    const u64 v = ld_gpu(p);
+    if ((uint32_t)(v >> 32) == tag) return __uint_as_float((uint32_t)v);
+  }
+  __trap();
+  return 0.f;
+}
+__device__ __forceinline__ float wait_smem(const volatile u64* p, uint32_t tag) {
+  for (uint32_t i = 0; i < (1u << 28); ++i) {
+    const u64 v = *p;
+    if ((uint32_t)(v >> 32) == tag) return __uint_as_float((uint32_t)v);
+  }
+  __trap();
+  return 0.f;
+}
+// same, polling politely (long waits: one lane of a post / sampler CTA waiting for the chain)
+__device__ __forceinline__ void wait_hint(const u64* p, uint32_t tag) {
+  for (uint32_t i = 0; i < (1u << 24); ++i) {
+    if ((uint32_t)(ld_gpu(p) >> 32) == tag) return;
+    __nanosleep(64);
+  }
+  __trap();
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// ------------------------------------------------------------------------------------------------
+// chain: one warp = one layer
+// ------------------------------------------------------------------------------------------------
+__device__ void chain_warp(const LatArgs& a, int c, int w, volatile u64* xbuf /*[LPC+1][32]*/, float* priv /*[64]*/,
+                           const float* causal_s) {
+  const GenArgs& g = a.g;
+  const int lane = threadIdx.x & 31;
+  const int l = c * LPC + w;
+  if (l >= g.L) return;
+  const int d = g.dil[l];
+  u64* comm = a.comm;
+  u64* xg_in = comm + off_xg() + c * 32;
+  u64* xg_out = comm + off_xg() + (c + 1) * 32;
+  u64* zt = comm + off_zt(a.NC) + l * 32;
+  u64* misc = comm + off_misc(a.NC, g.L, g.S, g.Q);
+  float* ring = g.rings + (size_t)g.ring_off[l] * C;
+  float* xs = priv;         // [32] layer input, broadcast source
+  float* zs = priv + 32;    // [32] gated output, broadcast source
+
+  // ---- this layer's weights -> registers (k-pairs for the packed FMA) ----
+  float2 wfp[16], wfc[16], wgp[16], wgc[16], wd[16];
+  {
+    const float* F = g.filter + (size_t)l * 2 * C * C;   // [tap][k][n]
+    const float* G = g.gate + (size_t)l * 2 * C * C;
+    const float* D = g.dense + (size_t)l * C * C;        // [d][r]
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      wfp[kk] = make_float2(F[(2 * kk) * C + lane], F[(2 * kk + 1) * C + lane]);
+      wfc[kk] = make_float2(F[(C + 2 * kk) * C + lane], F[(C + 2 * kk + 1) * C + lane]);
+      wgp[kk] = make_float2(G[(2 * kk) * C + lane], G[(2 * kk + 1) * C + lane]);
+      wgc[kk] = make_float2(G[(C + 2 * kk) * C + lane], G[(C + 2 * kk + 1) * C + lane]);
+      wd[kk] = make_float2(D[(2 * kk) * C + lane], D[(2 * kk + 1) * C + lane]);
+    }
+  }
+  float pbf = 0.f, pbg = 0.f, bd = 0.f;
+  if (g.use_biases) {
+    pbf = g.filter_bias[l * C + lane];
+    pbg = g.gate_bias[l * C + lane];
+    bd = g.dense_bias[l * C + lane];
+  }
+  if (g.G > 0 && g.gc_ids) {   // global conditioning: h . Wgc  (model.py:357-371)
+    const float* e = g.gc_embedding + (size_t)g.gc_ids[0] * g.G;
+    const float* wf = g.gc_filter + (size_t)l * g.G * C;
+    const float* wg = g.gc_gate + (size_t)l * g.G * C;
+    for (int k = 0; k < g.G; ++k) {
+      pbf = fmaf(e[k], wf[k * C + lane], pbf);
+      pbg = fmaf(e[k], wg[k * C + lane], pbg);
+    }
+  }
+  const int step0 = g.hdr[1];
+  int prev_id = g.hdr[0];
+  const bool head = (l == 0);
+  const bool sampling = g.uniforms != nullptr;
+
+  for (int step = 0; step < g.n_steps; ++step) {
+    const uint32_t T = a.tag_base + (uint32_t)step + 1u;
+    const int slot = (step0 + step) % d;
+    // ---- delay-line output x[t-d]: every lane reads the whole 128-byte slot; its half of the gated product
+    //      is finished before this layer's input arrives ----
+    float2 fa = make_float2(0.f, 0.f), ga = make_float2(0.f, 0.f);
+    {
+      const float* rp = ring + (size_t)slot * C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 pv;
+        asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w) : "l"(rp + 4 * j) : "memory");
+        fa = ffma2(make_float2(pv.x, pv.y), wfp[2 * j], fa);
+        ga = ffma2(make_float2(pv.x, pv.y), wgp[2 * j], ga);
+        fa = ffma2(make_float2(pv.z, pv.w), wfp[2 * j + 1], fa);
+        ga = ffma2(make_float2(pv.z, pv.w), wgp[2 * j + 1], ga);
+      }
+    }
+    // ---- this layer's input ----
+    float x_own;
+    if (head) {
+      int cur;
+      if (g.forced) {
+        cur = g.forced[step];
+        if (step > 0) wait_gpu(misc + 2, T - 1);                         // previous step has left the chain
+      } else if (step == 0) {
+        cur = g.inputs[0];
+      } else if (sampling) {
+        cur = __float_as_int(wait_gpu(misc + 0, T - 1));                 // id drawn by the sampler for step-1
+      } else {
+        cur = g.inputs[0];
+        wait_gpu(misc + 2, T - 1);
+      }
+      // causal layer: x = Wc[0][prev] + Wc[1][cur]   (model.py:341-346; zero history at the first step)
+      const float* wc = a.causal_in_smem ? causal_s : g.causal;
+      float v = 0.f;
+      if (prev_id >= 0 && prev_id < g.Q) v += wc[(size_t)prev_id * C + lane];
+      if (cur >= 0 && cur < g.Q) v += wc[(size_t)(g.Q + cur) * C + lane];
+      x_own = v;
+      prev_id = cur;
+    } else if (w == 0) {
+      x_own = wait_gpu(xg_in + lane, T);
+    } else {
+      x_own = wait_smem(xbuf + w * 32 + lane, T);
+    }
+    xs[lane] = x_own;
+    __syncwarp();
+    st_gpu_f32(ring + (size_t)slot * C + lane, x_own);      // push_ops: enqueue the layer input (model.py:461,482)
+    float2 fb = make_float2(0.f, 0.f), gb = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * j);
+      fb = ffma2(make_float2(xv.x, xv.y), wfc[2 * j], fb);
+      gb = ffma2(make_float2(xv.x, xv.y), wgc[2 * j], gb);
+      fb = ffma2(make_float2(xv.z, xv.w), wfc[2 * j + 1], fb);
+      gb = ffma2(make_float2(xv.z, xv.w), wgc[2 * j + 1], gb);
+    }
+    const float f = (fa.x + fa.y) + (fb.x + fb.y) + pbf;
+    const float gg = (ga.x + ga.y) + (gb.x + gb.y) + pbg;
+    const float z = tanhf(f) * (1.0f / (1.0f + expf(-gg)));
+    zs[lane] = z;
+    __syncwarp();
+    if (l + 1 < g.L) {      // the last layer's dense output is discarded by the reference (model.py:377-380)
+      float2 oa = make_float2(0.f, 0.f), ob = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 zv = *reinterpret_cast<const float4*>(zs + 4 * j);
+        oa = ffma2(make_float2(zv.x, zv.y), wd[2 * j], oa);
+        ob = ffma2(make_float2(zv.z, zv.w), wd[2 * j + 1], ob);
+      }
+      const float x_out = x_own + bd + ((oa.x + oa.y) + (ob.x + ob.y));
+      if (w + 1 < LPC) xbuf[(w + 1) * 32 + lane] = pack(x_out, T);
+      else st_gpu(xg_out + lane, pack(x_out, T));
+    }
+    st_gpu(zt + lane, pack(z, T));
+    if (l == g.L - 1) {
+      __syncwarp();
+      if (lane == 0) {
+        st_gpu(misc + 1, pack(0.f, T));     // hint for the post CTAs: the last z of this step is on its way
+        st_gpu(misc + 2, pack(0.f, T));     // the chain is free for the next forced step
+      }
+    }
+    __syncwarp();      // xs / zs are rewritten next step
+  }
+  if (head && lane == 0) {   // generator header: model.py push of the causal queue + step counter
+    g.hdr[0] = prev_id;
+    g.hdr[1] = step0 + g.n_steps;
+    g.hdr[3] = 0;
+  }
+}
+
+// block-wide sum of a float4 per thread (256 threads); result valid in every thread
+__device__ __forceinline__ float4 block_sum4(float4 v, float4* red /*[8]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  __syncthreads();      // previous use of red[] is over
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float4 t = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) {
+    t.x += red[w].x; t.y += red[w].y; t.z += red[w].z; t.w += red[w].w;
+  }
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-processing CTA p: columns [4p, 4p+4) of skip / postprocess1, [cq*p, cq*p+cq) of postprocess2
+// ------------------------------------------------------------------------------------------------
+__device__ void post_cta(const LatArgs& a, int p, float* sm) {
+  const GenArgs& g = a.g;
+  const int tid = threadIdx.x;
+  const int LD = g.L * C, S = g.S, Q = g.Q, cq = a.cq;
+  float4* ws = reinterpret_cast<float4*>(sm);            // [LD]  skip weights, 4 columns
+  float4* w1 = ws + LD;                                   // [S]
+  float4* w2 = w1 + S;                                    // [S]   (cq <= 4 columns used)
+  float4* red = w2 + S;                                   // [8]
+  __shared__ float bias_s[12];                            // skip-bias sum | post1 bias | post2 bias of my columns
+  for (int k = tid; k < LD; k += THREADS) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = g.skip + (size_t)k * S + CS * p;
+    if (CS * p + 0 < S) v.x = src[0];
+    if (CS * p + 1 < S) v.y = src[1];
+    if (CS * p + 2 < S) v.z = src[2];
+    if (CS * p + 3 < S) v.w = src[3];
+    ws[k] = v;
+  }
+  for (int k = tid; k < S; k += THREADS) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = g.post1 + (size_t)k * S + CS * p;
+    if (CS * p + 0 < S) v.x = src[0];
+    if (CS * p + 1 < S) v.y = src[1];
+    if (CS * p + 2 < S) v.z = src[2];
+    if (CS * p + 3 < S) v.w = src[3];
+    w1[k] = v;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* s2 = g.post2 + (size_t)k * Q + cq * p;
+    if (0 < cq && cq * p + 0 < Q) u.x = s2[0];
+    if (1 < cq && cq * p + 1 < Q) u.y = s2[1];
+    if (2 < cq && cq * p + 2 < Q) u.z = s2[2];
+    if (3 < cq && cq * p + 3 < Q) u.w = s2[3];
+    w2[k] = u;
+  }
+  if (tid < 12) {
+    float v = 0.f;
+    if (g.use_biases) {
+      const int j = tid & 3;
+      if (tid < 4) {
+        if (CS * p + j < S)
+          for (int l = 0; l < g.L; ++l) v += g.skip_bias[(size_t)l * S + CS * p + j];   // model.py:430 sum of skips
+      } else if (tid < 8) {
+        if (CS * p + j < S) v = g.post1_bias[CS * p + j];
+      } else {
+        if (j < cq && cq * p + j < Q) v = g.post2_bias[cq * p + j];
+      }
+    }
+    bias_s[tid] = v;
+  }
+  __syncthreads();
+  u64* comm = a.comm;
+  const u64* zt = comm + off_zt(a.NC);
+  u64* v0t = comm + off_v0(a.NC, g.L);
+  u64* v1t = comm + off_v1(a.NC, g.L, S);
+  u64* lgt = comm + off_lg(a.NC, g.L, S);
+  const u64* misc = comm + off_misc(a.NC, g.L, S, Q);
+  const bool sampling = g.uniforms != nullptr;
+
+  for (int step = 0; step < g.n_steps; ++step) {
+    if (!sampling && step != g.n_steps - 1) continue;       // priming: only the last distribution is needed
+    const uint32_t T = a.tag_base + (uint32_t)step + 1u;
+    if (tid == 0) wait_hint(misc + 1, T);
+    __syncthreads();
+    // ---- skip sum -> relu            (model.py:505-507)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = tid; k < LD; k += THREADS) {
+      const float zv = wait_gpu(zt + k, T);
+      const float4 w = ws[k];
+      acc.x = fmaf(zv, w.x, acc.x); acc.y = fmaf(zv, w.y, acc.y); acc.z = fmaf(zv, w.z, acc.z); acc.w = fmaf(zv, w.w, acc.w);
+    }
+    acc = block_sum4(acc, red);
+    if (tid < CS && CS * p + tid < S) {
+      const float v = (tid == 0 ? acc.x : tid == 1 ? acc.y : tid == 2 ? acc.z : acc.w) + bias_s[tid];
+      st_gpu(v0t + CS * p + tid, pack(fmaxf(v, 0.f), T));
+    }
+    // ---- postprocess1 -> relu        (model.py:508-511)
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = tid; k < S; k += THREADS) {
+      const float xv = wait_gpu(v0t + k, T);
+      const float4 w = w1[k];
+      acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+    }
+    acc = block_sum4(acc, red);
+    if (tid < CS && CS * p + tid < S) {
+      const float v = (tid == 0 ? acc.x : tid == 1 ? acc.y : tid == 2 ? acc.z : acc.w) + bias_s[4 + tid];
+      st_gpu(v1t + CS * p + tid, pack(fmaxf(v, 0.f), T));
+    }
+    // ---- postprocess2                (model.py:512-514)
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = tid; k < S; k += THREADS) {
+      const float xv = wait_gpu(v1t + k, T);
+      const float4 w = w2[k];
+      acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+    }
+    acc = block_sum4(acc, red);
+    if (tid < cq && cq * p + tid < Q) {
+      const float v = (tid == 0 ? acc.x : tid == 1 ? acc.y : tid == 2 ? acc.z : acc.w) + bias_s[8 + tid];
+      st_gpu(lgt + cq * p + tid, pack(v, T));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler CTA: float64 softmax, temperature, inverse-cdf draw
+// ------------------------------------------------------------------------------------------------
+__device__ void sampler_cta(const LatArgs& a, float* sm) {
+  const GenArgs& g = a.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Q = g.Q;
+  double* dsm = reinterpret_cast<double*>(sm);     // [Q] exp values, later the cdf
+  float* ps = reinterpret_cast<float*>(dsm + Q);   // [Q] float32 probabilities
+  __shared__ double redd[8];
+  __shared__ float redf[8];
+  __shared__ int redi[8];
+  u64* comm = a.comm;
+  const u64* lgt = comm + off_lg(a.NC, g.L, g.S);
+  u64* misc = comm + off_misc(a.NC, g.L, g.S, Q);
+  const bool sampling = g.uniforms != nullptr;
+
+  for (int step = 0; step < g.n_steps; ++step) {
+    if (!sampling && step != g.n_steps - 1) continue;
+    const uint32_t T = a.tag_base + (uint32_t)step + 1u;
+    if (tid == 0) wait_hint(misc + 1, T);
+    __syncthreads();
+    // float64 softmax of the logits, cast back to float32   (model.py:619-621)
+    double mx = -1e300;
+    for (int i = tid; i < Q; i += THREADS) {
+      const double v = (double)wait_gpu(lgt + i, T);
+      dsm[i] = v;
+      mx = fmax(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redd[warp] = mx;
+    __syncthreads();
+    mx = redd[0];
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, redd[w]);
+    __syncthreads();
+    double sum = 0.0;
+    for (int i = tid; i < Q; i += THREADS) {
+      const double e = exp(dsm[i] - mx);
+      dsm[i] = e;
+      sum += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) redd[warp] = sum;
+    __syncthreads();
+    sum = redd[0];
+    for (int w = 1; w < 8; ++w) sum += redd[w];
+    for (int i = tid; i < Q; i += THREADS) ps[i] = (float)(dsm[i] / sum);
+    __syncthreads();
+    if (g.temperature != 1.0f) {     // generate.py:229-233, float32 log-space
+      float m2 = -INFINITY;
+      for (int i = tid; i < Q; i += THREADS) {
+        const float q = logf(ps[i]) / g.temperature;
+        ps[i] = q;
+        m2 = fmaxf(m2, q);
+      }
+      m2 = warp_max(m2);
+      if (lane == 0) redf[warp] = m2;
+      __syncthreads();
+      m2 = redf[0];
+      for (int w = 1; w < 8; ++w) m2 = fmaxf(m2, redf[w]);
+      __syncthreads();
+      float s2 = 0.f;
+      for (int i = tid; i < Q; i += THREADS) s2 += expf(ps[i] - m2);
+      s2 = warp_sum(s2);
+      if (lane == 0) redf[warp] = s2;
+      __syncthreads();
+      s2 = redf[0];
+      for (int w = 1; w < 8; ++w) s2 += redf[w];
+      const float lse = m2 + logf(s2);
+      for (int i = tid; i < Q; i += THREADS) ps[i] = expf(ps[i] - lse);
+      __syncthreads();
+    }
+    if (g.proba_out && step == g.n_steps - 1)
+      for (int i = tid; i < Q; i += THREADS) g.proba_out[i] = ps[i];
+    if (sampling) {
+      // np.random.choice: cdf = cumsum(p) (sequential float64 adds), normalise by the last, searchsorted right.
+      // Every partial sum of float32 values >= 2^-28 below 2 is exact in float64, so then any order gives
+      // np.cumsum's bits and the scan runs in parallel; otherwise one lane repeats the sequential sum.
+      int tiny = 0;
+      for (int i = tid; i < Q; i += THREADS) tiny |= (ps[i] != 0.f && ps[i] < 3.7252903e-09f) ? 1 : 0;
+      tiny = __syncthreads_or(tiny);
+      if (!tiny && Q <= 8 * 32) {
+        if (warp == 0) {
+          double run[8];
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = lane * 8 + j;
+            t += (i < Q) ? (double)ps[i] : 0.0;
+            run[j] = t;
+          }
+          double incl = t;
+          for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          const double excl = incl - t;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = lane * 8 + j;
+            if (i < Q) dsm[i] = excl + run[j];
+          }
+        }
+      } else if (tid == 0) {
+        double run = 0.0;
+        for (int i = 0; i < Q; ++i) { run += (double)ps[i]; dsm[i] = run; }
+      }
+      __syncthreads();
+      const double total = dsm[Q - 1];
+      const double u = g.uniforms[step];
+      int cnt = 0;
+      for (int i = tid; i < Q; i += THREADS) cnt += (dsm[i] / total <= u) ? 1 : 0;
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0) redi[warp] = cnt;
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += redi[w];
+        const int drawn = tot < Q ? tot : Q - 1;
+        st_gpu(misc + 0, pack(__int_as_float(drawn), T));      // feeds the chain head of the next step
+        g.samples_out[step] = drawn;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) generator_lat_kernel(LatArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x;
+  if (b < a.NC) {
+    volatile u64* xbuf = reinterpret_cast<volatile u64*>(sm);                 // [LPC+1][32] tagged words
+    float* priv = sm + 2 * (LPC + 1) * 32 + (threadIdx.x >> 5) * 64;          // per warp [64]
+    float* causal_s = sm + 2 * (LPC + 1) * 32 + LPC * 64;
+    for (int i = threadIdx.x; i < (LPC + 1) * 32; i += THREADS) xbuf[i] = 0ull;
+    if (b == 0 && a.causal_in_smem)
+      for (int i = threadIdx.x; i < 2 * a.g.Q * C; i += THREADS) causal_s[i] = a.g.causal[i];
+    __syncthreads();
+    chain_warp(a, b, threadIdx.x >> 5, xbuf, priv, causal_s);
+  } else if (b == a.NC) {
+    sampler_cta(a, sm);
+  } else if (b < a.NC + 1 + a.NP) {
+    post_cta(a, b - a.NC - 1, sm);
+  }
+}
+
+size_t chain_smem(const GenArgs& g, int causal_in_smem) {
+  return sizeof(float) * (2 * (LPC + 1) * 32 + LPC * 64 + (causal_in_smem ? 2 * g.Q * C : 0));
+}
+size_t post_smem(const GenArgs& g) { return sizeof(float4) * ((size_t)g.L * C + 2 * g.S + 8); }
+size_t sampler_smem(const GenArgs& g) { return (sizeof(double) + sizeof(float)) * (size_t)g.Q; }
+}  // namespace
+
+int64_t gen_lat_comm_bytes(const wn_config* cfg) {
+  const int L = cfg->n_layers, NC = (L + LPC - 1) / LPC;
+  return 8LL * (off_misc(NC, L, cfg->skip_channels, cfg->quantization_channels) + 8);
+}
+
+bool gen_lat_eligible(const GenArgs& a) {
+  if (a.streams != 1 || !a.commit || a.C != C || a.n_steps < 1 || a.n_steps >= (1 << 20)) return false;
+  if (!a.forced && !a.uniforms && a.n_steps != 1) return false;
+  const int NC = (a.L + LPC - 1) / LPC;
+  const int NP = (a.S + CS - 1) / CS;
+  if ((a.Q + NP - 1) / NP > 4) return false;
+  if (NC + 1 + NP > sm_count()) return false;
+  if (post_smem(a) > 200 * 1024 || sampler_smem(a) > 200 * 1024) return false;
+  return true;
+}
+
+int gen_lat_run(const GenArgs& g, void* comm, uint32_t launch_seq, cudaStream_t st) {
+  if (!gen_lat_eligible(g) || !comm) return -2;
+  LatArgs a;
+  a.g = g;
+  a.comm = (u64*)comm;
+  a.tag_base = (launch_seq & 0xFFFu) << 20;
+  a.NC = (g.L + LPC - 1) / LPC;
+  a.NP = (g.S + CS - 1) / CS;
+  a.cq = (g.Q + a.NP - 1) / a.NP;
+  a.causal_in_smem = (2 * g.Q * C * sizeof(float) <= 128 * 1024) ? 1 : 0;
+  size_t smem = chain_smem(g, a.causal_in_smem);
+  if (post_smem(g) > smem) smem = post_smem(g);
+  if (sampler_smem(g) > smem) smem = sampler_smem(g);
+  cudaError_t e = cudaFuncSetAttribute(generator_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  // every CTA spins on words other CTAs produce: all of them must be resident -> cooperative launch
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)generator_lat_kernel, dim3(a.NC + 1 + a.NP), dim3(THREADS), args, smem, st);
+  if (e != cudaSuccess) return (int)e;
+  return 0;
+}
+
+}  // namespace wn

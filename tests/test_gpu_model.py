@@ -202,6 +202,58 @@ def test_generate_batched_gc_streams_vs_oracle():
         cur = out
 
 
+@pytest.mark.parametrize('kw,gc', [
+    (dict(TEST_NET, use_biases=True, skip_channels=64, global_condition_channels=4, global_condition_cardinality=6), 3),
+    (dict(DEFAULT_NET), None)], ids=['test_net_gc', 'default_params'])
+def test_generate_latency_kernel(kw, gc):
+    """One stream = the latency-mode kernel (layer-per-warp chain CTAs + resident post-processing CTAs + sampler
+    CTA talking through tagged words).  Its distributions, teacher-forced with its own draws, match the oracle;
+    its draws are np.random.choice on those distributions; the delay lines / header it leaves behind are the
+    ones the throughput-mode kernel continues from."""
+    import wavenet
+    from wavenet import _lib
+    lib = _lib.load()
+    onet, net = make_pair(O, wavenet, seed=7, **kw)
+    n = 48 if len(kw['dilations']) > 20 else 150
+    rs = np.random.RandomState(3)
+    u = rs.random_sample((1, n))
+    first = [int(rs.randint(0, 256))]
+    lib.wn_debug_set_gen_impl(1)
+    samples, proba = net.generate(n, first, global_condition=gc, uniforms=u, return_proba=True)
+    samples = samples.cpu().numpy()[0]
+    assert samples.min() >= 0 and samples.max() < 256
+    onet.init_ops()
+    seq = first + [int(v) for v in samples]
+    exact = 0
+    p_ref = None
+    for i in range(n):
+        p_ref = onet.predict_proba_incremental(seq[i], gc) if gc is not None else onet.predict_proba_incremental(seq[i])
+        exact += int(O.choice_from_uniform(p_ref, u[0, i]) == samples[i])
+    assert exact >= n - 1          # a draw may differ only when u sits within float noise of a cdf edge
+    np.testing.assert_allclose(proba.cpu().numpy()[0], p_ref, rtol=5e-3, atol=1e-6)
+    # continue a few more steps with the throughput-mode kernel from the state the latency kernel left ...
+    u2 = rs.random_sample((1, 8))
+    lib.wn_debug_set_gen_impl(0)
+    try:
+        cont_v1 = net.generate(8, [int(samples[-1])], global_condition=gc, uniforms=u2, reset=False).cpu().numpy()[0]
+        # ... and the same with the latency kernel after replaying the identical history through the v1 kernel
+        net.prime(np.concatenate([first, samples[:-1]]).astype(np.int32), global_condition=gc)
+    finally:
+        lib.wn_debug_set_gen_impl(1)
+    cont_lat = net.generate(8, [int(samples[-1])], global_condition=gc, uniforms=u2, reset=False).cpu().numpy()[0]
+    assert (cont_v1 != cont_lat).sum() <= 1
+    # priming (forced ids, no draws) through both kernels
+    ids = np.concatenate([first, samples[:-1]]).astype(np.int32)
+    p_lat = net.prime(ids, global_condition=gc).cpu().numpy()[0]
+    lib.wn_debug_set_gen_impl(0)
+    try:
+        p_v1 = net.prime(ids, global_condition=gc).cpu().numpy()[0]
+    finally:
+        lib.wn_debug_set_gen_impl(1)
+    np.testing.assert_allclose(p_lat, p_v1, rtol=2e-3, atol=1e-7)
+    np.testing.assert_allclose(p_lat, p_ref, rtol=5e-3, atol=1e-6)
+
+
 def test_generate_temperature_and_many_streams():
     import wavenet
     net = wavenet.WaveNetModel(**dict(TEST_NET, use_biases=True), seed=3)
