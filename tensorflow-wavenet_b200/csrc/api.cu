@@ -7,6 +7,7 @@
 #include "../../include/wavenet_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "gen_common.h"
 
 namespace wn {
 
@@ -281,6 +282,7 @@ int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma) {
 
 int wn_debug_timeline(long long* stamps) {
   set_block_timeline(stamps);
+  set_gen_timeline(stamps);
   return 0;
 }
 

@@ -29,6 +29,7 @@ struct GenArgs {
 // that differs between consecutive launches on the same state (tags stale words of earlier launches as invalid).
 int64_t gen_lat_comm_bytes(const wn_config* cfg);
 bool gen_lat_eligible(const GenArgs& a);
+void set_gen_timeline(long long* p);   // debug: 16 int64 %globaltimer stamps of one step
 int gen_lat_run(const GenArgs& a, void* comm, uint32_t launch_seq, cudaStream_t st);
 
 }  // namespace wn

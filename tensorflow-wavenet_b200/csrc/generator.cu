@@ -537,6 +537,14 @@ int wn_gen_run(const wn_config* cfg, const float* params, void* state, int32_t s
   int spb = 1;
   if (streams > nsm) spb = 2;
   if (streams > 2 * nsm) spb = 4;
+  {   // experiment knob: streams per CTA (more streams per CTA = fewer re-reads of the weights from L2)
+    static int forced_spb = -1;
+    if (forced_spb < 0) {
+      const char* e = getenv("WN_GEN_SPB");
+      forced_spb = e ? atoi(e) : 0;
+    }
+    if (forced_spb == 1 || forced_spb == 2 || forced_spb == 4) spb = forced_spb;
+  }
   if (a.C == 32) {
     if (spb == 1) return launch_gen<1, 32>(a, st);
     if (spb == 2) return launch_gen<2, 32>(a, st);

@@ -40,7 +40,16 @@ struct LatArgs {
   uint32_t tag_base;             // (launch_seq << 20); word tag = tag_base + step + 1
   int NC, NP, cq;                // chain CTAs, post CTAs, post2 columns per post CTA
   int causal_in_smem;
+  long long* timeline;           // debug (wn_debug_timeline): %globaltimer stamps of step TL_STEP
 };
+constexpr int TL_STEP = 200;
+__device__ __forceinline__ void tl_stamp(const LatArgs& a, int step, int slot) {
+  if (a.timeline && step == TL_STEP) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    a.timeline[slot] = (long long)g;
+  }
+}
 
 // comm layout (u64 words)
 __host__ __device__ inline int off_xg() { return 0; }                                   // [NC+1][32]
@@ -84,7 +93,7 @@ __device__ __forceinline__ float wait_smem(const volatile u64* p, uint32_t tag) 
 __device__ __forceinline__ void wait_hint(const u64* p, uint32_t tag) {
   for (uint32_t i = 0; i < (1u << 24); ++i) {
     if ((uint32_t)(ld_gpu(p) >> 32) == tag) return;
-    __nanosleep(64);
+    __nanosleep(32);
   }
   __trap();
 }
@@ -186,6 +195,7 @@ __device__ void chain_warp(const LatArgs& a, int c, int w, volatile u64* xbuf /*
       if (cur >= 0 && cur < g.Q) v += wc[(size_t)(g.Q + cur) * C + lane];
       x_own = v;
       prev_id = cur;
+      if (lane == 0) { tl_stamp(a, step, 0); if (step == TL_STEP + 1 && a.timeline) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); a.timeline[15] = (long long)gt; } }
     } else if (w == 0) {
       x_own = wait_gpu(xg_in + lane, T);
     } else {
@@ -194,18 +204,18 @@ __device__ void chain_warp(const LatArgs& a, int c, int w, volatile u64* xbuf /*
     xs[lane] = x_own;
     __syncwarp();
     st_gpu_f32(ring + (size_t)slot * C + lane, x_own);      // push_ops: enqueue the layer input (model.py:461,482)
-    float2 fb = make_float2(0.f, 0.f), gb = make_float2(0.f, 0.f);
+    float2 fb = make_float2(0.f, 0.f), gb = make_float2(0.f, 0.f), fc = fb, gc = gb;   // short dependent chains
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * j);
       fb = ffma2(make_float2(xv.x, xv.y), wfc[2 * j], fb);
       gb = ffma2(make_float2(xv.x, xv.y), wgc[2 * j], gb);
-      fb = ffma2(make_float2(xv.z, xv.w), wfc[2 * j + 1], fb);
-      gb = ffma2(make_float2(xv.z, xv.w), wgc[2 * j + 1], gb);
+      fc = ffma2(make_float2(xv.z, xv.w), wfc[2 * j + 1], fc);
+      gc = ffma2(make_float2(xv.z, xv.w), wgc[2 * j + 1], gc);
     }
-    const float f = (fa.x + fa.y) + (fb.x + fb.y) + pbf;
-    const float gg = (ga.x + ga.y) + (gb.x + gb.y) + pbg;
-    const float z = tanhf(f) * (1.0f / (1.0f + expf(-gg)));
+    const float f = ((fa.x + fa.y) + pbf) + ((fb.x + fb.y) + (fc.x + fc.y));
+    const float gg = ((ga.x + ga.y) + pbg) + ((gb.x + gb.y) + (gc.x + gc.y));
+    const float z = tanh_fast(f) * sigmoid_fast(gg);
     zs[lane] = z;
     __syncwarp();
     if (l + 1 < g.L) {      // the last layer's dense output is discarded by the reference (model.py:377-380)
@@ -218,14 +228,15 @@ __device__ void chain_warp(const LatArgs& a, int c, int w, volatile u64* xbuf /*
       }
       const float x_out = x_own + bd + ((oa.x + oa.y) + (ob.x + ob.y));
       if (w + 1 < LPC) xbuf[(w + 1) * 32 + lane] = pack(x_out, T);
-      else st_gpu(xg_out + lane, pack(x_out, T));
+      else { st_gpu(xg_out + lane, pack(x_out, T)); if (lane == 0) tl_stamp(a, step, 1 + c); }
     }
     st_gpu(zt + lane, pack(z, T));
     if (l == g.L - 1) {
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 31) {
         st_gpu(misc + 1, pack(0.f, T));     // hint for the post CTAs: the last z of this step is on its way
         st_gpu(misc + 2, pack(0.f, T));     // the chain is free for the next forced step
+        tl_stamp(a, step, 1 + c);
       }
     }
     __syncwarp();      // xs / zs are rewritten next step
@@ -237,8 +248,30 @@ __device__ void chain_warp(const LatArgs& a, int c, int w, volatile u64* xbuf /*
   }
 }
 
+// Loads words p[tid], p[tid + 256], ... (n <= 8 * 256) in one batch and spins on the batch until every word
+// carries `tag`: one L2 round trip when the producers are done, instead of one per word.
+template <int MAXW>
+__device__ __forceinline__ void wait_batch(const u64* p, int n, uint32_t tag, float (&v)[MAXW]) {
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    u64 w[MAXW];
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) {
+      const int k = threadIdx.x + j * THREADS;
+      w[j] = (k < n) ? ld_gpu(p + k) : ((u64)tag << 32);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) {
+      ok = ok && ((uint32_t)(w[j] >> 32) == tag);
+      v[j] = __uint_as_float((uint32_t)w[j]);
+    }
+    if (ok) return;
+  }
+  __trap();
+}
+
 // block-wide sum of a float4 per thread (256 threads); result valid in every thread
-__device__ __forceinline__ float4 block_sum4(float4 v, float4* red /*[8]*/) {
+__device__ __forceinline__ float4 block_sum4(float4 v, float4* red /*[2][8]*/, int& flip) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
@@ -246,13 +279,14 @@ __device__ __forceinline__ float4 block_sum4(float4 v, float4* red /*[8]*/) {
     v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
     v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
   }
-  __syncthreads();      // previous use of red[] is over
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  float4* r = red + 8 * flip;      // alternating scratch: the barrier of call i+1 protects the buffer of call i
+  flip ^= 1;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
   __syncthreads();
-  float4 t = red[0];
+  float4 t = r[0];
 #pragma unroll
   for (int w = 1; w < 8; ++w) {
-    t.x += red[w].x; t.y += red[w].y; t.z += red[w].z; t.w += red[w].w;
+    t.x += r[w].x; t.y += r[w].y; t.z += r[w].z; t.w += r[w].w;
   }
   return t;
 }
@@ -317,47 +351,73 @@ __device__ void post_cta(const LatArgs& a, int p, float* sm) {
   u64* lgt = comm + off_lg(a.NC, g.L, S);
   const u64* misc = comm + off_misc(a.NC, g.L, S, Q);
   const bool sampling = g.uniforms != nullptr;
+  int flip = 0;
 
   for (int step = 0; step < g.n_steps; ++step) {
     if (!sampling && step != g.n_steps - 1) continue;       // priming: only the last distribution is needed
     const uint32_t T = a.tag_base + (uint32_t)step + 1u;
     if (tid == 0) wait_hint(misc + 1, T);
     __syncthreads();
+    if (p == 0 && tid == 0) tl_stamp(a, step, 8);
     // ---- skip sum -> relu            (model.py:505-507)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = tid; k < LD; k += THREADS) {
-      const float zv = wait_gpu(zt + k, T);
-      const float4 w = ws[k];
-      acc.x = fmaf(zv, w.x, acc.x); acc.y = fmaf(zv, w.y, acc.y); acc.z = fmaf(zv, w.z, acc.z); acc.w = fmaf(zv, w.w, acc.w);
+    {
+      float zv[8];
+      wait_batch<8>(zt, LD, T, zv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = tid + j * THREADS;
+        if (k < LD) {
+          const float4 w = ws[k];
+          acc.x = fmaf(zv[j], w.x, acc.x); acc.y = fmaf(zv[j], w.y, acc.y); acc.z = fmaf(zv[j], w.z, acc.z); acc.w = fmaf(zv[j], w.w, acc.w);
+        }
+      }
     }
-    acc = block_sum4(acc, red);
+    acc = block_sum4(acc, red, flip);
     if (tid < CS && CS * p + tid < S) {
       const float v = (tid == 0 ? acc.x : tid == 1 ? acc.y : tid == 2 ? acc.z : acc.w) + bias_s[tid];
       st_gpu(v0t + CS * p + tid, pack(fmaxf(v, 0.f), T));
+      if (p == 0 && tid == 0) tl_stamp(a, step, 9);
     }
     // ---- postprocess1 -> relu        (model.py:508-511)
     acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = tid; k < S; k += THREADS) {
-      const float xv = wait_gpu(v0t + k, T);
-      const float4 w = w1[k];
-      acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+    {
+      float xv[4];
+      wait_batch<4>(v0t, S, T, xv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = tid + j * THREADS;
+        if (k < S) {
+          const float4 w = w1[k];
+          acc.x = fmaf(xv[j], w.x, acc.x); acc.y = fmaf(xv[j], w.y, acc.y); acc.z = fmaf(xv[j], w.z, acc.z); acc.w = fmaf(xv[j], w.w, acc.w);
+        }
+      }
     }
-    acc = block_sum4(acc, red);
+    acc = block_sum4(acc, red, flip);
     if (tid < CS && CS * p + tid < S) {
       const float v = (tid == 0 ? acc.x : tid == 1 ? acc.y : tid == 2 ? acc.z : acc.w) + bias_s[4 + tid];
       st_gpu(v1t + CS * p + tid, pack(fmaxf(v, 0.f), T));
+      if (p == 0 && tid == 0) tl_stamp(a, step, 10);
     }
     // ---- postprocess2                (model.py:512-514)
     acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = tid; k < S; k += THREADS) {
-      const float xv = wait_gpu(v1t + k, T);
-      const float4 w = w2[k];
-      acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+    {
+      float xv[4];
+      wait_batch<4>(v1t, S, T, xv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = tid + j * THREADS;
+        if (k < S) {
+          const float4 w = w2[k];
+          acc.x = fmaf(xv[j], w.x, acc.x); acc.y = fmaf(xv[j], w.y, acc.y); acc.z = fmaf(xv[j], w.z, acc.z); acc.w = fmaf(xv[j], w.w, acc.w);
+        }
+      }
     }
-    acc = block_sum4(acc, red);
+    acc = block_sum4(acc, red, flip);
     if (tid < cq && cq * p + tid < Q) {
       const float v = (tid == 0 ? acc.x : tid == 1 ? acc.y : tid == 2 ? acc.z : acc.w) + bias_s[8 + tid];
       st_gpu(lgt + cq * p + tid, pack(v, T));
+      if (p == 0 && tid == 0) tl_stamp(a, step, 11);
     }
   }
 }
@@ -369,48 +429,63 @@ __device__ void sampler_cta(const LatArgs& a, float* sm) {
   const GenArgs& g = a.g;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Q = g.Q;
-  double* dsm = reinterpret_cast<double*>(sm);     // [Q] exp values, later the cdf
+  double* dsm = reinterpret_cast<double*>(sm);     // [Q] exp values
   float* ps = reinterpret_cast<float*>(dsm + Q);   // [Q] float32 probabilities
-  __shared__ double redd[8];
-  __shared__ float redf[8];
-  __shared__ int redi[8];
+  __shared__ double redd[2][8];
+  __shared__ float redf[2][8];
   u64* comm = a.comm;
   const u64* lgt = comm + off_lg(a.NC, g.L, g.S);
   u64* misc = comm + off_misc(a.NC, g.L, g.S, Q);
   const bool sampling = g.uniforms != nullptr;
+  const int per = (Q + 31) / 32;                   // cdf elements per lane of warp 0 (Q <= 1024)
+  int flip = 0;
 
   for (int step = 0; step < g.n_steps; ++step) {
     if (!sampling && step != g.n_steps - 1) continue;
     const uint32_t T = a.tag_base + (uint32_t)step + 1u;
+    const double u = sampling ? g.uniforms[step] : 0.0;     // fetched while the chain is still running
     if (tid == 0) wait_hint(misc + 1, T);
     __syncthreads();
     // float64 softmax of the logits, cast back to float32   (model.py:619-621)
-    double mx = -1e300;
-    for (int i = tid; i < Q; i += THREADS) {
-      const double v = (double)wait_gpu(lgt + i, T);
-      dsm[i] = v;
-      mx = fmax(mx, v);
-    }
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) redd[warp] = mx;
+    float lg[4];
+    wait_batch<4>(lgt, Q, T, lg);
+    float mxf = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (tid + j * THREADS < Q) mxf = fmaxf(mxf, lg[j]);
+    mxf = warp_max(mxf);
+    if (lane == 0) redf[flip][warp] = mxf;
     __syncthreads();
-    mx = redd[0];
-    for (int w = 1; w < 8; ++w) mx = fmax(mx, redd[w]);
-    __syncthreads();
+    mxf = redf[flip][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mxf = fmaxf(mxf, redf[flip][w]);
+    const double mx = (double)mxf;
+    double e[4];
     double sum = 0.0;
-    for (int i = tid; i < Q; i += THREADS) {
-      const double e = exp(dsm[i] - mx);
-      dsm[i] = e;
-      sum += e;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      e[j] = (tid + j * THREADS < Q) ? exp((double)lg[j] - mx) : 0.0;
+      sum += e[j];
     }
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) redd[warp] = sum;
+    if (lane == 0) redd[flip][warp] = sum;
     __syncthreads();
-    sum = redd[0];
-    for (int w = 1; w < 8; ++w) sum += redd[w];
-    for (int i = tid; i < Q; i += THREADS) ps[i] = (float)(dsm[i] / sum);
-    __syncthreads();
+    sum = redd[flip][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sum += redd[flip][w];
+    flip ^= 1;
+    int tiny = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + j * THREADS;
+      if (i < Q) {
+        const float pv = (float)(e[j] / sum);
+        ps[i] = pv;
+        tiny |= (pv != 0.f && pv < 3.7252903e-09f) ? 1 : 0;
+      }
+    }
     if (g.temperature != 1.0f) {     // generate.py:229-233, float32 log-space
+      __syncthreads();
       float m2 = -INFINITY;
       for (int i = tid; i < Q; i += THREADS) {
         const float q = logf(ps[i]) / g.temperature;
@@ -418,74 +493,77 @@ __device__ void sampler_cta(const LatArgs& a, float* sm) {
         m2 = fmaxf(m2, q);
       }
       m2 = warp_max(m2);
-      if (lane == 0) redf[warp] = m2;
+      if (lane == 0) redf[flip][warp] = m2;
       __syncthreads();
-      m2 = redf[0];
-      for (int w = 1; w < 8; ++w) m2 = fmaxf(m2, redf[w]);
-      __syncthreads();
+      m2 = redf[flip][0];
+      for (int w = 1; w < 8; ++w) m2 = fmaxf(m2, redf[flip][w]);
       float s2 = 0.f;
       for (int i = tid; i < Q; i += THREADS) s2 += expf(ps[i] - m2);
       s2 = warp_sum(s2);
-      if (lane == 0) redf[warp] = s2;
+      flip ^= 1;
+      if (lane == 0) redf[flip][warp] = s2;
       __syncthreads();
-      s2 = redf[0];
-      for (int w = 1; w < 8; ++w) s2 += redf[w];
+      s2 = redf[flip][0];
+      for (int w = 1; w < 8; ++w) s2 += redf[flip][w];
       const float lse = m2 + logf(s2);
-      for (int i = tid; i < Q; i += THREADS) ps[i] = expf(ps[i] - lse);
-      __syncthreads();
+      tiny = 0;
+      for (int i = tid; i < Q; i += THREADS) {
+        const float pv = expf(ps[i] - lse);
+        ps[i] = pv;
+        tiny |= (pv != 0.f && pv < 3.7252903e-09f) ? 1 : 0;
+      }
     }
+    tiny = __syncthreads_or(tiny);      // also publishes ps[] to warp 0
+    if (tid == 0) tl_stamp(a, step, 12);
     if (g.proba_out && step == g.n_steps - 1)
       for (int i = tid; i < Q; i += THREADS) g.proba_out[i] = ps[i];
-    if (sampling) {
+    if (sampling && warp == 0) {
       // np.random.choice: cdf = cumsum(p) (sequential float64 adds), normalise by the last, searchsorted right.
-      // Every partial sum of float32 values >= 2^-28 below 2 is exact in float64, so then any order gives
-      // np.cumsum's bits and the scan runs in parallel; otherwise one lane repeats the sequential sum.
-      int tiny = 0;
-      for (int i = tid; i < Q; i += THREADS) tiny |= (ps[i] != 0.f && ps[i] < 3.7252903e-09f) ? 1 : 0;
-      tiny = __syncthreads_or(tiny);
-      if (!tiny && Q <= 8 * 32) {
-        if (warp == 0) {
-          double run[8];
-          double t = 0.0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int i = lane * 8 + j;
-            t += (i < Q) ? (double)ps[i] : 0.0;
-            run[j] = t;
-          }
-          double incl = t;
-          for (int o = 1; o < 32; o <<= 1) {
-            const double up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-          }
-          const double excl = incl - t;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int i = lane * 8 + j;
-            if (i < Q) dsm[i] = excl + run[j];
+      // Every partial sum of float32 values >= 2^-28 (total < 2) is exact in float64, so then any association
+      // gives np.cumsum's bits and a warp scan is used; otherwise lane 0 repeats the sequential sum.
+      int cnt = 0;
+      if (!tiny) {
+        double t = 0.0;
+        for (int j = 0; j < per; ++j) {
+          const int i = lane * per + j;
+          t += (i < Q) ? (double)ps[i] : 0.0;
+        }
+        double incl = t;
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const double total = __shfl_sync(0xffffffffu, incl, 31);
+        // cdf[i] / total <= u  is decided by  cdf[i] <= u * total  unless the two are within a few ulps of each
+        // other (then the exact quotient is formed): same result as np.searchsorted on cdf / cdf[-1]
+        const double thr = u * total, eps = thr * 1e-15;
+        double run = incl - t;
+        for (int j = 0; j < per; ++j) {
+          const int i = lane * per + j;
+          if (i < Q) {
+            run += (double)ps[i];
+            const double dlt = run - thr;
+            const bool le = (fabs(dlt) > eps) ? (dlt < 0.0) : (run / total <= u);
+            cnt += le ? 1 : 0;
           }
         }
-      } else if (tid == 0) {
-        double run = 0.0;
-        for (int i = 0; i < Q; ++i) { run += (double)ps[i]; dsm[i] = run; }
+      } else {
+        if (lane == 0) {
+          double run = 0.0;
+          for (int i = 0; i < Q; ++i) { run += (double)ps[i]; dsm[i] = run; }
+        }
+        __syncwarp();
+        const double total = dsm[Q - 1];
+        for (int i = lane; i < Q; i += 32) cnt += (dsm[i] / total <= u) ? 1 : 0;
       }
-      __syncthreads();
-      const double total = dsm[Q - 1];
-      const double u = g.uniforms[step];
-      int cnt = 0;
-      for (int i = tid; i < Q; i += THREADS) cnt += (dsm[i] / total <= u) ? 1 : 0;
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (lane == 0) redi[warp] = cnt;
-      __syncthreads();
-      if (tid == 0) {
-        int tot = 0;
-        for (int w = 0; w < 8; ++w) tot += redi[w];
-        const int drawn = tot < Q ? tot : Q - 1;
+      if (lane == 0) {
+        const int drawn = cnt < Q ? cnt : Q - 1;
         st_gpu(misc + 0, pack(__int_as_float(drawn), T));      // feeds the chain head of the next step
         g.samples_out[step] = drawn;
+        tl_stamp(a, step, 13);
       }
     }
-    __syncthreads();
   }
 }
 
@@ -511,9 +589,12 @@ __global__ void __launch_bounds__(THREADS, 1) generator_lat_kernel(LatArgs a) {
 size_t chain_smem(const GenArgs& g, int causal_in_smem) {
   return sizeof(float) * (2 * (LPC + 1) * 32 + LPC * 64 + (causal_in_smem ? 2 * g.Q * C : 0));
 }
-size_t post_smem(const GenArgs& g) { return sizeof(float4) * ((size_t)g.L * C + 2 * g.S + 8); }
+size_t post_smem(const GenArgs& g) { return sizeof(float4) * ((size_t)g.L * C + 2 * g.S + 16); }
 size_t sampler_smem(const GenArgs& g) { return (sizeof(double) + sizeof(float)) * (size_t)g.Q; }
 }  // namespace
+
+static long long* g_gen_timeline = nullptr;
+void set_gen_timeline(long long* p) { g_gen_timeline = p; }
 
 int64_t gen_lat_comm_bytes(const wn_config* cfg) {
   const int L = cfg->n_layers, NC = (L + LPC - 1) / LPC;
@@ -526,6 +607,7 @@ bool gen_lat_eligible(const GenArgs& a) {
   const int NC = (a.L + LPC - 1) / LPC;
   const int NP = (a.S + CS - 1) / CS;
   if ((a.Q + NP - 1) / NP > 4) return false;
+  if (a.L * C > 8 * THREADS || a.S > 4 * THREADS || a.Q > 4 * THREADS) return false;      // wait_batch<8> / <4>
   if (NC + 1 + NP > sm_count()) return false;
   if (post_smem(a) > 200 * 1024 || sampler_smem(a) > 200 * 1024) return false;
   return true;
@@ -541,6 +623,7 @@ int gen_lat_run(const GenArgs& g, void* comm, uint32_t launch_seq, cudaStream_t 
   a.NP = (g.S + CS - 1) / CS;
   a.cq = (g.Q + a.NP - 1) / a.NP;
   a.causal_in_smem = (2 * g.Q * C * sizeof(float) <= 128 * 1024) ? 1 : 0;
+  a.timeline = g_gen_timeline;
   size_t smem = chain_smem(g, a.causal_in_smem);
   if (post_smem(g) > smem) smem = post_smem(g);
   if (sampler_smem(g) > smem) smem = sampler_smem(g);
