@@ -97,8 +97,8 @@ struct Workspace {
   float* G2;       // [M,S]
   float* G3;       // [M,S]                         (residual_postproc only)
   float* dZcat;    // [M, L*D]
-  float* dX;       // 2 x [M,R]
-  float* dpre;     // [M,2D]
+  float* dX;       // 3 x [M,R]   (rotating: the side-stream weight-gradient kernel still reads the older ones)
+  float* dpre;     // 2 x [M,2D]
   float* prebias;  // [L,B,2D]
   float* gprebias; // [L,B,2D]
   float* bsum;     // [S]
@@ -144,8 +144,8 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->G2 = (float*)take(M * S * f);
     w->G3 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
     w->dZcat = (float*)take(M * L * D * f);
-    w->dX = (float*)take(2 * M * R * f);
-    w->dpre = (float*)take(M * 2 * D * f);
+    w->dX = (float*)take(3 * M * R * f);
+    w->dpre = (float*)take(2 * M * 2 * D * f);
     w->gprebias = (float*)take(L * B * 2 * D * f);
     w->gtmp = (float*)take(S * f);
   } else {
@@ -530,30 +530,59 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     prof_mark(st, PT_GEMM_SKIP_DGRAD);
   }
   const int64_t xs = (int64_t)M * R;
-  float* dcur = w.dX;        // gradient wrt the output of the layer being processed
-  float* dnext = w.dX + xs;  // gradient wrt its input
-  for (int l = L - 1; l >= 0; --l) {
-    const int last = (l == L - 1);
-    if (w.umma_bwd) {
-      const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
-      RC(block_bwd_umma(w.X + l * xs, last ? nullptr : dcur, w.dZcat, w.Zcat, ldz, l * D, dnext, w.dpre,
-                        img + block_img_off_pre(), img + block_img_off_dx(), w.prebias + (int64_t)l * B * 2 * D,
-                        grads + lo.filter + (int64_t)l * 2 * R * D, grads + lo.gate + (int64_t)l * 2 * R * D,
-                        grads + lo.dense + (int64_t)l * D * R, w.gprebias + (int64_t)l * B * 2 * D,
-                        lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, B, T, cfg->dilations[l],
-                        last, st));
-      float* tmp = dcur; dcur = dnext; dnext = tmp;
-      continue;
+  const float* dcur = nullptr;     // gradient wrt the output of the layer being processed
+  if (w.umma_bwd) {
+    // Critical chain on `st`: pre(l) -> dx(l) -> pre(l-1) -> ...  The weight-gradient GEMM of a layer only feeds
+    // the gradient buffers, so it runs on a side stream, concurrently with the chain.  Buffers rotate (dpre x2,
+    // dx x3); before layer l reuses them the chain waits for wgrad(l+2), their last reader.
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_pre = nullptr, ev_fork = nullptr, ev_wg[3] = {nullptr, nullptr, nullptr};
+    if (!side) {
+      RC((int)cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      RC((int)cudaEventCreateWithFlags(&ev_pre, cudaEventDisableTiming));
+      RC((int)cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      for (int i = 0; i < 3; ++i) RC((int)cudaEventCreateWithFlags(&ev_wg[i], cudaEventDisableTiming));
     }
-    RC(block_bwd(w.X + l * xs, last ? nullptr : dcur, w.dZcat + (int64_t)l * D, ldz, dnext, w.dpre,
-                 w.Zcat + (int64_t)l * D, params + lo.filter + (int64_t)l * 2 * R * D,
-                 params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
-                 w.prebias + (int64_t)l * B * 2 * D, grads + lo.filter + (int64_t)l * 2 * R * D,
-                 grads + lo.gate + (int64_t)l * 2 * R * D, grads + lo.dense + (int64_t)l * D * R,
-                 w.gprebias + (int64_t)l * B * 2 * D,
-                 lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, M, T, cfg->dilations[l], R,
-                 last, st));
-    float* tmp = dcur; dcur = dnext; dnext = tmp;
+    // (per-kernel profiling serialises everything on one stream so that event deltas are kernel times)
+    cudaStream_t ws = g_prof_on ? st : side;
+    for (int l = L - 1; l >= 0; --l) {
+      const int last = (l == L - 1);
+      const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
+      float* dpre = w.dpre + (int64_t)(l & 1) * M * 2 * D;
+      float* dnext = w.dX + (int64_t)(l % 3) * xs;                 // gradient wrt this layer's input
+      if (l + 2 <= L - 1) RC((int)cudaStreamWaitEvent(st, ev_wg[(l + 2) % 3], 0));
+      RC(block_bwd_pre_umma(w.X + l * xs, dcur, w.dZcat, ldz, l * D, dpre, img + block_img_off_pre(),
+                            w.prebias + (int64_t)l * B * 2 * D, B, T, cfg->dilations[l], last, st));
+      RC((int)cudaEventRecord(ev_pre, st));
+      RC((int)cudaStreamWaitEvent(ws, ev_pre, 0));
+      RC(block_wgrad_umma(w.X + l * xs, dcur, dpre, w.Zcat, ldz, l * D, grads + lo.filter + (int64_t)l * 2 * R * D,
+                          grads + lo.gate + (int64_t)l * 2 * R * D, grads + lo.dense + (int64_t)l * D * R,
+                          w.gprebias + (int64_t)l * B * 2 * D,
+                          lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, B, T, cfg->dilations[l],
+                          last, ws));
+      RC((int)cudaEventRecord(ev_wg[l % 3], ws));
+      RC(block_bwd_dx_umma(dcur, dpre, dnext, img + block_img_off_dx(), B, T, cfg->dilations[l], last, st));
+      dcur = dnext;
+    }
+    // join: the bias / conditioning gradients below read what the weight-gradient kernels accumulated
+    for (int i = 0; i < 3 && i < L; ++i) RC((int)cudaStreamWaitEvent(st, ev_wg[i], 0));
+  } else {
+    float* bufs[2] = {w.dX, w.dX + xs};
+    int cur_i = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      const int last = (l == L - 1);
+      float* dnext = bufs[cur_i ^ 1];
+      RC(block_bwd(w.X + l * xs, last ? nullptr : dcur, w.dZcat + (int64_t)l * D, ldz, dnext, w.dpre,
+                   w.Zcat + (int64_t)l * D, params + lo.filter + (int64_t)l * 2 * R * D,
+                   params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,
+                   w.prebias + (int64_t)l * B * 2 * D, grads + lo.filter + (int64_t)l * 2 * R * D,
+                   grads + lo.gate + (int64_t)l * 2 * R * D, grads + lo.dense + (int64_t)l * D * R,
+                   w.gprebias + (int64_t)l * B * 2 * D,
+                   lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, M, T, cfg->dilations[l], R,
+                   last, st));
+      dcur = dnext;
+      cur_i ^= 1;
+    }
   }
   RC(frontend_bwd(w.ids, dcur, grads + lo.causal, M, T, Q, R, st));
   prof_mark(st, PT_FRONTEND_BWD);

@@ -22,6 +22,8 @@
 //              [x ; x[t-d] ; z ; 1]^T . [dpre ; dx']  with both operands read MN-major straight from the
 //              [time][channel] activations (no transposed copies)
 //   bwd_dx   : dx = dx' + dpre[t].Wcur^T + dpre[t+d].Wpast^T                       -> dx
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "umma_common.cuh"
@@ -592,6 +594,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
 // The dilated past x[t-d] is the same tensor at time coordinate t-d (zero filled for t < d).
 // grid = (splits, B): a CTA reduces a contiguous range of 32-step blocks of one batch element.
 // =========================================================================================
+constexpr int WG_STAGES = 3;
 struct WgArgs {
   float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;
   int B, T, d, is_last, zcol;   // zcol: first column of this layer inside Zcat
@@ -604,7 +607,7 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 __global__ void __launch_bounds__(192, 2)
 block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
                         const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapDn, WgArgs a) {
-  constexpr int STG = 3;
+  constexpr int STG = WG_STAGES;   // (a deeper ring does not help: measured, the kernel is bound by its fixed costs)
   constexpr uint32_t BLK = 32 * 128;                       // one [32 steps][32 channels] block
   constexpr uint32_t A_BYTES = 4 * BLK, B_BYTES = 3 * BLK, STAGE = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
@@ -708,69 +711,79 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
-int block_bwd_umma(const float* x, const float* dxn, const float* dZcat, const float* Zcat, int ldz, int zcol,
-                   float* dx, float* dpre, const unsigned char* img_pre, const unsigned char* img_dx,
-                   const float* prebias, float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias,
-                   int B, int T, int d, int is_last, cudaStream_t st) {
+// The three backward kernels of a layer are separate entry points: the weight-gradient GEMM only feeds the
+// gradient buffers, so the caller runs it on a side stream next to the dx / next layer's pre kernels.
+int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int ldz, int zcol, float* dpre,
+                       const unsigned char* img_pre, const float* prebias, int B, int T, int d, int is_last,
+                       cudaStream_t st) {
   const int n_tiles = B * ((T + TM - 1) / TM);
   int grid = n_tiles;
   const int cap = 2 * sm_count();
   if (grid > cap) grid = cap;
-  {
-    CUtensorMap mX, mDn, mDz;
-    int rc = make_map_3d(&mX, x, B, T, C, C, TM);
-    if (rc) return rc;
-    rc = make_map_3d(&mDn, is_last ? x : dxn, B, T, C, C, TM);
-    if (rc) return rc;
-    rc = make_map_3d(&mDz, dZcat, B, T, ldz, ldz, TM);
-    if (rc) return rc;
-    PreArgs a;
-    a.dpre = dpre; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
-    a.is_last = is_last; a.zcol = zcol;
-    const size_t smem = 1024 + 4 * TILE + IMG_PRE;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(block_bwd_pre_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    { cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, a); if (e != cudaSuccess) return (int)e; }
-    WN_CHECK_LAUNCH();
-    prof_mark(st, PT_BLOCK_BWD_PRE);
-  }
-  {
-    CUtensorMap mX, mZ, mP, mDn;
-    int rc = make_map_3d_mn(&mX, x, B, T, C, C, 32);
-    if (rc) return rc;
-    rc = make_map_3d_mn(&mZ, Zcat, B, T, ldz, ldz, 32);
-    if (rc) return rc;
-    rc = make_map_3d_mn(&mP, dpre, B, T, 64, 64, 32);
-    if (rc) return rc;
-    rc = make_map_3d_mn(&mDn, is_last ? x : dxn, B, T, C, C, 32);
-    if (rc) return rc;
-    WgArgs a;
-    a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias; a.B = B; a.T = T;
-    a.d = d; a.is_last = is_last; a.zcol = zcol;
-    const size_t smem = 1024 + 3 * (7 * 4096);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(block_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    const int nkb = (T + 31) / 32;
-    int splits = 2 * sm_count() / (B > 0 ? B : 1);
-    if (splits < 1) splits = 1;
-    if (splits > nkb) splits = nkb;
-    { cudaError_t e = launch_pdl(block_wgrad_umma_kernel, dim3(splits, B), dim3(192), smem, st, mX, mZ, mP, mDn, a); if (e != cudaSuccess) return (int)e; }
-    WN_CHECK_LAUNCH();
-    prof_mark(st, PT_BLOCK_WGRAD);
-  }
-  {
-    CUtensorMap mP;
-    int rc = make_map_3d(&mP, dpre, B, T, 64, 64, TM);
-    if (rc) return rc;
-    DxArgs a;
-    a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.img = img_dx; a.B = B; a.T = T; a.d = d;
-    const size_t smem = 1024 + 4 * TILE + IMG_DX;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    { cudaError_t e = launch_pdl(block_bwd_dx_umma_kernel, dim3(grid), dim3(256), smem, st, mP, a); if (e != cudaSuccess) return (int)e; }
-    WN_CHECK_LAUNCH();
-    prof_mark(st, PT_BLOCK_BWD_DX);
-  }
+  CUtensorMap mX, mDn, mDz;
+  int rc = make_map_3d(&mX, x, B, T, C, C, TM);
+  if (rc) return rc;
+  rc = make_map_3d(&mDn, is_last ? x : dxn, B, T, C, C, TM);
+  if (rc) return rc;
+  rc = make_map_3d(&mDz, dZcat, B, T, ldz, ldz, TM);
+  if (rc) return rc;
+  PreArgs a;
+  a.dpre = dpre; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
+  a.is_last = is_last; a.zcol = zcol;
+  const size_t smem = 1024 + 4 * TILE + IMG_PRE;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(block_bwd_pre_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, a);
+  if (e != cudaSuccess) return (int)e;
+  prof_mark(st, PT_BLOCK_BWD_PRE);
+  return 0;
+}
+
+int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
+                     float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
+                     int is_last, cudaStream_t st) {
+  CUtensorMap mX, mZ, mP, mDn;
+  int rc = make_map_3d_mn(&mX, x, B, T, C, C, 32);
+  if (rc) return rc;
+  rc = make_map_3d_mn(&mZ, Zcat, B, T, ldz, ldz, 32);
+  if (rc) return rc;
+  rc = make_map_3d_mn(&mP, dpre, B, T, 64, 64, 32);
+  if (rc) return rc;
+  rc = make_map_3d_mn(&mDn, is_last ? x : dxn, B, T, C, C, 32);
+  if (rc) return rc;
+  WgArgs a;
+  a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias; a.B = B; a.T = T;
+  a.d = d; a.is_last = is_last; a.zcol = zcol;
+  const size_t smem = 1024 + WG_STAGES * (7 * 4096);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(block_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const int nkb = (T + 31) / 32;
+  int splits = sm_count() / (B > 0 ? B : 1);
+  if (splits < 1) splits = 1;
+  if (splits > nkb) splits = nkb;
+  cudaError_t e = launch_pdl(block_wgrad_umma_kernel, dim3(splits, B), dim3(192), smem, st, mX, mZ, mP, mDn, a);
+  if (e != cudaSuccess) return (int)e;
+  prof_mark(st, PT_BLOCK_WGRAD);
+  return 0;
+}
+
+int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsigned char* img_dx, int B, int T, int d,
+                      int is_last, cudaStream_t st) {
+  const int n_tiles = B * ((T + TM - 1) / TM);
+  int grid = n_tiles;
+  const int cap = 2 * sm_count();
+  if (grid > cap) grid = cap;
+  CUtensorMap mP;
+  int rc = make_map_3d(&mP, dpre, B, T, 64, 64, TM);
+  if (rc) return rc;
+  DxArgs a;
+  a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.img = img_dx; a.B = B; a.T = T; a.d = d;
+  const size_t smem = 1024 + 4 * TILE + IMG_DX;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  cudaError_t e = launch_pdl(block_bwd_dx_umma_kernel, dim3(grid), dim3(256), smem, st, mP, a);
+  if (e != cudaSuccess) return (int)e;
+  prof_mark(st, PT_BLOCK_BWD_DX);
   return 0;
 }
 

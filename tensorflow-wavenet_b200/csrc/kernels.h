@@ -46,10 +46,14 @@ void set_block_timeline(long long* p);   // debug: clock64 stamps of block_fwd_u
 void set_block_impl(int mma);
 int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsigned char* img, const float* wf, const float* wg, const float* dense,
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
-int block_bwd_umma(const float* x, const float* dxn, const float* dZcat, const float* Zcat, int ldz, int zcol,
-                   float* dx, float* dpre, const unsigned char* img_pre, const unsigned char* img_dx,
-                   const float* prebias, float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias,
-                   int B, int T, int d, int is_last, cudaStream_t st);
+int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int ldz, int zcol, float* dpre,
+                       const unsigned char* img_pre, const float* prebias, int B, int T, int d, int is_last,
+                       cudaStream_t st);
+int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
+                     float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
+                     int is_last, cudaStream_t st);
+int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsigned char* img_dx, int B, int T, int d,
+                      int is_last, cudaStream_t st);
 int64_t block_images_bytes(int L);
 uint32_t block_img_off_pre();
 uint32_t block_img_off_dx();
