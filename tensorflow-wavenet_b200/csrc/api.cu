@@ -480,12 +480,23 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, st));
   prof_mark(st, PT_XENT);
 
+  // Weight / bias gradients of the post-processing path only feed the gradient buffers: they run on a second
+  // side stream while `st` carries the dependent chain  dlogits -> G1 -> G2 -> dZcat -> residual blocks.
+  static cudaStream_t side2 = nullptr;
+  static cudaEvent_t ev_g[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (!side2) {
+    RC((int)cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) RC((int)cudaEventCreateWithFlags(&ev_g[i], cudaEventDisableTiming));
+  }
+  cudaStream_t s2 = g_prof_on ? st : side2;   // (per-kernel profiling keeps everything on one stream)
   const float* x2 = rp ? w.T2 : w.A2;   // input of postprocess2
+  RC((int)cudaEventRecord(ev_g[0], st));
+  RC((int)cudaStreamWaitEvent(s2, ev_g[0], 0));
   {  // postprocess2 gradients:  dW2[S,Q] = X2^T . dlogits
     GemmParams p = gp(x2, S, w.logits, Q, grads + lo.post2, Q, S, Q, M);
-    RC(gemm(2, p, split_for(S, Q, M), st));
-    prof_mark(st, PT_GEMM_POST2_WGRAD);
-    if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, st)); prof_mark(st, PT_COLSUM); }
+    RC(gemm(2, p, split_for(S, Q, M), s2));
+    prof_mark(s2, PT_GEMM_POST2_WGRAD);
+    if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, s2)); prof_mark(s2, PT_COLSUM); }
   }
   {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
     GemmParams p = gp(w.logits, Q, w.W2R, Q, w.G1, S, M, S, Q);
@@ -495,11 +506,13 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     RC(gemm(1, p, 1, st));
     prof_mark(st, PT_GEMM_POST2_DGRAD);
   }
+  RC((int)cudaEventRecord(ev_g[1], st));
+  RC((int)cudaStreamWaitEvent(s2, ev_g[1], 0));
   {  // postprocess1 gradients:  dW1[S,S] = A1^T . G1
     GemmParams p = gp(w.A1, S, w.G1, S, grads + lo.post1, S, S, S, M);
-    RC(gemm(2, p, split_for(S, S, M), st));
-    prof_mark(st, PT_GEMM_POST1_WGRAD);
-    if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, st)); prof_mark(st, PT_COLSUM); }
+    RC(gemm(2, p, split_for(S, S, M), s2));
+    prof_mark(s2, PT_GEMM_POST1_WGRAD);
+    if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, s2)); prof_mark(s2, PT_COLSUM); }
   }
   {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
     GemmParams p = gp(w.G1, S, w.W1R, S, w.G2, S, M, S, S);
@@ -512,18 +525,21 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       prof_mark(st, PT_MISC);
     }
   }
+  RC((int)cudaEventRecord(ev_g[2], st));
+  RC((int)cudaStreamWaitEvent(s2, ev_g[2], 0));
   {  // skip weights / biases:  dWskip[L*D,S] = Zcat^T . G2
     GemmParams p = gp(w.Zcat, ldz, w.G2, S, grads + lo.skip, S, ldz, S, M);
-    RC(gemm(2, p, split_for(ldz, S, M), st));
-    prof_mark(st, PT_GEMM_SKIP_WGRAD);
+    RC(gemm(2, p, split_for(ldz, S, M), s2));
+    prof_mark(s2, PT_GEMM_SKIP_WGRAD);
     if (lo.skip_bias >= 0) {
-      RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), st));
-      RC(colsum(w.G2, S, M, S, w.gtmp, st));
-      prof_mark(st, PT_COLSUM);
-      RC(bcast_rows(w.gtmp, S, grads + lo.skip_bias, L, st));
-      prof_mark(st, PT_MISC);
+      RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), s2));
+      RC(colsum(w.G2, S, M, S, w.gtmp, s2));
+      prof_mark(s2, PT_COLSUM);
+      RC(bcast_rows(w.gtmp, S, grads + lo.skip_bias, L, s2));
+      prof_mark(s2, PT_MISC);
     }
   }
+  RC((int)cudaEventRecord(ev_g[3], s2));
   {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
     GemmParams p = gp(w.G2, S, w.WskipR, S, w.dZcat, ldz, M, ldz, S);
     RC(gemm(1, p, 1, st));
@@ -584,6 +600,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       cur_i ^= 1;
     }
   }
+  RC((int)cudaStreamWaitEvent(st, ev_g[3], 0));    // join the post-processing weight-gradient stream
   RC(frontend_bwd(w.ids, dcur, grads + lo.causal, M, T, Q, R, st));
   prof_mark(st, PT_FRONTEND_BWD);
   if (lo.filter_bias >= 0 || G > 0) {
