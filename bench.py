@@ -338,7 +338,9 @@ def main():
         torch.cuda.synchronize()
         b1 = n1 / (time.perf_counter() - t0)
         streams_total = 256
-        per_rank = streams_total // world
+        from wavenet.train_step import shard_streams
+        lo_s, hi_s = shard_streams(streams_total, rank, world)
+        per_rank = hi_s - lo_s
         first = np.random.RandomState(rank).randint(0, 256, per_rank)
         n2 = 1000
         u = np.random.RandomState(100 + rank).random_sample((per_rank, n2))

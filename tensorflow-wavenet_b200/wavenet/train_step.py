@@ -14,6 +14,27 @@ from . import _lib
 from .ops import as_cuda, device_tables
 
 
+def allreduce_gradients(flat_grads, group=None):
+    """Sum the flat gradient buffer over all ranks (NCCL on GPUs, any backend in tests) and return the factor
+    the optimizer must scale it by so that the update uses the MEAN over ranks -- with equal B*T per rank that
+    is the reference's reduce_mean over the global batch (model.py:666)."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return 1.0
+    world = torch.distributed.get_world_size(group)
+    if world == 1:
+        return 1.0
+    torch.distributed.all_reduce(flat_grads, op=torch.distributed.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def shard_streams(n_streams, rank, world):
+    """Generation streams are independent: rank r generates streams [lo, hi) and no collective is needed
+    (SURVEY section 8e).  Remainders go to the lowest ranks."""
+    base, rem = divmod(int(n_streams), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class TrainStep(object):
     def __init__(self, net, optimizer, batch, time, l2_regularization_strength=None, process_group=None,
                  use_cuda_graph=True):
@@ -69,9 +90,6 @@ class TrainStep(object):
             self._graph.replay()
         else:
             self._launch()
-        scale = 1.0
-        if self.world > 1:
-            torch.distributed.all_reduce(self.net.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-            scale = 1.0 / self.world
+        scale = allreduce_gradients(self.net.flat_grads, self.pg) if self.world > 1 else 1.0
         self.opt.apply(self.net.flat_params, self.net.flat_grads, l2=self.l2, grad_scale=scale)
         return self.loss

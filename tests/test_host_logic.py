@@ -124,3 +124,49 @@ def test_golden_fixture_matches_oracle():
     np.testing.assert_allclose(logits, g['logits'], atol=2e-5)
     np.testing.assert_allclose(grads['wavenet/postprocessing/postprocess2'], g['grad_post2'], atol=1e-6)
     np.testing.assert_array_equal(O.mu_law_encode(g['mulaw_x'], 256), g['mulaw_ids'])
+
+
+# ----------------------------------------------------------------------------- data parallel host logic (N > 1)
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from wavenet.train_step import allreduce_gradients, shard_streams
+        # per-rank gradient of a per-rank batch: the all-reduced, rescaled buffer is the global-batch mean
+        g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        scale = allreduce_gradients(g)
+        mean = g * scale
+        lo, hi = shard_streams(257, rank, world)
+        out[rank] = (float(scale), mean[:5].tolist(), float(mean.sum()), lo, hi)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_and_stream_sharding_world2():
+    """World size 2 over gloo on CPU: the same helpers TrainStep / bench.py use over NCCL."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    ref = torch.arange(1000, dtype=torch.float32) * 1.5         # mean of 1x and 2x
+    for rank in range(world):
+        scale, head, total, lo, hi = res[rank]
+        assert scale == 0.5
+        assert head == ref[:5].tolist()
+        assert abs(total - float(ref.sum())) < 1e-3 * float(ref.sum())
+    assert (res[0][3], res[0][4], res[1][3], res[1][4]) == (0, 129, 129, 257)   # contiguous, disjoint, covering
+
+
+def test_single_process_allreduce_is_identity():
+    from wavenet.train_step import allreduce_gradients, shard_streams
+    g = torch.ones(8)
+    assert allreduce_gradients(g) == 1.0 and float(g.sum()) == 8.0
+    assert shard_streams(256, 3, 8) == (96, 128)
