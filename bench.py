@@ -319,6 +319,13 @@ def main():
         rooflines[name] = {'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
                            'traffic': None, 'share_of_step': kernels[name]['ms_per_step'] /
                            sum(k['ms_per_step'] for k in kernels.values())}
+    # measured DRAM traffic per launch of the dominant kernels (one `ncu --set full` capture, tools/ncu_summary.py traffic)
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath))
+        for name in rooflines:
+            if name in tr and args.batch == B_PER_GPU and args.time == T_WINDOW:
+                rooflines[name]['traffic'] = tr[name]['dram_bytes_per_launch']
     dominant = max(rooflines, key=lambda n: kernels[n]['ms_per_step']) if rooflines else None
     roofline = dict(rooflines[dominant], kernel=dominant, peak_source=peaks['source'] +
                     (' (bf16 dense GEMM; this kernel runs tf32, nominal half rate)'
@@ -329,7 +336,7 @@ def main():
     if not args.no_fastgen:
         gnet = net
         gnet.batch_size = 1
-        n1 = 2000
+        n1 = 16000          # BASELINE config 4: 16,000 samples per stream
         torch.cuda.synchronize()
         gnet.generate(64, [128], seed=0)                         # warm-up
         torch.cuda.synchronize()
@@ -356,8 +363,8 @@ def main():
                    'streams': streams_total, 'streams_per_gpu': per_rank,
                    'b256_samples_per_sec_per_stream': n2 / float(dt),
                    'b256_aggregate_samples_per_sec': streams_total * n2 / float(dt),
-                   'note': 'timed over {} (B=1) / {} (256 streams) samples incl. launch + H2D of the uniforms; '
-                           'per-sample cost is constant so 16000 samples scale linearly'.format(n1, n2)}
+                   'note': 'timed over {} (B=1, latency-mode kernel) / {} (256 streams, throughput-mode kernel) samples '
+                           'incl. launch + H2D of the uniforms'.format(n1, n2)}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

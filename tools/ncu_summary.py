@@ -89,5 +89,38 @@ def full(path):
             print('  %5d %5.1f%%  %-70s <- %s' % (i, 100.0 * data[i][0] / tot, data[i][1].strip()[:70], prev))
 
 
+def traffic(paths):
+    """JSON: kernel tag -> mean (dram__bytes_read + dram__bytes_write) per launch, from `ncu --set full` reports."""
+    import json
+    import re
+    tags = [('block_fwd_umma', 'block_fwd'), ('block_bwd_pre_umma', 'block_bwd_pre'), ('block_bwd_dx_umma', 'block_bwd_dx'),
+            ('block_wgrad_umma', 'block_wgrad'), ('gemm_umma_kernel', 'gemm_umma'), ('generator_lat', 'generator_lat'),
+            ('generator_kernel', 'generator')]
+    acc = {}
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for path in paths:
+        raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik, it = (hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('Kernel Name'),
+                          hdr.index('gpu__time_duration.sum'))
+        for r in rows[2:]:
+            name = r[ik]
+            tag = next((t for k, t in tags if k in name), None)
+            if tag is None:
+                continue
+            b = float(r[ir].replace(',', '')) * scale[units[ir]] + float(r[iw].replace(',', '')) * scale[units[iw]]
+            a = acc.setdefault(tag, {'launches': 0, 'dram_bytes': 0.0, 'us': 0.0})
+            a['launches'] += 1
+            a['dram_bytes'] += b
+            a['us'] += float(r[it].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'usecond': 1.0, 'nsecond': 1e-3, 'msecond': 1e3}.get(units[it], 1.0)
+    out = {k: {'dram_bytes_per_launch': v['dram_bytes'] / v['launches'], 'ncu_us_per_launch': v['us'] / v['launches'],
+               'launches_profiled': v['launches']} for k, v in acc.items()}
+    print(json.dumps(out, indent=1, sort_keys=True))
+
+
 if __name__ == '__main__':
-    (launches if sys.argv[1] == 'launches' else full)(sys.argv[2])
+    if sys.argv[1] == 'traffic':
+        traffic(sys.argv[2:])
+    else:
+        (launches if sys.argv[1] == 'launches' else full)(sys.argv[2])
