@@ -474,15 +474,10 @@ __device__ void sampler_cta(const LatArgs& a, float* sm) {
 #pragma unroll
     for (int w = 1; w < 8; ++w) sum += redd[flip][w];
     flip ^= 1;
-    int tiny = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = tid + j * THREADS;
-      if (i < Q) {
-        const float pv = (float)(e[j] / sum);
-        ps[i] = pv;
-        tiny |= (pv != 0.f && pv < 3.7252903e-09f) ? 1 : 0;
-      }
+      if (i < Q) ps[i] = (float)(e[j] / sum);
     }
     if (g.temperature != 1.0f) {     // generate.py:229-233, float32 log-space
       __syncthreads();
@@ -506,55 +501,51 @@ __device__ void sampler_cta(const LatArgs& a, float* sm) {
       s2 = redf[flip][0];
       for (int w = 1; w < 8; ++w) s2 += redf[flip][w];
       const float lse = m2 + logf(s2);
-      tiny = 0;
-      for (int i = tid; i < Q; i += THREADS) {
-        const float pv = expf(ps[i] - lse);
-        ps[i] = pv;
-        tiny |= (pv != 0.f && pv < 3.7252903e-09f) ? 1 : 0;
-      }
+      for (int i = tid; i < Q; i += THREADS) ps[i] = expf(ps[i] - lse);
     }
-    tiny = __syncthreads_or(tiny);      // also publishes ps[] to warp 0
+    __syncthreads();      // publishes ps[] to warp 0
     if (tid == 0) tl_stamp(a, step, 12);
     if (g.proba_out && step == g.n_steps - 1)
       for (int i = tid; i < Q; i += THREADS) g.proba_out[i] = ps[i];
     if (sampling && warp == 0) {
       // np.random.choice: cdf = cumsum(p) (sequential float64 adds), normalise by the last, searchsorted right.
-      // Every partial sum of float32 values >= 2^-28 (total < 2) is exact in float64, so then any association
-      // gives np.cumsum's bits and a warp scan is used; otherwise lane 0 repeats the sequential sum.
+      // A warp scan computes the same sums in another association: every partial sum differs from np.cumsum's
+      // by < Q * 2^-53 relative (all terms are positive), so  cdf[i] / total <= u  has the same truth value unless
+      // cdf[i] lies within 1e-12 (relative) of u * total.  Only in that case (p ~ 1e-10 per sample) lane 0
+      // repeats the sum sequentially and the exact quotients are compared.
       int cnt = 0;
-      if (!tiny) {
-        double t = 0.0;
-        for (int j = 0; j < per; ++j) {
-          const int i = lane * per + j;
-          t += (i < Q) ? (double)ps[i] : 0.0;
+      double t = 0.0;
+      for (int j = 0; j < per; ++j) {
+        const int i = lane * per + j;
+        t += (i < Q) ? (double)ps[i] : 0.0;
+      }
+      double incl = t;
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const double total = __shfl_sync(0xffffffffu, incl, 31);
+      const double thr = u * total, eps = thr * 1e-12;
+      double run = incl - t;
+      bool ambiguous = false;
+      for (int j = 0; j < per; ++j) {
+        const int i = lane * per + j;
+        if (i < Q) {
+          run += (double)ps[i];
+          const double dlt = run - thr;
+          ambiguous = ambiguous || (fabs(dlt) <= eps);
+          cnt += (dlt < 0.0) ? 1 : 0;
         }
-        double incl = t;
-        for (int o = 1; o < 32; o <<= 1) {
-          const double up = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += up;
-        }
-        const double total = __shfl_sync(0xffffffffu, incl, 31);
-        // cdf[i] / total <= u  is decided by  cdf[i] <= u * total  unless the two are within a few ulps of each
-        // other (then the exact quotient is formed): same result as np.searchsorted on cdf / cdf[-1]
-        const double thr = u * total, eps = thr * 1e-15;
-        double run = incl - t;
-        for (int j = 0; j < per; ++j) {
-          const int i = lane * per + j;
-          if (i < Q) {
-            run += (double)ps[i];
-            const double dlt = run - thr;
-            const bool le = (fabs(dlt) > eps) ? (dlt < 0.0) : (run / total <= u);
-            cnt += le ? 1 : 0;
-          }
-        }
-      } else {
+      }
+      if (__any_sync(0xffffffffu, ambiguous)) {
         if (lane == 0) {
-          double run = 0.0;
-          for (int i = 0; i < Q; ++i) { run += (double)ps[i]; dsm[i] = run; }
+          double r2 = 0.0;
+          for (int i = 0; i < Q; ++i) { r2 += (double)ps[i]; dsm[i] = r2; }
         }
         __syncwarp();
-        const double total = dsm[Q - 1];
-        for (int i = lane; i < Q; i += 32) cnt += (dsm[i] / total <= u) ? 1 : 0;
+        const double tot2 = dsm[Q - 1];
+        cnt = 0;
+        for (int i = lane; i < Q; i += 32) cnt += (dsm[i] / tot2 <= u) ? 1 : 0;
       }
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       if (lane == 0) {
