@@ -191,6 +191,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fastgen', action='store_true')
+    ap.add_argument('--no-batch4', action='store_true')
     ap.add_argument('--batch', type=int, default=B_PER_GPU)
     ap.add_argument('--time', type=int, default=T_WINDOW)
     args = ap.parse_args()
@@ -331,6 +332,32 @@ def main():
                     (' (bf16 dense GEMM; this kernel runs tf32, nominal half rate)'
                      if rooflines[dominant]['bound'] == 'tensor' else '')) if dominant else None
 
+    # ---------------- the same step at B=4 windows per GPU (SURVEY section 8d "also report B=4/GPU") ----------------
+    batch4 = None
+    if not args.no_batch4 and args.batch == B_PER_GPU and args.time == T_WINDOW:
+        try:
+            net4 = wavenet.WaveNetModel(**net_kwargs(4), seed=0)
+            step4 = wavenet.TrainStep(net4, wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9), 4, T)
+            step4.audio.copy_(torch.as_tensor(synthetic_audio(4, T, 100 + rank)))
+            for _ in range(3):
+                step4()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(10):
+                step4()
+            f1.record()
+            barrier()
+            ms4 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(ms4, op=torch.distributed.ReduceOp.MAX)
+            batch4 = {'value': world * 4 * T / (float(ms4) / 10 * 1e-3), 'unit': UNIT, 'ms_per_step': float(ms4) / 10,
+                      'batch_per_gpu': 4}
+            del step4, net4
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001  (an optional extra must not take the headline down)
+            batch4 = {'error': repr(e)[:200]}
+
     # ---------------- fast generation (second half of the BASELINE metric) ----------------
     fastgen = None
     if not args.no_fastgen:
@@ -399,6 +426,7 @@ def main():
             'kernel_timing': prof_mode + ': CUDA events after every launch of one step',
             'cpu_baseline': cpu,
             'fastgen': fastgen,
+            'batch4': batch4,
             'loss': {'after_timed_steps': final_loss, 'e2e_last': loss_host},
         }
         print(json.dumps(line))

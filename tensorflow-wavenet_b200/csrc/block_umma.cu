@@ -207,12 +207,16 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
     TL(0);
     mbar_wait(&bar_tma, par);
     TL(1);
-    if (tid == 0) {   // hi*hi terms: the tensor core reads the upper 19 bits of the raw fp32 tile
-      tc_fence_after();
+    if (tid == 0) {   // hi(x) terms first (the tensor core reads the upper 19 bits of the raw fp32 tile): they run
+      tc_fence_after();   // while the threads split off the lo parts below
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXp + 2 * k, dW0h + 2 * k, ID64, k > 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1h + 2 * k, ID64, 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXp + 2 * k, dW0l + 2 * k, ID64, 1);   // hi(x_past) . lo(W0)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1l + 2 * k, ID64, 1);   // hi(x_cur)  . lo(W1)
     }
     // lo parts of this thread's half rows: x - trunc_tf32(x), same swizzled position; x_cur stays in registers
     float4 xr[4];
@@ -235,11 +239,7 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dL0 + 2 * k, dW0h + 2 * k, ID64, 1);   // lo(x_past) . hi(W0)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXp + 2 * k, dW0l + 2 * k, ID64, 1);   // hi(x_past) . lo(W0)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dL1 + 2 * k, dW1h + 2 * k, ID64, 1);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1l + 2 * k, ID64, 1);
+      for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dL1 + 2 * k, dW1h + 2 * k, ID64, 1);   // lo(x_cur)  . hi(W1)
       mma_commit(&bar_m1);
     }
     const bool valid = (t0 + r) < a.T;
@@ -258,8 +258,7 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
       tmem_ld16(lane_addr + 32, gv);
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        z[j] = tanh_fast(__uint_as_float(fv[j]) + pb_s[16 * half + j]) *
-               sigmoid_fast(__uint_as_float(gv[j]) + pb_s[32 + 16 * half + j]);
+        z[j] = gated_fast(__uint_as_float(fv[j]) + pb_s[16 * half + j], __uint_as_float(gv[j]) + pb_s[32 + 16 * half + j]);
     }
     // z -> Zcat (tf32-rounded: it feeds the single-pass skip GEMM) and the hi/lo A operand of the dense product
 #pragma unroll

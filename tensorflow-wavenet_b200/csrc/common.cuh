@@ -50,6 +50,19 @@ __device__ __forceinline__ float sigmoid_fast(float x) {
 }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, sigmoid_fast(2.0f * x), -1.0f); }
 
+// tanh(f) * sigmoid(g) = (1 - a) / ((1 + a)(1 + b)),  a = e^-2f, b = e^-g : two ex2 and ONE rcp (the SFU is the
+// busiest unit of the block epilogue).  Arguments are clamped so that a, b stay finite (tanh and sigmoid are
+// saturated to fp32 precision long before |f| = 20, |g| = 40).
+__device__ __forceinline__ float gated_fast(float f, float g) {
+  float a, b, r;
+  f = fminf(fmaxf(f, -20.f), 20.f);
+  g = fmaxf(g, -40.f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(-2.8853900817779268f * f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(-1.4426950408889634f * g));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((1.0f + a) * (1.0f + b)));
+  return (1.0f - a) * r;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   int sz = valid ? 16 : 0;

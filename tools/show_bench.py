@@ -9,3 +9,5 @@ if d.get('fastgen'):
     print({k: v for k, v in d['fastgen'].items() if k != 'note'})
 if d.get('cpu_baseline'):
     print('cpu', d['cpu_baseline']['value'])
+if d.get('batch4'):
+    print('batch4', d['batch4'])
