@@ -108,10 +108,13 @@ struct Workspace {
   float* W1R;      // [S, S]
   float* W2R;      // [S, Q]
   unsigned char* Wimg;  // per-layer weight images of the tcgen05 block kernels (C == 32)
+  unsigned char* WimgH; // per-layer fp16 split weight images of the forward block (block_fwd_h.cu)
+  void* XS;             // 2 x [M][hi 32 | lo 32] fp16 split rows: the residual stream between forward layers
   int umma_bwd;    // 1 when the tcgen05 backward path is used
   int64_t bytes;
 };
 
+static bool fwd_h_enabled();
 static void carve(const wn_config* c, int B, int T, bool training, void* base, Workspace* w) {
   const int64_t M = (int64_t)B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
                 S = c->skip_channels, Q = c->quantization_channels;
@@ -138,6 +141,9 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   const bool umma_blocks = (R == 32) && block_umma_enabled();
   w->Wimg = umma_blocks ? (unsigned char*)take(block_images_bytes((int)L)) : nullptr;
   w->umma_bwd = (training && umma_blocks) ? 1 : 0;
+  const bool fwd_h = umma_blocks && fwd_h_enabled();
+  w->WimgH = fwd_h ? (unsigned char*)take(block_h_images_bytes((int)L)) : nullptr;
+  w->XS = fwd_h ? take(2 * M * 128) : nullptr;
   if (training) {
     w->logits = (float*)take(M * Q * f);
     w->G1 = (float*)take(M * S * f);
@@ -152,6 +158,16 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->logits = w->G1 = w->G2 = w->G3 = w->dZcat = w->dX = w->dpre = w->gprebias = w->gtmp = nullptr;
   }
   w->bytes = off;
+}
+
+// forward block implementation: fp16 split rows (default) or the TF32 3-term kernel (WN_BLOCK_FWD=tf32)
+static bool fwd_h_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WN_BLOCK_FWD");
+    v = (e && strcmp(e, "tf32") == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static inline const float* P(const float* base, int64_t off) { return off >= 0 ? base + off : nullptr; }
@@ -207,6 +223,7 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   if (G > 0 && !gc_ids) return -1;
   if (w.Wimg) {   // first, so that at least two launches separate it from the first block kernel (PDL, common.cuh)
     RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
+    if (w.WimgH) RC(block_h_images(w.WimgH, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
     prof_mark(st, PT_MISC);
   }
   RC(cond_bias_fwd(w.prebias, P(params, lo.filter_bias), P(params, lo.gate_bias), P(params, lo.gc_filter),
@@ -215,10 +232,22 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, st));
   prof_mark(st, PT_FRONTEND_FWD);
   const int64_t xs = (int64_t)M * R;
+  if (w.WimgH) {   // residual stream as fp16 split rows between the forward layers
+    RC(split_rows(w.X, w.XS, M, st));
+    prof_mark(st, PT_MISC);
+  }
   for (int l = 0; l < L; ++l) {
     const float* xin = training ? w.X + l * xs : w.X + (l & 1) * xs;
     float* xout = training ? w.X + (l + 1) * xs : w.X + ((l + 1) & 1) * xs;
     const int last = (l == L - 1);
+    if (w.WimgH) {
+      char* xs_in = (char*)w.XS + (int64_t)(l & 1) * M * 128;
+      char* xs_out = (char*)w.XS + (int64_t)((l + 1) & 1) * M * 128;
+      RC(block_fwd_h(xs_in, last ? nullptr : xs_out, last ? nullptr : xout, w.Zcat, ldz, l * D,
+                     w.WimgH + (size_t)l * block_h_img_stride(), w.prebias + (int64_t)l * B * 2 * D,
+                     lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, B, T, c->dilations[l], last, st));
+      continue;
+    }
     RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz,
                  w.Wimg ? w.Wimg + (size_t)l * block_img_stride() : nullptr, params + lo.filter + (int64_t)l * 2 * R * D,
                  params + lo.gate + (int64_t)l * 2 * R * D, params + lo.dense + (int64_t)l * D * R,

@@ -1,0 +1,346 @@
+// Forward gated residual block, second generation: fp16 split-precision operands on tcgen05 kind::f16.
+// Reference: wavenet/model.py:236-330 (_create_dilation_layer), wavenet/ops.py:46-62 (causal_conv).
+//
+// The residual stream travels between layers as "split rows": every 32-channel fp32 row is stored as
+// [hi(32 x fp16) | lo(32 x fp16)] = 128 bytes, hi = fp16(x), lo = fp16(x - hi)  (22 significant bits, the same
+// as the hi/lo TF32 split of block_umma.cu, and the same bytes as the fp32 row).  A split row IS a K-major
+// operand row of 64 fp16: K steps 0,1 are hi, K steps 2,3 are lo.  With weights stored the same way
+// ([hi | lo] per output channel) a full-precision product is six K=16 MMAs per tap
+//        hi.Whi (2)  +  lo.Whi (2)  +  hi.Wlo (2)
+// selected purely by descriptor start addresses -- versus twelve K=8 TF32 MMAs plus a thread pass that splits
+// the fp32 tile in block_umma.cu.  Per 128-step tile: no split pass, half the MMAs, half the shared-memory
+// operand traffic.
+// The kernel also writes the fp32 x' (kept for the backward pass) and z (tf32-rounded, into Zcat).
+// Range: fp16 tops out at 65504; a residual stream that large has diverged anyway (documented in DESIGN.md).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "umma_common.cuh"
+
+namespace wn {
+using namespace umma;
+
+namespace {
+constexpr int C = 32;
+constexpr int TM = 128;
+constexpr uint32_t TILE = TM * 128;                 // [128 rows][64 fp16]
+constexpr uint32_t IMG_H = 8192 + 8192 + 4096;      // W0cat | W1cat | Wdcat
+
+// byte offset of fp16 element (row, k) in a [rows][64 fp16] 128B-swizzled K-major tile
+__device__ __forceinline__ uint32_t swzh(int row, int k) {
+  return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7))) << 4) + ((k & 7) << 1));
+}
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // fp16 x fp16 -> fp32, K-major
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// the six (A k-step, B k-step) pairs of a split-precision product: hi.hi, lo.hi, hi.lo
+__device__ __forceinline__ void mma_split(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool first) {
+  mma_f16_ss(tmem_d, da + 0, db + 0, idesc, first ? 0u : 1u);
+  mma_f16_ss(tmem_d, da + 2, db + 2, idesc, 1u);
+  mma_f16_ss(tmem_d, da + 4, db + 0, idesc, 1u);
+  mma_f16_ss(tmem_d, da + 6, db + 2, idesc, 1u);
+  mma_f16_ss(tmem_d, da + 0, db + 4, idesc, 1u);
+  mma_f16_ss(tmem_d, da + 2, db + 6, idesc, 1u);
+}
+__device__ __forceinline__ void split_h(float x, __half& h, __half& l) {
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+
+static int make_map_split(CUtensorMap* m, const __half* ptr, int64_t B, int64_t T) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {64, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {128, (cuuint64_t)T * 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)TM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+}  // namespace
+
+// ---- weight images: per layer  W0cat [64 n][hi 32 | lo 32] | W1cat | Wdcat [32 n][hi | lo]  (swizzled rows) ----
+__global__ void block_h_images_kernel(unsigned char* __restrict__ img, const float* __restrict__ filter,
+                                      const float* __restrict__ gate, const float* __restrict__ dense) {
+  const int l = blockIdx.x;
+  unsigned char* base = img + (size_t)l * IMG_H;
+  const float* wf = filter + (size_t)l * 2 * C * C;
+  const float* wg = gate + (size_t)l * 2 * C * C;
+  const float* wd = dense + (size_t)l * C * C;
+  for (int i = threadIdx.x; i < 2 * 64 * 32; i += blockDim.x) {      // tap, n (fastest: coalesced), k
+    const int tap = i / (64 * 32), k = (i / 64) % 32, n = i % 64;
+    const float w = n < C ? wf[(tap * C + k) * C + n] : wg[(tap * C + k) * C + (n - C)];
+    __half h, lo;
+    split_h(w, h, lo);
+    unsigned char* t = base + tap * 8192;
+    *reinterpret_cast<__half*>(t + swzh(n, k)) = h;
+    *reinterpret_cast<__half*>(t + swzh(n, 32 + k)) = lo;
+  }
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {          // n = residual channel r, k = dilation channel d
+    const int k = i / 32, n = i % 32;
+    __half h, lo;
+    split_h(wd[k * C + n], h, lo);
+    unsigned char* t = base + 16384;
+    *reinterpret_cast<__half*>(t + swzh(n, k)) = h;
+    *reinterpret_cast<__half*>(t + swzh(n, 32 + k)) = lo;
+  }
+}
+
+int64_t block_h_images_bytes(int L) { return (int64_t)L * IMG_H; }
+uint32_t block_h_img_stride() { return IMG_H; }
+int block_h_images(unsigned char* img, const float* filter, const float* gate, const float* dense, int L, cudaStream_t st) {
+  block_h_images_kernel<<<L, 256, 0, st>>>(img, filter, gate, dense);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+// fp32 rows [M][32] -> split rows [M][hi 32 | lo 32]   (input of the first layer)
+__global__ void split_rows_kernel(const float* __restrict__ x, __half* __restrict__ xs, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int64_t m = i >> 3;
+    const int c4 = (int)(i & 7) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    __half h[4], l[4];
+    split_h(v.x, h[0], l[0]); split_h(v.y, h[1], l[1]); split_h(v.z, h[2], l[2]); split_h(v.w, h[3], l[3]);
+    __half* row = xs + m * 64;
+    *reinterpret_cast<uint2*>(row + c4) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(row + 32 + c4) = *reinterpret_cast<uint2*>(l);
+  }
+}
+int split_rows(const float* x, void* xs, int64_t M, cudaStream_t st) {
+  const int64_t n4 = M * 8;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  split_rows_kernel<<<(int)blocks, 256, 0, st>>>(x, (__half*)xs, n4);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+struct FwdHArgs {
+  const unsigned char* img;        // IMG_H bytes
+  const float *prebias, *dense_bias;
+  int B, T, d, is_last, zcol;      // zcol: first column of this layer inside Zcat
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// All three outputs of a tile (z -> Zcat column block, fp32 x', split x') leave through TMA stores from swizzled
+// staging tiles: measured, per-thread 16-byte global stores (32 lines per warp instruction) cost 12 of the 22 us.
+__global__ void __launch_bounds__(256, 2)
+block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
+                   const __grid_constant__ CUtensorMap mapXo, const __grid_constant__ CUtensorMap mapXs, FwdHArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* Xc = smem;                 // split rows x[t]
+  unsigned char* Xp = smem + TILE;          // split rows x[t-d]
+  unsigned char* Zs = smem + 2 * TILE;      // split rows z (A operand of the dense product), later split rows of x'
+  unsigned char* St = smem + 3 * TILE;      // fp32 staging: z (-> Zcat), later x'
+  unsigned char* W0 = smem + 4 * TILE;      // [64][hi|lo] past tap (filter | gate)
+  unsigned char* W1 = W0 + 8192;            // current tap
+  unsigned char* Wd = W1 + 8192;            // [32][hi|lo] dense^T
+  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_m2, bar_w;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float pb_s[64];
+  __shared__ float bd_s[32];
+
+  // thread (r, half): time step t0 + r, channels [16*half, 16*half + 16)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid & 127, half = tid >> 7;
+  if (tid == 0) {
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_m1, 1);
+    mbar_init(&bar_m2, 1);
+    mbar_init(&bar_w, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 128);
+  if (tid < 32) bd_s[tid] = a.dense_bias ? a.dense_bias[tid] : 0.f;
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_w, IMG_H);
+    bulk_g2s(W0, a.img, IMG_H, &bar_w);
+  }
+  const int n_tt = (a.T + TM - 1) / TM;
+  const int n_tiles = a.B * n_tt;
+  auto issue_loads = [&](int tile) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    mbar_expect_tx(&bar_tma, 2 * TILE);
+    tma_load_3d(Xc, &mapX, &bar_tma, 0, t0, b);
+    tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);       // rows before the start of the window arrive as zeros
+  };
+  pdl_wait();      // the previous layer's output is complete and visible from here on
+  pdl_trigger();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+  mbar_wait(&bar_w, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
+  constexpr uint32_t ID64 = idesc_f16(128, 64), ID32 = idesc_f16(128, 32);
+  const uint64_t dXc = kmajor_desc(smem_u32(Xc)), dXp = kmajor_desc(smem_u32(Xp)), dZs = kmajor_desc(smem_u32(Zs));
+  const uint64_t dW0 = kmajor_desc(smem_u32(W0)), dW1 = kmajor_desc(smem_u32(W1)), dWd = kmajor_desc(smem_u32(Wd));
+  // this thread's four 16-byte chunks of a split row: hi channels [16 half, +16) and the matching lo channels
+  const uint32_t row_off = (uint32_t)r * 128;
+  const uint32_t ch0 = (uint32_t)((2 * half) ^ (r & 7)) << 4, ch1 = (uint32_t)((2 * half + 1) ^ (r & 7)) << 4;
+  const uint32_t cl0 = (uint32_t)((4 + 2 * half) ^ (r & 7)) << 4, cl1 = (uint32_t)((5 + 2 * half) ^ (r & 7)) << 4;
+
+  int it = 0, pb_batch = -1;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    const uint32_t par = it & 1;
+    if (b != pb_batch) {   // block-uniform: conditioning + bias row of this batch element
+      __syncthreads();
+      if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
+      pb_batch = b;
+    }
+    mbar_wait(&bar_tma, par);
+    if (tid == 0) {
+      tc_fence_after();
+      mma_split(tmem, dXp, dW0, ID64, true);      // x[t-d] . W[0]
+      mma_split(tmem, dXc, dW1, ID64, false);     // x[t]   . W[1]
+      bulk_wait_read0();                          // the previous tile's output stores have left St / Zs
+      mma_commit(&bar_m1);
+    }
+    // this thread's part of x[t] (for the residual sum), reassembled from its split row while the MMAs run
+    float xo[16];
+    {
+      const uint4 h0 = *reinterpret_cast<const uint4*>(Xc + row_off + ch0), h1 = *reinterpret_cast<const uint4*>(Xc + row_off + ch1);
+      const uint4 l0 = *reinterpret_cast<const uint4*>(Xc + row_off + cl0), l1 = *reinterpret_cast<const uint4*>(Xc + row_off + cl1);
+      const __half2* hh0 = reinterpret_cast<const __half2*>(&h0);
+      const __half2* hh1 = reinterpret_cast<const __half2*>(&h1);
+      const __half2* ll0 = reinterpret_cast<const __half2*>(&l0);
+      const __half2* ll1 = reinterpret_cast<const __half2*>(&l1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a0 = __half22float2(hh0[j]), b0 = __half22float2(ll0[j]);
+        const float2 a1 = __half22float2(hh1[j]), b1 = __half22float2(ll1[j]);
+        xo[2 * j] = a0.x + b0.x; xo[2 * j + 1] = a0.y + b0.y;
+        xo[8 + 2 * j] = a1.x + b1.x; xo[8 + 2 * j + 1] = a1.y + b1.y;
+      }
+    }
+    mbar_wait(&bar_m1, par);
+    tc_fence_after();
+    float z[16];
+    {
+      uint32_t fv[16], gv[16];
+      tmem_ld16(lane_addr + 0, fv);
+      tmem_ld16(lane_addr + 32, gv);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        z[j] = gated_fast(__uint_as_float(fv[j]) + pb_s[16 * half + j], __uint_as_float(gv[j]) + pb_s[32 + 16 * half + j]);
+    }
+    // z -> staging (tf32-rounded: it feeds the single-pass skip GEMM) and, split, the A operand of the dense product
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      *reinterpret_cast<float4*>(St + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4)) =
+          make_float4(round_tf32(z[4 * jj]), round_tf32(z[4 * jj + 1]), round_tf32(z[4 * jj + 2]), round_tf32(z[4 * jj + 3]));
+    if (!a.is_last) {
+      __half zh[16], zl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) split_h(z[j], zh[j], zl[j]);
+      *reinterpret_cast<uint4*>(Zs + row_off + ch0) = *reinterpret_cast<const uint4*>(zh);
+      *reinterpret_cast<uint4*>(Zs + row_off + ch1) = *reinterpret_cast<const uint4*>(zh + 8);
+      *reinterpret_cast<uint4*>(Zs + row_off + cl0) = *reinterpret_cast<const uint4*>(zl);
+      *reinterpret_cast<uint4*>(Zs + row_off + cl1) = *reinterpret_cast<const uint4*>(zl + 8);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();      // every thread has read its x row and written its z row
+    if (tid == 0) {
+      tma_store_3d(&mapZ, St, a.zcol, t0, b);      // rows past the end of the window are clipped by the tensor map
+      bulk_commit();
+      if (tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);     // both input tiles are free
+      if (!a.is_last) {
+        tc_fence_after();
+        mma_split(tmem + 64, dZs, dWd, ID32, true);      // z . Wd
+        bulk_wait_read0();                               // the z store has left St before x' is staged there
+        mma_commit(&bar_m2);
+      }
+    }
+    if (!a.is_last) {
+      mbar_wait(&bar_m2, par);
+      tc_fence_after();
+      uint32_t ov[16];
+      tmem_ld16(lane_addr + 64, ov);
+      float xn[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) xn[j] = xo[j] + __uint_as_float(ov[j]) + bd_s[16 * half + j];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        *reinterpret_cast<float4*>(St + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4)) =
+            make_float4(xn[4 * jj], xn[4 * jj + 1], xn[4 * jj + 2], xn[4 * jj + 3]);
+      __half xh[16], xl[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) split_h(xn[j], xh[j], xl[j]);
+      *reinterpret_cast<uint4*>(Zs + row_off + ch0) = *reinterpret_cast<const uint4*>(xh);
+      *reinterpret_cast<uint4*>(Zs + row_off + ch1) = *reinterpret_cast<const uint4*>(xh + 8);
+      *reinterpret_cast<uint4*>(Zs + row_off + cl0) = *reinterpret_cast<const uint4*>(xl);
+      *reinterpret_cast<uint4*>(Zs + row_off + cl1) = *reinterpret_cast<const uint4*>(xl + 8);
+      fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();   // staging tiles complete; the TMEM columns are free for the next tile
+    if (tid == 0 && !a.is_last) {
+      tma_store_3d(&mapXo, St, 0, t0, b);      // fp32 x' (kept for the backward pass)
+      tma_store_3d(&mapXs, Zs, 0, t0, b);      // split x' (next layer's operand rows)
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait0();      // every output store has landed before the grid counts as complete
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int ldz, int zcol, const unsigned char* img,
+                const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st) {
+  CUtensorMap mapX, mapZ, mapXo, mapXs;
+  int rc = make_map_split(&mapX, (const __half*)xs_in, B, T);
+  if (rc) return rc;
+  rc = make_map_3d(&mapZ, zcat, B, T, ldz, ldz, TM);
+  if (rc) return rc;
+  mapXo = mapZ;
+  mapXs = mapX;
+  if (!is_last) {
+    rc = make_map_3d(&mapXo, xout, B, T, C, C, TM);
+    if (rc) return rc;
+    rc = make_map_split(&mapXs, (const __half*)xs_out, B, T);
+    if (rc) return rc;
+  }
+  FwdHArgs a;
+  a.img = img; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
+  a.zcol = zcol;
+  const size_t smem = 1024 + 4 * TILE + IMG_H;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(block_fwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  const int n_tiles = B * ((T + TM - 1) / TM);
+  int grid = n_tiles;
+  const int cap = 2 * sm_count();
+  if (grid > cap) grid = cap;
+  cudaError_t e = launch_pdl(block_fwd_h_kernel, dim3(grid), dim3(256), smem, st, mapX, mapZ, mapXo, mapXs, a);
+  if (e != cudaSuccess) return (int)e;
+  prof_mark(st, PT_BLOCK_FWD);
+  return 0;
+}
+
+}  // namespace wn

@@ -54,6 +54,13 @@ int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const 
                      int is_last, cudaStream_t st);
 int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsigned char* img_dx, int B, int T, int d,
                       int is_last, cudaStream_t st);
+// second-generation forward block (block_fwd_h.cu): fp16 split rows [hi 32 | lo 32] between layers
+int64_t block_h_images_bytes(int L);
+uint32_t block_h_img_stride();
+int block_h_images(unsigned char* img, const float* filter, const float* gate, const float* dense, int L, cudaStream_t st);
+int split_rows(const float* x, void* xs, int64_t M, cudaStream_t st);
+int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int ldz, int zcol, const unsigned char* img,
+                const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
 int64_t block_images_bytes(int L);
 uint32_t block_img_off_pre();
 uint32_t block_img_off_dx();
