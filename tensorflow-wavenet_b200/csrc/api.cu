@@ -115,6 +115,12 @@ struct Workspace {
 };
 
 static bool fwd_h_enabled();
+// WN_NO_SIDE=1 keeps every kernel of the step on the caller's stream (debugging aid)
+static bool no_side_streams() {
+  static int v = -1;
+  if (v < 0) v = getenv("WN_NO_SIDE") ? 1 : 0;
+  return v == 1;
+}
 static void carve(const wn_config* c, int B, int T, bool training, void* base, Workspace* w) {
   const int64_t M = (int64_t)B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
                 S = c->skip_channels, Q = c->quantization_channels;
@@ -517,7 +523,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     RC((int)cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) RC((int)cudaEventCreateWithFlags(&ev_g[i], cudaEventDisableTiming));
   }
-  cudaStream_t s2 = g_prof_on ? st : side2;   // (per-kernel profiling keeps everything on one stream)
+  cudaStream_t s2 = (g_prof_on || no_side_streams()) ? st : side2;   // (per-kernel profiling keeps everything on one stream)
   const float* x2 = rp ? w.T2 : w.A2;   // input of postprocess2
   RC((int)cudaEventRecord(ev_g[0], st));
   RC((int)cudaStreamWaitEvent(s2, ev_g[0], 0));
@@ -589,7 +595,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       for (int i = 0; i < 3; ++i) RC((int)cudaEventCreateWithFlags(&ev_wg[i], cudaEventDisableTiming));
     }
     // (per-kernel profiling serialises everything on one stream so that event deltas are kernel times)
-    cudaStream_t ws = g_prof_on ? st : side;
+    cudaStream_t ws = (g_prof_on || no_side_streams()) ? st : side;
     for (int l = L - 1; l >= 0; --l) {
       const int last = (l == L - 1);
       const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();

@@ -495,21 +495,24 @@ struct DxArgs {
 };
 
 __global__ void __launch_bounds__(256, 2)
-block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
+block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapDn,
+                         const __grid_constant__ CUtensorMap mapDx, DxArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* P0f = smem;
   unsigned char* P0g = smem + TILE;
   unsigned char* P1f = smem + 2 * TILE;
   unsigned char* P1g = smem + 3 * TILE;
-  unsigned char* Wb = smem + 4 * TILE;     // Bcf Bcg Bpf Bpg
-  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_w;
+  unsigned char* St = smem + 4 * TILE;     // dx' tile on the way in, dx tile on the way out (TMA both ways)
+  unsigned char* Wb = smem + 5 * TILE;     // Bcf Bcg Bpf Bpg
+  __shared__ __align__(8) uint64_t bar_tma, bar_n, bar_m1, bar_w;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;   // thread = (time step, 16-channel half)
   if (tid == 0) {
     mbar_init(&bar_tma, 1);
+    mbar_init(&bar_n, 1);
     mbar_init(&bar_m1, 1);
     mbar_init(&bar_w, 1);
     mbar_fence_init();
@@ -518,6 +521,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
   __syncthreads();
   const int n_tt = (a.T + TM - 1) / TM;
   const int n_tiles = a.B * n_tt;
+  const bool have_dxn = a.dxn != nullptr;
   auto issue_loads = [&](int tile) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
     mbar_expect_tx(&bar_tma, 4 * TILE);
@@ -526,13 +530,21 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
     tma_load_3d(P1f, &mapP, &bar_tma, 0, t0 + a.d, b);     // rows with t + d >= T arrive as zeros
     tma_load_3d(P1g, &mapP, &bar_tma, 32, t0 + a.d, b);
   };
+  auto issue_dxn = [&](int tile) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    mbar_expect_tx(&bar_n, TILE);
+    tma_load_3d(St, &mapDn, &bar_n, 0, t0, b);
+  };
   if (tid == 0) {
     mbar_expect_tx(&bar_w, IMG_DX);
     bulk_g2s(Wb, a.img, IMG_DX, &bar_w);
   }
   pdl_wait();
   pdl_trigger();
-  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    issue_loads(blockIdx.x);
+    if (have_dxn) issue_dxn(blockIdx.x);
+  }
   mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();
@@ -540,6 +552,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
   constexpr uint32_t ID32 = idesc_tf32(128, 32);
+  const uint32_t row_off = (uint32_t)r * 128;
   int it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
@@ -553,31 +566,45 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, DxArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dp + 2 * k, db + 2 * k, ID32, (q | k) > 0);
       }
+      // the previous tile's output store has left the staging tile before anybody (who waits for bar_m1) rewrites it
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       mma_commit(&bar_m1);
     }
-    const bool valid = (t0 + r) < a.T;
-    const size_t m = (size_t)b * a.T + t0 + r;
     float4 xn[4];
+    if (have_dxn) {
+      mbar_wait(&bar_n, par);
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      xn[jj] = (a.dxn && valid) ? __ldg(reinterpret_cast<const float4*>(a.dxn + m * C + 16 * half) + jj)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int jj = 0; jj < 4; ++jj)
+        xn[jj] = *reinterpret_cast<const float4*>(St + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4));
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) xn[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     mbar_wait(&bar_m1, par);
     tc_fence_after();
     if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
     uint32_t ov[16];
     tmem_ld16(lane_addr, ov);
-    if (valid) {
+    // each thread overwrites exactly the staging chunks it read its dx' values from
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const float4 o = make_float4(xn[jj].x + __uint_as_float(ov[4 * jj]), xn[jj].y + __uint_as_float(ov[4 * jj + 1]),
-                                     xn[jj].z + __uint_as_float(ov[4 * jj + 2]), xn[jj].w + __uint_as_float(ov[4 * jj + 3]));
-        *reinterpret_cast<float4*>(a.dx + m * C + 16 * half + 4 * jj) = o;
-      }
-    }
+    for (int jj = 0; jj < 4; ++jj)
+      *reinterpret_cast<float4*>(St + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4)) =
+          make_float4(xn[jj].x + __uint_as_float(ov[4 * jj]), xn[jj].y + __uint_as_float(ov[4 * jj + 1]),
+                      xn[jj].z + __uint_as_float(ov[4 * jj + 2]), xn[jj].w + __uint_as_float(ov[4 * jj + 3]));
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                   ::"l"(&mapDx), "r"(smem_u32(St)), "r"(0), "r"(t0), "r"(b) : "memory");   // clipped at the window end
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (tile + (int)gridDim.x < n_tiles && have_dxn) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store has left the staging tile
+        issue_dxn(tile + gridDim.x);
+      }
+    }
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (warp == 0) tmem_dealloc(tmem, 32);
 }
 
@@ -772,15 +799,22 @@ int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsi
   int grid = n_tiles;
   const int cap = 2 * sm_count();
   if (grid > cap) grid = cap;
-  CUtensorMap mP;
+  CUtensorMap mP, mDn, mDx;
   int rc = make_map_3d(&mP, dpre, B, T, 64, 64, TM);
   if (rc) return rc;
+  rc = make_map_3d(&mDx, dx, B, T, C, C, TM);
+  if (rc) return rc;
+  mDn = mDx;
+  if (!is_last) {
+    rc = make_map_3d(&mDn, dxn, B, T, C, C, TM);
+    if (rc) return rc;
+  }
   DxArgs a;
   a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.img = img_dx; a.B = B; a.T = T; a.d = d;
-  const size_t smem = 1024 + 4 * TILE + IMG_DX;
+  const size_t smem = 1024 + 5 * TILE + IMG_DX;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  cudaError_t e = launch_pdl(block_bwd_dx_umma_kernel, dim3(grid), dim3(256), smem, st, mP, a);
+  cudaError_t e = launch_pdl(block_bwd_dx_umma_kernel, dim3(grid), dim3(256), smem, st, mP, mDn, mDx, a);
   if (e != cudaSuccess) return (int)e;
   prof_mark(st, PT_BLOCK_BWD_DX);
   return 0;
