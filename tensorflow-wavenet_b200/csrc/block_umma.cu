@@ -362,24 +362,25 @@ struct PreArgs {
 
 __global__ void __launch_bounds__(256, 2)
 block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDn,
-                          const __grid_constant__ CUtensorMap mapDz, PreArgs a) {
+                          const __grid_constant__ CUtensorMap mapDz, const __grid_constant__ CUtensorMap mapDp, PreArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* Xc = smem;
   unsigned char* Xp = smem + TILE;
-  unsigned char* Dn = smem + 2 * TILE;
-  unsigned char* Dz = smem + 3 * TILE;
+  unsigned char* Dn = smem + 2 * TILE;     // dx' tile (A operand of dx'.Wd^T); later staging of dg
+  unsigned char* Dz = smem + 3 * TILE;     // skip-path gradient tile (read by the threads); later staging of df
   unsigned char* W0 = smem + 4 * TILE;
   unsigned char* W1 = W0 + 8192;
   unsigned char* Wd = W1 + 8192;
-  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_w;
+  __shared__ __align__(8) uint64_t bar_x, bar_d, bar_m1, bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float pb_s[64];
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;   // thread = (time step, 16-channel half), see block_fwd_umma_kernel
   if (tid == 0) {
-    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_x, 1);
+    mbar_init(&bar_d, 1);
     mbar_init(&bar_m1, 1);
     mbar_init(&bar_w, 1);
     mbar_fence_init();
@@ -388,14 +389,19 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
   __syncthreads();
   const int n_tt = (a.T + TM - 1) / TM;
   const int n_tiles = a.B * n_tt;
-  const uint32_t tile_bytes = (a.is_last ? 3 : 4) * TILE;
-  auto issue_loads = [&](int tile) {
+  // Two groups of input tiles: x tiles are consumed by the MMAs only and are prefetched as soon as those are
+  // done; the Dn / Dz tiles double as the staging tiles of the dpre output (TMA store) and are reloaded late.
+  auto issue_x = [&](int tile) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
-    mbar_expect_tx(&bar_tma, tile_bytes);
-    tma_load_3d(Xc, &mapX, &bar_tma, 0, t0, b);
-    tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);
-    tma_load_3d(Dz, &mapDz, &bar_tma, a.zcol, t0, b);
-    if (!a.is_last) tma_load_3d(Dn, &mapDn, &bar_tma, 0, t0, b);
+    mbar_expect_tx(&bar_x, 2 * TILE);
+    tma_load_3d(Xc, &mapX, &bar_x, 0, t0, b);
+    tma_load_3d(Xp, &mapX, &bar_x, 0, t0 - a.d, b);
+  };
+  auto issue_d = [&](int tile) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
+    mbar_expect_tx(&bar_d, (a.is_last ? 1 : 2) * TILE);
+    tma_load_3d(Dz, &mapDz, &bar_d, a.zcol, t0, b);
+    if (!a.is_last) tma_load_3d(Dn, &mapDn, &bar_d, 0, t0, b);
   };
   if (tid == 0) {
     mbar_expect_tx(&bar_w, IMG_PRE);
@@ -403,7 +409,10 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
   }
   pdl_wait();
   pdl_trigger();
-  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    issue_x(blockIdx.x);
+    issue_d(blockIdx.x);
+  }
   mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();
@@ -413,6 +422,7 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
   constexpr uint32_t ID64 = idesc_tf32(128, 64), ID32 = idesc_tf32(128, 32);
   const uint64_t dXc = kmajor_desc(smem_u32(Xc)), dXp = kmajor_desc(smem_u32(Xp)), dDn = kmajor_desc(smem_u32(Dn));
   const uint64_t dW0 = kmajor_desc(smem_u32(W0)), dW1 = kmajor_desc(smem_u32(W1)), dWd = kmajor_desc(smem_u32(Wd));
+  const uint32_t row_off = (uint32_t)r * 128;
 
   int it = 0, pb_batch = -1;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -423,14 +433,18 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
       if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
       pb_batch = b;
     }
-    mbar_wait(&bar_tma, par);
+    mbar_wait(&bar_x, par);
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXp + 2 * k, dW0 + 2 * k, ID64, k > 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, dXc + 2 * k, dW1 + 2 * k, ID64, 1);
+    }
+    mbar_wait(&bar_d, par);
+    if (tid == 0) {
       if (!a.is_last) {
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem + 64, dDn + 2 * k, dWd + 2 * k, ID32, k > 0);   // dx' . Wd^T
       }
@@ -440,18 +454,14 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     float dz[16];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      const int j = 4 * half + jj;
-      const uint32_t off = (uint32_t)r * 128 + ((uint32_t)(j ^ (r & 7)) << 4);
-      const float4 v = *reinterpret_cast<const float4*>(Dz + off);
+      const float4 v = *reinterpret_cast<const float4*>(Dz + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4));
       dz[4 * jj] = v.x; dz[4 * jj + 1] = v.y; dz[4 * jj + 2] = v.z; dz[4 * jj + 3] = v.w;
     }
     mbar_wait(&bar_m1, par);
     tc_fence_after();
-    __syncthreads();   // every thread has read its Dz row and the MMAs are done: the tiles are free
-    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_x(tile + gridDim.x);     // x tiles: only the MMAs read them
 
     const bool valid = (t0 + r) < a.T;
-    const size_t m = (size_t)b * a.T + t0 + r;
     if (!a.is_last) {
       uint32_t av[16];
       tmem_ld16(lane_addr + 64, av);
@@ -470,17 +480,30 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
       df[j] = round_tf32(dzv * sg * (1.f - tf * tf));
       dg[j] = round_tf32(dzv * tf * sg * (1.f - sg));
     }
-    if (valid) {
-      float* row = a.dpre + m * 64 + 16 * half;
+    // dpre = [df | dg] leaves through two TMA stores: df is staged in the Dz tile (each thread overwrites exactly
+    // the chunks it read), dg in the Dn tile (read by the finished MMAs only)
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        *reinterpret_cast<float4*>(row + 4 * jj) = make_float4(df[4 * jj], df[4 * jj + 1], df[4 * jj + 2], df[4 * jj + 3]);
-        *reinterpret_cast<float4*>(row + 32 + 4 * jj) = make_float4(dg[4 * jj], dg[4 * jj + 1], dg[4 * jj + 2], dg[4 * jj + 3]);
-      }
+    for (int jj = 0; jj < 4; ++jj) {
+      const uint32_t off = row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4);
+      *reinterpret_cast<float4*>(Dz + off) = make_float4(df[4 * jj], df[4 * jj + 1], df[4 * jj + 2], df[4 * jj + 3]);
+      *reinterpret_cast<float4*>(Dn + off) = make_float4(dg[4 * jj], dg[4 * jj + 1], dg[4 * jj + 2], dg[4 * jj + 3]);
     }
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                   ::"l"(&mapDp), "r"(smem_u32(Dz)), "r"(0), "r"(t0), "r"(b) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                   ::"l"(&mapDp), "r"(smem_u32(Dn)), "r"(32), "r"(t0), "r"(b) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (tile + (int)gridDim.x < n_tiles) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stores have left the two tiles
+        issue_d(tile + gridDim.x);
+      }
+    }
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
@@ -753,13 +776,16 @@ int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int
   if (rc) return rc;
   rc = make_map_3d(&mDz, dZcat, B, T, ldz, ldz, TM);
   if (rc) return rc;
+  CUtensorMap mDp;
+  rc = make_map_3d(&mDp, dpre, B, T, 64, 64, TM);
+  if (rc) return rc;
   PreArgs a;
   a.dpre = dpre; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
   a.is_last = is_last; a.zcol = zcol;
   const size_t smem = 1024 + 4 * TILE + IMG_PRE;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_bwd_pre_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, a);
+  cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, mDp, a);
   if (e != cudaSuccess) return (int)e;
   prof_mark(st, PT_BLOCK_BWD_PRE);
   return 0;
