@@ -42,12 +42,17 @@ void prof_mark(cudaStream_t st, int tag) {
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline bool fused_blocks(const wn_config* c) {
+  return c->residual_channels == c->dilation_channels && (c->residual_channels == 16 || c->residual_channels == 32);
+}
 
 static int check_cfg(const wn_config* c) {
   if (!c) return -1;
   if (c->n_layers < 1 || c->n_layers > WN_MAX_LAYERS) return -1;
-  if (c->residual_channels != c->dilation_channels) return -2;
-  if (c->residual_channels != 16 && c->residual_channels != 32) return -2;
+  // R = D in {16, 32}: fused block kernels; any other widths (multiples of 4): GEMM-built blocks (block_generic.cu)
+  if (c->residual_channels < 4 || (c->residual_channels & 3) || c->residual_channels > 256 ||
+      (256 % c->residual_channels)) return -2;
+  if (c->dilation_channels < 4 || (c->dilation_channels & 3) || c->dilation_channels > 1024) return -2;
   if (c->skip_channels < 4 || (c->skip_channels & 3)) return -2;
   if (c->quantization_channels < 4 || (c->quantization_channels & 3) || c->quantization_channels > 1024) return -2;
   if (c->gc_channels < 0 || c->gc_channels > 1024) return -2;
@@ -111,6 +116,8 @@ struct Workspace {
   unsigned char* WimgH; // per-layer fp16 split weight images of the forward block (block_fwd_h.cu)
   void* XS;             // 2 x [M][hi 32 | lo 32] fp16 split rows: the residual stream between forward layers
   int umma_bwd;    // 1 when the tcgen05 backward path is used
+  float* Pall;     // generic-width blocks: saved pre-activations [L or 1][M][2D]
+  float* gscratch; // generic-width blocks: operand splits / temporaries (generic_scratch_floats)
   int64_t bytes;
 };
 
@@ -144,7 +151,13 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->WskipR = (float*)take(S * L * D * f);
   w->W1R = (float*)take(S * S * f);
   w->W2R = (float*)take(Q * S * f);
-  const bool umma_blocks = (R == 32) && block_umma_enabled();
+  const bool umma_blocks = fused_blocks(c) && (R == 32) && block_umma_enabled();
+  if (!fused_blocks(c)) {
+    w->Pall = (float*)take((training ? L : 1) * M * 2 * D * f);
+    w->gscratch = (float*)take(generic_scratch_floats(M, (int)R, (int)D) * f);
+  } else {
+    w->Pall = w->gscratch = nullptr;
+  }
   w->Wimg = umma_blocks ? (unsigned char*)take(block_images_bytes((int)L)) : nullptr;
   w->umma_bwd = (training && umma_blocks) ? 1 : 0;
   const bool fwd_h = umma_blocks && fwd_h_enabled();
@@ -207,7 +220,9 @@ static bool use_mma_gemm() {
   }
   return g_gemm_impl == 1;
 }
-static int gemm(int mode, GemmParams p, int split_k, cudaStream_t st) {
+int gemm_dispatch(int mode, GemmParams p, int split_k, cudaStream_t st);
+static int gemm(int mode, GemmParams p, int split_k, cudaStream_t st) { return gemm_dispatch(mode, p, split_k, st); }
+int gemm_dispatch(int mode, GemmParams p, int split_k, cudaStream_t st) {
   if (mode == 2) p.flags |= GEMM_ATOMIC;
   if (!use_mma_gemm() && gemm_umma_supported(mode, p)) return gemm_umma(mode, p, nullptr, 0, split_k, st);
   return gemm_tf32(mode, p, split_k, st);
@@ -252,6 +267,14 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
       RC(block_fwd_h(xs_in, last ? nullptr : xs_out, last ? nullptr : xout, w.Zcat, ldz, l * D,
                      w.WimgH + (size_t)l * block_h_img_stride(), w.prebias + (int64_t)l * B * 2 * D,
                      lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, B, T, c->dilations[l], last, st));
+      continue;
+    }
+    if (w.gscratch) {
+      RC(generic_block_fwd(xin, last ? nullptr : xout, w.Zcat, ldz, l * D, w.Pall + (training ? (int64_t)l * M * 2 * D : 0),
+                           params + lo.filter + (int64_t)l * 2 * R * D, params + lo.gate + (int64_t)l * 2 * R * D,
+                           params + lo.dense + (int64_t)l * D * R, w.prebias + (int64_t)l * B * 2 * D,
+                           lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, w.gscratch, B, T,
+                           c->dilations[l], R, D, last, st));
       continue;
     }
     RC(block_fwd(xin, last ? nullptr : xout, w.Zcat + (int64_t)l * D, ldz,
@@ -617,6 +640,22 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
     // join: the bias / conditioning gradients below read what the weight-gradient kernels accumulated
     for (int i = 0; i < 3 && i < L; ++i) RC((int)cudaStreamWaitEvent(st, ev_wg[i], 0));
+  } else if (w.gscratch) {
+    float* bufs[2] = {w.dX, w.dX + xs};
+    int cur_i = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      const int last = (l == L - 1);
+      float* dnext = bufs[cur_i ^ 1];
+      RC(generic_block_bwd(w.X + l * xs, last ? nullptr : dcur, w.dZcat, w.Zcat, ldz, l * D, w.Pall + (int64_t)l * M * 2 * D,
+                           dnext, w.dpre, params + lo.filter + (int64_t)l * 2 * R * D, params + lo.gate + (int64_t)l * 2 * R * D,
+                           params + lo.dense + (int64_t)l * D * R, grads + lo.filter + (int64_t)l * 2 * R * D,
+                           grads + lo.gate + (int64_t)l * 2 * R * D, grads + lo.dense + (int64_t)l * D * R,
+                           w.gprebias + (int64_t)l * B * 2 * D,
+                           lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, w.gscratch, B, T,
+                           cfg->dilations[l], R, D, last, st));
+      dcur = dnext;
+      cur_i ^= 1;
+    }
   } else {
     float* bufs[2] = {w.dX, w.dX + xs};
     int cur_i = 0;

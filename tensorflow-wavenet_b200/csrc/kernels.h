@@ -54,6 +54,17 @@ int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const 
                      int is_last, cudaStream_t st);
 int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsigned char* img_dx, int B, int T, int d,
                       int is_last, cudaStream_t st);
+// tcgen05 GEMM when the shape allows, mma.sync otherwise (api.cu); mode as gemm_umma
+int gemm_dispatch(int mode, GemmParams p, int split_k, cudaStream_t st);
+// blocks of arbitrary channel widths built from GEMMs (block_generic.cu)
+int64_t generic_scratch_floats(int64_t M, int R, int D);
+int generic_block_fwd(const float* x, float* xout, float* zcat, int ldz, int zcol, float* P, const float* wf,
+                      const float* wg, const float* dense, const float* prebias, const float* dense_bias,
+                      float* scratch, int B, int T, int d, int R, int D, int is_last, cudaStream_t st);
+int generic_block_bwd(const float* x, const float* dxn, const float* dZcat, const float* zcat, int ldz, int zcol,
+                      const float* P, float* dx, float* dpre, const float* wf, const float* wg, const float* dense,
+                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, float* scratch,
+                      int B, int T, int d, int R, int D, int is_last, cudaStream_t st);
 // second-generation forward block (block_fwd_h.cu): fp16 split rows [hi 32 | lo 32] between layers
 int64_t block_h_images_bytes(int L);
 uint32_t block_h_img_stride();

@@ -149,7 +149,7 @@ def param_layout(cfg):
     rc = load().wn_param_layout(C.byref(cfg), C.byref(lo))
     if rc != 0:
         raise NotImplementedError(
-            'no sm_100a kernel for this configuration (rc={}): this build needs '
-            'residual_channels == dilation_channels in {{16, 32}}, skip/quantization channels '
-            'multiples of 4 and quantization_channels <= 1024'.format(rc))
+            'no sm_100a kernel for this configuration (rc={}): this build needs residual_channels in '
+            '{{4, 8, ..., 256}} (a divisor of 256), dilation / skip / quantization channels multiples of 4 and '
+            'quantization_channels <= 1024'.format(rc))
     return lo

@@ -56,6 +56,15 @@ CASES = {
                           500, None),
     'gen_net_r16': (dict(GEN_NET, batch_size=2, use_biases=True), 777, None),
     'default_params_short': (dict(DEFAULT_NET), 6000, None),
+    # widths other than R = D = 32 run on the GEMM-built blocks (block_generic.cu)
+    'wide_r64_d64': (dict(TEST_NET, batch_size=2, residual_channels=64, dilation_channels=64, skip_channels=64,
+                          use_biases=True), 600, None),
+    'r32_d64_gc': (dict(TEST_NET, batch_size=2, residual_channels=32, dilation_channels=64, use_biases=True,
+                        global_condition_channels=8, global_condition_cardinality=5), 500, [3, 0]),
+    'scaled_r128_short': (dict(batch_size=1, dilations=[2 ** i for i in range(10)] * 2, filter_width=2,
+                               residual_channels=128, dilation_channels=128, quantization_channels=256,
+                               skip_channels=512, use_biases=True), 3000, None),
+    'narrow_r8_d12': (dict(TEST_NET, residual_channels=8, dilation_channels=12, skip_channels=20), 300, None),
 }
 
 

@@ -51,9 +51,12 @@ def test_param_layout_matches_reference_shapes():
 def test_unsupported_configs_fail_loudly():
     from wavenet import _lib
     with pytest.raises(NotImplementedError):
-        _lib.param_layout(_lib.make_config([1, 2], 24, 24, 32, 256, None, None, False, False))   # R not in {16,32}
+        _lib.param_layout(_lib.make_config([1, 2], 24, 24, 32, 256, None, None, False, False))   # R does not divide 256
     with pytest.raises(NotImplementedError):
-        _lib.param_layout(_lib.make_config([1, 2], 32, 16, 32, 256, None, None, False, False))   # R != D
+        _lib.param_layout(_lib.make_config([1, 2], 32, 18, 32, 256, None, None, False, False))   # D not a multiple of 4
+    # any other widths are served by the GEMM-built blocks (block_generic.cu)
+    assert _lib.param_layout(_lib.make_config([1, 2], 32, 16, 32, 256, None, None, False, False)).total > 0   # R != D
+    assert _lib.param_layout(_lib.make_config([1, 2], 128, 128, 512, 256, None, None, True, False)).total > 0
     with pytest.raises(ValueError):
         _lib.make_config(list(range(1, 200)), 32, 32, 32, 256, None, None, False, False)
 
