@@ -278,6 +278,24 @@ def main():
         assert lib.wn_profile_begin() == 0
         step._launch()
         assert lib.wn_profile_end(ms_tag, n_tag, n_tags) == 0
+    # cost of one event-record node between two kernel nodes: 64 back-to-back marks in a captured graph
+    event_us = None
+    if prof_mode == 'graph':
+        try:
+            cal_ms = (C.c_float * n_tags)()
+            cal_n = (C.c_int32 * n_tags)()
+            assert lib.wn_profile_begin() == 0
+            gcal = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gcal):
+                for _ in range(65):
+                    lib.wn_profile_mark(0, _lib.stream_ptr())
+            for _ in range(3):
+                gcal.replay()
+            torch.cuda.synchronize()
+            assert lib.wn_profile_end(cal_ms, cal_n, n_tags) == 0
+            event_us = 1e3 * cal_ms[0] / max(1, cal_n[0])
+        except Exception:
+            event_us = None
     kernels = {}
     buf = C.create_string_buffer(64)
     for i in range(n_tags):
@@ -317,7 +335,10 @@ def main():
             ach, peak, unit = work / sec / 1e9, peaks['hbm_gbs'], 'GB/s'
         else:
             ach, peak, unit = work / sec / 1e12, peaks['tflops'], 'TFLOP/s'
+        net_sec = max(sec - (event_us or 0.0) * 1e-6, 1e-9)      # without the event node that follows the kernel
+        ach_net = work / net_sec / (1e9 if bound == 'hbm' else 1e12)
         rooflines[name] = {'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
+                           'achieved_net_of_event_node': ach_net, 'frac_net_of_event_node': ach_net / peak,
                            'traffic': None, 'share_of_step': kernels[name]['ms_per_step'] /
                            sum(k['ms_per_step'] for k in kernels.values())}
     # measured DRAM traffic per launch of the dominant kernels (one `ncu --set full` capture, tools/ncu_summary.py traffic)
@@ -423,7 +444,9 @@ def main():
             'roofline': roofline,
             'roofline_all': rooflines,
             'kernels': kernels,
-            'kernel_timing': prof_mode + ': CUDA events after every launch of one step',
+            'kernel_timing': prof_mode + ': CUDA events after every launch of one step (times include one event '
+                             'node each; event_node_us = its cost measured with back-to-back marks)',
+            'event_node_us': event_us,
             'cpu_baseline': cpu,
             'fastgen': fastgen,
             'batch4': batch4,

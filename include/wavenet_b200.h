@@ -192,6 +192,8 @@ int wn_debug_set_gen_impl(int32_t latency_kernel);
 int wn_debug_timeline(long long* stamps);
 #define WN_PROFILE_TAGS 23
 int wn_profile_begin(void);
+/* records one more profiling event on `stream` (calibration of the per-event overhead: back-to-back marks) */
+int wn_profile_mark(int32_t tag, wn_stream_t stream);
 int wn_profile_end(float* ms_per_tag /*host*/, int32_t* launches_per_tag /*host*/, int32_t n_tags);
 int wn_profile_tag_name(int32_t tag, char* out /*host*/, int32_t n);
 

@@ -355,6 +355,12 @@ int wn_profile_begin(void) {
   return 0;
 }
 
+int wn_profile_mark(int32_t tag, wn_stream_t stream) {
+  if (tag < 0 || tag >= PT_COUNT) return -1;
+  prof_mark((cudaStream_t)stream, tag);
+  return 0;
+}
+
 int wn_profile_end(float* ms_per_tag, int32_t* launches_per_tag, int32_t n_tags) {
   g_prof_on = false;
   if (!ms_per_tag || !launches_per_tag || n_tags < PT_COUNT) return -1;
