@@ -212,6 +212,10 @@ def main():
     K = max(1, args.steps)
     B, T = args.batch, args.time
 
+    trap = None
+    if os.environ.get('WN_TRAP_INFO'):      # debug: identity of a bounded wait that timed out (wn_debug_trap_info)
+        trap = torch.zeros(8, dtype=torch.int32).pin_memory()
+        _lib.load().wn_debug_trap_info(C.c_void_p(trap.data_ptr()))
     net = wavenet.WaveNetModel(**net_kwargs(B), seed=0)      # same seed -> replicated weights
     opt = wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9)
     step = wavenet.TrainStep(net, opt, B, T)
@@ -225,9 +229,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
-    for _ in range(W):
-        step()
-    barrier()
+    try:
+        for _ in range(W):
+            step()
+        barrier()
+    except Exception:
+        if trap is not None:
+            print('trap info {bar_smem, parity, blockDim, gridDim.x, blockIdx, threadIdx, gridDim.y}:', trap.tolist(), flush=True)
+        raise
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -190,6 +190,10 @@ int wn_debug_set_gen_impl(int32_t latency_kernel);
  * %globaltimer entry / first-tile / exit stamps of the first, middle and last CTA, of the next
  * wn_block_fwd launches on the tcgen05 path; null disables. */
 int wn_debug_timeline(long long* stamps);
+/* debug: 8 host-mapped (cudaHostAlloc mapped / pinned) words that receive the identity of the first bounded
+ * mbarrier wait that times out before the kernel traps: {barrier smem address, parity, blockDim.x, gridDim.x,
+ * blockIdx.x, threadIdx.x, gridDim.y, claimed}. */
+int wn_debug_trap_info(unsigned int* host_mapped_words);
 #define WN_PROFILE_TAGS 23
 int wn_profile_begin(void);
 /* records one more profiling event on `stream` (calibration of the per-event overhead: back-to-back marks) */

@@ -7,6 +7,7 @@
 #include "../../include/wavenet_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "umma_common.cuh"
 #include "gen_common.h"
 
 namespace wn {
@@ -30,6 +31,9 @@ void prof_mark(cudaStream_t st, int tag) {
     cudaError_t e = cudaStreamSynchronize(st);
     fprintf(stderr, "[wn debug] after tag %d: %s\n", tag, cudaGetErrorString(e));
   }
+  static int sync_tag = -2;     // WN_SYNC_TAG=<ProfTag>: synchronise after every launch of that kind (race hunting)
+  if (sync_tag == -2) { const char* e = getenv("WN_SYNC_TAG"); sync_tag = e ? atoi(e) : -1; }
+  if (sync_tag == tag) cudaStreamSynchronize(st);
   if (!g_prof_on || g_prof_n >= PROF_MAX) return;
   // inside a stream capture the record becomes an external event node, so that the graph replay stamps a
   // real, timeable event after every kernel node (an eager pass is host-launch-bound for the short kernels)
@@ -102,8 +106,9 @@ struct Workspace {
   float* G2;       // [M,S]
   float* G3;       // [M,S]                         (residual_postproc only)
   float* dZcat;    // [M, L*D]
-  float* dX;       // 3 x [M,R]   (rotating: the side-stream weight-gradient kernel still reads the older ones)
-  float* dpre;     // 2 x [M,2D]
+  float* dX;       // tcgen05 path: L x [M,R], one per layer (the side-stream weight-gradient kernels read them
+                   // long after the chain has moved on; no buffer is ever reused within a step); else 2 x [M,R]
+  float* dpre;     // tcgen05 path: L x [M,2D]; else [M,2D]
   float* prebias;  // [L,B,2D]
   float* gprebias; // [L,B,2D]
   float* bsum;     // [S]
@@ -123,11 +128,12 @@ struct Workspace {
 
 static bool fwd_h_enabled();
 // WN_NO_SIDE=1 keeps every kernel of the step on the caller's stream (debugging aid)
-static bool no_side_streams() {
+static int side_mode() {      // WN_NO_SIDE: 1 = no side streams, 2 = no post-processing side stream, 3 = no block side stream
   static int v = -1;
-  if (v < 0) v = getenv("WN_NO_SIDE") ? 1 : 0;
-  return v == 1;
+  if (v < 0) { const char* e = getenv("WN_NO_SIDE"); v = e ? atoi(e) : 0; }
+  return v;
 }
+static bool no_side_streams() { return side_mode() == 1; }
 static void carve(const wn_config* c, int B, int T, bool training, void* base, Workspace* w) {
   const int64_t M = (int64_t)B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
                 S = c->skip_channels, Q = c->quantization_channels;
@@ -169,8 +175,8 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->G2 = (float*)take(M * S * f);
     w->G3 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
     w->dZcat = (float*)take(M * L * D * f);
-    w->dX = (float*)take(3 * M * R * f);
-    w->dpre = (float*)take(2 * M * 2 * D * f);
+    w->dX = (float*)take((w->umma_bwd ? L : 2) * M * R * f);
+    w->dpre = (float*)take((w->umma_bwd ? L : 1) * M * 2 * D * f);
     w->gprebias = (float*)take(L * B * 2 * D * f);
     w->gtmp = (float*)take(S * f);
   } else {
@@ -266,7 +272,8 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
       char* xs_out = (char*)w.XS + (int64_t)((l + 1) & 1) * M * 128;
       RC(block_fwd_h(xs_in, last ? nullptr : xs_out, last ? nullptr : xout, w.Zcat, ldz, l * D,
                      w.WimgH + (size_t)l * block_h_img_stride(), w.prebias + (int64_t)l * B * 2 * D,
-                     lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, B, T, c->dilations[l], last, st));
+                     lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, B, T, c->dilations[l], last,
+                     /*pdl_next=*/!last, st));
       continue;
     }
     if (w.gscratch) {
@@ -336,6 +343,12 @@ int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma) {
   g_gemm_impl = gemm_mma ? 1 : 0;
   set_block_impl(block_mma);
   return 0;
+}
+
+int wn_debug_trap_info(unsigned int* host_mapped_words) {
+  int rc = block_umma_set_trap_info(host_mapped_words);
+  if (rc == 0) rc = block_fwd_h_set_trap_info(host_mapped_words);
+  return rc;
 }
 
 int wn_debug_timeline(long long* stamps) {
@@ -552,7 +565,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     RC((int)cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) RC((int)cudaEventCreateWithFlags(&ev_g[i], cudaEventDisableTiming));
   }
-  cudaStream_t s2 = (g_prof_on || no_side_streams()) ? st : side2;   // (per-kernel profiling keeps everything on one stream)
+  cudaStream_t s2 = (g_prof_on || no_side_streams() || side_mode() == 2) ? st : side2;   // (per-kernel profiling keeps everything on one stream)
   const float* x2 = rp ? w.T2 : w.A2;   // input of postprocess2
   RC((int)cudaEventRecord(ev_g[0], st));
   RC((int)cudaStreamWaitEvent(s2, ev_g[0], 0));
@@ -613,8 +626,9 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   const float* dcur = nullptr;     // gradient wrt the output of the layer being processed
   if (w.umma_bwd) {
     // Critical chain on `st`: pre(l) -> dx(l) -> pre(l-1) -> ...  The weight-gradient GEMM of a layer only feeds
-    // the gradient buffers, so it runs on a side stream, concurrently with the chain.  Buffers rotate (dpre x2,
-    // dx x3); before layer l reuses them the chain waits for wgrad(l+2), their last reader.
+    // the gradient buffers, so it runs on a side stream, concurrently with the chain.  Every layer has its own dpre
+    // and dx buffer: the chain never has to wait for the side stream (a cross-stream wait in front of a
+    // programmatically launched kernel proved racy), only the final join does.
     static cudaStream_t side = nullptr;
     static cudaEvent_t ev_pre = nullptr, ev_fork = nullptr, ev_wg[3] = {nullptr, nullptr, nullptr};
     if (!side) {
@@ -624,15 +638,25 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       for (int i = 0; i < 3; ++i) RC((int)cudaEventCreateWithFlags(&ev_wg[i], cudaEventDisableTiming));
     }
     // (per-kernel profiling serialises everything on one stream so that event deltas are kernel times)
-    cudaStream_t ws = (g_prof_on || no_side_streams()) ? st : side;
+    // Default: the layer weight-gradient kernels stay on the caller's stream.  Running them on the side stream
+    // (WN_SIDE_WGRAD=1) hides ~0.15 ms per step but hung graph replays on some B200 boxes (bounded waits
+    // trapped after ~60 s; never reproduced with the kernels serialised) -- kept switchable until understood.
+    static int side_wgrad = -1;
+    if (side_wgrad < 0) side_wgrad = getenv("WN_SIDE_WGRAD") ? 1 : 0;
+    cudaStream_t ws = (g_prof_on || no_side_streams() || side_mode() == 3 || !side_wgrad) ? st : side;
     for (int l = L - 1; l >= 0; --l) {
       const int last = (l == L - 1);
       const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
-      float* dpre = w.dpre + (int64_t)(l & 1) * M * 2 * D;
-      float* dnext = w.dX + (int64_t)(l % 3) * xs;                 // gradient wrt this layer's input
-      if (l + 2 <= L - 1) RC((int)cudaStreamWaitEvent(st, ev_wg[(l + 2) % 3], 0));
+      float* dpre = w.dpre + (int64_t)l * M * 2 * D;
+      float* dnext = w.dX + (int64_t)l * xs;                       // gradient wrt this layer's input
       RC(block_bwd_pre_umma(w.X + l * xs, dcur, w.dZcat, ldz, l * D, dpre, img + block_img_off_pre(),
-                            w.prebias + (int64_t)l * B * 2 * D, B, T, cfg->dilations[l], last, st));
+                            w.prebias + (int64_t)l * B * 2 * D, B, T, cfg->dilations[l], last, /*pdl_next=*/1, st));
+      RC(block_bwd_dx_umma(dcur, dpre, dnext, img + block_img_off_dx(), B, T, cfg->dilations[l], last,
+                           /*pdl_next=*/l > 0, st));
+      // The event is recorded AFTER the (programmatically launched) dx kernel: an event that sits between a kernel
+      // and its programmatic dependent was observed to fire when that kernel TRIGGERS, not when it completes
+      // (weight-gradient kernels started on half-written dpre).  Recorded here it fires, at the earliest, when
+      // dx(l) has passed its griddepcontrol.wait, i.e. when pre(l) is complete -- all wgrad(l) needs.
       RC((int)cudaEventRecord(ev_pre, st));
       RC((int)cudaStreamWaitEvent(ws, ev_pre, 0));
       RC(block_wgrad_umma(w.X + l * xs, dcur, dpre, w.Zcat, ldz, l * D, grads + lo.filter + (int64_t)l * 2 * R * D,
@@ -641,7 +665,6 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
                           lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, B, T, cfg->dilations[l],
                           last, ws));
       RC((int)cudaEventRecord(ev_wg[l % 3], ws));
-      RC(block_bwd_dx_umma(dcur, dpre, dnext, img + block_img_off_dx(), B, T, cfg->dilations[l], last, st));
       dcur = dnext;
     }
     // join: the bias / conditioning gradients below read what the weight-gradient kernels accumulated

@@ -132,6 +132,7 @@ struct FwdHArgs {
   const unsigned char* img;        // IMG_H bytes
   const float *prebias, *dense_bias;
   int B, T, d, is_last, zcol;      // zcol: first column of this layer inside Zcat
+  int pdl_next;                    // the next kernel in the stream is launched programmatically and waits
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
@@ -187,7 +188,7 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);       // rows before the start of the window arrive as zeros
   };
   pdl_wait();      // the previous layer's output is complete and visible from here on
-  pdl_trigger();
+  if (a.pdl_next) pdl_trigger();
   if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   mbar_wait(&bar_w, 0);
   tc_fence_before();
@@ -211,6 +212,7 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
       __syncthreads();
       if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
       pb_batch = b;
+      __syncthreads();      // (readers sit behind mbarrier waits only: without this a slow writer warp races them)
     }
     mbar_wait(&bar_tma, par);
     if (tid == 0) {
@@ -310,7 +312,8 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
 }
 
 int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int ldz, int zcol, const unsigned char* img,
-                const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st) {
+                const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, int pdl_next,
+                cudaStream_t st) {
   CUtensorMap mapX, mapZ, mapXo, mapXs;
   int rc = make_map_split(&mapX, (const __half*)xs_in, B, T);
   if (rc) return rc;
@@ -326,7 +329,7 @@ int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int l
   }
   FwdHArgs a;
   a.img = img; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
-  a.zcol = zcol;
+  a.zcol = zcol; a.pdl_next = pdl_next;
   const size_t smem = 1024 + 4 * TILE + IMG_H;
   static bool attr = false;
   if (!attr) {
@@ -342,5 +345,7 @@ int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int l
   prof_mark(st, PT_BLOCK_FWD);
   return 0;
 }
+
+int block_fwd_h_set_trap_info(unsigned int* p) { return umma::set_trap_info_tu(p); }
 
 }  // namespace wn

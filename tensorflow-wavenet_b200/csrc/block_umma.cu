@@ -112,6 +112,7 @@ struct FwdArgs {
   const float *wf, *wg, *dense, *prebias, *dense_bias;
   int B, T, d, is_last;
   long long* timeline;              // debug: per-phase clock64 stamps of CTA 0 (wn_debug_timeline), else null
+  int pdl_next;
 };
 
 static long long* g_timeline = nullptr;
@@ -179,7 +180,7 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
     tma_load_3d(Xp, &mapX, &bar_tma, 0, t0 - a.d, b);
   };
   pdl_wait();      // x (previous layer's output) is complete and visible from here on
-  pdl_trigger();
+  if (a.pdl_next) pdl_trigger();
   if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   if (a.img) mbar_wait(&bar_w, 0);
   tc_fence_before();
@@ -203,6 +204,7 @@ block_fwd_umma_kernel(const __grid_constant__ CUtensorMap mapX, FwdArgs a) {
       __syncthreads();
       if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
       pb_batch = b;
+      __syncthreads();      // (readers sit behind mbarrier waits only: without this a slow writer warp races them)
     }
     TL(0);
     mbar_wait(&bar_tma, par);
@@ -334,6 +336,7 @@ int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsign
   a.xout = xout; a.zc = zc; a.ldz = ldz; a.img = img; a.wf = wf; a.wg = wg;
   a.dense = dense; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
   a.timeline = g_timeline;
+  a.pdl_next = 0;      // callers mix this kernel with plain launches (stand-alone C ABI entry, WN_BLOCK_FWD=tf32)
   const size_t smem = 1024 + 4 * TILE + IMG_FWD;
   static bool attr = false;
   if (!attr) {
@@ -358,6 +361,7 @@ struct PreArgs {
   const unsigned char* img;    // IMG_PRE bytes
   const float* prebias;
   int B, T, d, is_last, zcol;  // zcol: column of this layer inside dZcat
+  int pdl_next;                // the next kernel in the stream is launched programmatically and waits (common.cuh)
 };
 
 __global__ void __launch_bounds__(256, 2)
@@ -408,7 +412,7 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     bulk_g2s(W0, a.img, IMG_PRE, &bar_w);
   }
   pdl_wait();
-  pdl_trigger();
+  if (a.pdl_next) pdl_trigger();
   if (tid == 0 && (int)blockIdx.x < n_tiles) {
     issue_x(blockIdx.x);
     issue_d(blockIdx.x);
@@ -432,6 +436,7 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
       __syncthreads();
       if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
       pb_batch = b;
+      __syncthreads();      // (readers sit behind mbarrier waits only: without this a slow writer warp races them)
     }
     mbar_wait(&bar_x, par);
     if (tid == 0) {
@@ -459,6 +464,10 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     }
     mbar_wait(&bar_m1, par);
     tc_fence_after();
+    // Re-arming an mbarrier while a slow thread has not yet observed the phase it waits for lets the barrier wrap
+    // around to the same parity: that thread then waits forever (rare, box dependent hangs).  Every thread must
+    // be past its bar_x wait first.
+    __syncthreads();
     if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_x(tile + gridDim.x);     // x tiles: only the MMAs read them
 
     const bool valid = (t0 + r) < a.T;
@@ -515,6 +524,7 @@ struct DxArgs {
   float* dx;                   // [M][32]
   const unsigned char* img;    // IMG_DX bytes
   int B, T, d;
+  int pdl_next;
 };
 
 __global__ void __launch_bounds__(256, 2)
@@ -563,7 +573,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
     bulk_g2s(Wb, a.img, IMG_DX, &bar_w);
   }
   pdl_wait();
-  pdl_trigger();
+  if (a.pdl_next) pdl_trigger();
   if (tid == 0 && (int)blockIdx.x < n_tiles) {
     issue_loads(blockIdx.x);
     if (have_dxn) issue_dxn(blockIdx.x);
@@ -605,6 +615,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
     }
     mbar_wait(&bar_m1, par);
     tc_fence_after();
+    __syncthreads();      // every thread is past its bar_tma wait before the barrier is re-armed (see bwd_pre)
     if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
     uint32_t ov[16];
     tmem_ld16(lane_addr, ov);
@@ -692,8 +703,6 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  pdl_wait();
-  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -764,7 +773,7 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
 // gradient buffers, so the caller runs it on a side stream next to the dx / next layer's pre kernels.
 int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int ldz, int zcol, float* dpre,
                        const unsigned char* img_pre, const float* prebias, int B, int T, int d, int is_last,
-                       cudaStream_t st) {
+                       int pdl_next, cudaStream_t st) {
   const int n_tiles = B * ((T + TM - 1) / TM);
   int grid = n_tiles;
   const int cap = 2 * sm_count();
@@ -781,12 +790,17 @@ int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int
   if (rc) return rc;
   PreArgs a;
   a.dpre = dpre; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
-  a.is_last = is_last; a.zcol = zcol;
+  a.is_last = is_last; a.zcol = zcol; a.pdl_next = pdl_next;
   const size_t smem = 1024 + 4 * TILE + IMG_PRE;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_bwd_pre_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, mDp, a);
-  if (e != cudaSuccess) return (int)e;
+  // Plain stream-ordered launches in the backward chain: with programmatic dependent launch next to the cross-stream
+  // events of the side-stream weight-gradient kernels, consumers were observed to start on half-written gradients
+  // (tools/sweep_impls.py, tools/debug_case.py); the forward chain (no events) keeps PDL.
+  (void)pdl_next;
+  a.pdl_next = 0;
+  block_bwd_pre_umma_kernel<<<grid, 256, smem, st>>>(mX, mDn, mDz, mDp, a);
+  WN_CHECK_LAUNCH();
   prof_mark(st, PT_BLOCK_BWD_PRE);
   return 0;
 }
@@ -813,14 +827,15 @@ int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const 
   int splits = sm_count() / (B > 0 ? B : 1);
   if (splits < 1) splits = 1;
   if (splits > nkb) splits = nkb;
-  cudaError_t e = launch_pdl(block_wgrad_umma_kernel, dim3(splits, B), dim3(192), smem, st, mX, mZ, mP, mDn, a);
-  if (e != cudaSuccess) return (int)e;
+  // plain (fully stream-ordered) launch: this kernel follows a cross-stream event wait on the side stream
+  block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mX, mZ, mP, mDn, a);
+  WN_CHECK_LAUNCH();
   prof_mark(st, PT_BLOCK_WGRAD);
   return 0;
 }
 
 int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsigned char* img_dx, int B, int T, int d,
-                      int is_last, cudaStream_t st) {
+                      int is_last, int pdl_next, cudaStream_t st) {
   const int n_tiles = B * ((T + TM - 1) / TM);
   int grid = n_tiles;
   const int cap = 2 * sm_count();
@@ -836,14 +851,18 @@ int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsi
     if (rc) return rc;
   }
   DxArgs a;
-  a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.img = img_dx; a.B = B; a.T = T; a.d = d;
+  a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.img = img_dx; a.B = B; a.T = T; a.d = d; a.pdl_next = pdl_next;
   const size_t smem = 1024 + 5 * TILE + IMG_DX;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  cudaError_t e = launch_pdl(block_bwd_dx_umma_kernel, dim3(grid), dim3(256), smem, st, mP, mDn, mDx, a);
-  if (e != cudaSuccess) return (int)e;
+  (void)pdl_next;
+  a.pdl_next = 0;
+  block_bwd_dx_umma_kernel<<<grid, 256, smem, st>>>(mP, mDn, mDx, a);
+  WN_CHECK_LAUNCH();
   prof_mark(st, PT_BLOCK_BWD_DX);
   return 0;
 }
+
+int block_umma_set_trap_info(unsigned int* p) { return umma::set_trap_info_tu(p); }
 
 }  // namespace wn

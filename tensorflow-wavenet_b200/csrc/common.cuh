@@ -1,6 +1,7 @@
 // Shared device helpers for the sm_100a WaveNet kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #define WN_CHECK_LAUNCH()                         \
@@ -92,6 +93,9 @@ __device__ __forceinline__ float warp_max(float v) {
 // returns when the predecessor grid has completed and its writes are visible.  Every kernel calls
 // pdl_trigger() only AFTER its own pdl_wait(), so "my predecessor has triggered" implies "everything older
 // than my predecessor has completed" -- data written two or more launches earlier may be read before the wait.
+// A kernel triggers ONLY when the host tells it that its stream successor is such a waiting kernel (pdl_next):
+// plain successors and event records behind a triggering kernel were observed to run / fire at the trigger,
+// before the grid had finished (NaNs from half-written gradients).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -107,7 +111,9 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static int no_pdl = -1;      // WN_NO_PDL=1: plain stream-ordered launches (debugging aid)
+  if (no_pdl < 0) no_pdl = getenv("WN_NO_PDL") ? 1 : 0;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

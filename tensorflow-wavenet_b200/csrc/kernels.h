@@ -41,6 +41,8 @@ int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
 int block_fwd(const float* x, float* xout, float* zc, int ldz, const unsigned char* img,
               const float* wf, const float* wg, const float* dense, const float* prebias, const float* dense_bias,
               int M, int T, int d, int C, int is_last, cudaStream_t st);
+int block_umma_set_trap_info(unsigned int* p);     // debug: see wn_debug_trap_info
+int block_fwd_h_set_trap_info(unsigned int* p);
 bool block_umma_enabled();
 void set_block_timeline(long long* p);   // debug: clock64 stamps of block_fwd_umma CTA 0 (4 tiles x 8 phases)
 void set_block_impl(int mma);
@@ -48,12 +50,12 @@ int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsign
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
 int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int ldz, int zcol, float* dpre,
                        const unsigned char* img_pre, const float* prebias, int B, int T, int d, int is_last,
-                       cudaStream_t st);
+                       int pdl_next, cudaStream_t st);
 int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
                      int is_last, cudaStream_t st);
 int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsigned char* img_dx, int B, int T, int d,
-                      int is_last, cudaStream_t st);
+                      int is_last, int pdl_next, cudaStream_t st);
 // tcgen05 GEMM when the shape allows, mma.sync otherwise (api.cu); mode as gemm_umma
 int gemm_dispatch(int mode, GemmParams p, int split_k, cudaStream_t st);
 // blocks of arbitrary channel widths built from GEMMs (block_generic.cu)
@@ -71,7 +73,8 @@ uint32_t block_h_img_stride();
 int block_h_images(unsigned char* img, const float* filter, const float* gate, const float* dense, int L, cudaStream_t st);
 int split_rows(const float* x, void* xs, int64_t M, cudaStream_t st);
 int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int ldz, int zcol, const unsigned char* img,
-                const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
+                const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, int pdl_next,
+                cudaStream_t st);
 int64_t block_images_bytes(int L);
 uint32_t block_img_off_pre();
 uint32_t block_img_off_dx();

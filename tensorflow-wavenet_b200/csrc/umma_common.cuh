@@ -116,12 +116,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 // Bounded wait: a protocol bug must fail loudly (trap -> launch error), never hang the GPU.
+// (debug) host-mapped words that receive {barrier smem address, parity, blockDim.x, gridDim.x, blockIdx.x, threadIdx.x}
+// of the first wait that times out (wn_debug_trap_info)
+static __device__ unsigned int* g_trap_info = nullptr;      // one copy per translation unit (no -rdc)
+static inline int set_trap_info_tu(unsigned int* p) { return (int)cudaMemcpyToSymbol(g_trap_info, &p, sizeof(p)); }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   for (uint32_t i = 0; i < (1u << 24); ++i) {
     uint32_t ok;
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
     if (ok) return;
+  }
+  if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
+    g_trap_info[0] = smem_u32(b); g_trap_info[1] = parity; g_trap_info[2] = blockDim.x; g_trap_info[3] = gridDim.x;
+    g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x; g_trap_info[6] = gridDim.y;
+    __threadfence_system();
   }
   __trap();
 }

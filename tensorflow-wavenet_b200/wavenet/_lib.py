@@ -57,6 +57,7 @@ SIGNATURES = {
                                   _I32, _P]),
     'wn_profile_mark': (C.c_int, [_I32, _P]),
     'wn_debug_timeline': (C.c_int, [_P]),
+    'wn_debug_trap_info': (C.c_int, [_P]),
     'wn_debug_set_gen_impl': (C.c_int, [_I32]),
     'wn_gemm_umma': (C.c_int, [_I32, _P, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32,
                                _I32, _P]),
