@@ -134,6 +134,11 @@ static int side_mode() {      // WN_NO_SIDE: 1 = no side streams, 2 = no post-pr
   return v;
 }
 static bool no_side_streams() { return side_mode() == 1; }
+static bool bwd_pdl_enabled() {      // WN_BWD_PDL=0: plain launches in the backward chain
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("WN_BWD_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
 static void carve(const wn_config* c, int B, int T, bool training, void* base, Workspace* w) {
   const int64_t M = (int64_t)B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
                 S = c->skip_channels, Q = c->quantization_channels;
@@ -649,26 +654,31 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
       float* dpre = w.dpre + (int64_t)l * M * 2 * D;
       float* dnext = w.dX + (int64_t)l * xs;                       // gradient wrt this layer's input
+      // single-stream chain  pre(l) -> dx(l) -> wgrad(l) -> pre(l-1) ...  : programmatic dependent launches (every
+      // kernel waits, then triggers iff its successor waits too).  With the weight-gradient kernels on the side
+      // stream the chain uses plain launches: events next to programmatic launches proved racy (see below).
+      const bool chain_pdl = (ws == st) && bwd_pdl_enabled();
       RC(block_bwd_pre_umma(w.X + l * xs, dcur, w.dZcat, ldz, l * D, dpre, img + block_img_off_pre(),
-                            w.prebias + (int64_t)l * B * 2 * D, B, T, cfg->dilations[l], last, /*pdl_next=*/1, st));
+                            w.prebias + (int64_t)l * B * 2 * D, B, T, cfg->dilations[l], last, chain_pdl ? 1 : -1, st));
       RC(block_bwd_dx_umma(dcur, dpre, dnext, img + block_img_off_dx(), B, T, cfg->dilations[l], last,
-                           /*pdl_next=*/l > 0, st));
-      // The event is recorded AFTER the (programmatically launched) dx kernel: an event that sits between a kernel
-      // and its programmatic dependent was observed to fire when that kernel TRIGGERS, not when it completes
-      // (weight-gradient kernels started on half-written dpre).  Recorded here it fires, at the earliest, when
-      // dx(l) has passed its griddepcontrol.wait, i.e. when pre(l) is complete -- all wgrad(l) needs.
-      RC((int)cudaEventRecord(ev_pre, st));
-      RC((int)cudaStreamWaitEvent(ws, ev_pre, 0));
+                           chain_pdl ? 1 : -1, st));
+      if (ws != st) {
+        // The event is recorded AFTER the dx kernel (never between a kernel and a programmatic dependent: such an
+        // event was observed to fire when the kernel TRIGGERS, not when it completes).
+        RC((int)cudaEventRecord(ev_pre, st));
+        RC((int)cudaStreamWaitEvent(ws, ev_pre, 0));
+      }
       RC(block_wgrad_umma(w.X + l * xs, dcur, dpre, w.Zcat, ldz, l * D, grads + lo.filter + (int64_t)l * 2 * R * D,
                           grads + lo.gate + (int64_t)l * 2 * R * D, grads + lo.dense + (int64_t)l * D * R,
                           w.gprebias + (int64_t)l * B * 2 * D,
                           lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr, B, T, cfg->dilations[l],
-                          last, ws));
-      RC((int)cudaEventRecord(ev_wg[l % 3], ws));
+                          last, chain_pdl ? (l > 0 ? 1 : 2) : 0, ws));
+      if (ws != st) RC((int)cudaEventRecord(ev_wg[l % 3], ws));
       dcur = dnext;
     }
     // join: the bias / conditioning gradients below read what the weight-gradient kernels accumulated
-    for (int i = 0; i < 3 && i < L; ++i) RC((int)cudaStreamWaitEvent(st, ev_wg[i], 0));
+    if (ws != st)
+      for (int i = 0; i < 3 && i < L; ++i) RC((int)cudaStreamWaitEvent(st, ev_wg[i], 0));
   } else if (w.gscratch) {
     float* bufs[2] = {w.dX, w.dX + xs};
     int cur_i = 0;

@@ -658,6 +658,7 @@ constexpr int WG_STAGES = 3;
 struct WgArgs {
   float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;
   int B, T, d, is_last, zcol;   // zcol: first column of this layer inside Zcat
+  int pdl;                      // launched programmatically inside the single-stream backward chain: wait + trigger
 };
 
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
@@ -703,6 +704,10 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (a.pdl) {
+    pdl_wait();
+    if (a.pdl == 1) pdl_trigger();      // 2: the successor is a plain launch (end of the chain)
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -797,17 +802,22 @@ int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int
   // Plain stream-ordered launches in the backward chain: with programmatic dependent launch next to the cross-stream
   // events of the side-stream weight-gradient kernels, consumers were observed to start on half-written gradients
   // (tools/sweep_impls.py, tools/debug_case.py); the forward chain (no events) keeps PDL.
-  (void)pdl_next;
-  a.pdl_next = 0;
-  block_bwd_pre_umma_kernel<<<grid, 256, smem, st>>>(mX, mDn, mDz, mDp, a);
-  WN_CHECK_LAUNCH();
+  if (pdl_next >= 0) {      // whole backward chain on one stream, no events in between: PDL as in the forward chain
+    a.pdl_next = pdl_next;
+    cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, mDp, a);
+    if (e != cudaSuccess) return (int)e;
+  } else {
+    a.pdl_next = 0;
+    block_bwd_pre_umma_kernel<<<grid, 256, smem, st>>>(mX, mDn, mDz, mDp, a);
+    WN_CHECK_LAUNCH();
+  }
   prof_mark(st, PT_BLOCK_BWD_PRE);
   return 0;
 }
 
 int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
-                     int is_last, cudaStream_t st) {
+                     int is_last, int pdl, cudaStream_t st) {
   CUtensorMap mX, mZ, mP, mDn;
   int rc = make_map_3d_mn(&mX, x, B, T, C, C, 32);
   if (rc) return rc;
@@ -819,7 +829,7 @@ int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const 
   if (rc) return rc;
   WgArgs a;
   a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias; a.B = B; a.T = T;
-  a.d = d; a.is_last = is_last; a.zcol = zcol;
+  a.d = d; a.is_last = is_last; a.zcol = zcol; a.pdl = pdl;
   const size_t smem = 1024 + WG_STAGES * (7 * 4096);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
@@ -827,9 +837,13 @@ int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const 
   int splits = sm_count() / (B > 0 ? B : 1);
   if (splits < 1) splits = 1;
   if (splits > nkb) splits = nkb;
-  // plain (fully stream-ordered) launch: this kernel follows a cross-stream event wait on the side stream
-  block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mX, mZ, mP, mDn, a);
-  WN_CHECK_LAUNCH();
+  if (pdl) {
+    cudaError_t e = launch_pdl(block_wgrad_umma_kernel, dim3(splits, B), dim3(192), smem, st, mX, mZ, mP, mDn, a);
+    if (e != cudaSuccess) return (int)e;
+  } else {   // plain (fully stream-ordered) launch: on the side stream this kernel follows a cross-stream event wait
+    block_wgrad_umma_kernel<<<dim3(splits, B), 192, smem, st>>>(mX, mZ, mP, mDn, a);
+    WN_CHECK_LAUNCH();
+  }
   prof_mark(st, PT_BLOCK_WGRAD);
   return 0;
 }
@@ -855,10 +869,15 @@ int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsi
   const size_t smem = 1024 + 5 * TILE + IMG_DX;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  (void)pdl_next;
-  a.pdl_next = 0;
-  block_bwd_dx_umma_kernel<<<grid, 256, smem, st>>>(mP, mDn, mDx, a);
-  WN_CHECK_LAUNCH();
+  if (pdl_next >= 0) {
+    a.pdl_next = pdl_next;
+    cudaError_t e = launch_pdl(block_bwd_dx_umma_kernel, dim3(grid), dim3(256), smem, st, mP, mDn, mDx, a);
+    if (e != cudaSuccess) return (int)e;
+  } else {
+    a.pdl_next = 0;
+    block_bwd_dx_umma_kernel<<<grid, 256, smem, st>>>(mP, mDn, mDx, a);
+    WN_CHECK_LAUNCH();
+  }
   prof_mark(st, PT_BLOCK_BWD_DX);
   return 0;
 }

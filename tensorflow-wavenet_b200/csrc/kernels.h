@@ -53,7 +53,7 @@ int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int
                        int pdl_next, cudaStream_t st);
 int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
-                     int is_last, cudaStream_t st);
+                     int is_last, int pdl, cudaStream_t st);
 int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsigned char* img_dx, int B, int T, int d,
                       int is_last, int pdl_next, cudaStream_t st);
 // tcgen05 GEMM when the shape allows, mma.sync otherwise (api.cu); mode as gemm_umma
