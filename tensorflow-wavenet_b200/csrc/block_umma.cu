@@ -483,8 +483,8 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     float df[16], dg[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float tf = tanh_fast(__uint_as_float(fv[j]) + pb_s[16 * half + j]);
-      const float sg = sigmoid_fast(__uint_as_float(gv[j]) + pb_s[32 + 16 * half + j]);
+      float tf, sg;
+      gated_parts_fast(__uint_as_float(fv[j]) + pb_s[16 * half + j], __uint_as_float(gv[j]) + pb_s[32 + 16 * half + j], tf, sg);
       const float dzv = valid ? dz[j] : 0.f;
       df[j] = round_tf32(dzv * sg * (1.f - tf * tf));
       dg[j] = round_tf32(dzv * tf * sg * (1.f - sg));

@@ -64,6 +64,18 @@ __device__ __forceinline__ float gated_fast(float f, float g) {
   return (1.0f - a) * r;
 }
 
+// tanh(f) and sigmoid(g) from the same three SFU operations (backward recompute)
+__device__ __forceinline__ void gated_parts_fast(float f, float g, float& tf, float& sg) {
+  float a, b, r;
+  f = fminf(fmaxf(f, -20.f), 20.f);
+  g = fmaxf(g, -40.f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(-2.8853900817779268f * f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(-1.4426950408889634f * g));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((1.0f + a) * (1.0f + b)));
+  sg = r * (1.0f + a);
+  tf = (1.0f - a) * (r * (1.0f + b));
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   int sz = valid ? 16 : 0;
