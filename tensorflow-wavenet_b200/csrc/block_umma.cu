@@ -655,21 +655,31 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
 // grid = (splits, B): a CTA reduces a contiguous range of 32-step blocks of one batch element.
 // =========================================================================================
 constexpr int WG_STAGES = 3;
+constexpr int WG_ROWS = 64;      // time steps per stage: the kernel is bound by the TMA issue rate of its single producer
+                                 // thread (~130 cycles per cp.async.bulk.tensor, measured), so boxes are as tall as smem allows
 struct WgArgs {
   float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;
   int B, T, d, is_last, zcol;   // zcol: first column of this layer inside Zcat
   int pdl;                      // launched programmatically inside the single-stream backward chain: wait + trigger
+  long long* timeline;          // debug: %globaltimer stamps of CTA 0 (wn_debug_timeline slots 40..47)
 };
+__device__ __forceinline__ void wg_stamp(const WgArgs& a, int slot) {
+  if (a.timeline && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+    a.timeline[40 + slot] = (long long)g;
+  }
+}
 
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
   asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, 1)
 block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
                         const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapDn, WgArgs a) {
   constexpr int STG = WG_STAGES;   // (a deeper ring does not help: measured, the kernel is bound by its fixed costs)
-  constexpr uint32_t BLK = 32 * 128;                       // one [32 steps][32 channels] block
+  constexpr uint32_t BLK = WG_ROWS * 128;                  // one [64 steps][32 channels] block
   constexpr uint32_t A_BYTES = 4 * BLK, B_BYTES = 3 * BLK, STAGE = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -677,7 +687,7 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
-  const int nkb_total = (a.T + 31) / 32;
+  const int nkb_total = (a.T + WG_ROWS - 1) / WG_ROWS;
   const int per = (nkb_total + gridDim.x - 1) / gridDim.x;
   const int kb0 = blockIdx.x * per;
   int kb1 = kb0 + per;
@@ -686,10 +696,11 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   if (nk <= 0) {   // (exiting counts as the trigger; nothing of the predecessor is touched)
     return;
   }
+  if (tid == 0) wg_stamp(a, 0);
 
   // constant block of every stage: column 96 = 1, columns 97..127 = 0; dx' block is zero for the last layer
-  for (int i = tid; i < STG * 32 * 32; i += blockDim.x) {
-    const int s = i / 1024, rr = (i / 32) % 32, cc = i % 32;
+  for (int i = tid; i < STG * WG_ROWS * 32; i += blockDim.x) {
+    const int s = i / (WG_ROWS * 32), rr = (i / 32) % WG_ROWS, cc = i % 32;
     *reinterpret_cast<float*>(smem + s * STAGE + 3 * BLK + swz32(rr, cc)) = (cc == 0) ? 1.0f : 0.0f;
     if (a.is_last) *reinterpret_cast<float*>(smem + s * STAGE + A_BYTES + 2 * BLK + swz32(rr, cc)) = 0.f;
   }
@@ -704,26 +715,27 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) wg_stamp(a, 1);
   if (a.pdl) {
     pdl_wait();
     if (a.pdl == 1) pdl_trigger();      // 2: the successor is a plain launch (end of the chain)
   }
+  if (tid == 0) wg_stamp(a, 2);
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t bytes = (a.is_last ? 5 : 6) * BLK;
+      const uint32_t bytes = (a.is_last ? 5 : 6) * BLK;      // x, x[t-d], z, [df | dg] (one 4-D box), dx'
       for (int i = 0; i < nk; ++i) {
         const int s = i % STG;
         const uint32_t ph = (i / STG) & 1;
-        const int t = (kb0 + i) * 32;
+        const int t = (kb0 + i) * WG_ROWS;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], bytes);
         unsigned char* sa = smem + s * STAGE;
         tma_load_3d(sa, &mapX, &full_bar[s], 0, t, b);                      // x[t]
         tma_load_3d(sa + BLK, &mapX, &full_bar[s], 0, t - a.d, b);          // x[t-d]  (zeros for t < d)
         tma_load_3d(sa + 2 * BLK, &mapZ, &full_bar[s], a.zcol, t, b);       // z[t]
-        tma_load_3d(sa + A_BYTES, &mapP, &full_bar[s], 0, t, b);            // df
-        tma_load_3d(sa + A_BYTES + BLK, &mapP, &full_bar[s], 32, t, b);     // dg
+        tma_load_4d(sa + A_BYTES, &mapP, &full_bar[s], 0, t, 0, b);         // df | dg as two consecutive blocks
         if (!a.is_last) tma_load_3d(sa + A_BYTES + 2 * BLK, &mapDn, &full_bar[s], 0, t, b);   // dx'
       }
     }
@@ -734,11 +746,12 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
         const int s = i % STG;
         const uint32_t ph = (i / STG) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (i == 0) wg_stamp(a, 3);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE);
         const uint64_t da = mnmajor_desc(sa, BLK), db = mnmajor_desc(sa + A_BYTES, BLK);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem, da + 64 * k, db + 64 * k, ID, (i | k) > 0);   // +1024 B per K=8
+        for (int k = 0; k < WG_ROWS / 8; ++k) mma_tf32_ss(tmem, da + 64 * k, db + 64 * k, ID, (i | k) > 0);   // +1024 B per K=8
         mma_commit(&empty_bar[s]);
       }
       mma_commit(&done_bar);
@@ -747,6 +760,7 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     mbar_wait(&done_bar, 0);
+    if (tid == 64) wg_stamp(a, 4);
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < 96; c0 += 32) {
@@ -771,6 +785,7 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) wg_stamp(a, 5);
   if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
@@ -819,21 +834,21 @@ int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const 
                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
                      int is_last, int pdl, cudaStream_t st) {
   CUtensorMap mX, mZ, mP, mDn;
-  int rc = make_map_3d_mn(&mX, x, B, T, C, C, 32);
+  int rc = make_map_3d_mn(&mX, x, B, T, C, C, WG_ROWS);
   if (rc) return rc;
-  rc = make_map_3d_mn(&mZ, Zcat, B, T, ldz, ldz, 32);
+  rc = make_map_3d_mn(&mZ, Zcat, B, T, ldz, ldz, WG_ROWS);
   if (rc) return rc;
-  rc = make_map_3d_mn(&mP, dpre, B, T, 64, 64, 32);
+  rc = make_map_4d_mn_blocks(&mP, dpre, B, T, 64, WG_ROWS, 2);
   if (rc) return rc;
-  rc = make_map_3d_mn(&mDn, is_last ? x : dxn, B, T, C, C, 32);
+  rc = make_map_3d_mn(&mDn, is_last ? x : dxn, B, T, C, C, WG_ROWS);
   if (rc) return rc;
   WgArgs a;
   a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias; a.B = B; a.T = T;
-  a.d = d; a.is_last = is_last; a.zcol = zcol; a.pdl = pdl;
-  const size_t smem = 1024 + WG_STAGES * (7 * 4096);
+  a.d = d; a.is_last = is_last; a.zcol = zcol; a.pdl = pdl; a.timeline = g_timeline;
+  const size_t smem = 1024 + WG_STAGES * (7 * WG_ROWS * 128);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  const int nkb = (T + 31) / 32;
+  const int nkb = (T + WG_ROWS - 1) / WG_ROWS;
   int splits = sm_count() / (B > 0 ? B : 1);
   if (splits < 1) splits = 1;
   if (splits > nkb) splits = nkb;

@@ -104,6 +104,22 @@ static inline int make_map_3d_mn(CUtensorMap* m, const float* ptr, int64_t B, in
   return r == CUDA_SUCCESS ? 0 : -9;
 }
 
+// activations [B][T][cols] with cols = 32 * n_blocks viewed as {32, T, cols/32, B}: ONE box {32, box_rows, n_blocks, 1}
+// lands as n_blocks consecutive MN-major [box_rows][32] blocks.  Coordinates: (0, t, 0, b).
+static inline int make_map_4d_mn_blocks(CUtensorMap* m, const float* ptr, int64_t B, int64_t T, int64_t cols, int box_rows,
+                                        int n_blocks) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[4] = {32, (cuuint64_t)T, (cuuint64_t)(cols / 32), (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)cols * 4, 128, (cuuint64_t)T * cols * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_rows, (cuuint32_t)n_blocks, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int n) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n));
@@ -141,6 +157,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 // Shared-memory matrix descriptor, K-major operand, 128B swizzle: rows are 128 bytes (32 tf32), 8-row
