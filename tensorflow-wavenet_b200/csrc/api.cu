@@ -119,6 +119,8 @@ struct Workspace {
   float* W2R;      // [S, Q]
   unsigned char* Wimg;  // per-layer weight images of the tcgen05 block kernels (C == 32)
   unsigned char* WimgH; // per-layer fp16 split weight images of the forward block (block_fwd_h.cu)
+  void *Zcat16, *A1h, *A2h;       // fp16 copies of the forward GEMM A operands (fp16 forward chain)
+  void *Wskip16, *W1h, *W2h;      // fp16 K-major weight copies: [S][L*D], [S][S], [Q][S]
   void* XS;             // 2 x [M][hi 32 | lo 32] fp16 split rows: the residual stream between forward layers
   int umma_bwd;    // 1 when the tcgen05 backward path is used
   float* Pall;     // generic-width blocks: saved pre-activations [L or 1][M][2D]
@@ -137,6 +139,16 @@ static bool no_side_streams() { return side_mode() == 1; }
 static bool bwd_pdl_enabled() {      // WN_BWD_PDL=0: plain launches in the backward chain
   static int v = -1;
   if (v < 0) { const char* e = getenv("WN_BWD_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
+// forward GEMM chain (skip sum, postprocess1, postprocess2) on fp16 operands (default) or tf32 (WN_FWD_GEMM=tf32)
+static bool fwd16_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WN_FWD_GEMM");
+    const char* g = getenv("WN_GEMM_IMPL");
+    v = ((e && strcmp(e, "tf32") == 0) || (g && strcmp(g, "mma") == 0)) ? 0 : 1;
+  }
   return v == 1;
 }
 static void carve(const wn_config* c, int B, int T, bool training, void* base, Workspace* w) {
@@ -174,6 +186,16 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   const bool fwd_h = umma_blocks && fwd_h_enabled();
   w->WimgH = fwd_h ? (unsigned char*)take(block_h_images_bytes((int)L)) : nullptr;
   w->XS = fwd_h ? take(2 * M * 128) : nullptr;
+  if (fwd_h && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0) {
+    w->Zcat16 = take(M * L * D * 2);
+    w->A1h = take(M * S * 2);
+    w->A2h = take(M * S * 2);
+    w->Wskip16 = take(S * L * D * 2);
+    w->W1h = take(S * S * 2);
+    w->W2h = take(Q * S * 2);
+  } else {
+    w->Zcat16 = w->A1h = w->A2h = w->Wskip16 = w->W1h = w->W2h = nullptr;
+  }
   if (training) {
     w->logits = (float*)take(M * Q * f);
     w->G1 = (float*)take(M * S * f);
@@ -275,7 +297,7 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     if (w.WimgH) {
       char* xs_in = (char*)w.XS + (int64_t)(l & 1) * M * 128;
       char* xs_out = (char*)w.XS + (int64_t)((l + 1) & 1) * M * 128;
-      RC(block_fwd_h(xs_in, last ? nullptr : xs_out, last ? nullptr : xout, w.Zcat, ldz, l * D,
+      RC(block_fwd_h(xs_in, last ? nullptr : xs_out, last ? nullptr : xout, w.Zcat, w.Zcat16, ldz, l * D,
                      w.WimgH + (size_t)l * block_h_img_stride(), w.prebias + (int64_t)l * B * 2 * D,
                      lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, B, T, c->dilations[l], last,
                      /*pdl_next=*/!last, st));
@@ -305,6 +327,19 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, st));
   RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, st));
   RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
+  if (w.Zcat16) {   // fp16 forward chain: same 11-bit operand mantissas as tf32, half the L2 -> SM operand bytes
+    RC(transpose_half(params + lo.skip, ldz, S, w.Wskip16, ldz, st));
+    RC(transpose_half(params + lo.post1, S, S, w.W1h, S, st));
+    RC(transpose_half(params + lo.post2, S, Q, w.W2h, S, st));
+    prof_mark(st, PT_MISC);
+    RC(gemm_f16_nt(w.Zcat16, ldz, w.Wskip16, ldz, w.A1, S, w.A1h, S, M, S, ldz, bsum, GEMM_RELU | GEMM_ROUND, st));
+    prof_mark(st, PT_GEMM_SKIP_FWD);
+    RC(gemm_f16_nt(w.A1h, S, w.W1h, S, w.A2, S, w.A2h, S, M, S, S, P(params, lo.post1_bias), GEMM_RELU | GEMM_ROUND, st));
+    prof_mark(st, PT_GEMM_POST1_FWD);
+    RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, M, Q, S, P(params, lo.post2_bias), 0, st));
+    prof_mark(st, PT_GEMM_POST2_FWD);
+    return 0;
+  }
   prof_mark(st, PT_MISC);
   {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
     GemmParams p = gp(w.Zcat, ldz, w.WskipR, S, w.A1, S, M, S, ldz);
@@ -358,6 +393,7 @@ int wn_debug_trap_info(unsigned int* host_mapped_words) {
 
 int wn_debug_timeline(long long* stamps) {
   set_block_timeline(stamps);
+  set_fwd_h_timeline(stamps);
   set_gen_timeline(stamps);
   return 0;
 }
@@ -487,6 +523,13 @@ int wn_gemm_nt_umma(const float* a, int32_t lda, const float* b, int32_t ldb, fl
   p.ldaux = ldmask;
   p.flags = flags;
   return gemm_nt_umma(p, ct, ldct, split_k, (cudaStream_t)stream);
+}
+
+int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, void* c16,
+                   int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, int32_t flags,
+                   wn_stream_t stream) {
+  if (!a16 || !b16 || !c) return -1;
+  return gemm_f16_nt(a16, lda, b16, ldb, c, ldc, c16, ldc16, m, n, k, bias, flags, (cudaStream_t)stream);
 }
 
 int wn_gemm_umma(int32_t mode, const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc,

@@ -68,6 +68,19 @@ static int make_map_split(CUtensorMap* m, const __half* ptr, int64_t B, int64_t 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -9;
 }
+// fp16 copy of Zcat: [B][T][ldz] halfs, box = [TM rows][32 halfs] (64-byte rows, 64B swizzle)
+static int make_map_z16(CUtensorMap* m, const __half* ptr, int64_t B, int64_t T, int64_t ldz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {(cuuint64_t)ldz, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ldz * 2, (cuuint64_t)T * ldz * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)TM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
 }  // namespace
 
 // ---- weight images: per layer  W0cat [64 n][hi 32 | lo 32] | W1cat | Wdcat [32 n][hi | lo]  (swizzled rows) ----
@@ -133,7 +146,13 @@ struct FwdHArgs {
   const float *prebias, *dense_bias;
   int B, T, d, is_last, zcol;      // zcol: first column of this layer inside Zcat
   int pdl_next;                    // the next kernel in the stream is launched programmatically and waits
+  int z16;                         // also write z as fp16 (A operand of the fp16 skip GEMM)
+  long long* timeline;             // debug (wn_debug_timeline): clock64 stamps of CTA 0, layers with d == 32 only
 };
+static long long* g_timeline_h = nullptr;
+void set_fwd_h_timeline(long long* p) { g_timeline_h = p; }
+#define TLH(i) do { if (a.timeline && blockIdx.x == 0 && tid == 0 && it < 4) a.timeline[it * 8 + (i)] = clock64(); } while (0)
+
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -147,7 +166,8 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // staging tiles: measured, per-thread 16-byte global stores (32 lines per warp instruction) cost 12 of the 22 us.
 __global__ void __launch_bounds__(256, 2)
 block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
-                   const __grid_constant__ CUtensorMap mapXo, const __grid_constant__ CUtensorMap mapXs, FwdHArgs a) {
+                   const __grid_constant__ CUtensorMap mapXo, const __grid_constant__ CUtensorMap mapXs,
+                   const __grid_constant__ CUtensorMap mapZ16, FwdHArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* Xc = smem;                 // split rows x[t]
@@ -157,6 +177,7 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
   unsigned char* W0 = smem + 4 * TILE;      // [64][hi|lo] past tap (filter | gate)
   unsigned char* W1 = W0 + 8192;            // current tap
   unsigned char* Wd = W1 + 8192;            // [32][hi|lo] dense^T
+  unsigned char* Zh = W0 + IMG_H;           // fp16 staging of z: [128 rows][32 halfs], 64B-swizzled
   __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_m2, bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float pb_s[64];
@@ -208,6 +229,7 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
     const uint32_t par = it & 1;
+    TLH(0);
     if (b != pb_batch) {   // block-uniform: conditioning + bias row of this batch element
       __syncthreads();
       if (tid < 64) pb_s[tid] = a.prebias[(size_t)b * 64 + tid];
@@ -215,6 +237,7 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
       __syncthreads();      // (readers sit behind mbarrier waits only: without this a slow writer warp races them)
     }
     mbar_wait(&bar_tma, par);
+    TLH(1);
     if (tid == 0) {
       tc_fence_after();
       mma_split(tmem, dXp, dW0, ID64, true);      // x[t-d] . W[0]
@@ -239,7 +262,9 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         xo[8 + 2 * j] = a1.x + b1.x; xo[8 + 2 * j + 1] = a1.y + b1.y;
       }
     }
+    TLH(2);
     mbar_wait(&bar_m1, par);
+    TLH(3);
     tc_fence_after();
     float z[16];
     {
@@ -255,6 +280,14 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     for (int jj = 0; jj < 4; ++jj)
       *reinterpret_cast<float4*>(St + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4)) =
           make_float4(round_tf32(z[4 * jj]), round_tf32(z[4 * jj + 1]), round_tf32(z[4 * jj + 2]), round_tf32(z[4 * jj + 3]));
+    if (a.z16) {
+      __align__(16) __half zq[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) zq[j] = __float2half_rn(z[j]);
+      unsigned char* zr = Zh + (uint32_t)r * 64;
+      *reinterpret_cast<uint4*>(zr + ((uint32_t)((2 * half) ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(zq);
+      *reinterpret_cast<uint4*>(zr + ((uint32_t)((2 * half + 1) ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(zq + 8);
+    }
     if (!a.is_last) {
       __half zh[16], zl[16];
 #pragma unroll
@@ -266,9 +299,12 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     }
     fence_async_smem();
     tc_fence_before();
+    TLH(4);
     __syncthreads();      // every thread has read its x row and written its z row
+    TLH(5);
     if (tid == 0) {
       tma_store_3d(&mapZ, St, a.zcol, t0, b);      // rows past the end of the window are clipped by the tensor map
+      if (a.z16) tma_store_3d(&mapZ16, Zh, a.zcol, t0, b);
       bulk_commit();
       if (tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);     // both input tiles are free
       if (!a.is_last) {
@@ -280,6 +316,7 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     }
     if (!a.is_last) {
       mbar_wait(&bar_m2, par);
+      TLH(6);
       tc_fence_after();
       uint32_t ov[16];
       tmem_ld16(lane_addr + 64, ov);
@@ -301,6 +338,7 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();   // staging tiles complete; the TMEM columns are free for the next tile
+    TLH(7);
     if (tid == 0 && !a.is_last) {
       tma_store_3d(&mapXo, St, 0, t0, b);      // fp32 x' (kept for the backward pass)
       tma_store_3d(&mapXs, Zs, 0, t0, b);      // split x' (next layer's operand rows)
@@ -311,16 +349,21 @@ block_fwd_h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int ldz, int zcol, const unsigned char* img,
+int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, void* zcat16, int ldz, int zcol, const unsigned char* img,
                 const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, int pdl_next,
                 cudaStream_t st) {
-  CUtensorMap mapX, mapZ, mapXo, mapXs;
+  CUtensorMap mapX, mapZ, mapXo, mapXs, mapZ16;
   int rc = make_map_split(&mapX, (const __half*)xs_in, B, T);
   if (rc) return rc;
   rc = make_map_3d(&mapZ, zcat, B, T, ldz, ldz, TM);
   if (rc) return rc;
   mapXo = mapZ;
   mapXs = mapX;
+  mapZ16 = mapX;
+  if (zcat16) {
+    rc = make_map_z16(&mapZ16, (const __half*)zcat16, B, T, ldz);
+    if (rc) return rc;
+  }
   if (!is_last) {
     rc = make_map_3d(&mapXo, xout, B, T, C, C, TM);
     if (rc) return rc;
@@ -329,8 +372,9 @@ int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int l
   }
   FwdHArgs a;
   a.img = img; a.prebias = prebias; a.dense_bias = dense_bias; a.B = B; a.T = T; a.d = d; a.is_last = is_last;
-  a.zcol = zcol; a.pdl_next = pdl_next;
-  const size_t smem = 1024 + 4 * TILE + IMG_H;
+  a.zcol = zcol; a.pdl_next = pdl_next; a.z16 = zcat16 ? 1 : 0;
+  a.timeline = (d == 32 && !is_last) ? g_timeline_h : nullptr;
+  const size_t smem = 1024 + 4 * TILE + IMG_H + TM * 64;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(block_fwd_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -340,7 +384,7 @@ int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int l
   int grid = n_tiles;
   const int cap = 2 * sm_count();
   if (grid > cap) grid = cap;
-  cudaError_t e = launch_pdl(block_fwd_h_kernel, dim3(grid), dim3(256), smem, st, mapX, mapZ, mapXo, mapXs, a);
+  cudaError_t e = launch_pdl(block_fwd_h_kernel, dim3(grid), dim3(256), smem, st, mapX, mapZ, mapXo, mapXs, mapZ16, a);
   if (e != cudaSuccess) return (int)e;
   prof_mark(st, PT_BLOCK_FWD);
   return 0;

@@ -18,6 +18,7 @@
 //            transposed copy (coalesced: lanes hold consecutive rows), or red.add for split-K.
 // Descriptor conventions were validated on B200 by probe/umma_probe.cu.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -58,6 +59,20 @@ int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+
+// fp16 row-major [rows][cols] (row pitch ld halfs); box = [box_rows][box_cols halfs]
+int make_map16(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+               CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -9;
 }
 
@@ -107,6 +122,8 @@ struct UmmaParams {
   int splits;
   int stages;                     // depth of the TMA -> MMA ring
   int a_mn, b_mn;                 // operand majors: 0 = K contiguous, 1 = M / N contiguous
+  int f16;                        // operands are fp16 (K-major, 64 elements per stage, kind::f16); C stays fp32
+  int has_c16;                    // additional fp16 copy of C through mapAux (forward chain: the next GEMM's A operand)
 };
 
 template <int BN>
@@ -148,6 +165,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
+  const int ukk = p.f16 ? 2 * UK : UK;      // K elements per stage: one 128-byte row of either type
   auto decode = [&](int item, int& m0, int& n0, int& k_begin, int& nk) {
     const int nt = item % n_nt;
     const int rest = item / n_nt;
@@ -157,7 +175,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     k_begin = sp * p.k_per_split;
     int k_end = k_begin + p.k_per_split;
     if (k_end > p.K) k_end = p.K;
-    nk = (k_end - k_begin + UK - 1) / UK;
+    nk = (k_end - k_begin + ukk - 1) / ukk;
   };
 
   if (warp == 0) {
@@ -172,7 +190,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           unsigned char* sa = smem + s * STAGE_BYTES;
-          const int kc = k_begin + i * UK;
+          const int kc = k_begin + i * ukk;
           if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> 5);     // [UM/32 blocks][32 k][32 m]
           else tma_load_2d(sa, &mapA, &full_bar[s], kc, m0);
           if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> 5);
@@ -182,7 +200,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma::idesc_tf32(UM, BN, p.a_mn, p.b_mn);
+      const uint32_t idesc = p.f16 ? ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24))
+                                   : umma::idesc_tf32(UM, BN, p.a_mn, p.b_mn);
       const uint32_t astep = p.a_mn ? 64 : 2, bstep = p.b_mn ? 64 : 2;   // descriptor start-address step per K=8
       uint32_t it = 0, local = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
@@ -203,8 +222,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < UK / 8; ++k) {
             const uint32_t accum = (i > 0 || k > 0) ? 1u : 0u;
-            asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                         ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
+            if (p.f16)
+              asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                           ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
+            else
+              asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                           ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
           }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
         }
@@ -325,11 +348,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(os + ((uint32_t)(j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          if (p.has_c16) {      // same values as fp16 [32 rows][32 halfs] (64-byte rows, 64B swizzle) for the next GEMM
+            __align__(16) __half hv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hv[j] = __float2half_rn(fminf(f[j], 65504.f));
+            unsigned char* hs = my_aux + buf * STG_BYTES + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(hs + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(hv + 8 * j);
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                          ::"l"(&mapC), "r"(smem_u32(my_out + buf * STG_BYTES)), "r"(nb), "r"(row0) : "memory");
+            if (p.has_c16)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&mapAux), "r"(smem_u32(my_aux + buf * STG_BYTES)), "r"(nb), "r"(row0) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++out_cnt;
@@ -388,7 +423,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   UmmaParams p;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
-  p.a_mn = a_mn; p.b_mn = b_mn;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.f16 = 0; p.has_c16 = 0;
   int splits = (g.flags & GEMM_ATOMIC) ? (split_k > 0 ? split_k : 1) : 1;
   int kps = ((g.K + splits - 1) / splits + UK - 1) / UK * UK;
   splits = (g.K + kps - 1) / kps;
@@ -409,6 +444,72 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
     if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 4 * (UM + 128) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
     gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
   }
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+// Forward chain in fp16: C[M,N] = A16[M,K] . B16[N,K]^T (+bias, relu), fp32 accumulate; C is written as fp32 (kept for
+// the backward pass) and, when c16 is given, also as fp16 (A operand of the next GEMM).  Every GEMM of the step is bound
+// by the L2 -> SM operand traffic, so halving the operand bytes (and doubling the MMA rate) halves these three.
+int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
+                int K, const float* bias, int flags, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || !C) return -1;
+  if ((lda & 7) || (ldb & 7) || (ldc & 3) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
+      ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (flags & GEMM_ATOMIC))
+    return -3;
+  const int BN = N > 128 ? 256 : 128;
+  CUtensorMap mA, mB, mC, mAux;
+  int rc = make_map16(&mA, A16, M, K, lda, UM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_map16(&mB, B16, N, K, ldb, BN, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_map(&mC, C, M, N, ldc, 32);
+  if (rc) return rc;
+  mAux = mC;
+  if (C16) {
+    rc = make_map16(&mAux, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  UmmaParams p;
+  p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
+  p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = flags;
+  p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
+  p.k_per_split = (K + 63) / 64 * 64;
+  p.splits = 1;
+  p.stages = 3;
+  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + UM - 1) / UM);
+  dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
+  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + 2 * 4 * 2 * STG_BYTES;
+  if (BN == 256) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 3 * (UM + 256) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
+    gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 4 * (UM + 128) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
+    gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
+  }
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+// out16[n][k] = half(in[k][n])   (fp16 K-major weight copies for gemm_f16_nt; [K][N] fp32 row-major in)
+__global__ void transpose_half_kernel(const float* __restrict__ in, int K, int N, __half* __restrict__ out, int ldo) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? in[(size_t)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) out[(size_t)n * ldo + k] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+int transpose_half(const float* in, int K, int N, void* out, int ldo, cudaStream_t st) {
+  dim3 grid((N + 31) / 32, (K + 31) / 32);
+  transpose_half_kernel<<<grid, dim3(32, 8), 0, st>>>(in, K, N, (__half*)out, ldo);
   WN_CHECK_LAUNCH();
   return 0;
 }

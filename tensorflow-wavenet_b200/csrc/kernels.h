@@ -34,6 +34,10 @@ int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStre
 // tcgen05 path, mode 0 NN (p.B = [K,N]) / 1 NT (p.B = [N,K]) / 2 TN (p.A = [K,M], p.B = [K,N]; GEMM_ATOMIC)
 int gemm_umma(int mode, const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st);
 bool gemm_umma_supported(int mode, const GemmParams& p);
+// forward chain in fp16 (operands K-major fp16, fp32 accumulate / output, optional fp16 copy of the output)
+int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
+                int K, const float* bias, int flags, cudaStream_t st);
+int transpose_half(const float* in, int K, int N, void* out, int ldo, cudaStream_t st);
 int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st);
 int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
 
@@ -43,6 +47,7 @@ int block_fwd(const float* x, float* xout, float* zc, int ldz, const unsigned ch
               int M, int T, int d, int C, int is_last, cudaStream_t st);
 int block_umma_set_trap_info(unsigned int* p);     // debug: see wn_debug_trap_info
 int block_fwd_h_set_trap_info(unsigned int* p);
+void set_fwd_h_timeline(long long* p);
 bool block_umma_enabled();
 void set_block_timeline(long long* p);   // debug: clock64 stamps of block_fwd_umma CTA 0 (4 tiles x 8 phases)
 void set_block_impl(int mma);
@@ -72,7 +77,7 @@ int64_t block_h_images_bytes(int L);
 uint32_t block_h_img_stride();
 int block_h_images(unsigned char* img, const float* filter, const float* gate, const float* dense, int L, cudaStream_t st);
 int split_rows(const float* x, void* xs, int64_t M, cudaStream_t st);
-int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, int ldz, int zcol, const unsigned char* img,
+int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, void* zcat16, int ldz, int zcol, const unsigned char* img,
                 const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, int pdl_next,
                 cudaStream_t st);
 int64_t block_images_bytes(int L);

@@ -304,6 +304,36 @@ def test_gemm_umma_modes(lib, mode, M, N, K, split):
     assert rel_err(c.cpu().numpy(), ref) < 1e-5      # fp32 accumulation order only
 
 
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (1000, 512, 1600), (333, 256, 512), (257, 96, 200), (4100, 512, 512)])
+def test_gemm_f16_nt(lib, M, N, K):
+    """fp16-operand tcgen05 GEMM of the forward chain: exact products of fp16 inputs, fp32 accumulate; fp32 output
+    (tf32-rounded, relu, bias) and its fp16 copy."""
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((M, K)).astype(np.float16)
+    b = (0.1 * rng.standard_normal((N, K))).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float32)
+    da, db = torch.tensor(a, device='cuda'), torch.tensor(b, device='cuda')
+    c = torch.full((M, N), -7.0, device='cuda')
+    c16 = torch.full((M, N), -7.0, device='cuda', dtype=torch.float16)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    assert lib.wn_gemm_f16_nt(p(da), K, p(db), K, p(c), N, None, 0, M, N, K, None, 0, stream()) == 0
+    torch.cuda.synchronize()
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5
+    assert lib.wn_gemm_f16_nt(p(da), K, p(db), K, p(c), N, p(c16), N, M, N, K, p(dev(bias)), 1 | 2, stream()) == 0
+    torch.cuda.synchronize()
+    ref = np.maximum(ref + bias, 0)
+    out = c.cpu().numpy()
+    assert rel_err(out, ref) < LOGIT_RTOL
+    np.testing.assert_array_equal(out, O.round_tf32(torch.tensor(out)).numpy())          # tf32-exact values ...
+    np.testing.assert_array_equal(c16.cpu().numpy(), out.astype(np.float16))              # ... whose fp16 copy is exact
+
+
+def test_gemm_f16_rejects_unaligned(lib):
+    a = torch.zeros(64, 44, device='cuda', dtype=torch.float16)
+    c = torch.zeros(64, 64, device='cuda')
+    assert lib.wn_gemm_f16_nt(p(a), 44, p(a), 44, p(c), 64, None, 0, 64, 64, 44, None, 0, stream()) == -3
+
+
 def test_gemm_umma_rejects_unaligned_mn(lib):
     a = torch.zeros(64, 48, device='cuda')
     c = torch.zeros(64, 48, device='cuda')
