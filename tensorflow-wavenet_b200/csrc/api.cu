@@ -121,6 +121,7 @@ struct Workspace {
   unsigned char* WimgH; // per-layer fp16 split weight images of the forward block (block_fwd_h.cu)
   void *Zcat16, *A1h, *A2h;       // fp16 copies of the forward GEMM A operands (fp16 forward chain)
   void *Wskip16, *W1h, *W2h;      // fp16 K-major weight copies: [S][L*D], [S][S], [Q][S]
+  unsigned int* chain_flags;      // [L][B * ceil(T/128)] tile flags of the persistent forward kernel (null: per-layer launches)
   void* XS;             // 2 x [M][hi 32 | lo 32] fp16 split rows: the residual stream between forward layers
   int umma_bwd;    // 1 when the tcgen05 backward path is used
   float* Pall;     // generic-width blocks: saved pre-activations [L or 1][M][2D]
@@ -148,6 +149,15 @@ static bool fwd16_enabled() {
     const char* e = getenv("WN_FWD_GEMM");
     const char* g = getenv("WN_GEMM_IMPL");
     v = ((e && strcmp(e, "tf32") == 0) || (g && strcmp(g, "mma") == 0)) ? 0 : 1;
+  }
+  return v == 1;
+}
+// forward layers: one persistent kernel ordered by tile flags (default) or one launch per layer (WN_FWD_CHAIN=0)
+static bool fwd_chain_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WN_FWD_CHAIN");
+    v = (e && strcmp(e, "0") == 0) ? 0 : 1;
   }
   return v == 1;
 }
@@ -185,7 +195,9 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->umma_bwd = (training && umma_blocks) ? 1 : 0;
   const bool fwd_h = umma_blocks && fwd_h_enabled();
   w->WimgH = fwd_h ? (unsigned char*)take(block_h_images_bytes((int)L)) : nullptr;
-  w->XS = fwd_h ? take(2 * M * 128) : nullptr;
+  const bool chain = fwd_h && fwd_chain_enabled();
+  w->XS = fwd_h ? take(chain ? block_fwd_chain_ring_bytes(M) : 2 * M * 128) : nullptr;
+  w->chain_flags = chain ? (unsigned int*)take((L * (int64_t)B * ((T + 127) / 128) + 1) * 4) : nullptr;
   if (fwd_h && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0) {
     w->Zcat16 = take(M * L * D * 2);
     w->A1h = take(M * S * 2);
@@ -268,6 +280,14 @@ int gemm_dispatch(int mode, GemmParams p, int split_k, cudaStream_t st) {
   } while (0)
 
 // network forward from ids: X (all layers when training), Zcat, A1, A2 and logits
+// debug (tools/stage_times.py): WN_TRUNCATE=k cuts the step's launch sequence after stage k -- 1 forward layers,
+// 2 forward GEMMs + loss, 3 post-processing gradient GEMMs, 4 layer backward -- so that graph replay times of the
+// prefixes give the real incremental cost of every stage (event-node kernel times undo the overlap between launches)
+static int truncate_stage() {
+  const char* e = getenv("WN_TRUNCATE");
+  return e ? atoi(e) : 0;
+}
+
 static int run_forward(const wn_config* c, const wn_layout& lo, const float* params, Workspace& w,
                        const int32_t* ids, const int32_t* gc_ids, int B, int T, bool training, float* logits,
                        cudaStream_t st) {
@@ -290,7 +310,11 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     RC(split_rows(w.X, w.XS, M, st));
     prof_mark(st, PT_MISC);
   }
-  for (int l = 0; l < L; ++l) {
+  if (w.chain_flags) {
+    RC(block_fwd_chain(w.XS, training ? w.X : nullptr, w.Zcat, w.Zcat16, ldz, w.WimgH, w.prebias,
+                       lo.dense_bias >= 0 ? params + lo.dense_bias : nullptr, c->dilations, L, B, T, w.chain_flags, st));
+  }
+  for (int l = 0; l < L && !w.chain_flags; ++l) {
     const float* xin = training ? w.X + l * xs : w.X + (l & 1) * xs;
     float* xout = training ? w.X + (l + 1) * xs : w.X + ((l + 1) & 1) * xs;
     const int last = (l == L - 1);
@@ -317,6 +341,7 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
                  w.prebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr,
                  M, T, c->dilations[l], R, last, st));
   }
+  if (training && truncate_stage() == 1) return 0;
   const float* bsum = nullptr;
   if (c->use_biases) {
     RC(skip_bias_sum(params + lo.skip_bias, L, S, w.bsum, st));
@@ -602,8 +627,11 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC(mulaw_encode(audio, M, mulaw_thresholds, Q, w.ids, st));            // model.py:639
   prof_mark(st, PT_MULAW);
   RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, w.logits, st));
+  const int trunc = truncate_stage();
+  if (trunc == 1) return 0;
   RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, st));
   prof_mark(st, PT_XENT);
+  if (trunc == 2) return 0;
 
   // Weight / bias gradients of the post-processing path only feed the gradient buffers: they run on a second
   // side stream while `st` carries the dependent chain  dlogits -> G1 -> G2 -> dZcat -> residual blocks.
@@ -669,6 +697,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     GemmParams p = gp(w.G2, S, w.WskipR, S, w.dZcat, ldz, M, ldz, S);
     RC(gemm(1, p, 1, st));
     prof_mark(st, PT_GEMM_SKIP_DGRAD);
+  }
+  if (trunc == 3) {
+    RC((int)cudaStreamWaitEvent(st, ev_g[3], 0));
+    return 0;
   }
   const int64_t xs = (int64_t)M * R;
   const float* dcur = nullptr;     // gradient wrt the output of the layer being processed

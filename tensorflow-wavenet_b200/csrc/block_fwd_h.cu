@@ -12,8 +12,11 @@
 // operand traffic.
 // The kernel also writes the fp32 x' (kept for the backward pass) and z (tf32-rounded, into Zcat).
 // Range: fp16 tops out at 65504; a residual stream that large has diverged anyway (documented in DESIGN.md).
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
+#include "../../include/wavenet_b200.h"
 #include "common.cuh"
 #include "kernels.h"
 #include "umma_common.cuh"
@@ -389,6 +392,489 @@ int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, void*
   prof_mark(st, PT_BLOCK_FWD);
   return 0;
 }
+
+// ===================================================================================================================
+// All forward layers in ONE persistent kernel ("chain").  The per-layer kernels above spend about half of each
+// ~20 us launch outside their tile loop (grid ramp, weight fetch, store drain, inter-kernel dependency latency), 50
+// times per step.  Here the CTAs stay resident for the whole stack and the layers are ordered by per-tile flags
+// instead of kernel boundaries: tile (l, b, t0) needs the rows [t0-d, t0+128) of layer l-1, i.e. at most three tiles of
+// it, and starts as soon as those have been published -- no grid-wide barrier anywhere.
+//   warps 0-7  epilogue (thread = one time step x 16 channels, exactly as block_fwd_h_kernel)
+//   warp  8    issuer   : claims work, waits for the producer tiles' flags, TMA loads, tcgen05 MMAs, weight images
+//   warp  9    publisher: TMA stores of the staged outputs, then (stores complete) the tile's flag
+// Work items are claimed from ONE global counter in (layer, tile) order.  That makes the kernel deadlock-free for any
+// number of resident CTAs (no cooperative launch needed): an item only depends on items with a smaller index, those have
+// been claimed by CTAs that are running, and a running CTA only ever waits on smaller items -- the issuer blocks on the
+// flags of its next item only after it has issued everything its current one needs.  It also balances the 2.64 tiles
+// per CTA per layer that the static launches round up to 3.
+// The split rows travel through a ring of RING buffers [slot][B][T][hi|lo]; layer l reads slot l % RING and writes slot
+// (l+1) % RING.  Before overwriting rows of a slot the publisher checks the flags of the layer-(l+1-RING) tiles that
+// read them (write-after-read), which are RING-1 layers behind and practically always set.
+constexpr int RING = 4;
+constexpr int CH_THREADS = 320;
+
+struct ChainArgs {
+  const unsigned char* img;        // [L] weight images (IMG_H bytes each)
+  const float* prebias;            // [L][B][64]
+  const float* dense_bias;         // [L][32] or null
+  unsigned int* flags;             // [L][n_tiles] tile flags, then the work counter; zeroed before the launch
+  int L, B, T, n_tt;
+  int has_xout, z16;
+  long long* timeline;             // debug: cycles CTA 0 spent in each kind of wait (wn_debug_timeline)
+  int dil[WN_MAX_LAYERS];
+};
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_flag(const unsigned int* p) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    if (ld_acquire(p)) return;
+    __nanosleep(32);
+  }
+  if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
+    g_trap_info[0] = 0xF1A6u; g_trap_info[1] = (unsigned int)(uintptr_t)p; g_trap_info[2] = blockDim.x;
+    g_trap_info[3] = gridDim.x; g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x;
+    __threadfence_system();
+  }
+  __trap();
+}
+// three flags at once (the loads overlap): all set?
+__device__ __forceinline__ bool flags_set(const unsigned int* f0, const unsigned int* f1, const unsigned int* f2) {
+  const unsigned int v0 = ld_acquire(f0), v1 = ld_acquire(f1), v2 = ld_acquire(f2);
+  return (v0 & v1 & v2) != 0u;
+}
+__device__ __forceinline__ void wait_flags(const unsigned int* f0, const unsigned int* f1, const unsigned int* f2) {
+  if (flags_set(f0, f1, f2)) return;
+  wait_flag(f0);
+  wait_flag(f1);
+  wait_flag(f2);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return ok != 0u;
+}
+
+__global__ void __launch_bounds__(384, 2)      // 10 warps land 3+3 on one scheduler: 6 x 32 x regs <= 16384 needs <= 80 registers
+block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_constant__ CUtensorMap mapZ,
+                       const __grid_constant__ CUtensorMap mapXo, const __grid_constant__ CUtensorMap mapZ16,
+                       const __grid_constant__ ChainArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* Xc = smem;                 // split rows x[t]
+  unsigned char* Xp = smem + TILE;          // split rows x[t-d]
+  unsigned char* Zs = smem + 2 * TILE;      // split rows z (A operand of the dense product), later split rows of x'
+  unsigned char* Sz = smem + 3 * TILE;      // fp32 staging of z (-> Zcat)
+  unsigned char* Sx = smem + 4 * TILE;      // fp32 staging of x'
+  unsigned char* W0 = smem + 5 * TILE;      // [64][hi|lo] past tap (filter | gate)
+  unsigned char* W1 = W0 + 8192;            // current tap
+  unsigned char* Wd = W1 + 8192;            // [32][hi|lo] dense^T
+  unsigned char* Zh = W0 + IMG_H;           // fp16 staging of z: [128 rows][32 halfs], 64B-swizzled
+  __shared__ __align__(8) uint64_t bar_tma, bar_m1, bar_m2, bar_w, bar_z, bar_o, bar_sfree, bar_xr;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int item_s[4];                 // work item of tile i in item_s[i & 3] (-1: no more work), published through bar_tma
+  __shared__ float pb_s[64];
+  __shared__ float bd_s[32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar_tma, 1);
+    mbar_init(&bar_m1, 1);
+    mbar_init(&bar_m2, 1);
+    mbar_init(&bar_w, 1);
+    mbar_init(&bar_z, 256);
+    mbar_init(&bar_o, 257);      // 256 epilogue threads + the issuer (write-after-read check of the ring slot)
+    mbar_init(&bar_sfree, 1);
+    mbar_init(&bar_xr, 256);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int n_tiles = a.B * a.n_tt;
+  const int n_items = a.L * n_tiles;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------------------------------------ issuer
+    if (lane == 0) {
+      constexpr uint32_t ID64 = idesc_f16(128, 64), ID32 = idesc_f16(128, 32);
+      const uint64_t dXc = kmajor_desc(smem_u32(Xc)), dXp = kmajor_desc(smem_u32(Xp)), dZs = kmajor_desc(smem_u32(Zs));
+      const uint64_t dW0 = kmajor_desc(smem_u32(W0)), dW1 = kmajor_desc(smem_u32(W1)), dWd = kmajor_desc(smem_u32(Wd));
+      unsigned int* counter = a.flags + n_items;
+      auto claim = [&]() -> int {
+        const unsigned int w = atomicAdd(counter, 1u);
+        return w < (unsigned int)n_items ? (int)w : -1;
+      };
+      const unsigned int *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;      // flags of the producer tiles of the next item
+      auto producer_flags = [&](int item) {
+        const int l = item / n_tiles, j = item - l * n_tiles;
+        const int b = j / a.n_tt, tt = j - b * a.n_tt, t0 = tt * TM, d = a.dil[l];
+        if (l == 0) { f0 = nullptr; return; }
+        const unsigned int* f = a.flags + (size_t)(l - 1) * n_tiles + (size_t)b * a.n_tt;
+        f0 = f1 = f2 = f + tt;
+        const int hi_t = t0 - d + TM - 1;
+        if (hi_t >= 0) {
+          const int lo_t = t0 - d > 0 ? t0 - d : 0;
+          f1 = f + lo_t / TM;
+          f2 = f + (hi_t < a.T ? hi_t : a.T - 1) / TM;
+        }
+      };
+      auto issue_loads = [&](int item, bool ready) {     // producer tiles of layer l-1 published -> load both taps
+        const int l = item / n_tiles, j = item - l * n_tiles;
+        const int b = j / a.n_tt, tt = j - b * a.n_tt, t0 = tt * TM, d = a.dil[l];
+        // (acquire, then TMA loads issued by this thread -- the pattern of griddepcontrol.wait + TMA; a fence.proxy.async
+        // here was measured at ~2500 cycles on the critical path of every tile)
+        if (f0 && !ready) wait_flags(f0, f1, f2);
+        const int slot = l % RING;
+        mbar_expect_tx(&bar_tma, 2 * TILE);      // (release: publishes item_s to the waiters of this phase)
+        tma_load_3d(Xc, &mapXS, &bar_tma, 0, t0, slot * a.B + b);
+        tma_load_3d(Xp, &mapXS, &bar_tma, 0, t0 - d, slot * a.B + b);     // rows before the window start arrive as zeros
+      };
+      long long c_flag = 0, c_w = 0, c_tma = 0, c_z = 0, c_m2 = 0, c_issue = 0, t_a, t_start = clock64();
+      int item = claim();
+      item_s[0] = item;
+      uint32_t i = 0, wphase = 0;
+      if (item < 0) {
+        mbar_arrive(&bar_tma);
+      } else {
+        mbar_expect_tx(&bar_w, IMG_H);
+        bulk_g2s(W0, a.img + (size_t)(item / n_tiles) * IMG_H, IMG_H, &bar_w);
+        producer_flags(item);
+        issue_loads(item, false);
+        mbar_wait(&bar_w, 0);
+        mbar_wait(&bar_tma, 0);
+        tc_fence_after();
+        mma_split(tmem, dXp, dW0, ID64, true);      // x[t-d] . W[0]
+        mma_split(tmem, dXc, dW1, ID64, false);     // x[t]   . W[1]
+        mma_commit(&bar_m1);
+      }
+      // Invariant at the loop top: the first product of tile i has been issued.
+      while (item >= 0) {
+        const uint32_t par = i & 1;
+        const int l = item / n_tiles;
+        const bool last = (l == a.L - 1);
+        // the next item is claimed and its producers' flags are looked at while the epilogue warps work on this one;
+        // BLOCKING on flags has to wait until everything this tile needs has been issued (see the header)
+        const int nx = claim();
+        item_s[(i + 1) & 3] = nx;
+        const int nl = nx >= 0 ? nx / n_tiles : l;
+        bool ready = true;
+        if (nx >= 0) {
+          producer_flags(nx);
+          ready = (f0 == nullptr);
+        }
+        // write-after-read: the ring slot this tile's x' goes to was read by layer l + 1 - RING (own rows and the
+        // shifted tap of the tiles d later); those tiles are RING - 1 layers behind and practically always published
+        const unsigned int *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
+        if (!last && l + 1 - RING >= 0) {
+          const int lr = l + 1 - RING, j = item - l * n_tiles;
+          const int b = j / a.n_tt, tt = j - b * a.n_tt, t0 = tt * TM, dr = a.dil[lr];
+          const unsigned int* f = a.flags + (size_t)lr * n_tiles + (size_t)b * a.n_tt;
+          const int ta = (t0 + dr) / TM, tb = (t0 + TM - 1 + dr) / TM;
+          w0 = f + tt; w1 = f + (ta < a.n_tt ? ta : tt); w2 = f + (tb < a.n_tt ? tb : tt);
+        }
+        bool war_ok = (w0 == nullptr);
+        // both input tiles are free as soon as the first product has read them and every epilogue thread has its x row:
+        // the next tile's loads (and W0/W1 of a new layer) start here, a whole epilogue ahead of the z barrier
+        t_a = clock64();
+        mbar_wait(&bar_m1, par);
+        mbar_wait(&bar_xr, par);
+        c_tma += clock64() - t_a;
+        bool loaded = (nx < 0);
+        auto early = [&]() {
+          if (nl != l) {
+            mbar_expect_tx(&bar_w, IMG_H);
+            bulk_g2s(W0, a.img + (size_t)nl * IMG_H, 16384, &bar_w);
+          }
+          issue_loads(nx, true);
+          loaded = true;
+        };
+        t_a = clock64();
+        for (;;) {
+          if (!ready) ready = flags_set(f0, f1, f2);
+          if (ready && !loaded) early();
+          if (!war_ok) war_ok = flags_set(w0, w1, w2);
+          if ((loaded && war_ok) || mbar_test(&bar_z, par)) break;
+        }
+        mbar_wait(&bar_z, par);                     // z staged in Zs
+        c_z += clock64() - t_a;
+        t_a = clock64();
+        tc_fence_after();
+        if (!last) {
+          mma_split(tmem + 64, dZs, dWd, ID32, true);      // z . Wd
+          mma_commit(&bar_m2);
+          if (!war_ok) wait_flags(w0, w1, w2);
+          mbar_arrive(&bar_o);                              // the publisher may overwrite the slot rows
+        }
+        c_issue += clock64() - t_a;
+        if (nx < 0) {
+          mbar_arrive(&bar_tma);      // completes the next phase without data: the other warps see "no more work"
+          break;
+        }
+        t_a = clock64();
+        if (!loaded) {
+          wait_flags(f0, f1, f2);
+          early();
+        }
+        c_flag += clock64() - t_a;
+        if (nl != l) {      // Wd is free once the dense product has finished
+          t_a = clock64();
+          if (!last) mbar_wait(&bar_m2, par);
+          c_m2 += clock64() - t_a;
+          bulk_g2s(Wd, a.img + (size_t)nl * IMG_H + 16384, 4096, &bar_w);
+          wphase ^= 1;
+          t_a = clock64();
+          mbar_wait(&bar_w, wphase);
+          c_w += clock64() - t_a;
+        }
+        t_a = clock64();
+        mbar_wait(&bar_tma, par ^ 1u);
+        c_tma += clock64() - t_a;
+        tc_fence_after();
+        mma_split(tmem, dXp, dW0, ID64, true);      // (the accumulator columns are free: every thread has staged its z)
+        mma_split(tmem, dXc, dW1, ID64, false);
+        mma_commit(&bar_m1);
+        item = nx;
+        ++i;
+      }
+      if (a.timeline && blockIdx.x == 0) {
+        a.timeline[0] = clock64() - t_start; a.timeline[1] = c_flag; a.timeline[2] = c_w; a.timeline[3] = c_tma;
+        a.timeline[4] = c_z; a.timeline[5] = c_m2; a.timeline[6] = c_issue; a.timeline[7] = i; a.timeline[8] = gridDim.x;
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------------------------------------ publisher
+    if (lane == 0) {
+      long long p_z = 0, p_war = 0, p_o = 0, p_read = 0, p_done = 0, t_a;
+      int pending = -1;      // tile whose flag waits for its stores (published after the next tile's z store)
+      for (uint32_t i = 0;; ++i) {
+        const uint32_t par = i & 1;
+        // (not bar_tma: its phase i+1 can complete while this thread is still publishing tile i-1, and a parity wait
+        // that is two phases late never returns.  bar_z cannot run ahead: phase i+1 needs this thread's bar_sfree(i).)
+        t_a = clock64();
+        mbar_wait(&bar_z, par);
+        p_z += clock64() - t_a;
+        const int item = item_s[i & 3];
+        if (item < 0) break;
+        const int l = item / n_tiles, j = item - l * n_tiles;
+        const bool last = (l == a.L - 1);
+        const int b = j / a.n_tt, tt = j - b * a.n_tt, t0 = tt * TM;
+        tma_store_3d(&mapZ, Sz, l * C, t0, b);      // rows past the end of the window are clipped by the tensor map
+        if (a.z16) tma_store_3d(&mapZ16, Zh, l * C, t0, b);
+        bulk_commit();
+        if (pending >= 0) {      // the previous tile's stores: every group but the one just committed has completed
+          t_a = clock64();
+          asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+          __threadfence();
+          st_release(a.flags + pending, 1u);
+          pending = -1;
+          p_war += clock64() - t_a;
+        }
+        if (!last) {
+          t_a = clock64();
+          mbar_wait(&bar_o, par);                  // x' staged, and the issuer has seen the old readers of the slot finish
+          p_o += clock64() - t_a;
+          if (a.has_xout) tma_store_3d(&mapXo, Sx, 0, t0, (l + 1) * a.B + b);      // fp32 x' (kept for the backward pass)
+          tma_store_3d(&mapXS, Zs, 0, t0, ((l + 1) % RING) * a.B + b);             // split x' (next layer's operand rows)
+          bulk_commit();
+        }
+        t_a = clock64();
+        bulk_wait_read0();
+        p_read += clock64() - t_a;
+        mbar_arrive(&bar_sfree);
+        if (!last) {
+          // publish the tile once its stores have completed.  When the next tile is already staged its z store goes
+          // first and the flag follows it (wait_group 1 above); only then: a flag held back behind a tile that is not
+          // staged yet could be the very flag that tile's loads wait for.
+          if (mbar_test(&bar_z, par ^ 1u)) {
+            pending = item;
+          } else {
+            t_a = clock64();
+            bulk_wait0();                 // the stores have completed and are visible to this thread ...
+            __threadfence();
+            st_release(a.flags + item, 1u);      // ... publish the tile
+            p_done += clock64() - t_a;
+          }
+        }
+      }
+      bulk_wait0();
+      if (pending >= 0) {
+        __threadfence();
+        st_release(a.flags + pending, 1u);
+      }
+      if (a.timeline && blockIdx.x == 0) {
+        a.timeline[10] = p_z; a.timeline[11] = p_war; a.timeline[12] = p_o; a.timeline[13] = p_read; a.timeline[14] = p_done;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------ epilogue
+    const int r = tid & 127, half = tid >> 7;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
+    const uint32_t row_off = (uint32_t)r * 128;
+    const uint32_t ch0 = (uint32_t)((2 * half) ^ (r & 7)) << 4, ch1 = (uint32_t)((2 * half + 1) ^ (r & 7)) << 4;
+    const uint32_t cl0 = (uint32_t)((4 + 2 * half) ^ (r & 7)) << 4, cl1 = (uint32_t)((5 + 2 * half) ^ (r & 7)) << 4;
+    int key = -1;
+    for (uint32_t i = 0;; ++i) {
+      const uint32_t par = i & 1;
+      mbar_wait(&bar_tma, par);
+      const int item = item_s[i & 3];
+      if (item < 0) {
+        // hands the end marker on to the publisher -- once it has consumed the previous phase of bar_z (its
+        // bar_sfree arrival follows its bar_z wait): a parity wait that falls two phases behind never returns
+        if (i > 0) mbar_wait(&bar_sfree, (i - 1) & 1);
+        mbar_arrive(&bar_z);
+        break;
+      }
+      const int l = item / n_tiles, j = item - l * n_tiles;
+      const bool last = (l == a.L - 1);
+      const int b = j / a.n_tt;
+      if (l * a.B + b != key) {      // uniform over the epilogue warps: bias rows of this (layer, batch element)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < 64) pb_s[tid] = a.prebias[((size_t)l * a.B + b) * 64 + tid];
+        else if (tid < 96) bd_s[tid - 64] = a.dense_bias ? a.dense_bias[(size_t)l * C + tid - 64] : 0.f;
+        key = l * a.B + b;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      float xo[16];
+      {
+        const uint4 h0 = *reinterpret_cast<const uint4*>(Xc + row_off + ch0), h1 = *reinterpret_cast<const uint4*>(Xc + row_off + ch1);
+        const uint4 l0 = *reinterpret_cast<const uint4*>(Xc + row_off + cl0), l1 = *reinterpret_cast<const uint4*>(Xc + row_off + cl1);
+        const __half2* hh0 = reinterpret_cast<const __half2*>(&h0);
+        const __half2* hh1 = reinterpret_cast<const __half2*>(&h1);
+        const __half2* ll0 = reinterpret_cast<const __half2*>(&l0);
+        const __half2* ll1 = reinterpret_cast<const __half2*>(&l1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a0 = __half22float2(hh0[q]), b0 = __half22float2(ll0[q]);
+          const float2 a1 = __half22float2(hh1[q]), b1 = __half22float2(ll1[q]);
+          xo[2 * q] = a0.x + b0.x; xo[2 * q + 1] = a0.y + b0.y;
+          xo[8 + 2 * q] = a1.x + b1.x; xo[8 + 2 * q + 1] = a1.y + b1.y;
+        }
+      }
+      mbar_arrive(&bar_xr);      // this thread no longer needs the x tile
+      mbar_wait(&bar_m1, par);
+      tc_fence_after();
+      float z[16];
+      {
+        uint32_t fv[16], gv[16];
+        tmem_ld16(lane_addr + 0, fv);
+        tmem_ld16(lane_addr + 32, gv);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          z[q] = gated_fast(__uint_as_float(fv[q]) + pb_s[16 * half + q], __uint_as_float(gv[q]) + pb_s[32 + 16 * half + q]);
+      }
+      if (i > 0) mbar_wait(&bar_sfree, (i - 1) & 1);      // the previous tile's stores have left the staging tiles
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        *reinterpret_cast<float4*>(Sz + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4)) =
+            make_float4(round_tf32(z[4 * jj]), round_tf32(z[4 * jj + 1]), round_tf32(z[4 * jj + 2]), round_tf32(z[4 * jj + 3]));
+      if (a.z16) {
+        __align__(16) __half zq[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) zq[q] = __float2half_rn(z[q]);
+        unsigned char* zr = Zh + (uint32_t)r * 64;
+        *reinterpret_cast<uint4*>(zr + ((uint32_t)((2 * half) ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(zq);
+        *reinterpret_cast<uint4*>(zr + ((uint32_t)((2 * half + 1) ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(zq + 8);
+      }
+      if (!last) {
+        __align__(16) __half zh[16], zl[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) split_h(z[q], zh[q], zl[q]);
+        *reinterpret_cast<uint4*>(Zs + row_off + ch0) = *reinterpret_cast<const uint4*>(zh);
+        *reinterpret_cast<uint4*>(Zs + row_off + ch1) = *reinterpret_cast<const uint4*>(zh + 8);
+        *reinterpret_cast<uint4*>(Zs + row_off + cl0) = *reinterpret_cast<const uint4*>(zl);
+        *reinterpret_cast<uint4*>(Zs + row_off + cl1) = *reinterpret_cast<const uint4*>(zl + 8);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bar_z);
+      if (!last) {
+        mbar_wait(&bar_m2, par);
+        tc_fence_after();
+        uint32_t ov[16];
+        tmem_ld16(lane_addr + 64, ov);
+        float xn[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) xn[q] = xo[q] + __uint_as_float(ov[q]) + bd_s[16 * half + q];
+        if (a.has_xout) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<float4*>(Sx + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4)) =
+                make_float4(xn[4 * jj], xn[4 * jj + 1], xn[4 * jj + 2], xn[4 * jj + 3]);
+        }
+        __align__(16) __half xh[16], xl[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) split_h(xn[q], xh[q], xl[q]);
+        *reinterpret_cast<uint4*>(Zs + row_off + ch0) = *reinterpret_cast<const uint4*>(xh);
+        *reinterpret_cast<uint4*>(Zs + row_off + ch1) = *reinterpret_cast<const uint4*>(xh + 8);
+        *reinterpret_cast<uint4*>(Zs + row_off + cl0) = *reinterpret_cast<const uint4*>(xl);
+        *reinterpret_cast<uint4*>(Zs + row_off + cl1) = *reinterpret_cast<const uint4*>(xl + 8);
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_o);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 128);
+}
+
+// xs_ring: RING x [B][T][hi 32 | lo 32] fp16 (slot 0 holds the input of layer 0); xall: fp32 [L][B][T][32] with
+// xall[0] the input of layer 0 (layer l writes xall[l+1]; null: forward only); flags: L * B * ceil(T/128) + 1 words.
+int block_fwd_chain(void* xs_ring, float* xall, float* zcat, void* zcat16, int ldz, const unsigned char* img,
+                    const float* prebias, const float* dense_bias, const int* dilations, int L, int B, int T,
+                    unsigned int* flags, cudaStream_t st) {
+  if (L < 1 || L > WN_MAX_LAYERS) return -1;
+  CUtensorMap mapXS, mapZ, mapXo, mapZ16;
+  int rc = make_map_split(&mapXS, (const __half*)xs_ring, (int64_t)RING * B, T);
+  if (rc) return rc;
+  rc = make_map_3d(&mapZ, zcat, B, T, ldz, ldz, TM);
+  if (rc) return rc;
+  mapXo = mapZ;
+  if (xall) {
+    rc = make_map_3d(&mapXo, xall, (int64_t)L * B, T, C, C, TM);
+    if (rc) return rc;
+  }
+  mapZ16 = mapXS;
+  if (zcat16) {
+    rc = make_map_z16(&mapZ16, (const __half*)zcat16, B, T, ldz);
+    if (rc) return rc;
+  }
+  ChainArgs a;
+  a.img = img; a.prebias = prebias; a.dense_bias = dense_bias; a.flags = flags;
+  a.L = L; a.B = B; a.T = T; a.n_tt = (T + TM - 1) / TM;
+  a.has_xout = xall ? 1 : 0; a.z16 = zcat16 ? 1 : 0;
+  a.timeline = g_timeline_h;
+  for (int l = 0; l < WN_MAX_LAYERS; ++l) a.dil[l] = l < L ? dilations[l] : 0;
+  const size_t smem = 1024 + 5 * TILE + IMG_H + TM * 64;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(block_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -5;
+    cudaFuncSetAttribute(block_fwd_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr = true;
+  }
+  const int64_t n_items = (int64_t)L * B * a.n_tt;
+  if (n_items >= (1ll << 31) - 4096) return -1;
+  int grid = 2 * sm_count();      // two CTAs fit an SM (111 KB shared memory, 80 registers x 320 threads each)
+  if (grid > B * a.n_tt) grid = B * a.n_tt;
+  cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(n_items + 1) * sizeof(unsigned int), st);
+  if (e != cudaSuccess) return (int)e;
+  block_fwd_chain_kernel<<<grid, CH_THREADS, smem, st>>>(mapXS, mapZ, mapXo, mapZ16, a);
+  WN_CHECK_LAUNCH();
+  prof_mark(st, PT_BLOCK_FWD);
+  return 0;
+}
+int64_t block_fwd_chain_ring_bytes(int64_t M) { return (int64_t)RING * M * 128; }
 
 int block_fwd_h_set_trap_info(unsigned int* p) { return umma::set_trap_info_tu(p); }
 

@@ -48,6 +48,11 @@ int block_fwd(const float* x, float* xout, float* zc, int ldz, const unsigned ch
 int block_umma_set_trap_info(unsigned int* p);     // debug: see wn_debug_trap_info
 int block_fwd_h_set_trap_info(unsigned int* p);
 void set_fwd_h_timeline(long long* p);
+// all forward layers in one persistent kernel (block_fwd_h.cu, "chain")
+int block_fwd_chain(void* xs_ring, float* xall, float* zcat, void* zcat16, int ldz, const unsigned char* img,
+                    const float* prebias, const float* dense_bias, const int* dilations, int L, int B, int T,
+                    unsigned int* flags, cudaStream_t st);
+int64_t block_fwd_chain_ring_bytes(int64_t M);
 bool block_umma_enabled();
 void set_block_timeline(long long* p);   // debug: clock64 stamps of block_fwd_umma CTA 0 (4 tiles x 8 phases)
 void set_block_impl(int mma);
