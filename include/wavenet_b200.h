@@ -126,13 +126,15 @@ int wn_gemm_umma(int32_t mode, const float* a, int32_t lda, const float* b, int3
                  int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask, int32_t ldmask,
                  int32_t flags, int32_t split_k, wn_stream_t stream);
 
-/* The forward chain's fp16 form (skip sum / postprocess1 / postprocess2, model.py:430-440):
- * c[m,n] = a16[m,k] . b16[n,k]^T (+bias; flags: 1 relu, 2 tf32 rounding of c), both operands IEEE fp16 with
- * k contiguous, fp32 accumulation.  c16 (optional) receives the same values rounded to fp16 -- the next
- * product's operand.  lda/ldb/ldc16 multiples of 8, ldc multiple of 4; returns -3 otherwise. */
+/* The fp16 form of the post-processing products (model.py:430-440 forward, and their input gradients):
+ * v[m,n] = mask(relu(a16[m,k] . b16[n,k]^T + bias)), both operands IEEE fp16 with k contiguous, fp32
+ * accumulation; flags: 1 relu, 2 tf32 rounding of c; relu_mask (optional, fp32 [m,n]) zeroes v where mask <= 0.
+ * c = c_scale * v as fp32; c16 (optional) = v rounded to fp16 (NOT scaled) -- the next product's operand.
+ * The gradient chain runs in a domain scaled by a power of two: c16 stays in it, c_scale takes c out of it.
+ * lda/ldb/ldc16 multiples of 8, ldc/ldmask multiples of 4; returns -3 otherwise. */
 int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, void* c16,
-                   int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, int32_t flags,
-                   wn_stream_t stream);
+                   int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
+                   int32_t ldmask, float c_scale, int32_t flags, wn_stream_t stream);
 
 /* ---- softmax cross entropy vs the next sample: model.py:654-666 ---------------------------
  * logits [B*T, Q] are overwritten by d loss / d logits (TF backprop semantics) when write_grad. */

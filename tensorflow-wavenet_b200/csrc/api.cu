@@ -121,6 +121,8 @@ struct Workspace {
   unsigned char* WimgH; // per-layer fp16 split weight images of the forward block (block_fwd_h.cu)
   void *Zcat16, *A1h, *A2h;       // fp16 copies of the forward GEMM A operands (fp16 forward chain)
   void *Wskip16, *W1h, *W2h;      // fp16 K-major weight copies: [S][L*D], [S][S], [Q][S]
+  void *dlog16, *G1h, *G2h;       // gradients of the post-processing chain as fp16, scaled by gscale (training, fp16 chain)
+  void *Wskipg, *W1g, *W2g;       // fp16 copies of the weights as stored ([L*D][S], [S][S], [S][Q]): input-gradient operands
   unsigned int* chain_flags;      // [L][B * ceil(T/128)] tile flags of the persistent forward kernel (null: per-layer launches)
   void* XS;             // 2 x [M][hi 32 | lo 32] fp16 split rows: the residual stream between forward layers
   int umma_bwd;    // 1 when the tcgen05 backward path is used
@@ -198,7 +200,8 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   const bool chain = fwd_h && fwd_chain_enabled();
   w->XS = fwd_h ? take(chain ? block_fwd_chain_ring_bytes(M) : 2 * M * 128) : nullptr;
   w->chain_flags = chain ? (unsigned int*)take((L * (int64_t)B * ((T + 127) / 128) + 1) * 4) : nullptr;
-  if (fwd_h && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0) {
+  const bool f16_chain = fwd_h && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0;
+  if (f16_chain) {
     w->Zcat16 = take(M * L * D * 2);
     w->A1h = take(M * S * 2);
     w->A2h = take(M * S * 2);
@@ -207,6 +210,16 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->W2h = take(Q * S * 2);
   } else {
     w->Zcat16 = w->A1h = w->A2h = w->Wskip16 = w->W1h = w->W2h = nullptr;
+  }
+  if (training && f16_chain && (Q % 8) == 0) {      // (not a pointer test: a size query carves from a null base)
+    w->dlog16 = take(M * Q * 2);
+    w->G1h = take(M * S * 2);
+    w->G2h = take(M * S * 2);
+    w->Wskipg = take(L * D * S * 2);
+    w->W1g = take(S * S * 2);
+    w->W2g = take(S * Q * 2);
+  } else {
+    w->dlog16 = w->G1h = w->G2h = w->Wskipg = w->W1g = w->W2g = nullptr;
   }
   if (training) {
     w->logits = (float*)take(M * Q * f);
@@ -356,12 +369,17 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     RC(transpose_half(params + lo.skip, ldz, S, w.Wskip16, ldz, st));
     RC(transpose_half(params + lo.post1, S, S, w.W1h, S, st));
     RC(transpose_half(params + lo.post2, S, Q, w.W2h, S, st));
+    if (w.dlog16) {   // operands of the fp16 input-gradient chain (the weights as stored)
+      RC(to_half(params + lo.post2, w.W2g, (int64_t)S * Q, st));
+      RC(to_half(params + lo.post1, w.W1g, (int64_t)S * S, st));
+      RC(to_half(params + lo.skip, w.Wskipg, (int64_t)ldz * S, st));
+    }
     prof_mark(st, PT_MISC);
-    RC(gemm_f16_nt(w.Zcat16, ldz, w.Wskip16, ldz, w.A1, S, w.A1h, S, M, S, ldz, bsum, GEMM_RELU | GEMM_ROUND, st));
+    RC(gemm_f16_nt(w.Zcat16, ldz, w.Wskip16, ldz, w.A1, S, w.A1h, S, M, S, ldz, bsum, nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st));
     prof_mark(st, PT_GEMM_SKIP_FWD);
-    RC(gemm_f16_nt(w.A1h, S, w.W1h, S, w.A2, S, w.A2h, S, M, S, S, P(params, lo.post1_bias), GEMM_RELU | GEMM_ROUND, st));
+    RC(gemm_f16_nt(w.A1h, S, w.W1h, S, w.A2, S, w.A2h, S, M, S, S, P(params, lo.post1_bias), nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st));
     prof_mark(st, PT_GEMM_POST1_FWD);
-    RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, M, Q, S, P(params, lo.post2_bias), 0, st));
+    RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, M, Q, S, P(params, lo.post2_bias), nullptr, 0, 1.f, 0, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
     return 0;
   }
@@ -551,10 +569,11 @@ int wn_gemm_nt_umma(const float* a, int32_t lda, const float* b, int32_t ldb, fl
 }
 
 int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, void* c16,
-                   int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, int32_t flags,
-                   wn_stream_t stream) {
+                   int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
+                   int32_t ldmask, float c_scale, int32_t flags, wn_stream_t stream) {
   if (!a16 || !b16 || !c) return -1;
-  return gemm_f16_nt(a16, lda, b16, ldb, c, ldc, c16, ldc16, m, n, k, bias, flags, (cudaStream_t)stream);
+  return gemm_f16_nt(a16, lda, b16, ldb, c, ldc, c16, ldc16, m, n, k, bias, relu_mask, ldmask, c_scale, flags,
+                     (cudaStream_t)stream);
 }
 
 int wn_gemm_umma(int32_t mode, const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc,
@@ -574,7 +593,7 @@ int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t ti
                     int32_t n_partials, float* loss_out, int32_t write_grad, wn_stream_t stream) {
   if (!logits || !ids || !partials || !loss_out || batch < 1 || time < 1) return -1;
   const int M = batch * time;
-  return softmax_xent(logits, ids, M, time, q, 1.0f / (float)M, partials, n_partials, loss_out, write_grad,
+  return softmax_xent(logits, ids, M, time, q, 1.0f / (float)M, partials, n_partials, loss_out, write_grad, nullptr, 0.f,
                       (cudaStream_t)stream);
 }
 
@@ -629,7 +648,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, w.logits, st));
   const int trunc = truncate_stage();
   if (trunc == 1) return 0;
-  RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, st));
+  // fp16 input-gradient chain: gradients travel scaled by gscale = 2^ceil(log2 M), i.e. (softmax - onehot) * [1, 2)
+  float gscale = 1.f;
+  while (gscale < (float)M) gscale *= 2.f;
+  RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, w.dlog16, gscale / (float)M, st));
   prof_mark(st, PT_XENT);
   if (trunc == 2) return 0;
 
@@ -651,7 +673,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     prof_mark(s2, PT_GEMM_POST2_WGRAD);
     if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, s2)); prof_mark(s2, PT_COLSUM); }
   }
-  {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
+  if (w.dlog16) {
+    RC(gemm_f16_nt(w.dlog16, Q, w.W2g, Q, w.G1, S, w.G1h, S, M, S, Q, nullptr, w.A2, S, 1.f / gscale, GEMM_ROUND, st));
+    prof_mark(st, PT_GEMM_POST2_DGRAD);
+  } else {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
     GemmParams p = gp(w.logits, Q, w.W2R, Q, w.G1, S, M, S, Q);
     p.aux = w.A2; p.ldaux = S;
     p.flags = GEMM_ROUND;
@@ -667,7 +692,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     prof_mark(s2, PT_GEMM_POST1_WGRAD);
     if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, s2)); prof_mark(s2, PT_COLSUM); }
   }
-  {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
+  if (w.dlog16) {
+    RC(gemm_f16_nt(w.G1h, S, w.W1g, S, w.G2, S, w.G2h, S, M, S, S, nullptr, w.A1, S, 1.f / gscale, GEMM_ROUND, st));
+    prof_mark(st, PT_GEMM_POST1_DGRAD);
+  } else {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
     GemmParams p = gp(w.G1, S, w.W1R, S, w.G2, S, M, S, S);
     p.aux = w.A1; p.ldaux = S;
     p.flags = rp ? 0 : GEMM_ROUND;
@@ -693,7 +721,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
   }
   RC((int)cudaEventRecord(ev_g[3], s2));
-  {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
+  if (w.dlog16) {
+    RC(gemm_f16_nt(w.G2h, S, w.Wskipg, S, w.dZcat, ldz, nullptr, 0, M, ldz, S, nullptr, nullptr, 0, 1.f / gscale, 0, st));
+    prof_mark(st, PT_GEMM_SKIP_DGRAD);
+  } else {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
     GemmParams p = gp(w.G2, S, w.WskipR, S, w.dZcat, ldz, M, ldz, S);
     RC(gemm(1, p, 1, st));
     prof_mark(st, PT_GEMM_SKIP_DGRAD);

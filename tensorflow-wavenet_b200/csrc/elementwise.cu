@@ -1,6 +1,8 @@
 // HBM-bound kernels around the dilated stack: mu-law companding (integer, bit exact),
 // one-hot front end as a row gather, softmax cross entropy (forward + TF-style backprop),
 // conditioning / bias helpers and the TF-semantics optimizers.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -199,7 +201,7 @@ int frontend_bwd(const int32_t* ids, const float* dx0, float* gwc, int M, int T,
 template <int NV>   // float4 vectors per lane: Q <= 128*NV
 __global__ void __launch_bounds__(256)
 xent_kernel(float* __restrict__ logits, const int32_t* __restrict__ ids, int M, int T, int Q, float scale,
-            float* __restrict__ partials, int write_grad) {
+            float* __restrict__ partials, int write_grad, __half* __restrict__ g16, float scale16) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
   double local = 0.0;
@@ -250,6 +252,10 @@ xent_kernel(float* __restrict__ logits, const int32_t* __restrict__ ids, int M, 
           o.x = round_tf32(p0 * scale); o.y = round_tf32(p1 * scale);
           o.z = round_tf32(p2 * scale); o.w = round_tf32(p3 * scale);
           *reinterpret_cast<float4*>(row + c) = o;
+          if (g16) {      // the same gradient in the scaled fp16 domain of the input-gradient GEMM chain
+            __half2 h[2] = {__floats2half2_rn(p0 * scale16, p1 * scale16), __floats2half2_rn(p2 * scale16, p3 * scale16)};
+            *reinterpret_cast<uint2*>(g16 + (size_t)m * Q + c) = *reinterpret_cast<uint2*>(h);
+          }
         }
       }
     }
@@ -281,14 +287,15 @@ __global__ void xent_finalize_kernel(const float* __restrict__ partials, int n, 
 }
 
 int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float scale, float* partials,
-                 int n_partials, float* loss_out, int write_grad, cudaStream_t st) {
+                 int n_partials, float* loss_out, int write_grad, void* g16v, float scale16, cudaStream_t st) {
+  __half* g16 = (__half*)g16v;
   if (M <= 0 || (Q & 3) || Q > 1024 || n_partials < 1) return -1;
   int grid = (M + 7) / 8;
   if (grid > n_partials) grid = n_partials;
-  if (Q <= 128) xent_kernel<1><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad);
-  else if (Q <= 256) xent_kernel<2><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad);
-  else if (Q <= 512) xent_kernel<4><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad);
-  else xent_kernel<8><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad);
+  if (Q <= 128) xent_kernel<1><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad, g16, scale16);
+  else if (Q <= 256) xent_kernel<2><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad, g16, scale16);
+  else if (Q <= 512) xent_kernel<4><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad, g16, scale16);
+  else xent_kernel<8><<<grid, 256, 0, st>>>(logits, ids, M, T, Q, scale, partials, write_grad, g16, scale16);
   WN_CHECK_LAUNCH();
   xent_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, scale, loss_out);
   WN_CHECK_LAUNCH();

@@ -123,13 +123,15 @@ struct UmmaParams {
   int stages;                     // depth of the TMA -> MMA ring
   int a_mn, b_mn;                 // operand majors: 0 = K contiguous, 1 = M / N contiguous
   int f16;                        // operands are fp16 (K-major, 64 elements per stage, kind::f16); C stays fp32
-  int has_c16;                    // additional fp16 copy of C through mapAux (forward chain: the next GEMM's A operand)
+  int has_c16;                    // additional fp16 copy of the accumulators through mapC16 (the next GEMM's A operand)
+  float c_scale;                  // C = c_scale * (accumulator, bias, relu, mask); the fp16 copy stays unscaled (0: no scaling)
 };
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapAux, UmmaParams p) {
+                 const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapAux, const __grid_constant__ CUtensorMap mapC16,
+                 UmmaParams p) {
   constexpr uint32_t A_BYTES = UM * UK * 4;       // 16 KB
   constexpr uint32_t B_BYTES = BN * UK * 4;       // 16 / 32 KB
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -143,6 +145,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int STAGES = p.stages;
   unsigned char* out_stage = smem + STAGES * STAGE_BYTES;
   unsigned char* aux_stage = out_stage + 4 * 2 * STG_BYTES;
+  unsigned char* c16_stage = aux_stage + 4 * 2 * STG_BYTES;      // [4 warps][2][32 rows][32 halfs] (only with has_c16)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Persistent CTA: work items (output tile x K split), N tile fastest so that CTAs running side by side share
@@ -240,6 +243,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int etid = threadIdx.x - 64;                       // 0..127 among the epilogue warps
     unsigned char* my_out = out_stage + quad * 2 * STG_BYTES;
     unsigned char* my_aux = aux_stage + quad * 2 * STG_BYTES;
+    unsigned char* my_c16 = c16_stage + quad * 2 * (STG_BYTES / 2);
     const bool staged = !(p.flags & GEMM_ATOMIC) && p.C != nullptr;
     uint32_t local = 0, out_cnt = 0, aux_cnt = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
@@ -336,6 +340,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           __syncwarp();      // every lane has read the buffer before a later load re-targets it
           ++aux_cnt;
         }
+        uint4 hq[4];      // fp16 copy of the (unscaled) values
+        if (p.has_c16) {
+          __half2* h2 = reinterpret_cast<__half2*>(hq);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            h2[j] = __floats2half2_rn(fminf(fmaxf(f[2 * j], -65504.f), 65504.f), fminf(fmaxf(f[2 * j + 1], -65504.f), 65504.f));
+        }
+        if (p.c_scale != 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= p.c_scale;
+        }
         if (p.flags & GEMM_ROUND) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
@@ -348,14 +363,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(os + ((uint32_t)(j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          if (p.has_c16) {      // same values as fp16 [32 rows][32 halfs] (64-byte rows, 64B swizzle) for the next GEMM
-            __align__(16) __half hv[32];
+          if (p.has_c16) {      // [32 rows][32 halfs] (64-byte rows, 64B swizzle) for the next GEMM
+            unsigned char* hs = my_c16 + buf * (STG_BYTES / 2) + lane * 64;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) hv[j] = __float2half_rn(fminf(f[j], 65504.f));
-            unsigned char* hs = my_aux + buf * STG_BYTES + lane * 64;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(hs + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(hv + 8 * j);
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(hs + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4)) = hq[j];
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -364,7 +375,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                          ::"l"(&mapC), "r"(smem_u32(my_out + buf * STG_BYTES)), "r"(nb), "r"(row0) : "memory");
             if (p.has_c16)
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                           ::"l"(&mapAux), "r"(smem_u32(my_aux + buf * STG_BYTES)), "r"(nb), "r"(row0) : "memory");
+                           ::"l"(&mapC16), "r"(smem_u32(my_c16 + buf * (STG_BYTES / 2))), "r"(nb), "r"(row0) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++out_cnt;
@@ -385,6 +396,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN));
+}
+
+static int launch_umma(int BN, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB,
+                       const CUtensorMap& mC, const CUtensorMap& mAux, const CUtensorMap& mC16, const UmmaParams& p) {
+  constexpr int MAX_SMEM = 1024 + 3 * (UM + 256) * UK * 4 + 16 * (int)STG_BYTES + 8 * (int)(STG_BYTES / 2);
+  if (smem > (size_t)MAX_SMEM) return -5;
+  if (BN == 256) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM); attr = true; }
+    gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, mC16, p);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM); attr = true; }
+    gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, mC16, p);
+  }
+  WN_CHECK_LAUNCH();
+  return 0;
 }
 
 // mode 0 NN / 1 NT / 2 TN (see the file header).  Returns -3 for shapes the tcgen05 path does not take
@@ -435,30 +463,23 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   const bool atomic = (g.flags & GEMM_ATOMIC) != 0;
   p.stages = atomic ? 4 : 3;
   const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + (atomic ? 0 : 2 * 4 * 2 * STG_BYTES);
-  if (BN == 256) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 3 * (UM + 256) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
-    gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
-  } else {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 4 * (UM + 128) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
-    gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
-  }
-  WN_CHECK_LAUNCH();
-  return 0;
+  p.c_scale = 0.f;
+  return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mAux, p);
 }
 
-// Forward chain in fp16: C[M,N] = A16[M,K] . B16[N,K]^T (+bias, relu), fp32 accumulate; C is written as fp32 (kept for
-// the backward pass) and, when c16 is given, also as fp16 (A operand of the next GEMM).  Every GEMM of the step is bound
-// by the L2 -> SM operand traffic, so halving the operand bytes (and doubling the MMA rate) halves these three.
+// fp16 operands (K-major), fp32 accumulate:  C[M,N] = c_scale * mask(relu(A16[M,K] . B16[N,K]^T + bias)), written as fp32
+// and, when c16 is given, also as fp16 WITHOUT c_scale (the A operand of the next GEMM of a chain).
+// Forward chain (skip sum, postprocess1/2): every GEMM of the step is bound by the L2 -> SM operand traffic, so halving
+// the operand bytes (and doubling the MMA rate) nearly halves these.  Backward input-gradient chain: the gradients
+// travel as fp16 in a domain scaled by a power of two (c_scale undoes it for the fp32 copies).
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
-                int K, const float* bias, int flags, cudaStream_t st) {
+                int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || !C) return -1;
   if ((lda & 7) || (ldb & 7) || (ldc & 3) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
-      ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (flags & GEMM_ATOMIC))
+      ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & 3) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
     return -3;
   const int BN = N > 128 ? 256 : 128;
-  CUtensorMap mA, mB, mC, mAux;
+  CUtensorMap mA, mB, mC, mAux, mC16;
   int rc = make_map16(&mA, A16, M, K, lda, UM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   rc = make_map16(&mB, B16, N, K, ldb, BN, 64, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -466,31 +487,27 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   rc = make_map(&mC, C, M, N, ldc, 32);
   if (rc) return rc;
   mAux = mC;
+  if (aux) {
+    rc = make_map(&mAux, aux, M, N, ldaux, 32);
+    if (rc) return rc;
+  }
+  mC16 = mC;
   if (C16) {
-    rc = make_map16(&mAux, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_map16(&mC16, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   UmmaParams p;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
-  p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = flags;
+  p.aux = aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
   p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
+  p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
   p.k_per_split = (K + 63) / 64 * 64;
   p.splits = 1;
   p.stages = 3;
   const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + UM - 1) / UM);
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + 2 * 4 * 2 * STG_BYTES;
-  if (BN == 256) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 3 * (UM + 256) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
-    gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
-  } else {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 4 * (UM + 128) * UK * 4 + 16 * (int)STG_BYTES); attr = true; }
-    gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, p);
-  }
-  WN_CHECK_LAUNCH();
-  return 0;
+  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + 2 * 4 * 2 * STG_BYTES + (C16 ? 4 * 2 * (STG_BYTES / 2) : 0);
+  return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p);
 }
 
 // out16[n][k] = half(in[k][n])   (fp16 K-major weight copies for gemm_f16_nt; [K][N] fp32 row-major in)
@@ -506,6 +523,22 @@ __global__ void transpose_half_kernel(const float* __restrict__ in, int K, int N
     const int n = n0 + i, k = k0 + threadIdx.x;
     if (n < N && k < K) out[(size_t)n * ldo + k] = __float2half_rn(tile[threadIdx.x][i]);
   }
+}
+__global__ void to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    __half2 h[2] = {__floats2half2_rn(v.x, v.y), __floats2half2_rn(v.z, v.w)};
+    *reinterpret_cast<uint2*>(out + 4 * i) = *reinterpret_cast<uint2*>(h);
+  }
+}
+int to_half(const float* in, void* out, int64_t n, cudaStream_t st) {
+  if (n & 3) return -3;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  to_half_kernel<<<(int)blocks, 256, 0, st>>>(in, (__half*)out, n / 4);
+  WN_CHECK_LAUNCH();
+  return 0;
 }
 int transpose_half(const float* in, int K, int N, void* out, int ldo, cudaStream_t st) {
   dim3 grid((N + 31) / 32, (K + 31) / 32);

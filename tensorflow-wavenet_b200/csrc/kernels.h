@@ -36,7 +36,9 @@ int gemm_umma(int mode, const GemmParams& p, float* CT, int ldct, int split_k, c
 bool gemm_umma_supported(int mode, const GemmParams& p);
 // forward chain in fp16 (operands K-major fp16, fp32 accumulate / output, optional fp16 copy of the output)
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
-                int K, const float* bias, int flags, cudaStream_t st);
+                int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st);
+// out[i] = half(in[i])
+int to_half(const float* in, void* out, int64_t n, cudaStream_t st);
 int transpose_half(const float* in, int K, int N, void* out, int ldo, cudaStream_t st);
 int transpose(const float* in, int ldi, float* out, int ldo, int rows, int cols, int round_out, cudaStream_t st);
 int round_copy(const float* in, float* out, int64_t n, cudaStream_t st);
@@ -101,8 +103,9 @@ int mulaw_decode(const int32_t* ids, int64_t n, const float* lut, int Q, float* 
 int frontend_fwd(const int32_t* ids, const float* wc, float* x0, int M, int T, int Q, int R, cudaStream_t st);
 int frontend_bwd(const int32_t* ids, const float* dx0, float* gwc, int M, int T, int Q, int R, cudaStream_t st);
 
+// g16 (optional): the gradient also as fp16 [M,Q], (softmax - onehot) * scale16
 int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float scale, float* row_loss_partials,
-                 int n_partials, float* loss_out, int write_grad, cudaStream_t st);
+                 int n_partials, float* loss_out, int write_grad, void* g16, float scale16, cudaStream_t st);
 
 // prebias[l][b][2D] = [filter_bias_l | gate_bias_l] + emb[b] . [gc_filter_l | gc_gate_l]
 int cond_bias_fwd(float* prebias, const float* filter_bias, const float* gate_bias, const float* gc_filter,

@@ -316,22 +316,29 @@ def test_gemm_f16_nt(lib, M, N, K):
     c = torch.full((M, N), -7.0, device='cuda')
     c16 = torch.full((M, N), -7.0, device='cuda', dtype=torch.float16)
     ref = a.astype(np.float64) @ b.astype(np.float64).T
-    assert lib.wn_gemm_f16_nt(p(da), K, p(db), K, p(c), N, None, 0, M, N, K, None, 0, stream()) == 0
+    assert lib.wn_gemm_f16_nt(p(da), K, p(db), K, p(c), N, None, 0, M, N, K, None, None, 0, 1.0, 0, stream()) == 0
     torch.cuda.synchronize()
     assert rel_err(c.cpu().numpy(), ref) < 1e-5
-    assert lib.wn_gemm_f16_nt(p(da), K, p(db), K, p(c), N, p(c16), N, M, N, K, p(dev(bias)), 1 | 2, stream()) == 0
+    assert lib.wn_gemm_f16_nt(p(da), K, p(db), K, p(c), N, p(c16), N, M, N, K, p(dev(bias)), None, 0, 1.0, 1 | 2, stream()) == 0
     torch.cuda.synchronize()
     ref = np.maximum(ref + bias, 0)
     out = c.cpu().numpy()
     assert rel_err(out, ref) < LOGIT_RTOL
     np.testing.assert_array_equal(out, O.round_tf32(torch.tensor(out)).numpy())          # tf32-exact values ...
-    np.testing.assert_array_equal(c16.cpu().numpy(), out.astype(np.float16))              # ... whose fp16 copy is exact
+    np.testing.assert_allclose(c16.cpu().numpy().astype(np.float32), out, rtol=1e-3, atol=1e-7)   # the fp16 copy (one rounding)
+    # gradient-chain form: relu mask from another matrix, fp32 copy scaled out of the fp16 domain
+    mask = rng.standard_normal((M, N)).astype(np.float32)
+    assert lib.wn_gemm_f16_nt(p(da), K, p(db), K, p(c), N, p(c16), N, M, N, K, None, p(dev(mask)), N, 0.25, 2, stream()) == 0
+    torch.cuda.synchronize()
+    ref = (a.astype(np.float64) @ b.astype(np.float64).T) * (mask > 0)
+    assert rel_err(c.cpu().numpy(), 0.25 * ref) < LOGIT_RTOL
+    assert rel_err(c16.cpu().numpy().astype(np.float64), ref) < 1e-3
 
 
 def test_gemm_f16_rejects_unaligned(lib):
     a = torch.zeros(64, 44, device='cuda', dtype=torch.float16)
     c = torch.zeros(64, 64, device='cuda')
-    assert lib.wn_gemm_f16_nt(p(a), 44, p(a), 44, p(c), 64, None, 0, 64, 64, 44, None, 0, stream()) == -3
+    assert lib.wn_gemm_f16_nt(p(a), 44, p(a), 44, p(c), 64, None, 0, 64, 64, 44, None, None, 0, 1.0, 0, stream()) == -3
 
 
 def test_gemm_umma_rejects_unaligned_mn(lib):
