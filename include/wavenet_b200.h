@@ -136,6 +136,12 @@ int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, f
                    int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
                    int32_t ldmask, float c_scale, int32_t flags, wn_stream_t stream);
 
+/* Weight-gradient form on fp16 operands: c[m,n] += c_scale * sum_k a16[k,m] * b16[k,n]  (a16 [k][lda], b16 [k][ldb] as
+ * they lie in memory: time is the row index; fp32 accumulation, split over k, red.global.add into c).
+ * m, n multiples of 64, lda/ldb multiples of 8; returns -3 otherwise. */
+int wn_gemm_f16_tn(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, int32_t m, int32_t n,
+                   int32_t k, float c_scale, int32_t split_k, wn_stream_t stream);
+
 /* ---- softmax cross entropy vs the next sample: model.py:654-666 ---------------------------
  * logits [B*T, Q] are overwritten by d loss / d logits (TF backprop semantics) when write_grad. */
 int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t time, int32_t q,

@@ -576,6 +576,11 @@ int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, f
                      (cudaStream_t)stream);
 }
 
+int wn_gemm_f16_tn(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, int32_t m, int32_t n,
+                   int32_t k, float c_scale, int32_t split_k, wn_stream_t stream) {
+  return gemm_f16_tn(a16, lda, b16, ldb, c, ldc, m, n, k, c_scale, split_k, (cudaStream_t)stream);
+}
+
 int wn_gemm_umma(int32_t mode, const float* a, int32_t lda, const float* b, int32_t ldb, float* c, int32_t ldc,
                  int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask, int32_t ldmask,
                  int32_t flags, int32_t split_k, wn_stream_t stream) {
@@ -669,7 +674,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC((int)cudaStreamWaitEvent(s2, ev_g[0], 0));
   {  // postprocess2 gradients:  dW2[S,Q] = X2^T . dlogits
     GemmParams p = gp(x2, S, w.logits, Q, grads + lo.post2, Q, S, Q, M);
-    RC(gemm(2, p, split_for(S, Q, M), s2));
+    if (w.dlog16 && gemm_f16_tn_supported(S, Q, S, Q))      // fp16 operands: A2 copy and the scaled gradient
+      RC(gemm_f16_tn(w.A2h, S, w.dlog16, Q, grads + lo.post2, Q, S, Q, M, 1.f / gscale, split_for(S, Q, M), s2));
+    else
+      RC(gemm(2, p, split_for(S, Q, M), s2));
     prof_mark(s2, PT_GEMM_POST2_WGRAD);
     if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, s2)); prof_mark(s2, PT_COLSUM); }
   }
@@ -688,7 +696,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC((int)cudaStreamWaitEvent(s2, ev_g[1], 0));
   {  // postprocess1 gradients:  dW1[S,S] = A1^T . G1
     GemmParams p = gp(w.A1, S, w.G1, S, grads + lo.post1, S, S, S, M);
-    RC(gemm(2, p, split_for(S, S, M), s2));
+    if (w.dlog16 && gemm_f16_tn_supported(S, S, S, S))
+      RC(gemm_f16_tn(w.A1h, S, w.G1h, S, grads + lo.post1, S, S, S, M, 1.f / gscale, split_for(S, S, M), s2));
+    else
+      RC(gemm(2, p, split_for(S, S, M), s2));
     prof_mark(s2, PT_GEMM_POST1_WGRAD);
     if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, s2)); prof_mark(s2, PT_COLSUM); }
   }
@@ -710,7 +721,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC((int)cudaStreamWaitEvent(s2, ev_g[2], 0));
   {  // skip weights / biases:  dWskip[L*D,S] = Zcat^T . G2
     GemmParams p = gp(w.Zcat, ldz, w.G2, S, grads + lo.skip, S, ldz, S, M);
-    RC(gemm(2, p, split_for(ldz, S, M), s2));
+    if (w.dlog16 && gemm_f16_tn_supported(ldz, S, ldz, S))
+      RC(gemm_f16_tn(w.Zcat16, ldz, w.G2h, S, grads + lo.skip, S, ldz, S, M, 1.f / gscale, split_for(ldz, S, M), s2));
+    else
+      RC(gemm(2, p, split_for(ldz, S, M), s2));
     prof_mark(s2, PT_GEMM_SKIP_WGRAD);
     if (lo.skip_bias >= 0) {
       RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), s2));

@@ -194,18 +194,33 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           unsigned char* sa = smem + s * STAGE_BYTES;
           const int kc = k_begin + i * ukk;
-          if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> 5);     // [UM/32 blocks][32 k][32 m]
+          const int bsh = p.f16 ? 6 : 5;      // MN-major blocks: 32 floats / 64 halfs wide
+          if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> bsh);     // [blocks][k rows][128 B of m]
           else tma_load_2d(sa, &mapA, &full_bar[s], kc, m0);
-          if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> 5);
+          if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> bsh);
           else tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kc, n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = p.f16 ? ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24))
+      const uint32_t idesc = p.f16 ? ((1u << 4) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                                      ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24))
                                    : umma::idesc_tf32(UM, BN, p.a_mn, p.b_mn);
-      const uint32_t astep = p.a_mn ? 64 : 2, bstep = p.b_mn ? 64 : 2;   // descriptor start-address step per K=8
+      // descriptor start-address step per MMA (>> 4): K-major 32 B; MN-major tf32 8 rows x 128 B, fp16 16 rows x 128 B
+      const uint32_t mnstep = p.f16 ? 128 : 64;
+      const uint32_t astep = p.a_mn ? mnstep : 2, bstep = p.b_mn ? mnstep : 2;
+      // MN-major fp16 (probe/umma_probe_h.cu): plain 128B swizzle, blocks of 64 elements x 64 k rows (LBO 8192), SBO 1024
+      auto mn_desc = [&](uint32_t saddr) -> uint64_t {
+        if (!p.f16) return umma::mnmajor_desc(saddr, 4096);
+        uint64_t d = 0;
+        d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+        d |= (uint64_t)(8192 >> 4) << 16;
+        d |= (uint64_t)(1024 >> 4) << 32;
+        d |= (uint64_t)1 << 46;
+        d |= (uint64_t)2 << 61;
+        return d;
+      };
       uint32_t it = 0, local = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
         int m0, n0, k_begin, nk;
@@ -220,8 +235,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_wait(&full_bar[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t da = p.a_mn ? umma::mnmajor_desc(sa, 4096) : kmajor_desc(sa);
-          const uint64_t db = p.b_mn ? umma::mnmajor_desc(sa + A_BYTES, 4096) : kmajor_desc(sa + A_BYTES);
+          const uint64_t da = p.a_mn ? mn_desc(sa) : kmajor_desc(sa);
+          const uint64_t db = p.b_mn ? mn_desc(sa + A_BYTES) : kmajor_desc(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < UK / 8; ++k) {
             const uint32_t accum = (i > 0 || k > 0) ? 1u : 0u;
@@ -284,6 +299,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int nb = n0 + c0;
         const bool full = (nb + 32 <= p.N);
         if (p.flags & GEMM_ATOMIC) {
+          if (p.c_scale != 0.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.c_scale);
+          }
           if (row_ok) {
             float* dst = p.C + (size_t)row * p.ldc + nb;
             if (full) {
@@ -508,6 +527,55 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
   const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + 2 * 4 * 2 * STG_BYTES + (C16 ? 4 * 2 * (STG_BYTES / 2) : 0);
   return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p);
+}
+
+// fp16 [rows][cols] row-major viewed as [cols/64][rows][64]: one box {64, 64 rows, n_blocks} lands as n_blocks
+// consecutive [64 rows][64 halfs] blocks (128-byte rows, plain 128B swizzle).  Coordinates: (0, row, col / 64).
+static int make_map16_blocks_mn(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int n_blocks) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, 64, (cuuint32_t)n_blocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+
+bool gemm_f16_tn_supported(int lda, int ldb, int M, int N) {
+  return M > 0 && N > 0 && !(M & 63) && !(N & 63) && !(lda & 7) && !(ldb & 7);
+}
+
+// Weight-gradient form on fp16 operands:  C[M,N] += c_scale * A16[K,M]^T . B16[K,N]  (both operands as they lie in
+// memory: the contracted dimension -- time -- is the row index), split over K, accumulated with red.global.add.
+int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, int M, int N, int K, float c_scale,
+                int split_k, cudaStream_t st) {
+  if (K <= 0 || !A16 || !B16 || !C) return -1;
+  if (!gemm_f16_tn_supported(lda, ldb, M, N) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) || (ldc & 3) || ((uintptr_t)C & 15))
+    return -3;
+  const int BN = N > 128 ? 256 : 128;
+  CUtensorMap mA, mB;
+  int rc = make_map16_blocks_mn(&mA, A16, K, M, lda, UM / 64);
+  if (rc) return rc;
+  rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
+  if (rc) return rc;
+  UmmaParams p;
+  p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
+  p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
+  p.a_mn = 1; p.b_mn = 1; p.f16 = 1; p.has_c16 = 0;
+  p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
+  int splits = split_k > 0 ? split_k : 1;
+  int kps = ((K + splits - 1) / splits + 63) / 64 * 64;
+  splits = (K + kps - 1) / kps;
+  p.k_per_split = kps;
+  p.splits = splits;
+  p.stages = 4;
+  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + UM - 1) / UM) * splits;
+  if (items > (1 << 30)) return -1;
+  dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
+  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
+  return launch_umma(BN, grid, smem, st, mA, mB, mA, mA, mA, p);
 }
 
 // out16[n][k] = half(in[k][n])   (fp16 K-major weight copies for gemm_f16_nt; [K][N] fp32 row-major in)

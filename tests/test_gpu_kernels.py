@@ -335,6 +335,22 @@ def test_gemm_f16_nt(lib, M, N, K):
     assert rel_err(c16.cpu().numpy().astype(np.float64), ref) < 1e-3
 
 
+@pytest.mark.parametrize('M,N,K,split', [(128, 256, 64, 1), (512, 256, 5000, 6), (1600, 512, 3333, 3), (64, 64, 200, 2)])
+def test_gemm_f16_tn(lib, M, N, K, split):
+    """Weight-gradient form on fp16 MN-major operands (both read as they lie in memory), split-K atomics, scaled."""
+    rng = np.random.default_rng(M + N + K)
+    a = rng.standard_normal((K, M)).astype(np.float16)
+    b = rng.standard_normal((K, N)).astype(np.float16)
+    da, db = torch.tensor(a, device='cuda'), torch.tensor(b, device='cuda')
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    c = dev(c0)
+    assert lib.wn_gemm_f16_tn(p(da), M, p(db), N, p(c), N, M, N, K, 0.5, split, stream()) == 0
+    torch.cuda.synchronize()
+    ref = c0 + 0.5 * (a.astype(np.float64).T @ b.astype(np.float64))
+    assert rel_err(c.cpu().numpy(), ref) < 1e-5
+    assert lib.wn_gemm_f16_tn(p(da), M, p(db), N, p(c), N, M + 32, N, K, 1.0, 1, stream()) == -3
+
+
 def test_gemm_f16_rejects_unaligned(lib):
     a = torch.zeros(64, 44, device='cuda', dtype=torch.float16)
     c = torch.zeros(64, 64, device='cuda')
