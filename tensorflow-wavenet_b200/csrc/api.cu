@@ -211,7 +211,9 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   } else {
     w->Zcat16 = w->A1h = w->A2h = w->Wskip16 = w->W1h = w->W2h = nullptr;
   }
-  if (training && f16_chain && (Q % 8) == 0) {      // (not a pointer test: a size query carves from a null base)
+  // fp16 gradient chain of the post-processing layers: all-or-nothing (its GEMMs keep no fp32 copies of G1 / G2), so
+  // every weight-gradient shape must suit the fp16 MN-major form (multiples of 64); otherwise the tf32 chain runs
+  if (training && f16_chain && (Q % 64) == 0 && (S % 64) == 0 && ((L * D) % 64) == 0) {      // (not a pointer test: a size query carves from a null base)
     w->dlog16 = take(M * Q * 2);
     w->G1h = take(M * S * 2);
     w->G2h = take(M * S * 2);
@@ -674,15 +676,19 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC((int)cudaStreamWaitEvent(s2, ev_g[0], 0));
   {  // postprocess2 gradients:  dW2[S,Q] = X2^T . dlogits
     GemmParams p = gp(x2, S, w.logits, Q, grads + lo.post2, Q, S, Q, M);
-    if (w.dlog16 && gemm_f16_tn_supported(S, Q, S, Q))      // fp16 operands: A2 copy and the scaled gradient
+    if (w.dlog16)      // fp16 operands: A2 copy and the scaled gradient
       RC(gemm_f16_tn(w.A2h, S, w.dlog16, Q, grads + lo.post2, Q, S, Q, M, 1.f / gscale, split_for(S, Q, M), s2));
     else
       RC(gemm(2, p, split_for(S, Q, M), s2));
     prof_mark(s2, PT_GEMM_POST2_WGRAD);
-    if (lo.post2_bias >= 0) { RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, s2)); prof_mark(s2, PT_COLSUM); }
+    if (lo.post2_bias >= 0) {
+      if (w.dlog16) RC(colsum16(w.dlog16, Q, M, Q, 1.f / gscale, grads + lo.post2_bias, s2));
+      else RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, s2));
+      prof_mark(s2, PT_COLSUM);
+    }
   }
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.dlog16, Q, w.W2g, Q, w.G1, S, w.G1h, S, M, S, Q, nullptr, w.A2, S, 1.f / gscale, GEMM_ROUND, st));
+    RC(gemm_f16_nt(w.dlog16, Q, w.W2g, Q, nullptr, 0, w.G1h, S, M, S, Q, nullptr, w.A2, S, 1.f, 0, st));      // (fp16 only: every consumer of G1 reads the scaled copy)
     prof_mark(st, PT_GEMM_POST2_DGRAD);
   } else {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
     GemmParams p = gp(w.logits, Q, w.W2R, Q, w.G1, S, M, S, Q);
@@ -696,15 +702,19 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC((int)cudaStreamWaitEvent(s2, ev_g[1], 0));
   {  // postprocess1 gradients:  dW1[S,S] = A1^T . G1
     GemmParams p = gp(w.A1, S, w.G1, S, grads + lo.post1, S, S, S, M);
-    if (w.dlog16 && gemm_f16_tn_supported(S, S, S, S))
+    if (w.dlog16)
       RC(gemm_f16_tn(w.A1h, S, w.G1h, S, grads + lo.post1, S, S, S, M, 1.f / gscale, split_for(S, S, M), s2));
     else
       RC(gemm(2, p, split_for(S, S, M), s2));
     prof_mark(s2, PT_GEMM_POST1_WGRAD);
-    if (lo.post1_bias >= 0) { RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, s2)); prof_mark(s2, PT_COLSUM); }
+    if (lo.post1_bias >= 0) {
+      if (w.dlog16) RC(colsum16(w.G1h, S, M, S, 1.f / gscale, grads + lo.post1_bias, s2));
+      else RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, s2));
+      prof_mark(s2, PT_COLSUM);
+    }
   }
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.G1h, S, w.W1g, S, w.G2, S, w.G2h, S, M, S, S, nullptr, w.A1, S, 1.f / gscale, GEMM_ROUND, st));
+    RC(gemm_f16_nt(w.G1h, S, w.W1g, S, nullptr, 0, w.G2h, S, M, S, S, nullptr, w.A1, S, 1.f, 0, st));
     prof_mark(st, PT_GEMM_POST1_DGRAD);
   } else {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
     GemmParams p = gp(w.G1, S, w.W1R, S, w.G2, S, M, S, S);
@@ -721,14 +731,15 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC((int)cudaStreamWaitEvent(s2, ev_g[2], 0));
   {  // skip weights / biases:  dWskip[L*D,S] = Zcat^T . G2
     GemmParams p = gp(w.Zcat, ldz, w.G2, S, grads + lo.skip, S, ldz, S, M);
-    if (w.dlog16 && gemm_f16_tn_supported(ldz, S, ldz, S))
+    if (w.dlog16)
       RC(gemm_f16_tn(w.Zcat16, ldz, w.G2h, S, grads + lo.skip, S, ldz, S, M, 1.f / gscale, split_for(ldz, S, M), s2));
     else
       RC(gemm(2, p, split_for(ldz, S, M), s2));
     prof_mark(s2, PT_GEMM_SKIP_WGRAD);
     if (lo.skip_bias >= 0) {
       RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), s2));
-      RC(colsum(w.G2, S, M, S, w.gtmp, s2));
+      if (w.dlog16) RC(colsum16(w.G2h, S, M, S, 1.f / gscale, w.gtmp, s2));
+      else RC(colsum(w.G2, S, M, S, w.gtmp, s2));
       prof_mark(s2, PT_COLSUM);
       RC(bcast_rows(w.gtmp, S, grads + lo.skip_bias, L, s2));
       prof_mark(s2, PT_MISC);

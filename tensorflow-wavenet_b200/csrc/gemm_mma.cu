@@ -6,6 +6,8 @@
 //   TN: C[M,N] = A[Kr,M]^T . B[Kr,N]      weight gradients (Kr = B*T rows, split over grid.z,
 //                                          accumulated with atomics into a zeroed C)
 // 128x128x32 CTA tile, 8 warps (2x4, 64x32 each), 3-stage cp.async pipeline.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -240,6 +242,54 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A
     atomicAdd(out + col + 2, t.z);
     atomicAdd(out + col + 3, t.w);
   }
+}
+
+// the same for an fp16 matrix in a scaled domain: out[n] += scale * sum_m A16[m][n]   (a lane owns 8 columns)
+__global__ void __launch_bounds__(256) colsum16_kernel(const __half* __restrict__ A, int lda, int M, int N, float scale,
+                                                       float* __restrict__ out, int rows_per_cta) {
+  __shared__ float red[8][32][8];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
+  int r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float s[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[u] = 0.f;
+  if (col < N) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(A + (size_t)r * lda + col));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = __half22float2(h[u]);
+        s[2 * u] += f.x; s[2 * u + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[threadIdx.y][threadIdx.x][u] = s[u];
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x][u];
+      atomicAdd(out + col + u, t * scale);
+    }
+  }
+}
+int colsum16(const void* A16, int lda, int M, int N, float scale, float* out, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return -1;
+  if ((N & 7) || (lda & 7) || ((uintptr_t)A16 & 15)) return -3;
+  const int bx = (N + 255) / 256;
+  int chunks = (8 * sm_count() + bx - 1) / bx;
+  int rows = (M + chunks - 1) / chunks;
+  if (rows < 64) rows = 64;
+  chunks = (M + rows - 1) / rows;
+  colsum16_kernel<<<dim3(bx, chunks), dim3(32, 8), 0, st>>>((const __half*)A16, lda, M, N, scale, out, rows);
+  WN_CHECK_LAUNCH();
+  return 0;
 }
 
 int colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st) {

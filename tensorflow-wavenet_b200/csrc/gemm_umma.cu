@@ -259,7 +259,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     unsigned char* my_out = out_stage + quad * 2 * STG_BYTES;
     unsigned char* my_aux = aux_stage + quad * 2 * STG_BYTES;
     unsigned char* my_c16 = c16_stage + quad * 2 * (STG_BYTES / 2);
-    const bool staged = !(p.flags & GEMM_ATOMIC) && p.C != nullptr;
+    const bool staged = !(p.flags & GEMM_ATOMIC) && (p.C != nullptr || p.has_c16);
     uint32_t local = 0, out_cnt = 0, aux_cnt = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
       int m0, n0, k_begin, nk;
@@ -379,9 +379,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store of 2 chunks ago left the buffer
           __syncwarp();
           unsigned char* os = my_out + buf * STG_BYTES + lane * 128;
+          if (p.C) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(os + ((uint32_t)(j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(os + ((uint32_t)(j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
           if (p.has_c16) {      // [32 rows][32 halfs] (64-byte rows, 64B swizzle) for the next GEMM
             unsigned char* hs = my_c16 + buf * (STG_BYTES / 2) + lane * 64;
 #pragma unroll
@@ -390,8 +392,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(&mapC), "r"(smem_u32(my_out + buf * STG_BYTES)), "r"(nb), "r"(row0) : "memory");
+            if (p.C)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&mapC), "r"(smem_u32(my_out + buf * STG_BYTES)), "r"(nb), "r"(row0) : "memory");
             if (p.has_c16)
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                            ::"l"(&mapC16), "r"(smem_u32(my_c16 + buf * (STG_BYTES / 2))), "r"(nb), "r"(row0) : "memory");
@@ -493,8 +496,8 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
 // travel as fp16 in a domain scaled by a power of two (c_scale undoes it for the fp32 copies).
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
                 int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st) {
-  if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || !C) return -1;
-  if ((lda & 7) || (ldb & 7) || (ldc & 3) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
+  if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || (!C && !C16)) return -1;
+  if ((lda & 7) || (ldb & 7) || (C && (ldc & 3)) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
       ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & 3) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
     return -3;
   const int BN = N > 128 ? 256 : 128;
@@ -503,14 +506,17 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   if (rc) return rc;
   rc = make_map16(&mB, B16, N, K, ldb, BN, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_map(&mC, C, M, N, ldc, 32);
-  if (rc) return rc;
-  mAux = mC;
+  mC = mA;
+  if (C) {
+    rc = make_map(&mC, C, M, N, ldc, 32);
+    if (rc) return rc;
+  }
+  mAux = mA;
   if (aux) {
     rc = make_map(&mAux, aux, M, N, ldaux, 32);
     if (rc) return rc;
   }
-  mC16 = mC;
+  mC16 = mA;
   if (C16) {
     rc = make_map16(&mC16, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
