@@ -32,7 +32,7 @@ constexpr int UM = 128;        // UMMA M (rows of A per tile)
 constexpr int UK = 32;         // floats per stage along K (= one 128-byte swizzle row)
 constexpr int MAX_STAGES = 4;        // 4 for the split-K weight-gradient form (no staging buffers), else 3
 constexpr uint32_t STG_BYTES = 4096;   // one [32 rows][32 floats] epilogue staging block (128B-swizzled)
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;      // TMA warp, MMA warp, up to 8 epilogue warps (p.ewarps = 4 or 8)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -124,6 +124,12 @@ struct UmmaParams {
   int a_mn, b_mn;                 // operand majors: 0 = K contiguous, 1 = M / N contiguous
   int f16;                        // operands are fp16 (K-major, 64 elements per stage, kind::f16); C stays fp32
   int has_c16;                    // additional fp16 copy of the accumulators through mapC16 (the next GEMM's A operand)
+  uint32_t* mask_out;             // relu mask of this product as bits, [M][ldmw] words (bit j of word w: column 32 w + j)
+  const uint32_t* mask_in;        // zero the outputs whose bit is clear (the relu mask of the forward product)
+  int ldmw;
+  int ewarps;                     // epilogue warps: 4 (a warp takes all BN columns of its 32 rows) or 8 (two warps per row quadrant, BN/2 columns each)
+  int nbuf;                       // depth of the per-warp output staging rings (2..4 TMA stores in flight per warp)
+  int aux16;                      // the relu mask matrix is fp16 (64-byte rows, 64B swizzle)
   float c_scale;                  // C = c_scale * (accumulator, bias, relu, mask); the fp16 copy stays unscaled (0: no scaling)
 };
 
@@ -137,15 +143,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[4][2];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[8][2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[BN];
   // epilogue staging (per epilogue warp, double buffered): output chunks leave through TMA stores, the
   // relu-gradient mask chunks arrive through TMA loads -- no scattered 16-byte global accesses
   const int STAGES = p.stages;
   unsigned char* out_stage = smem + STAGES * STAGE_BYTES;
-  unsigned char* aux_stage = out_stage + 4 * 2 * STG_BYTES;
-  unsigned char* c16_stage = aux_stage + 4 * 2 * STG_BYTES;      // [4 warps][2][32 rows][32 halfs] (only with has_c16)
+  // staging regions exist only for what the launch uses (same arithmetic as staging_bytes() on the host)
+  unsigned char* aux_stage = out_stage + (p.C ? p.ewarps * p.nbuf * STG_BYTES : 0);         // [warps][nbuf][32 rows][32 floats]
+  unsigned char* c16_stage = aux_stage + (p.aux ? p.ewarps * 2 * STG_BYTES : 0);            // [warps][nbuf][32 rows][32 halfs]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Persistent CTA: work items (output tile x K split), N tile fastest so that CTAs running side by side share
@@ -155,8 +162,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
-    for (int s = 0; s < 8; ++s) mbar_init(&aux_bar[s >> 1][s & 1], 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], p.ewarps); }
+    for (int s = 0; s < 16; ++s) mbar_init(&aux_bar[s >> 1][s & 1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -252,13 +259,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tmem_full_bar[acc])) : "memory");
       }
     }
-  } else {
-    // ---------------- epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ----------------
+  } else if (warp - 2 < p.ewarps) {
+    // ---------------- epilogue: warps 2.. own TMEM lane quadrants (warp % 4) ----------------
+    // One warp per scheduler cannot hide its own instruction latencies: measured, the epilogue (not the MMA pipe, L2
+    // or HBM) set the pace of every GEMM with a short K loop at ~17.6 k cycles per 128 x 256 tile.  With 8 epilogue
+    // warps two warps share a TMEM lane quadrant (lanes 32 (warp % 4) ...) and split the tile's columns.
     const int quad = warp & 3;
-    const int etid = threadIdx.x - 64;                       // 0..127 among the epilogue warps
-    unsigned char* my_out = out_stage + quad * 2 * STG_BYTES;
-    unsigned char* my_aux = aux_stage + quad * 2 * STG_BYTES;
-    unsigned char* my_c16 = c16_stage + quad * 2 * (STG_BYTES / 2);
+    const int ew = warp - 2;                                 // 0 .. ewarps-1
+    const int etid = threadIdx.x - 64;                       // 0 .. 32 ewarps - 1 among the epilogue warps
+    const int ethreads = 32 * p.ewarps;
+    const int col_lo = (p.ewarps == 8 && ew >= 4) ? BN / 2 : 0;
+    const int col_hi = (p.ewarps == 8 && ew < 4) ? BN / 2 : BN;
+    unsigned char* my_out = out_stage + ew * p.nbuf * STG_BYTES;
+    unsigned char* my_aux = aux_stage + ew * 2 * STG_BYTES;
+    unsigned char* my_c16 = c16_stage + ew * p.nbuf * (STG_BYTES / 2);
     const bool staged = !(p.flags & GEMM_ATOMIC) && (p.C != nullptr || p.has_c16);
     uint32_t local = 0, out_cnt = 0, aux_cnt = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
@@ -269,20 +283,28 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       if (p.bias) {   // bias of this tile's columns -> shared memory (all four epilogue warps)
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
-        for (int i = etid; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");     // previous tile's readers are done
+        for (int i = etid; i < BN; i += ethreads) bias_s[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
       }
       auto issue_aux = [&](int c0) {   // lane 0: mask chunk [32 rows][32 cols] -> staging buffer (aux_cnt parity)
-        const uint32_t buf = (aux_cnt + (c0 > 0 ? 1u : 0u)) & 1u;
-        mbar_expect_tx(&aux_bar[quad][buf], STG_BYTES);
-        tma_load_2d(my_aux + buf * STG_BYTES, &mapAux, &aux_bar[quad][buf], n0 + c0, row0);
+        const uint32_t buf = (aux_cnt + (c0 > col_lo ? 1u : 0u)) & 1u;
+        mbar_expect_tx(&aux_bar[ew][buf], p.aux16 ? STG_BYTES / 2 : STG_BYTES);
+        tma_load_2d(my_aux + buf * STG_BYTES, &mapAux, &aux_bar[ew][buf], n0 + c0, row0);
       };
-      if (p.aux && lane == 0) issue_aux(0);
+      if (p.aux && lane == 0 && n0 + col_lo < p.N) issue_aux(col_lo);
+      uint32_t mw[8];      // this row's mask words of the tile, fetched before the accumulator is waited for
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mw[q] = 0xFFFFFFFFu;
+      if (p.mask_in && row_ok) {
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q)
+          if (n0 + 32 * q < p.N) mw[q] = __ldg(p.mask_in + (size_t)row * p.ldmw + (n0 >> 5) + q);
+      }
       mbar_wait(&tmem_full_bar[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
         if (n0 + c0 >= p.N) break;                      // warp-uniform
         uint32_t v[32];
         {
@@ -342,12 +364,40 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (p.flags & GEMM_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          if (p.mask_out && row_ok) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) word |= (f[j] > 0.f ? 1u : 0u) << j;
+            p.mask_out[(size_t)row * p.ldmw + (nb >> 5)] = word;
+          }
+        }
+        if (p.mask_in) {
+          uint32_t word = mw[0];
+#pragma unroll
+          for (int q = 1; q < 8; ++q) word = (c0 >> 5) == q ? mw[q] : word;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = ((word >> j) & 1u) ? f[j] : 0.f;
         }
         if (p.aux) {
           const uint32_t buf = aux_cnt & 1u;
-          if (lane == 0 && c0 + 32 < BN && nb + 32 < p.N) issue_aux(c0 + 32);   // next chunk, other buffer
-          mbar_wait(&aux_bar[quad][buf], (aux_cnt >> 1) & 1u);
+          if (lane == 0 && c0 + 32 < col_hi && nb + 32 < p.N) issue_aux(c0 + 32);   // next chunk, other buffer
+          mbar_wait(&aux_bar[ew][buf], (aux_cnt >> 1) & 1u);
           const unsigned char* ms = my_aux + buf * STG_BYTES + lane * 128;
+#pragma unroll
+          if (p.aux16) {
+            const unsigned char* mh = my_aux + buf * STG_BYTES + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(mh + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4));
+              const __half2* mh2 = reinterpret_cast<const __half2*>(&mk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 mv = __half22float2(mh2[q]);
+                f[8 * j + 2 * q] = mv.x > 0.f ? f[8 * j + 2 * q] : 0.f;
+                f[8 * j + 2 * q + 1] = mv.y > 0.f ? f[8 * j + 2 * q + 1] : 0.f;
+              }
+            }
+          } else
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 mk = *reinterpret_cast<const float4*>(ms + ((uint32_t)(j ^ (lane & 7)) << 4));
@@ -375,8 +425,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
         }
         if (staged) {   // row chunk -> swizzled staging block -> one TMA store (clipped to [M, N] by the tensor map)
-          const uint32_t buf = out_cnt & 1u;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store of 2 chunks ago left the buffer
+          // (measured: a TMA store takes ~1500 cycles to have READ its staging block -- with two blocks per warp
+          // that wait, not the arithmetic, set the pace of every GEMM with a short K loop)
+          const uint32_t buf = out_cnt % (uint32_t)p.nbuf;
+          if (lane == 0) {      // the store issued nbuf chunks ago has left its staging block
+            if (p.nbuf == 4) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            else if (p.nbuf == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
           __syncwarp();
           unsigned char* os = my_out + buf * STG_BYTES + lane * 128;
           if (p.C) {
@@ -420,9 +476,22 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN));
 }
 
+// shared memory of the epilogue staging regions, and the deepest output ring that fits
+static size_t staging_bytes(bool has_c, bool has_aux, bool has_c16, int nbuf, int ewarps) {
+  return (has_c ? ewarps * (size_t)nbuf * STG_BYTES : 0) + (has_aux ? ewarps * 2 * (size_t)STG_BYTES : 0) +
+         (has_c16 ? ewarps * (size_t)nbuf * (STG_BYTES / 2) : 0);
+}
+constexpr size_t SMEM_OPTIN = 232448 - 2048;      // 227 KB per CTA minus the kernel's static shared memory (barriers, bias row)
+// 8 epilogue warps when their staging fits next to the operand pipeline, else 4; two staging blocks per warp (deeper
+// rings were measured: no gain)
+static void pick_epilogue(size_t pipeline_bytes, bool has_c, bool has_aux, bool has_c16, UmmaParams& p) {
+  p.nbuf = 2;
+  p.ewarps = (pipeline_bytes + staging_bytes(has_c, has_aux, has_c16, 2, 8) <= SMEM_OPTIN) ? 8 : 4;
+}
+
 static int launch_umma(int BN, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB,
                        const CUtensorMap& mC, const CUtensorMap& mAux, const CUtensorMap& mC16, const UmmaParams& p) {
-  constexpr int MAX_SMEM = 1024 + 3 * (UM + 256) * UK * 4 + 16 * (int)STG_BYTES + 8 * (int)(STG_BYTES / 2);
+  constexpr int MAX_SMEM = (int)SMEM_OPTIN;
   if (smem > (size_t)MAX_SMEM) return -5;
   if (BN == 256) {
     static bool attr = false;
@@ -473,7 +542,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   UmmaParams p;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
-  p.a_mn = a_mn; p.b_mn = b_mn; p.f16 = 0; p.has_c16 = 0;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.f16 = 0; p.has_c16 = 0; p.aux16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
   int splits = (g.flags & GEMM_ATOMIC) ? (split_k > 0 ? split_k : 1) : 1;
   int kps = ((g.K + splits - 1) / splits + UK - 1) / UK * UK;
   splits = (g.K + kps - 1) / kps;
@@ -484,7 +553,9 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
   const bool atomic = (g.flags & GEMM_ATOMIC) != 0;
   p.stages = atomic ? 4 : 3;
-  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + (atomic ? 0 : 2 * 4 * 2 * STG_BYTES);
+  const size_t pipe = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
+  pick_epilogue(pipe, !atomic && g.C != nullptr, !atomic && g.aux != nullptr, false, p);
+  const size_t smem = pipe + (atomic ? 0 : staging_bytes(g.C != nullptr, g.aux != nullptr, false, p.nbuf, p.ewarps));
   p.c_scale = 0.f;
   return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mAux, p);
 }
@@ -495,10 +566,11 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
 // the operand bytes (and doubling the MMA rate) nearly halves these.  Backward input-gradient chain: the gradients
 // travel as fp16 in a domain scaled by a power of two (c_scale undoes it for the fp32 copies).
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
-                int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st) {
+                int K, const float* bias, const void* aux, int ldaux, int aux_half, float c_scale, int flags, cudaStream_t st,
+                uint32_t* mask_out, const uint32_t* mask_in, int ldmw) {
   if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || (!C && !C16)) return -1;
   if ((lda & 7) || (ldb & 7) || (C && (ldc & 3)) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
-      ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & 3) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
+      ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & (aux_half ? 7 : 3)) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
     return -3;
   const int BN = N > 128 ? 256 : 128;
   CUtensorMap mA, mB, mC, mAux, mC16;
@@ -513,7 +585,7 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   }
   mAux = mA;
   if (aux) {
-    rc = make_map(&mAux, aux, M, N, ldaux, 32);
+    rc = aux_half ? make_map16(&mAux, aux, M, N, ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) : make_map(&mAux, (const float*)aux, M, N, ldaux, 32);
     if (rc) return rc;
   }
   mC16 = mA;
@@ -523,15 +595,18 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   }
   UmmaParams p;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
-  p.aux = aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
+  p.aux = (const float*)aux; p.ldaux = ldaux; p.aux16 = aux_half; p.M = M; p.N = N; p.K = K; p.flags = flags;
   p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
+  p.mask_out = mask_out; p.mask_in = mask_in; p.ldmw = ldmw;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
   p.k_per_split = (K + 63) / 64 * 64;
   p.splits = 1;
   p.stages = 3;
   const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + UM - 1) / UM);
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4) + 2 * 4 * 2 * STG_BYTES + (C16 ? 4 * 2 * (STG_BYTES / 2) : 0);
+  const size_t pipe = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
+  pick_epilogue(pipe, C != nullptr, aux != nullptr, C16 != nullptr, p);
+  const size_t smem = pipe + staging_bytes(C != nullptr, aux != nullptr, C16 != nullptr, p.nbuf, p.ewarps);
   return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p);
 }
 
@@ -569,7 +644,8 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   UmmaParams p;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
-  p.a_mn = 1; p.b_mn = 1; p.f16 = 1; p.has_c16 = 0;
+  p.nbuf = 2; p.ewarps = 8;
+  p.a_mn = 1; p.b_mn = 1; p.f16 = 1; p.has_c16 = 0; p.aux16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
   int splits = split_k > 0 ? split_k : 1;
   int kps = ((K + splits - 1) / splits + 63) / 64 * 64;
