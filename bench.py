@@ -321,7 +321,10 @@ def main():
                      p['quantization_channels'], len(p['dilations']))
     # algorithmic bytes / flops per launch
     algo = {
-        'block_fwd': ('hbm', M * 4.0 * ((2 * R + D) * (L - 1) + (R + D)) / L),
+        # all forward layers (x in, x' and z out per layer; the last layer has no x'), divided by the launches that
+        # cover them: one persistent kernel by default, L per-layer launches with WN_FWD_CHAIN=0
+        'block_fwd': ('hbm', M * 4.0 * ((2 * R + D) * (L - 1) + (R + D)) / max(1, kernels.get('block_fwd', {}).get('launches_per_step', L))),
+        'block_bwd_pre': ('hbm', M * 4.0 * (2 * R + 3 * D)),     # x, dx', dz_skip in; dpre = [df | dg] out
         'block_bwd_dx': ('hbm', M * 4.0 * (3 * R + D)),          # x, dx', dz_skip in; dx out
         'block_wgrad': ('hbm', M * 4.0 * (2 * R + 3 * D)),       # x, dpre, z, dx' re-read (not algorithmic: see DESIGN)
         'softmax_xent': ('hbm', M * 4.0 * 2 * Q),
@@ -359,7 +362,7 @@ def main():
                 rooflines[name]['traffic'] = tr[name]['dram_bytes_per_launch']
     dominant = max(rooflines, key=lambda n: kernels[n]['ms_per_step']) if rooflines else None
     roofline = dict(rooflines[dominant], kernel=dominant, peak_source=peaks['source'] +
-                    (' (bf16 dense GEMM; this kernel runs tf32, nominal half rate)'
+                    (' (bf16 dense GEMM; the post-processing GEMMs run fp16 operands with fp32 accumulation, same nominal rate)'
                      if rooflines[dominant]['bound'] == 'tensor' else '')) if dominant else None
 
     # ---------------- the same step at B=4 windows per GPU (SURVEY section 8d "also report B=4/GPU") ----------------

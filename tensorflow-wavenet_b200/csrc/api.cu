@@ -367,10 +367,13 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     prof_mark(st, PT_SKIP_BIAS_SUM);
     bsum = w.bsum;
   }
-  // tf32-rounded weight copies: B operands of the forward products and of the input-gradient products
-  RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, st));
-  RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, st));
-  RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
+  // tf32-rounded weight copies: B operands of the TF32 forward products and of the TF32 input-gradient products
+  // (nothing reads them when both directions run the fp16 chain)
+  if (!w.Zcat16 || (training && !w.dlog16)) {
+    RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, st));
+    RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, st));
+    RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
+  }
   if (w.Zcat16) {   // fp16 forward chain: same 11-bit operand mantissas as tf32, half the L2 -> SM operand bytes
     RC(transpose_half(params + lo.skip, ldz, S, w.Wskip16, ldz, st));
     RC(transpose_half(params + lo.post1, S, S, w.W1h, S, st));

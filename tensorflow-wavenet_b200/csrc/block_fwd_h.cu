@@ -161,6 +161,22 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// TMA store with an L2 eviction policy (createpolicy): the fp32 outputs of the forward stack are streamed out and not
+// read again before the backward pass, the split rows are re-read by the next layer from the L2
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, const void* src, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -655,6 +671,7 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
     // ------------------------------------------------------------------------------------------------ publisher
     if (lane == 0) {
       long long p_z = 0, p_war = 0, p_o = 0, p_read = 0, p_done = 0, t_a;
+      const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
       int pending = -1;      // tile whose flag waits for its stores (published after the next tile's z store)
       for (uint32_t i = 0;; ++i) {
         const uint32_t par = i & 1;
@@ -668,8 +685,8 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
         const int l = item / n_tiles, j = item - l * n_tiles;
         const bool last = (l == a.L - 1);
         const int b = j / a.n_tt, tt = j - b * a.n_tt, t0 = tt * TM;
-        tma_store_3d(&mapZ, Sz, l * C, t0, b);      // rows past the end of the window are clipped by the tensor map
-        if (a.z16) tma_store_3d(&mapZ16, Zh, l * C, t0, b);
+        tma_store_3d_hint(&mapZ, Sz, l * C, t0, b, pol_stream);      // rows past the end of the window are clipped by the tensor map
+        if (a.z16) tma_store_3d_hint(&mapZ16, Zh, l * C, t0, b, pol_stream);
         bulk_commit();
         if (pending >= 0) {      // the previous tile's stores: every group but the one just committed has completed
           t_a = clock64();
@@ -683,8 +700,8 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
           t_a = clock64();
           mbar_wait(&bar_o, par);                  // x' staged, and the issuer has seen the old readers of the slot finish
           p_o += clock64() - t_a;
-          if (a.has_xout) tma_store_3d(&mapXo, Sx, 0, t0, (l + 1) * a.B + b);      // fp32 x' (kept for the backward pass)
-          tma_store_3d(&mapXS, Zs, 0, t0, ((l + 1) % RING) * a.B + b);             // split x' (next layer's operand rows)
+          if (a.has_xout) tma_store_3d_hint(&mapXo, Sx, 0, t0, (l + 1) * a.B + b, pol_stream);      // fp32 x' (kept for the backward pass)
+          tma_store_3d_hint(&mapXS, Zs, 0, t0, ((l + 1) % RING) * a.B + b, pol_keep);             // split x' (next layer's operand rows)
           bulk_commit();
         }
         t_a = clock64();
