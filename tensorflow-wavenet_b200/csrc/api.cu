@@ -105,7 +105,8 @@ struct Workspace {
   float* G1;       // [M,S]
   float* G2;       // [M,S]
   float* G3;       // [M,S]                         (residual_postproc only)
-  float* dZcat;    // [M, L*D]
+  float* dZcat;    // [M, L*D]   (tf32 gradient chain)
+  void* dZcat16;   // [M, L*D] fp16, scaled by gscale (fp16 gradient chain; then dZcat, G1, G2 are not allocated)
   float* dX;       // tcgen05 path: L x [M,R], one per layer (the side-stream weight-gradient kernels read them
                    // long after the chain has moved on; no buffer is ever reused within a step); else 2 x [M,R]
   float* dpre;     // tcgen05 path: L x [M,2D]; else [M,2D]
@@ -214,8 +215,10 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   }
   // fp16 gradient chain of the post-processing layers: all-or-nothing (its GEMMs keep no fp32 copies of G1 / G2), so
   // every weight-gradient shape must suit the fp16 MN-major form (multiples of 64); otherwise the tf32 chain runs
-  if (training && f16_chain && (Q % 64) == 0 && (S % 64) == 0 && ((L * D) % 64) == 0) {      // (not a pointer test: a size query carves from a null base)
+  const bool g16 = training && f16_chain && (Q % 64) == 0 && (S % 64) == 0 && ((L * D) % 64) == 0;
+  if (g16) {      // (not a pointer test: a size query carves from a null base)
     w->dlog16 = take(M * Q * 2);
+    w->dZcat16 = take(M * L * D * 2);
     w->G1h = take(M * S * 2);
     w->G2h = take(M * S * 2);
     w->Wskipg = take(L * D * S * 2);
@@ -224,15 +227,15 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->maskA1 = (uint32_t*)take(M * (S / 32) * 4);
     w->maskA2 = (uint32_t*)take(M * (S / 32) * 4);
   } else {
-    w->dlog16 = w->G1h = w->G2h = w->Wskipg = w->W1g = w->W2g = nullptr;
+    w->dlog16 = w->G1h = w->G2h = w->Wskipg = w->W1g = w->W2g = w->dZcat16 = nullptr;
     w->maskA1 = w->maskA2 = nullptr;
   }
   if (training) {
     w->logits = (float*)take(M * Q * f);
-    w->G1 = (float*)take(M * S * f);
-    w->G2 = (float*)take(M * S * f);
+    w->G1 = g16 ? nullptr : (float*)take(M * S * f);
+    w->G2 = g16 ? nullptr : (float*)take(M * S * f);
     w->G3 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
-    w->dZcat = (float*)take(M * L * D * f);
+    w->dZcat = g16 ? nullptr : (float*)take(M * L * D * f);
     w->dX = (float*)take((w->umma_bwd ? L : 2) * M * R * f);
     w->dpre = (float*)take((w->umma_bwd ? L : 1) * M * 2 * D * f);
     w->gprebias = (float*)take(L * B * 2 * D * f);
@@ -759,7 +762,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   }
   RC((int)cudaEventRecord(ev_g[3], s2));
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.G2h, S, w.Wskipg, S, w.dZcat, ldz, nullptr, 0, M, ldz, S, nullptr, nullptr, 0, 0, 1.f / gscale, 0, st));
+    RC(gemm_f16_nt(w.G2h, S, w.Wskipg, S, nullptr, 0, w.dZcat16, ldz, M, ldz, S, nullptr, nullptr, 0, 0, 1.f, 0, st));      // stays fp16 and scaled: block_bwd_pre rescales
     prof_mark(st, PT_GEMM_SKIP_DGRAD);
   } else {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
     GemmParams p = gp(w.G2, S, w.WskipR, S, w.dZcat, ldz, M, ldz, S);
@@ -801,7 +804,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       // kernel waits, then triggers iff its successor waits too).  With the weight-gradient kernels on the side
       // stream the chain uses plain launches: events next to programmatic launches proved racy (see below).
       const bool chain_pdl = (ws == st) && bwd_pdl_enabled();
-      RC(block_bwd_pre_umma(w.X + l * xs, dcur, w.dZcat, ldz, l * D, dpre, img + block_img_off_pre(),
+      RC(block_bwd_pre_umma(w.X + l * xs, dcur, w.dZcat, w.dZcat16, 1.f / gscale, ldz, l * D, dpre, img + block_img_off_pre(),
                             w.prebias + (int64_t)l * B * 2 * D, B, T, cfg->dilations[l], last, chain_pdl ? 1 : -1, st));
       RC(block_bwd_dx_umma(dcur, dpre, dnext, img + block_img_off_dx(), B, T, cfg->dilations[l], last,
                            chain_pdl ? 1 : -1, st));

@@ -24,6 +24,8 @@
 //   bwd_dx   : dx = dx' + dpre[t].Wcur^T + dpre[t+d].Wpast^T                       -> dx
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "umma_common.cuh"
@@ -362,8 +364,15 @@ struct PreArgs {
   const float* prebias;
   int B, T, d, is_last, zcol;  // zcol: column of this layer inside dZcat
   int pdl_next;                // the next kernel in the stream is launched programmatically and waits (common.cuh)
+  float dz_scale;              // DZ16: the skip-path gradient arrives as fp16 in a domain scaled by 1 / dz_scale
 };
 
+// DZ16 = false: the skip-path gradient is an fp32 tile and the two dpre halves are staged in the (dead) input tiles --
+//   the next tile's Dz / Dn loads have to wait until the stores have READ those tiles (~1500 cycles) and then take their
+//   own ~1500 cycles: a serial chain in every tile.
+// DZ16 = true (fp16 gradient chain): the fp16 tile is 8 KB, which leaves room (2 CTAs per SM) for separate staging tiles;
+//   every input tile of the next tile is requested at the mid-tile barrier and the stores drain on their own.
+template <bool DZ16>
 __global__ void __launch_bounds__(256, 2)
 block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDn,
                           const __grid_constant__ CUtensorMap mapDz, const __grid_constant__ CUtensorMap mapDp, PreArgs a) {
@@ -371,11 +380,14 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* Xc = smem;
   unsigned char* Xp = smem + TILE;
-  unsigned char* Dn = smem + 2 * TILE;     // dx' tile (A operand of dx'.Wd^T); later staging of dg
-  unsigned char* Dz = smem + 3 * TILE;     // skip-path gradient tile (read by the threads); later staging of df
+  unsigned char* Dn = smem + 2 * TILE;     // dx' tile (A operand of dx'.Wd^T); !DZ16: later staging of dg
+  unsigned char* Dz = smem + 3 * TILE;     // !DZ16: skip-path gradient tile (read by the threads), later staging of df; DZ16: staging of df
   unsigned char* W0 = smem + 4 * TILE;
   unsigned char* W1 = W0 + 8192;
   unsigned char* Wd = W1 + 8192;
+  unsigned char* Sg = W0 + IMG_PRE;        // DZ16: staging of dg
+  unsigned char* Zq = Sg + TILE;           // DZ16: skip-path gradient tile, [128 rows][32 halfs], 64B swizzle
+  unsigned char* Gs = DZ16 ? Sg : Dn;      // where dg is staged
   __shared__ __align__(8) uint64_t bar_x, bar_d, bar_m1, bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float pb_s[64];
@@ -403,8 +415,8 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
   };
   auto issue_d = [&](int tile) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
-    mbar_expect_tx(&bar_d, (a.is_last ? 1 : 2) * TILE);
-    tma_load_3d(Dz, &mapDz, &bar_d, a.zcol, t0, b);
+    mbar_expect_tx(&bar_d, (DZ16 ? TM * 64 : TILE) + (a.is_last ? 0 : TILE));
+    tma_load_3d(DZ16 ? Zq : Dz, &mapDz, &bar_d, a.zcol, t0, b);
     if (!a.is_last) tma_load_3d(Dn, &mapDn, &bar_d, 0, t0, b);
   };
   if (tid == 0) {
@@ -457,18 +469,36 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     }
     // gradient coming from the skip path (this thread's half row of the dZcat tile)
     float dz[16];
+    if (DZ16) {
+      const unsigned char* zr = Zq + (uint32_t)r * 64;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const float4 v = *reinterpret_cast<const float4*>(Dz + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4));
-      dz[4 * jj] = v.x; dz[4 * jj + 1] = v.y; dz[4 * jj + 2] = v.z; dz[4 * jj + 3] = v.w;
+      for (int c = 0; c < 2; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(zr + ((uint32_t)((2 * half + c) ^ ((r >> 1) & 3)) << 4));
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(h[q]);
+          dz[8 * c + 2 * q] = f.x * a.dz_scale; dz[8 * c + 2 * q + 1] = f.y * a.dz_scale;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 v = *reinterpret_cast<const float4*>(Dz + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4));
+        dz[4 * jj] = v.x; dz[4 * jj + 1] = v.y; dz[4 * jj + 2] = v.z; dz[4 * jj + 3] = v.w;
+      }
     }
     mbar_wait(&bar_m1, par);
     tc_fence_after();
+    if (DZ16 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's stores have left the staging tiles
     // Re-arming an mbarrier while a slow thread has not yet observed the phase it waits for lets the barrier wrap
     // around to the same parity: that thread then waits forever (rare, box dependent hangs).  Every thread must
     // be past its bar_x wait first.
     __syncthreads();
-    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_x(tile + gridDim.x);     // x tiles: only the MMAs read them
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
+      issue_x(tile + gridDim.x);                 // x tiles: only the MMAs read them
+      if (DZ16) issue_d(tile + gridDim.x);       // dx' tile: read by the finished MMAs; fp16 dz tile: every thread has its values
+    }
 
     const bool valid = (t0 + r) < a.T;
     if (!a.is_last) {
@@ -495,7 +525,7 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     for (int jj = 0; jj < 4; ++jj) {
       const uint32_t off = row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4);
       *reinterpret_cast<float4*>(Dz + off) = make_float4(df[4 * jj], df[4 * jj + 1], df[4 * jj + 2], df[4 * jj + 3]);
-      *reinterpret_cast<float4*>(Dn + off) = make_float4(dg[4 * jj], dg[4 * jj + 1], dg[4 * jj + 2], dg[4 * jj + 3]);
+      *reinterpret_cast<float4*>(Gs + off) = make_float4(dg[4 * jj], dg[4 * jj + 1], dg[4 * jj + 2], dg[4 * jj + 3]);
     }
     fence_async_smem();
     tc_fence_before();
@@ -504,9 +534,9 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                    ::"l"(&mapDp), "r"(smem_u32(Dz)), "r"(0), "r"(t0), "r"(b) : "memory");
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                   ::"l"(&mapDp), "r"(smem_u32(Dn)), "r"(32), "r"(t0), "r"(b) : "memory");
+                   ::"l"(&mapDp), "r"(smem_u32(Gs)), "r"(32), "r"(t0), "r"(b) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      if (tile + (int)gridDim.x < n_tiles) {
+      if (!DZ16 && tile + (int)gridDim.x < n_tiles) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the stores have left the two tiles
         issue_d(tile + gridDim.x);
       }
@@ -791,9 +821,23 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
 
 // The three backward kernels of a layer are separate entry points: the weight-gradient GEMM only feeds the
 // gradient buffers, so the caller runs it on a side stream next to the dx / next layer's pre kernels.
-int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int ldz, int zcol, float* dpre,
-                       const unsigned char* img_pre, const float* prebias, int B, int T, int d, int is_last,
-                       int pdl_next, cudaStream_t st) {
+// fp16 [B][T][ldz] (skip-path gradient of the fp16 chain): box = [TM rows][32 halfs], 64-byte rows, 64B swizzle
+static int make_map_dz16(CUtensorMap* m, const void* ptr, int64_t B, int64_t T, int64_t ldz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {(cuuint64_t)ldz, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ldz * 2, (cuuint64_t)T * ldz * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)TM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+
+// dZcat16 != null: the skip-path gradient is fp16 [M][ldz], scaled by 1 / dz_scale (dZcat is ignored)
+int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, const void* dZcat16, float dz_scale, int ldz,
+                       int zcol, float* dpre, const unsigned char* img_pre, const float* prebias, int B, int T, int d,
+                       int is_last, int pdl_next, cudaStream_t st) {
   const int n_tiles = B * ((T + TM - 1) / TM);
   int grid = n_tiles;
   const int cap = 2 * sm_count();
@@ -803,27 +847,32 @@ int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int
   if (rc) return rc;
   rc = make_map_3d(&mDn, is_last ? x : dxn, B, T, C, C, TM);
   if (rc) return rc;
-  rc = make_map_3d(&mDz, dZcat, B, T, ldz, ldz, TM);
+  rc = dZcat16 ? make_map_dz16(&mDz, dZcat16, B, T, ldz) : make_map_3d(&mDz, dZcat, B, T, ldz, ldz, TM);
   if (rc) return rc;
   CUtensorMap mDp;
   rc = make_map_3d(&mDp, dpre, B, T, 64, 64, TM);
   if (rc) return rc;
   PreArgs a;
   a.dpre = dpre; a.img = img_pre; a.prebias = prebias; a.B = B; a.T = T; a.d = d;
-  a.is_last = is_last; a.zcol = zcol; a.pdl_next = pdl_next;
-  const size_t smem = 1024 + 4 * TILE + IMG_PRE;
+  a.is_last = is_last; a.zcol = zcol; a.pdl_next = pdl_next; a.dz_scale = dz_scale;
+  const size_t smem = 1024 + 4 * TILE + IMG_PRE + (dZcat16 ? TILE + TM * 64 : 0);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(block_bwd_pre_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(block_bwd_pre_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 4 * TILE + IMG_PRE));
+    cudaFuncSetAttribute(block_bwd_pre_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + 5 * TILE + IMG_PRE + TM * 64));
+    attr = true;
+  }
+  auto kernel = dZcat16 ? block_bwd_pre_umma_kernel<true> : block_bwd_pre_umma_kernel<false>;
   // Plain stream-ordered launches in the backward chain: with programmatic dependent launch next to the cross-stream
   // events of the side-stream weight-gradient kernels, consumers were observed to start on half-written gradients
   // (tools/sweep_impls.py, tools/debug_case.py); the forward chain (no events) keeps PDL.
   if (pdl_next >= 0) {      // whole backward chain on one stream, no events in between: PDL as in the forward chain
     a.pdl_next = pdl_next;
-    cudaError_t e = launch_pdl(block_bwd_pre_umma_kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, mDp, a);
+    cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(256), smem, st, mX, mDn, mDz, mDp, a);
     if (e != cudaSuccess) return (int)e;
   } else {
     a.pdl_next = 0;
-    block_bwd_pre_umma_kernel<<<grid, 256, smem, st>>>(mX, mDn, mDz, mDp, a);
+    kernel<<<grid, 256, smem, st>>>(mX, mDn, mDz, mDp, a);
     WN_CHECK_LAUNCH();
   }
   prof_mark(st, PT_BLOCK_BWD_PRE);

@@ -66,9 +66,9 @@ void set_block_timeline(long long* p);   // debug: clock64 stamps of block_fwd_u
 void set_block_impl(int mma);
 int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsigned char* img, const float* wf, const float* wg, const float* dense,
                    const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, cudaStream_t st);
-int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, int ldz, int zcol, float* dpre,
-                       const unsigned char* img_pre, const float* prebias, int B, int T, int d, int is_last,
-                       int pdl_next, cudaStream_t st);
+int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, const void* dZcat16, float dz_scale, int ldz,
+                       int zcol, float* dpre, const unsigned char* img_pre, const float* prebias, int B, int T, int d,
+                       int is_last, int pdl_next, cudaStream_t st);
 int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
                      int is_last, int pdl, cudaStream_t st);
