@@ -560,16 +560,22 @@ struct DxArgs {
 __global__ void __launch_bounds__(256, 2)
 block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapDn,
                          const __grid_constant__ CUtensorMap mapDx, DxArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // No static shared memory and no alignment slack: with separate in / out tiles two CTAs fill the SM to within 2 KB.
+  // The dynamic window then starts at the CTA's (1 KB aligned) shared base; checked, because the swizzle needs it.
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();
   unsigned char* P0f = smem;
   unsigned char* P0g = smem + TILE;
   unsigned char* P1f = smem + 2 * TILE;
   unsigned char* P1g = smem + 3 * TILE;
-  unsigned char* St = smem + 4 * TILE;     // dx' tile on the way in, dx tile on the way out (TMA both ways)
-  unsigned char* Wb = smem + 5 * TILE;     // Bcf Bcg Bpf Bpg
-  __shared__ __align__(8) uint64_t bar_tma, bar_n, bar_m1, bar_w;
-  __shared__ uint32_t tmem_slot;
+  unsigned char* Sn = smem + 4 * TILE;     // dx' tile (TMA load, read by the threads)
+  unsigned char* St = smem + 5 * TILE;     // dx tile on the way out (TMA store).  Separate from Sn: the next dx' load does
+                                           // not have to wait until the store has read the tile (a serial ~3000-cycle chain)
+  unsigned char* Wb = smem + 6 * TILE;     // Bcf Bcg Bpf Bpg
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Wb + IMG_DX);
+  uint64_t &bar_tma = bars[0], &bar_n = bars[1], &bar_m1 = bars[2], &bar_w = bars[3];
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r = tid & 127, half = tid >> 7;   // thread = (time step, 16-channel half)
@@ -596,7 +602,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
   auto issue_dxn = [&](int tile) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
     mbar_expect_tx(&bar_n, TILE);
-    tma_load_3d(St, &mapDn, &bar_n, 0, t0, b);
+    tma_load_3d(Sn, &mapDn, &bar_n, 0, t0, b);
   };
   if (tid == 0) {
     mbar_expect_tx(&bar_w, IMG_DX);
@@ -638,7 +644,7 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
       mbar_wait(&bar_n, par);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
-        xn[jj] = *reinterpret_cast<const float4*>(St + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4));
+        xn[jj] = *reinterpret_cast<const float4*>(Sn + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4));
     } else {
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) xn[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -646,10 +652,12 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
     mbar_wait(&bar_m1, par);
     tc_fence_after();
     __syncthreads();      // every thread is past its bar_tma wait before the barrier is re-armed (see bwd_pre)
-    if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
+      issue_loads(tile + gridDim.x);
+      if (have_dxn) issue_dxn(tile + gridDim.x);      // every thread holds its dx' values
+    }
     uint32_t ov[16];
     tmem_ld16(lane_addr, ov);
-    // each thread overwrites exactly the staging chunks it read its dx' values from
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
       *reinterpret_cast<float4*>(St + row_off + ((uint32_t)((4 * half + jj) ^ (r & 7)) << 4)) =
@@ -662,10 +670,6 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                    ::"l"(&mapDx), "r"(smem_u32(St)), "r"(0), "r"(t0), "r"(b) : "memory");   // clipped at the window end
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      if (tile + (int)gridDim.x < n_tiles && have_dxn) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store has left the staging tile
-        issue_dxn(tile + gridDim.x);
-      }
     }
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -930,7 +934,7 @@ int block_bwd_dx_umma(const float* dxn, const float* dpre, float* dx, const unsi
   }
   DxArgs a;
   a.dxn = is_last ? nullptr : dxn; a.dx = dx; a.img = img_dx; a.B = B; a.T = T; a.d = d; a.pdl_next = pdl_next;
-  const size_t smem = 1024 + 5 * TILE + IMG_DX;
+  const size_t smem = 6 * TILE + IMG_DX + 64;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(block_bwd_dx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   if (pdl_next >= 0) {
