@@ -326,7 +326,8 @@ def main():
         'block_fwd': ('hbm', M * 4.0 * ((2 * R + D) * (L - 1) + (R + D)) / max(1, kernels.get('block_fwd', {}).get('launches_per_step', L))),
         'block_bwd_pre': ('hbm', M * 4.0 * (2 * R + 3 * D)),     # x, dx', dz_skip in; dpre = [df | dg] out
         'block_bwd_dx': ('hbm', M * 4.0 * (3 * R + D)),          # x, dx', dz_skip in; dx out
-        'block_wgrad': ('hbm', M * 4.0 * (2 * R + 3 * D)),       # x, dpre, z, dx' re-read (not algorithmic: see DESIGN)
+        # x, dpre, z, dx' re-read per layer (not algorithmic: see DESIGN); one persistent launch covers all layers
+        'block_wgrad': ('hbm', M * 4.0 * (2 * R + 3 * D) * L / max(1, kernels.get('block_wgrad', {}).get('launches_per_step', L))),
         'softmax_xent': ('hbm', M * 4.0 * 2 * Q),
         'gemm_skip_fwd': ('tensor', 2.0 * M * L * D * S),
         'gemm_skip_wgrad': ('tensor', 2.0 * M * L * D * S),

@@ -795,6 +795,10 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     static int side_wgrad = -1;
     if (side_wgrad < 0) side_wgrad = getenv("WN_SIDE_WGRAD") ? 1 : 0;
     cudaStream_t ws = (g_prof_on || no_side_streams() || side_mode() == 3 || !side_wgrad) ? st : side;
+    // Default: the weight gradients of all layers in ONE persistent launch behind the pre / dx chain (every layer keeps
+    // its own dpre / dx buffers).  WN_WGRAD_PER_LAYER=1: one launch per layer inside the chain, as before.
+    static int wgrad_all = -1;
+    if (wgrad_all < 0) wgrad_all = (getenv("WN_WGRAD_PER_LAYER") || side_wgrad) ? 0 : 1;
     for (int l = L - 1; l >= 0; --l) {
       const int last = (l == L - 1);
       const unsigned char* img = w.Wimg + (size_t)l * block_img_stride();
@@ -807,7 +811,11 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       RC(block_bwd_pre_umma(w.X + l * xs, dcur, w.dZcat, w.dZcat16, 1.f / gscale, ldz, l * D, dpre, img + block_img_off_pre(),
                             w.prebias + (int64_t)l * B * 2 * D, B, T, cfg->dilations[l], last, chain_pdl ? 1 : -1, st));
       RC(block_bwd_dx_umma(dcur, dpre, dnext, img + block_img_off_dx(), B, T, cfg->dilations[l], last,
-                           chain_pdl ? 1 : -1, st));
+                           chain_pdl ? ((wgrad_all && l == 0) ? 0 : 1) : -1, st));
+      if (wgrad_all) {
+        dcur = dnext;
+        continue;
+      }
       if (ws != st) {
         // The event is recorded AFTER the dx kernel (never between a kernel and a programmatic dependent: such an
         // event was observed to fire when the kernel TRIGGERS, not when it completes).
@@ -822,6 +830,9 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       if (ws != st) RC((int)cudaEventRecord(ev_wg[l % 3], ws));
       dcur = dnext;
     }
+    if (wgrad_all)
+      RC(block_wgrad_all(w.X, w.dX, w.dpre, w.Zcat, ldz, grads + lo.filter, grads + lo.gate, grads + lo.dense, w.gprebias,
+                         lo.dense_bias >= 0 ? grads + lo.dense_bias : nullptr, cfg->dilations, L, B, T, st));
     // join: the bias / conditioning gradients below read what the weight-gradient kernels accumulated
     if (ws != st)
       for (int i = 0; i < 3 && i < L; ++i) RC((int)cudaStreamWaitEvent(st, ev_wg[i], 0));

@@ -26,6 +26,7 @@
 
 #include <cuda_fp16.h>
 
+#include "../../include/wavenet_b200.h"
 #include "common.cuh"
 #include "kernels.h"
 #include "umma_common.cuh"
@@ -821,6 +822,188 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   __syncthreads();
   if (tid == 0) wg_stamp(a, 5);
   if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// ---- all layers in ONE launch ----
+// The per-layer launch above runs 148 CTAs for ~10 stages each and then sends 148 x 12,288 red.adds at the same
+// addresses; 50 times per step, inside the dependent backward chain although nothing in the chain reads its output.
+// Every layer keeps its own dpre / dx buffers, so once the chain  pre(l) -> dx(l) -> pre(l-1) ...  has finished all
+// weight gradients can be computed by one persistent kernel: the (layer, batch element, 64-step block) units are split
+// into one contiguous range per SM, the TMA ring runs through the whole range without a bubble, and the accumulators
+// are flushed only where (layer, batch element) changes -- ~3 CTAs add to an address instead of 148.
+struct WgAllArgs {
+  float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;   // bases of the per-layer gradient groups (gdense_bias may be null)
+  int L, B, T;
+  int dil[WN_MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(192, 1)
+block_wgrad_all_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
+                       const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapDn,
+                       const __grid_constant__ WgAllArgs a) {
+  constexpr int STG = WG_STAGES;
+  constexpr uint32_t BLK = WG_ROWS * 128;                  // one [64 steps][32 channels] block
+  constexpr uint32_t A_BYTES = 4 * BLK, B_BYTES = 3 * BLK, STAGE = A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full_bar[STG], empty_bar[STG], done_bar, free_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = (a.T + WG_ROWS - 1) / WG_ROWS;
+  const long long n_units = (long long)a.L * a.B * nkb;
+  const long long per = (n_units + gridDim.x - 1) / gridDim.x;
+  const long long u0 = (long long)blockIdx.x * per;
+  long long u1 = u0 + per;
+  if (u1 > n_units) u1 = n_units;
+  if (u0 >= u1) return;
+
+  // constant block of every stage: column 96 = 1, columns 97..127 = 0 (never overwritten by the loads)
+  for (int i = tid; i < STG * WG_ROWS * 32; i += blockDim.x) {
+    const int s = i / (WG_ROWS * 32), rr = (i / 32) % WG_ROWS, cc = i % 32;
+    *reinterpret_cast<float*>(smem + s * STAGE + 3 * BLK + swz32(rr, cc)) = (cc == 0) ? 1.0f : 0.0f;
+    *reinterpret_cast<float*>(smem + s * STAGE + A_BYTES + 2 * BLK + swz32(rr, cc)) = 0.f;      // (dx' block: defined before the first load)
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STG; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    mbar_init(&free_bar, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int per_lb = nkb;      // units per (layer, batch element)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t i = 0;
+      for (long long u = u0; u < u1; ++u, ++i) {
+        const int lb = (int)(u / per_lb), kb = (int)(u - (long long)lb * per_lb);
+        const int l = lb / a.B, b = lb - l * a.B;
+        const bool last = (l == a.L - 1);
+        const int s = i % STG;
+        const uint32_t ph = (i / STG) & 1;
+        const int t = kb * WG_ROWS;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        // x, x[t-d], z, [df | dg] (one 4-D box), dx' (the last layer has none: its dx' block keeps stale finite data of
+        // another layer, which only reaches accumulator columns that are not flushed for the last layer)
+        mbar_expect_tx(&full_bar[s], (last ? 5 : 6) * BLK);
+        unsigned char* sa = smem + s * STAGE;
+        tma_load_3d(sa, &mapX, &full_bar[s], 0, t, lb);                          // x[t] of layer l
+        tma_load_3d(sa + BLK, &mapX, &full_bar[s], 0, t - a.dil[l], lb);         // x[t-d]  (zeros for t < d)
+        tma_load_3d(sa + 2 * BLK, &mapZ, &full_bar[s], l * C, t, b);             // z[t]
+        tma_load_4d(sa + A_BYTES, &mapP, &full_bar[s], 0, t, 0, lb);             // df | dg as two consecutive blocks
+        if (!last) tma_load_3d(sa + A_BYTES + 2 * BLK, &mapDn, &full_bar[s], 0, t, lb + a.B);   // dx' = dx of layer l+1
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t ID = idesc_tf32(128, 96, 1, 1);
+      uint32_t i = 0, seg = 0;
+      int cur_lb = -1;
+      for (long long u = u0; u < u1; ++u, ++i) {
+        const int lb = (int)(u / per_lb);
+        const bool first = (lb != cur_lb);
+        if (first) {
+          if (cur_lb >= 0) {
+            mma_commit(&done_bar);                       // segment finished: hand the accumulator to the epilogue ...
+            mbar_wait(&free_bar, seg & 1);               // ... and wait until it has been read
+            tc_fence_after();
+            ++seg;
+          }
+          cur_lb = lb;
+        }
+        const int s = i % STG;
+        const uint32_t ph = (i / STG) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE);
+        const uint64_t da = mnmajor_desc(sa, BLK), db = mnmajor_desc(sa + A_BYTES, BLK);
+#pragma unroll
+        for (int k = 0; k < WG_ROWS / 8; ++k) mma_tf32_ss(tmem, da + 64 * k, db + 64 * k, ID, !(first && k == 0));   // +1024 B per K=8
+        mma_commit(&empty_bar[s]);
+      }
+      mma_commit(&done_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t seg = 0;
+    long long u = u0;
+    while (u < u1) {
+      const int lb = (int)(u / per_lb);
+      const int l = lb / a.B, b = lb - l * a.B;
+      const bool last = (l == a.L - 1);
+      long long ue = (long long)(lb + 1) * per_lb;      // end of this (layer, batch element) inside the range
+      if (ue > u1) ue = u1;
+      mbar_wait(&done_bar, seg & 1);
+      tc_fence_after();
+      float* gwf = a.gwf + (size_t)l * 2 * C * C;
+      float* gwg = a.gwg + (size_t)l * 2 * C * C;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 96; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + c0, v);   // warp-collective: every lane issues it
+        float* dst = nullptr;
+        if (row < 64) {
+          if (c0 < 64) dst = (c0 == 0 ? gwf : gwg) + ((row < 32 ? 1 : 0) * C + (row & 31)) * C;
+        } else if (row < 96) {
+          if (c0 == 64 && !last) dst = a.gdense + (size_t)l * C * C + (row - 64) * C;
+        } else if (row == 96) {
+          if (c0 < 64) dst = a.gprebias + ((size_t)l * a.B + b) * 64 + c0;
+          else if (!last && a.gdense_bias) dst = a.gdense_bias + (size_t)l * C;
+        }
+        if (dst) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                       __uint_as_float(v[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&free_bar);
+      ++seg;
+      u = ue;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// x: [L][B][T][32] layer inputs; dx: [L][B][T][32] input gradients (dx[l+1] is dx' of layer l); dpre: [L][B][T][64];
+// gradient group bases as in the parameter layout (per layer strides 2*C*C, 2*C*C, C*C, B*64, C)
+int block_wgrad_all(const float* x, const float* dx, const float* dpre, const float* Zcat, int ldz, float* gwf, float* gwg,
+                    float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B, int T,
+                    cudaStream_t st) {
+  if (L < 1 || L > WN_MAX_LAYERS) return -1;
+  CUtensorMap mX, mZ, mP, mDn;
+  int rc = make_map_3d_mn(&mX, x, (int64_t)L * B, T, C, C, WG_ROWS);
+  if (rc) return rc;
+  rc = make_map_3d_mn(&mZ, Zcat, B, T, ldz, ldz, WG_ROWS);
+  if (rc) return rc;
+  rc = make_map_4d_mn_blocks(&mP, dpre, (int64_t)L * B, T, 64, WG_ROWS, 2);
+  if (rc) return rc;
+  rc = make_map_3d_mn(&mDn, dx, (int64_t)L * B, T, C, C, WG_ROWS);
+  if (rc) return rc;
+  WgAllArgs a;
+  a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias;
+  a.L = L; a.B = B; a.T = T;
+  for (int l = 0; l < WN_MAX_LAYERS; ++l) a.dil[l] = l < L ? dilations[l] : 0;
+  const size_t smem = 1024 + WG_STAGES * (7 * WG_ROWS * 128);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(block_wgrad_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const long long n_units = (long long)L * B * ((T + WG_ROWS - 1) / WG_ROWS);
+  int grid = sm_count();
+  if (grid > n_units) grid = (int)n_units;
+  block_wgrad_all_kernel<<<grid, 192, smem, st>>>(mX, mZ, mP, mDn, a);
+  WN_CHECK_LAUNCH();
+  prof_mark(st, PT_BLOCK_WGRAD);
+  return 0;
 }
 
 // The three backward kernels of a layer are separate entry points: the weight-gradient GEMM only feeds the

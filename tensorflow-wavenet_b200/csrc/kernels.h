@@ -69,6 +69,10 @@ int block_fwd_umma(const float* x, float* xout, float* zc, int ldz, const unsign
 int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, const void* dZcat16, float dz_scale, int ldz,
                        int zcol, float* dpre, const unsigned char* img_pre, const float* prebias, int B, int T, int d,
                        int is_last, int pdl_next, cudaStream_t st);
+// weight gradients of ALL layers in one persistent launch (after the pre / dx chain has finished)
+int block_wgrad_all(const float* x, const float* dx, const float* dpre, const float* Zcat, int ldz, float* gwf, float* gwg,
+                    float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B, int T,
+                    cudaStream_t st);
 int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
                      int is_last, int pdl, cudaStream_t st);
