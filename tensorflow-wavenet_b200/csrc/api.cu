@@ -673,7 +673,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   // fp16 input-gradient chain: gradients travel scaled by gscale = 2^ceil(log2 M), i.e. (softmax - onehot) * [1, 2)
   float gscale = 1.f;
   while (gscale < (float)M) gscale *= 2.f;
-  RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, 1, w.dlog16, gscale / (float)M, st));
+  RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, w.dlog16 ? 0 : 1, w.dlog16, gscale / (float)M, st));      // (fp16 chain: nobody reads the fp32 gradient)
   prof_mark(st, PT_XENT);
   if (trunc == 2) return 0;
 

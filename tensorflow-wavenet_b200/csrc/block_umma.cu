@@ -414,22 +414,34 @@ block_bwd_pre_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid
     tma_load_3d(Xc, &mapX, &bar_x, 0, t0, b);
     tma_load_3d(Xp, &mapX, &bar_x, 0, t0 - a.d, b);
   };
-  auto issue_d = [&](int tile) {
+  // (two halves: the skip-path gradient was written long before this launch, dx' by the direct predecessor)
+  auto issue_dz = [&](int tile) {
     const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
     mbar_expect_tx(&bar_d, (DZ16 ? TM * 64 : TILE) + (a.is_last ? 0 : TILE));
     tma_load_3d(DZ16 ? Zq : Dz, &mapDz, &bar_d, a.zcol, t0, b);
+  };
+  auto issue_dn = [&](int tile) {
+    const int b = tile / n_tt, t0 = (tile - b * n_tt) * TM;
     if (!a.is_last) tma_load_3d(Dn, &mapDn, &bar_d, 0, t0, b);
+  };
+  auto issue_d = [&](int tile) {
+    issue_dz(tile);
+    issue_dn(tile);
   };
   if (tid == 0) {
     mbar_expect_tx(&bar_w, IMG_PRE);
     bulk_g2s(W0, a.img, IMG_PRE, &bar_w);
   }
-  pdl_wait();
-  if (a.pdl_next) pdl_trigger();
+  // Everything the first tile reads that is older than the direct predecessor (layer inputs from the forward pass, the
+  // skip-path gradient from the GEMM chain) is requested BEFORE the dependency wait (invariant in common.cuh); only dx'
+  // -- written by the dx kernel right before this launch -- has to wait.
   if (tid == 0 && (int)blockIdx.x < n_tiles) {
     issue_x(blockIdx.x);
-    issue_d(blockIdx.x);
+    issue_dz(blockIdx.x);
   }
+  pdl_wait();
+  if (a.pdl_next) pdl_trigger();
+  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_dn(blockIdx.x);
   mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();

@@ -252,6 +252,8 @@ xent_kernel(float* __restrict__ logits, const int32_t* __restrict__ ids, int M, 
           o.x = round_tf32(p0 * scale); o.y = round_tf32(p1 * scale);
           o.z = round_tf32(p2 * scale); o.w = round_tf32(p3 * scale);
           *reinterpret_cast<float4*>(row + c) = o;
+        }
+        {
           if (g16) {      // the same gradient in the scaled fp16 domain of the input-gradient GEMM chain
             __half2 h[2] = {__floats2half2_rn(p0 * scale16, p1 * scale16), __floats2half2_rn(p2 * scale16, p3 * scale16)};
             *reinterpret_cast<uint2*>(g16 + (size_t)m * Q + c) = *reinterpret_cast<uint2*>(h);

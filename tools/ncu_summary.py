@@ -94,7 +94,7 @@ def traffic(paths):
     import json
     import re
     tags = [('block_fwd_chain', 'block_fwd'), ('block_fwd_h', 'block_fwd'), ('block_fwd_umma', 'block_fwd'), ('block_bwd_pre_umma', 'block_bwd_pre'), ('block_bwd_dx_umma', 'block_bwd_dx'),
-            ('block_wgrad_umma', 'block_wgrad'), ('gemm_umma_kernel', 'gemm_umma'), ('generator_lat', 'generator_lat'),
+            ('block_wgrad_all', 'block_wgrad'), ('block_wgrad_umma', 'block_wgrad'), ('gemm_umma_kernel', 'gemm_umma'), ('generator_lat', 'generator_lat'),
             ('generator_kernel', 'generator')]
     acc = {}
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
