@@ -390,13 +390,13 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     // fp32 copies of the two hidden activations only where something reads them: the tf32 gradient chain
     float* a1_32 = (training && !w.dlog16) ? w.A1 : nullptr;
     float* a2_32 = (training && !w.dlog16) ? w.A2 : nullptr;
-    RC(gemm_f16_nt(w.Zcat16, ldz, w.Wskip16, ldz, a1_32, S, w.A1h, S, M, S, ldz, bsum, nullptr, 0, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
+    RC(gemm_f16_nt(w.Zcat16, ldz, w.Wskip16, ldz, a1_32, S, w.A1h, S, M, S, ldz, bsum, nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
                    training ? w.maskA1 : nullptr, nullptr, S / 32));
     prof_mark(st, PT_GEMM_SKIP_FWD);
-    RC(gemm_f16_nt(w.A1h, S, w.W1h, S, a2_32, S, w.A2h, S, M, S, S, P(params, lo.post1_bias), nullptr, 0, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
+    RC(gemm_f16_nt(w.A1h, S, w.W1h, S, a2_32, S, w.A2h, S, M, S, S, P(params, lo.post1_bias), nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
                    training ? w.maskA2 : nullptr, nullptr, S / 32));
     prof_mark(st, PT_GEMM_POST1_FWD);
-    RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, M, Q, S, P(params, lo.post2_bias), nullptr, 0, 0, 1.f, 0, st));
+    RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, M, Q, S, P(params, lo.post2_bias), nullptr, 0, 1.f, 0, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
     return 0;
   }
@@ -589,7 +589,7 @@ int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, f
                    int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
                    int32_t ldmask, float c_scale, int32_t flags, wn_stream_t stream) {
   if (!a16 || !b16 || !c) return -1;
-  return gemm_f16_nt(a16, lda, b16, ldb, c, ldc, c16, ldc16, m, n, k, bias, relu_mask, ldmask, 0, c_scale, flags,
+  return gemm_f16_nt(a16, lda, b16, ldb, c, ldc, c16, ldc16, m, n, k, bias, relu_mask, ldmask, c_scale, flags,
                      (cudaStream_t)stream);
 }
 
@@ -703,7 +703,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
   }
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.dlog16, Q, w.W2g, Q, nullptr, 0, w.G1h, S, M, S, Q, nullptr, nullptr, 0, 0, 1.f, 0, st, nullptr, w.maskA2, S / 32));      // (fp16 only: every consumer of G1 reads the scaled copy)
+    RC(gemm_f16_nt(w.dlog16, Q, w.W2g, Q, nullptr, 0, w.G1h, S, M, S, Q, nullptr, nullptr, 0, 1.f, 0, st, nullptr, w.maskA2, S / 32));      // (fp16 only: every consumer of G1 reads the scaled copy)
     prof_mark(st, PT_GEMM_POST2_DGRAD);
   } else {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
     GemmParams p = gp(w.logits, Q, w.W2R, Q, w.G1, S, M, S, Q);
@@ -729,7 +729,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
   }
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.G1h, S, w.W1g, S, nullptr, 0, w.G2h, S, M, S, S, nullptr, nullptr, 0, 0, 1.f, 0, st, nullptr, w.maskA1, S / 32));
+    RC(gemm_f16_nt(w.G1h, S, w.W1g, S, nullptr, 0, w.G2h, S, M, S, S, nullptr, nullptr, 0, 1.f, 0, st, nullptr, w.maskA1, S / 32));
     prof_mark(st, PT_GEMM_POST1_DGRAD);
   } else {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
     GemmParams p = gp(w.G1, S, w.W1R, S, w.G2, S, M, S, S);
@@ -762,7 +762,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   }
   RC((int)cudaEventRecord(ev_g[3], s2));
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.G2h, S, w.Wskipg, S, nullptr, 0, w.dZcat16, ldz, M, ldz, S, nullptr, nullptr, 0, 0, 1.f, 0, st));      // stays fp16 and scaled: block_bwd_pre rescales
+    RC(gemm_f16_nt(w.G2h, S, w.Wskipg, S, nullptr, 0, w.dZcat16, ldz, M, ldz, S, nullptr, nullptr, 0, 1.f, 0, st));      // stays fp16 and scaled: block_bwd_pre rescales
     prof_mark(st, PT_GEMM_SKIP_DGRAD);
   } else {  // d z (skip path) for every layer at once:  dZcat = G2 . Wskip^T
     GemmParams p = gp(w.G2, S, w.WskipR, S, w.dZcat, ldz, M, ldz, S);

@@ -129,7 +129,6 @@ struct UmmaParams {
   int ldmw;
   int ewarps;                     // epilogue warps: 4 (a warp takes all BN columns of its 32 rows) or 8 (two warps per row quadrant, BN/2 columns each)
   int nbuf;                       // depth of the per-warp output staging rings (2..4 TMA stores in flight per warp)
-  int aux16;                      // the relu mask matrix is fp16 (64-byte rows, 64B swizzle)
   float c_scale;                  // C = c_scale * (accumulator, bias, relu, mask); the fp16 copy stays unscaled (0: no scaling)
 };
 
@@ -289,7 +288,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       auto issue_aux = [&](int c0) {   // lane 0: mask chunk [32 rows][32 cols] -> staging buffer (aux_cnt parity)
         const uint32_t buf = (aux_cnt + (c0 > col_lo ? 1u : 0u)) & 1u;
-        mbar_expect_tx(&aux_bar[ew][buf], p.aux16 ? STG_BYTES / 2 : STG_BYTES);
+        mbar_expect_tx(&aux_bar[ew][buf], STG_BYTES);
         tma_load_2d(my_aux + buf * STG_BYTES, &mapAux, &aux_bar[ew][buf], n0 + c0, row0);
       };
       if (p.aux && lane == 0 && n0 + col_lo < p.N) issue_aux(col_lo);
@@ -384,20 +383,6 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_wait(&aux_bar[ew][buf], (aux_cnt >> 1) & 1u);
           const unsigned char* ms = my_aux + buf * STG_BYTES + lane * 128;
 #pragma unroll
-          if (p.aux16) {
-            const unsigned char* mh = my_aux + buf * STG_BYTES + lane * 64;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 mk = *reinterpret_cast<const uint4*>(mh + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4));
-              const __half2* mh2 = reinterpret_cast<const __half2*>(&mk);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 mv = __half22float2(mh2[q]);
-                f[8 * j + 2 * q] = mv.x > 0.f ? f[8 * j + 2 * q] : 0.f;
-                f[8 * j + 2 * q + 1] = mv.y > 0.f ? f[8 * j + 2 * q + 1] : 0.f;
-              }
-            }
-          } else
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 mk = *reinterpret_cast<const float4*>(ms + ((uint32_t)(j ^ (lane & 7)) << 4));
@@ -542,7 +527,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   UmmaParams p;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
-  p.a_mn = a_mn; p.b_mn = b_mn; p.f16 = 0; p.has_c16 = 0; p.aux16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.f16 = 0; p.has_c16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
   int splits = (g.flags & GEMM_ATOMIC) ? (split_k > 0 ? split_k : 1) : 1;
   int kps = ((g.K + splits - 1) / splits + UK - 1) / UK * UK;
   splits = (g.K + kps - 1) / kps;
@@ -566,11 +551,11 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
 // the operand bytes (and doubling the MMA rate) nearly halves these.  Backward input-gradient chain: the gradients
 // travel as fp16 in a domain scaled by a power of two (c_scale undoes it for the fp32 copies).
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
-                int K, const float* bias, const void* aux, int ldaux, int aux_half, float c_scale, int flags, cudaStream_t st,
+                int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st,
                 uint32_t* mask_out, const uint32_t* mask_in, int ldmw) {
   if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || (!C && !C16)) return -1;
   if ((lda & 7) || (ldb & 7) || (C && (ldc & 3)) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
-      ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & (aux_half ? 7 : 3)) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
+      ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & 3) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
     return -3;
   const int BN = N > 128 ? 256 : 128;
   CUtensorMap mA, mB, mC, mAux, mC16;
@@ -585,7 +570,7 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   }
   mAux = mA;
   if (aux) {
-    rc = aux_half ? make_map16(&mAux, aux, M, N, ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) : make_map(&mAux, (const float*)aux, M, N, ldaux, 32);
+    rc = make_map(&mAux, aux, M, N, ldaux, 32);
     if (rc) return rc;
   }
   mC16 = mA;
@@ -595,7 +580,7 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   }
   UmmaParams p;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
-  p.aux = (const float*)aux; p.ldaux = ldaux; p.aux16 = aux_half; p.M = M; p.N = N; p.K = K; p.flags = flags;
+  p.aux = aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
   p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
   p.mask_out = mask_out; p.mask_in = mask_in; p.ldmw = ldmw;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
@@ -645,7 +630,7 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
   p.nbuf = 2; p.ewarps = 8;
-  p.a_mn = 1; p.b_mn = 1; p.f16 = 1; p.has_c16 = 0; p.aux16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
+  p.a_mn = 1; p.b_mn = 1; p.f16 = 1; p.has_c16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
   int splits = split_k > 0 ? split_k : 1;
   int kps = ((K + splits - 1) / splits + 63) / 64 * 64;

@@ -1,12 +1,14 @@
 """Parity of the reference-facing Python API (WaveNetModel / ops) on sm_100a against the CPU
 oracle, plus ports of the reference's own model / generation tests."""
 import math
+import os
 
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 import wavenet_oracle as O
 from wn_helpers import (GRAD_L2_VS_EXACT, GRAD_RTOL, LOGIT_RTOL, LOSS_RTOL, l2_rel, make_pair, matched_oracle,
@@ -386,3 +388,46 @@ def test_default_params_full_size_properties():
     l_a = net.logits(ids)[0, :99000]
     l_b = net.logits(ids2)[0, :99000]
     assert torch.equal(l_a, l_b)
+
+
+_VARIANT_SCRIPT = r'''
+import json, os, sys
+sys.path.insert(0, os.path.join({root!r}, 'tensorflow-wavenet_b200'))
+import numpy as np, wavenet
+p = json.load(open(os.path.join({root!r}, 'tensorflow-wavenet_b200', 'wavenet_params.json')))
+net = wavenet.WaveNetModel(batch_size=2, dilations=p['dilations'], filter_width=2, residual_channels=32, dilation_channels=32,
+                           quantization_channels=256, skip_channels=512, use_biases=True, global_condition_channels=16,
+                           global_condition_cardinality=5, seed=3)
+rng = np.random.default_rng(5)
+T = 20011
+a = np.clip(0.5 * np.sin(np.arange(T) * 0.03)[None] + 0.2 * rng.standard_normal((2, T)), -1, 1).astype(np.float32)
+loss = float(net.loss(a, [1, 4]))
+np.savez(sys.argv[1], loss=loss, grads=net.flat_grads.cpu().numpy())
+'''
+
+
+def test_persistent_kernels_match_per_layer_launches(tmp_path):
+    """The default launch structure (all forward layers in one flag-ordered persistent kernel, the weight gradients of all
+    layers in one launch, fp16 post-processing GEMMs) against the per-layer / TF32 variants of the same arithmetic.
+    The switches are read once per process, hence the subprocesses."""
+    import subprocess
+    import sys
+    script = tmp_path / 'variant.py'
+    script.write_text(_VARIANT_SCRIPT.format(root=ROOT))
+    out = {}
+    variants = {'default': {}, 'per_layer': {'WN_FWD_CHAIN': '0', 'WN_WGRAD_PER_LAYER': '1'}, 'tf32_gemms': {'WN_FWD_GEMM': 'tf32'}}
+    for name, env in variants.items():
+        path = str(tmp_path / (name + '.npz'))
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, str(script), path], env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[name] = np.load(path)
+    ref = out['default']
+    assert math.isfinite(float(ref['loss'])) and np.isfinite(ref['grads']).all()
+    # same arithmetic, different launch structure: only the order of the split-K / atomic accumulations differs
+    assert abs(float(out['per_layer']['loss']) - float(ref['loss'])) <= 1e-6 * abs(float(ref['loss']))
+    assert rel_err(out['per_layer']['grads'], ref['grads']) < 1e-4
+    # fp16 vs TF32 operand copies: both 11-bit mantissas, different roundings
+    assert abs(float(out['tf32_gemms']['loss']) - float(ref['loss'])) <= LOSS_RTOL * abs(float(ref['loss']))
+    assert rel_err(out['tf32_gemms']['grads'], ref['grads']) < 2e-2
