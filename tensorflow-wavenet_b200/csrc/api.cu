@@ -317,7 +317,53 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
             S = c->skip_channels, Q = c->quantization_channels, G = c->gc_channels;
   const int ldz = L * D;
   if (G > 0 && !gc_ids) return -1;
-  if (w.Wimg) {   // first, so that at least two launches separate it from the first block kernel (PDL, common.cuh)
+  // Everything that only converts parameters (weight images of the backward kernels, fp16 / transposed weight copies,
+  // the skip bias sum: ~10 launches of a few microseconds each) runs on a side branch next to the forward-layer kernel
+  // -- its CTAs fit beside the two resident chain CTAs of an SM -- and is joined in front of the GEMMs.
+  static cudaStream_t prep = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const bool use_prep = training && w.chain_flags && w.Zcat16 && !g_prof_on && !no_side_streams();
+  if (use_prep && !prep) {
+    RC((int)cudaStreamCreateWithFlags(&prep, cudaStreamNonBlocking));
+    RC((int)cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    RC((int)cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t ps = use_prep ? prep : st;
+  const float* bsum = nullptr;
+  auto prep_weights = [&]() -> int {
+    if (c->use_biases) {
+      RC(skip_bias_sum(params + lo.skip_bias, L, S, w.bsum, ps));
+      prof_mark(ps, PT_SKIP_BIAS_SUM);
+      bsum = w.bsum;
+    }
+    // tf32-rounded weight copies: B operands of the TF32 forward products and of the TF32 input-gradient products
+    // (nothing reads them when both directions run the fp16 chain)
+    if (!w.Zcat16 || (training && !w.dlog16)) {
+      RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, ps));
+      RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, ps));
+      RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, ps));
+    }
+    if (w.Zcat16) {   // fp16 forward chain: same 11-bit operand mantissas as tf32, half the L2 -> SM operand bytes
+      RC(transpose_half(params + lo.skip, ldz, S, w.Wskip16, ldz, ps));
+      RC(transpose_half(params + lo.post1, S, S, w.W1h, S, ps));
+      RC(transpose_half(params + lo.post2, S, Q, w.W2h, S, ps));
+      if (w.dlog16) {   // operands of the fp16 input-gradient chain (the weights as stored)
+        RC(to_half(params + lo.post2, w.W2g, (int64_t)S * Q, ps));
+        RC(to_half(params + lo.post1, w.W1g, (int64_t)S * S, ps));
+        RC(to_half(params + lo.skip, w.Wskipg, (int64_t)ldz * S, ps));
+      }
+    }
+    prof_mark(ps, PT_MISC);
+    return 0;
+  };
+  if (use_prep) {
+    RC((int)cudaEventRecord(ev_fork, st));
+    RC((int)cudaStreamWaitEvent(prep, ev_fork, 0));
+    RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, prep));      // backward images
+    RC(prep_weights());
+    RC((int)cudaEventRecord(ev_join, prep));
+    RC(block_h_images(w.WimgH, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
+  } else if (w.Wimg) {   // first, so that at least two launches separate it from the first block kernel (PDL, common.cuh)
     RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
     if (w.WimgH) RC(block_h_images(w.WimgH, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
     prof_mark(st, PT_MISC);
@@ -363,30 +409,10 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
                  w.prebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr,
                  M, T, c->dilations[l], R, last, st));
   }
+  if (use_prep) RC((int)cudaStreamWaitEvent(st, ev_join, 0));      // join the parameter-conversion branch
+  else RC(prep_weights());
   if (training && truncate_stage() == 1) return 0;
-  const float* bsum = nullptr;
-  if (c->use_biases) {
-    RC(skip_bias_sum(params + lo.skip_bias, L, S, w.bsum, st));
-    prof_mark(st, PT_SKIP_BIAS_SUM);
-    bsum = w.bsum;
-  }
-  // tf32-rounded weight copies: B operands of the TF32 forward products and of the TF32 input-gradient products
-  // (nothing reads them when both directions run the fp16 chain)
-  if (!w.Zcat16 || (training && !w.dlog16)) {
-    RC(round_copy(params + lo.skip, w.WskipR, (int64_t)ldz * S, st));
-    RC(round_copy(params + lo.post1, w.W1R, (int64_t)S * S, st));
-    RC(round_copy(params + lo.post2, w.W2R, (int64_t)S * Q, st));
-  }
-  if (w.Zcat16) {   // fp16 forward chain: same 11-bit operand mantissas as tf32, half the L2 -> SM operand bytes
-    RC(transpose_half(params + lo.skip, ldz, S, w.Wskip16, ldz, st));
-    RC(transpose_half(params + lo.post1, S, S, w.W1h, S, st));
-    RC(transpose_half(params + lo.post2, S, Q, w.W2h, S, st));
-    if (w.dlog16) {   // operands of the fp16 input-gradient chain (the weights as stored)
-      RC(to_half(params + lo.post2, w.W2g, (int64_t)S * Q, st));
-      RC(to_half(params + lo.post1, w.W1g, (int64_t)S * S, st));
-      RC(to_half(params + lo.skip, w.Wskipg, (int64_t)ldz * S, st));
-    }
-    prof_mark(st, PT_MISC);
+  if (w.Zcat16) {
     // fp32 copies of the two hidden activations only where something reads them: the tf32 gradient chain
     float* a1_32 = (training && !w.dlog16) ? w.A1 : nullptr;
     float* a2_32 = (training && !w.dlog16) ? w.A2 : nullptr;
@@ -400,7 +426,6 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     prof_mark(st, PT_GEMM_POST2_FWD);
     return 0;
   }
-  prof_mark(st, PT_MISC);
   {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
     GemmParams p = gp(w.Zcat, ldz, w.WskipR, S, w.A1, S, M, S, ldz);
     p.bias = bsum;

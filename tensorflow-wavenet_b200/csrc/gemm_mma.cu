@@ -265,12 +265,12 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const __half* __restrict_
       }
     };
     int r = r0 + threadIdx.y;
-    for (; r + 24 < r1; r += 32) {      // four loads in flight per thread
-      uint4 v[4];
+    for (; r + 56 < r1; r += 64) {      // eight 16-byte loads in flight per thread (~64 KB per SM: enough to cover HBM latency)
+      uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(A + (size_t)(r + 8 * u) * lda + col));
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(A + (size_t)(r + 8 * u) * lda + col));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) add(v[u]);
+      for (int u = 0; u < 8; ++u) add(v[u]);
     }
     for (; r < r1; r += 8) add(__ldg(reinterpret_cast<const uint4*>(A + (size_t)r * lda + col)));
   }
