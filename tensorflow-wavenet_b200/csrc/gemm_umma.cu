@@ -127,6 +127,8 @@ struct UmmaParams {
   uint32_t* mask_out;             // relu mask of this product as bits, [M][ldmw] words (bit j of word w: column 32 w + j)
   const uint32_t* mask_in;        // zero the outputs whose bit is clear (the relu mask of the forward product)
   int ldmw;
+  int m2;                         // 256-row tiles: two M=128 MMAs per k-step share the B operand (split-K weight-gradient form only:
+                                  // both TMEM accumulators belong to one tile, no epilogue overlap)
   int ewarps;                     // epilogue warps: 4 (a warp takes all BN columns of its 32 rows) or 8 (two warps per row quadrant, BN/2 columns each)
   int nbuf;                       // depth of the per-warp output staging rings (2..4 TMA stores in flight per warp)
   float c_scale;                  // C = c_scale * (accumulator, bias, relu, mask); the fp16 copy stays unscaled (0: no scaling)
@@ -137,9 +139,10 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapAux, const __grid_constant__ CUtensorMap mapC16,
                  UmmaParams p) {
-  constexpr uint32_t A_BYTES = UM * UK * 4;       // 16 KB
-  constexpr uint32_t B_BYTES = BN * UK * 4;       // 16 / 32 KB
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t A_BYTES = (p.m2 ? 2 : 1) * UM * UK * 4;       // 16 KB (32 KB for 256-row tiles)
+  constexpr uint32_t B_BYTES = BN * UK * 4;                    // 16 / 32 KB
+  const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const int TM_ROWS = p.m2 ? 2 * UM : UM;                      // rows of an output tile
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[8][2];
@@ -156,7 +159,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Persistent CTA: work items (output tile x K split), N tile fastest so that CTAs running side by side share
   // the A tile in L2.  Two accumulators in TMEM: the epilogue of item i overlaps the main loop of item i+1.
-  const int n_nt = (p.N + BN - 1) / BN, n_mt = (p.M + UM - 1) / UM;
+  const int n_nt = (p.N + BN - 1) / BN, n_mt = (p.M + TM_ROWS - 1) / TM_ROWS;
   const int n_items = n_nt * n_mt * p.splits;
 
   if (warp == 0 && lane == 0) {
@@ -179,7 +182,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int nt = item % n_nt;
     const int rest = item / n_nt;
     const int mt = rest % n_mt, sp = rest / n_mt;
-    m0 = mt * UM;
+    m0 = mt * TM_ROWS;
     n0 = nt * BN;
     k_begin = sp * p.k_per_split;
     int k_end = k_begin + p.k_per_split;
@@ -231,7 +234,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
         int m0, n0, k_begin, nk;
         decode(item, m0, n0, k_begin, nk);
-        const uint32_t acc = local & 1, aph = (local >> 1) & 1;
+        const uint32_t acc = p.m2 ? 0u : (local & 1), aph = p.m2 ? (local & 1) : ((local >> 1) & 1);
         mbar_wait(&tmem_empty_bar[acc], aph ^ 1);      // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem + acc * BN;
@@ -246,10 +249,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < UK / 8; ++k) {
             const uint32_t accum = (i > 0 || k > 0) ? 1u : 0u;
-            if (p.f16)
+            if (p.f16) {
               asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                            ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
-            else
+              if (p.m2)      // rows 128..255 of the tile: the second half of the A stage (+16 KB), second accumulator
+                asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                             ::"r"(d_tmem + BN), "l"(da + 1024 + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
+            } else
               asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                            ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
           }
@@ -277,7 +283,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
       int m0, n0, k_begin, nk;
       decode(item, m0, n0, k_begin, nk);
-      const uint32_t acc = local & 1, aph = (local >> 1) & 1;
+      const uint32_t acc = p.m2 ? 0u : (local & 1), aph = p.m2 ? (local & 1) : ((local >> 1) & 1);
       const int row0 = m0 + quad * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
@@ -303,11 +309,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
+      for (int hc = 0; hc < (p.m2 ? 2 : 1); ++hc)      // 256-row tiles: rows 128.. live in the second accumulator
+#pragma unroll 1
       for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
         if (n0 + c0 >= p.N) break;                      // warp-uniform
         uint32_t v[32];
         {
-          const uint32_t taddr = tmem + acc * BN + ((uint32_t)(quad * 32) << 16) + c0;
+          const uint32_t taddr = tmem + (acc + hc) * BN + ((uint32_t)(quad * 32) << 16) + c0;
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -324,8 +332,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.c_scale);
           }
-          if (row_ok) {
-            float* dst = p.C + (size_t)row * p.ldc + nb;
+          if (row + hc * UM < p.M) {
+            float* dst = p.C + (size_t)(row + hc * UM) * p.ldc + nb;
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -527,6 +535,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
   UmmaParams p;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
+  p.m2 = 0;
   p.a_mn = a_mn; p.b_mn = b_mn; p.f16 = 0; p.has_c16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
   int splits = (g.flags & GEMM_ATOMIC) ? (split_k > 0 ? split_k : 1) : 1;
   int kps = ((g.K + splits - 1) / splits + UK - 1) / UK * UK;
@@ -581,6 +590,7 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   UmmaParams p;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
   p.aux = aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
+  p.m2 = 0;
   p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
   p.mask_out = mask_out; p.mask_in = mask_in; p.ldmw = ldmw;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
@@ -621,27 +631,38 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   if (!gemm_f16_tn_supported(lda, ldb, M, N) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) || (ldc & 3) || ((uintptr_t)C & 15))
     return -3;
   const int BN = N > 128 ? 256 : 128;
+  // 256-row tiles (two MMAs per k-step on one B stage): the GEMM is bound by the L2 -> SM operand traffic, and a
+  // 256 x 256 tile moves 64 KB per k-step where two 128 x 256 tiles move 96 KB (WN_GEMM_M2=0 switches it off)
+  static int m2_on = -1;
+  if (m2_on < 0) m2_on = (getenv("WN_GEMM_M2") && atoi(getenv("WN_GEMM_M2")) == 0) ? 0 : 1;
+  const int m2 = (m2_on && M >= 1024 && BN == 256) ? 1 : 0;      // (few output tiles -> many K splits -> the atomics of the bigger tiles cost more than the operand traffic saved: measured on the 512-row products)
+  const int TMR = m2 ? 2 * UM : UM;
   CUtensorMap mA, mB;
-  int rc = make_map16_blocks_mn(&mA, A16, K, M, lda, UM / 64);
+  int rc = make_map16_blocks_mn(&mA, A16, K, M, lda, TMR / 64);
   if (rc) return rc;
   rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
   if (rc) return rc;
   UmmaParams p;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
-  p.nbuf = 2; p.ewarps = 8;
+  p.nbuf = 2; p.ewarps = 8; p.m2 = m2;
   p.a_mn = 1; p.b_mn = 1; p.f16 = 1; p.has_c16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
   int splits = split_k > 0 ? split_k : 1;
+  if (m2) {      // about two work items per SM
+    const int tiles = ((N + BN - 1) / BN) * ((M + TMR - 1) / TMR);
+    splits = (2 * sm_count() + tiles - 1) / tiles;
+    if (splits > K / 256) splits = K / 256 > 0 ? K / 256 : 1;
+  }
   int kps = ((K + splits - 1) / splits + 63) / 64 * 64;
   splits = (K + kps - 1) / kps;
   p.k_per_split = kps;
   p.splits = splits;
-  p.stages = 4;
-  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + UM - 1) / UM) * splits;
+  p.stages = m2 ? 3 : 4;
+  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + TMR - 1) / TMR) * splits;
   if (items > (1 << 30)) return -1;
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-  const size_t smem = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
+  const size_t smem = 1024 + (size_t)p.stages * (TMR * UK * 4 + BN * UK * 4);
   return launch_umma(BN, grid, smem, st, mA, mB, mA, mA, mA, p);
 }
 

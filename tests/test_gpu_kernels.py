@@ -335,7 +335,8 @@ def test_gemm_f16_nt(lib, M, N, K):
     assert rel_err(c16.cpu().numpy().astype(np.float64), ref) < 1e-3
 
 
-@pytest.mark.parametrize('M,N,K,split', [(128, 256, 64, 1), (512, 256, 5000, 6), (1600, 512, 3333, 3), (64, 64, 200, 2)])
+@pytest.mark.parametrize('M,N,K,split', [(128, 256, 64, 1), (512, 256, 5000, 6), (1600, 512, 3333, 3), (64, 64, 200, 2),
+                                          (1024, 256, 2000, 1), (1088, 512, 700, 4)])      # >= 1024 rows: 256-row tiles
 def test_gemm_f16_tn(lib, M, N, K, split):
     """Weight-gradient form on fp16 MN-major operands (both read as they lie in memory), split-K atomics, scaled."""
     rng = np.random.default_rng(M + N + K)
