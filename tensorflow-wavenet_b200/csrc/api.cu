@@ -371,13 +371,10 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   RC(cond_bias_fwd(w.prebias, P(params, lo.filter_bias), P(params, lo.gate_bias), P(params, lo.gc_filter),
                    P(params, lo.gc_gate), P(params, lo.gc_embedding), gc_ids, L, B, D, gc_ids ? G : 0, st));
   prof_mark(st, PT_COND_BIAS);
-  RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, st));
+  // (residual stream as fp16 split rows between the forward layers: the front end writes both forms of its output)
+  RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, w.WimgH ? w.XS : nullptr, st));
   prof_mark(st, PT_FRONTEND_FWD);
   const int64_t xs = (int64_t)M * R;
-  if (w.WimgH) {   // residual stream as fp16 split rows between the forward layers
-    RC(split_rows(w.X, w.XS, M, st));
-    prof_mark(st, PT_MISC);
-  }
   if (w.chain_flags) {
     RC(block_fwd_chain(w.XS, training ? w.X : nullptr, w.Zcat, w.Zcat16, ldz, w.WimgH, w.prebias,
                        lo.dense_bias >= 0 ? params + lo.dense_bias : nullptr, c->dilations, L, B, T, w.chain_flags, st));
@@ -546,7 +543,7 @@ int wn_mulaw_decode(const int32_t* ids, int64_t n, const float* lut, int32_t q, 
 int wn_frontend_fwd(const int32_t* ids, const float* causal_filter, float* x0, int32_t batch, int32_t time,
                     int32_t q, int32_t r, wn_stream_t stream) {
   if (!ids || !causal_filter || !x0 || batch < 1 || time < 1) return -1;
-  return frontend_fwd(ids, causal_filter, x0, batch * time, time, q, r, (cudaStream_t)stream);
+  return frontend_fwd(ids, causal_filter, x0, batch * time, time, q, r, nullptr, (cudaStream_t)stream);
 }
 int wn_frontend_bwd(const int32_t* ids, const float* dx0, float* grad_causal_filter, int32_t batch, int32_t time,
                     int32_t q, int32_t r, wn_stream_t stream) {

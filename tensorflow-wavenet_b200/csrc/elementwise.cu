@@ -102,8 +102,9 @@ int mulaw_decode(const int32_t* ids, int64_t n, const float* lut, int Q, float* 
 // front end: one_hot (model.py:518-531) + causal layer (model.py:227-234) as a row gather
 //   x0[m] = Wc[0][id[m-1]] (t>0) + Wc[1][id[m]];   out-of-range ids are all-zero one-hot rows
 // =========================================================================================
+// xs (optional, R == 32): the same rows also as fp16 split rows [hi 32 | lo 32] (input of the first forward layer)
 __global__ void frontend_fwd_kernel(const int32_t* __restrict__ ids, const float* __restrict__ wc,
-                                    float* __restrict__ x0, int M, int T, int Q, int R) {
+                                    float* __restrict__ x0, int M, int T, int Q, int R, __half* __restrict__ xs) {
   const int r4 = R >> 2;
   const int64_t total = (int64_t)M * r4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -122,15 +123,27 @@ __global__ void frontend_fwd_kernel(const int32_t* __restrict__ ids, const float
       o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
     }
     *reinterpret_cast<float4*>(x0 + (size_t)m * R + c) = o;
+    if (xs) {
+      const float v[4] = {o.x, o.y, o.z, o.w};
+      __align__(8) __half h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        h[q] = __float2half_rn(v[q]);
+        l[q] = __float2half_rn(v[q] - __half2float(h[q]));
+      }
+      __half* row = xs + (size_t)m * 64;
+      *reinterpret_cast<uint2*>(row + c) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(row + 32 + c) = *reinterpret_cast<const uint2*>(l);
+    }
   }
 }
-
-int frontend_fwd(const int32_t* ids, const float* wc, float* x0, int M, int T, int Q, int R, cudaStream_t st) {
+int frontend_fwd(const int32_t* ids, const float* wc, float* x0, int M, int T, int Q, int R, void* xs, cudaStream_t st) {
+  if (xs && R != 32) return -1;
   if (M <= 0 || (R & 3)) return -1;
   int64_t blocks = ((int64_t)M * (R / 4) + 255) / 256;
   const int cap = 16 * sm_count();
   if (blocks > cap) blocks = cap;
-  frontend_fwd_kernel<<<(int)blocks, 256, 0, st>>>(ids, wc, x0, M, T, Q, R);
+  frontend_fwd_kernel<<<(int)blocks, 256, 0, st>>>(ids, wc, x0, M, T, Q, R, (__half*)xs);
   WN_CHECK_LAUNCH();
   return 0;
 }

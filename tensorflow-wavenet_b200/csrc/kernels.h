@@ -110,7 +110,7 @@ int block_bwd(const float* x, const float* dxn, const float* dzs, int ldz, float
 int mulaw_encode(const float* audio, int64_t n, const float* thresholds, int Q, int32_t* ids, cudaStream_t st);
 int mulaw_decode(const int32_t* ids, int64_t n, const float* lut, int Q, float* out, cudaStream_t st);
 
-int frontend_fwd(const int32_t* ids, const float* wc, float* x0, int M, int T, int Q, int R, cudaStream_t st);
+int frontend_fwd(const int32_t* ids, const float* wc, float* x0, int M, int T, int Q, int R, void* xs, cudaStream_t st);
 int frontend_bwd(const int32_t* ids, const float* dx0, float* gwc, int M, int T, int Q, int R, cudaStream_t st);
 
 // g16 (optional): the gradient also as fp16 [M,Q], (softmax - onehot) * scale16
