@@ -444,11 +444,11 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'tf32 tensor-core math, f32 accumulate/storage', 'data': 'synthetic',
+            'dtype': 'f32 storage and accumulation; tensor-core operands fp16 split rows (residual blocks), fp16 / tf32 (GEMMs)', 'data': 'synthetic',
             'config': {'workload': 'default wavenet_params.json (L=50, R=D=32, S=512, Q=256, biases) training step '
                                    '(fwd+bwd+allreduce+Adam), B={} x T={} per GPU'.format(B, T),
                        'parallelism': 'dp{}'.format(world),
-                       'l2_between_iterations': 'per-step working set (~2.7 GB of activations per GPU) exceeds the '
+                       'l2_between_iterations': 'per-step working set (~4.6 GB of activations per GPU) exceeds the '
                                                 '126 MB L2; no explicit flush'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * T * 4, 'd2h_bytes_per_step': 4},
