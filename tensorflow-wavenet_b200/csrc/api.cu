@@ -123,6 +123,7 @@ struct Workspace {
   void *Zcat16, *A1h, *A2h;       // fp16 copies of the forward GEMM A operands (fp16 forward chain)
   void *Wskip16, *W1h, *W2h;      // fp16 K-major weight copies: [S][L*D], [S][S], [Q][S]
   void *dlog16, *G1h, *G2h;       // gradients of the post-processing chain as fp16, scaled by gscale (training, fp16 chain)
+  float* cs_scratch;              // per-chunk partial column sums (bias gradients of the fp16 chain)
   uint32_t *maskA1, *maskA2;      // relu masks of the skip sum / postprocess1 outputs as bits, [M][S/32]
   void *Wskipg, *W1g, *W2g;       // fp16 copies of the weights as stored ([L*D][S], [S][S], [S][Q]): input-gradient operands
   unsigned int* chain_flags;      // [L][B * ceil(T/128)] tile flags of the persistent forward kernel (null: per-layer launches)
@@ -226,7 +227,9 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->W2g = take(S * Q * 2);
     w->maskA1 = (uint32_t*)take(M * (S / 32) * 4);
     w->maskA2 = (uint32_t*)take(M * (S / 32) * 4);
+    w->cs_scratch = (float*)take(colsum16_scratch_floats((int)(S > Q ? S : Q)) * f);
   } else {
+    w->cs_scratch = nullptr;
     w->dlog16 = w->G1h = w->G2h = w->Wskipg = w->W1g = w->W2g = w->dZcat16 = nullptr;
     w->maskA1 = w->maskA2 = nullptr;
   }
@@ -719,7 +722,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       RC(gemm(2, p, split_for(S, Q, M), s2));
     prof_mark(s2, PT_GEMM_POST2_WGRAD);
     if (lo.post2_bias >= 0) {
-      if (w.dlog16) RC(colsum16(w.dlog16, Q, M, Q, 1.f / gscale, grads + lo.post2_bias, s2));
+      if (w.dlog16) RC(colsum16(w.dlog16, Q, M, Q, 1.f / gscale, grads + lo.post2_bias, w.cs_scratch, s2));
       else RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, s2));
       prof_mark(s2, PT_COLSUM);
     }
@@ -745,7 +748,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       RC(gemm(2, p, split_for(S, S, M), s2));
     prof_mark(s2, PT_GEMM_POST1_WGRAD);
     if (lo.post1_bias >= 0) {
-      if (w.dlog16) RC(colsum16(w.G1h, S, M, S, 1.f / gscale, grads + lo.post1_bias, s2));
+      if (w.dlog16) RC(colsum16(w.G1h, S, M, S, 1.f / gscale, grads + lo.post1_bias, w.cs_scratch, s2));
       else RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, s2));
       prof_mark(s2, PT_COLSUM);
     }
@@ -775,7 +778,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     prof_mark(s2, PT_GEMM_SKIP_WGRAD);
     if (lo.skip_bias >= 0) {
       RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), s2));
-      if (w.dlog16) RC(colsum16(w.G2h, S, M, S, 1.f / gscale, w.gtmp, s2));
+      if (w.dlog16) RC(colsum16(w.G2h, S, M, S, 1.f / gscale, w.gtmp, w.cs_scratch, s2));
       else RC(colsum(w.G2, S, M, S, w.gtmp, s2));
       prof_mark(s2, PT_COLSUM);
       RC(bcast_rows(w.gtmp, S, grads + lo.skip_bias, L, s2));

@@ -245,8 +245,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A
 }
 
 // the same for an fp16 matrix in a scaled domain: out[n] += scale * sum_m A16[m][n]   (a lane owns 8 columns)
+// partials != null: every row chunk writes its sums to partials[chunk][N] and colsum_finish_kernel adds them up.  Atomics
+// on ONE address serialise at ~0.25 us each: 148 chunks adding to every column bounded the kernel at ~40 us for 100 MB.
 __global__ void __launch_bounds__(256) colsum16_kernel(const __half* __restrict__ A, int lda, int M, int N, float scale,
-                                                       float* __restrict__ out, int rows_per_cta) {
+                                                       float* __restrict__ out, int rows_per_cta, float* __restrict__ partials) {
   __shared__ float red[8][32][8];
   const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int r0 = blockIdx.y * rows_per_cta;
@@ -283,22 +285,42 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const __half* __restrict_
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x][u];
-      atomicAdd(out + col + u, t * scale);
+      if (partials) partials[(size_t)blockIdx.y * N + col + u] = t * scale;
+      else atomicAdd(out + col + u, t * scale);
     }
   }
 }
-int colsum16(const void* A16, int lda, int M, int N, float scale, float* out, cudaStream_t st) {
+__global__ void colsum_finish_kernel(const float* __restrict__ partials, int chunks, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 3 < chunks; c += 4) {
+    s0 += partials[(size_t)c * N + n]; s1 += partials[(size_t)(c + 1) * N + n];
+    s2 += partials[(size_t)(c + 2) * N + n]; s3 += partials[(size_t)(c + 3) * N + n];
+  }
+  for (; c < chunks; ++c) s0 += partials[(size_t)c * N + n];
+  out[n] += (s0 + s1) + (s2 + s3);
+}
+int64_t colsum16_scratch_floats(int N) { return (int64_t)(2 * sm_count() + 2) * N; }
+int colsum16(const void* A16, int lda, int M, int N, float scale, float* out, float* scratch, cudaStream_t st) {
   if (M <= 0 || N <= 0) return -1;
   if ((N & 7) || (lda & 7) || ((uintptr_t)A16 & 15)) return -3;
   const int bx = (N + 255) / 256;
   // (every CTA ends with one atomicAdd per column: 1184 row chunks of a 256-column matrix serialised ~1200 atomics on
   // every address and the kernel took 78 us for 50 MB; two CTAs per SM keep enough loads in flight)
+  // (more, smaller chunks were measured slower: the finishing kernel then walks 1184 partial rows per column)
   int chunks = (2 * sm_count() + bx - 1) / bx;
   int rows = (M + chunks - 1) / chunks;
   if (rows < 64) rows = 64;
   chunks = (M + rows - 1) / rows;
-  colsum16_kernel<<<dim3(bx, chunks), dim3(32, 8), 0, st>>>((const __half*)A16, lda, M, N, scale, out, rows);
+  if (chunks > 2 * sm_count() + 2) scratch = nullptr;
+  colsum16_kernel<<<dim3(bx, chunks), dim3(32, 8), 0, st>>>((const __half*)A16, lda, M, N, scale, out, rows, scratch);
   WN_CHECK_LAUNCH();
+  if (scratch) {
+    colsum_finish_kernel<<<(N + 127) / 128, 128, 0, st>>>(scratch, chunks, N, out);
+    WN_CHECK_LAUNCH();
+  }
   return 0;
 }
 

@@ -29,7 +29,9 @@ struct GemmParams {
 
 int gemm_tf32(int mode, const GemmParams& p, int split_k, cudaStream_t st);
 int colsum(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
-int colsum16(const void* A16, int lda, int M, int N, float scale, float* out, cudaStream_t st);
+// scratch (optional, colsum16_scratch_floats(N) floats): per-chunk partial sums + a finishing kernel instead of atomics
+int64_t colsum16_scratch_floats(int N);
+int colsum16(const void* A16, int lda, int M, int N, float scale, float* out, float* scratch, cudaStream_t st);
 // tcgen05 path: C[M,N] (+)= A[M,K] . B[N,K]^T (p.B is the [N,K] operand), optional transposed copy CT[N][M]
 int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st);
 // tcgen05 path, mode 0 NN (p.B = [K,N]) / 1 NT (p.B = [N,K]) / 2 TN (p.A = [K,M], p.B = [K,N]; GEMM_ATOMIC)
