@@ -165,7 +165,26 @@ __global__ void frontend_bwd_kernel(const int32_t* __restrict__ ids, const float
   const int rows_per_it = blockDim.x / R;
   const int rr = threadIdx.x / R, c = threadIdx.x % R;
   if (rr < rows_per_it) {
-    for (int m = m0 + rr; m < m1; m += rows_per_it) {
+    // four rows per thread per trip, all loads first: one row per trip left the loop bound by one global-load latency per
+    // row (85 trips per CTA, ~60 us for a kernel that moves 13 MB)
+    int m = m0 + rr;
+    for (; m + 3 * rows_per_it < m1; m += 4 * rows_per_it) {
+      float v[4];
+      int cur[4], prev[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int mm = m + u * rows_per_it;
+        v[u] = __ldg(dx0 + (size_t)mm * R + c);
+        cur[u] = __ldg(ids + mm);
+        prev[u] = (mm % T) > 0 ? __ldg(ids + mm - 1) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (prev[u] >= 0 && prev[u] < Q) atomicAdd(dst + (size_t)prev[u] * R + c, v[u]);
+        if (cur[u] >= 0 && cur[u] < Q) atomicAdd(dst + (size_t)(Q + cur[u]) * R + c, v[u]);
+      }
+    }
+    for (; m < m1; m += rows_per_it) {
       const float v = __ldg(dx0 + (size_t)m * R + c);
       const int t = m % T;
       const int cur = __ldg(ids + m);
@@ -182,7 +201,6 @@ __global__ void frontend_bwd_kernel(const int32_t* __restrict__ ids, const float
     }
   }
 }
-
 int frontend_bwd(const int32_t* ids, const float* dx0, float* gwc, int M, int T, int Q, int R, cudaStream_t st) {
   if (M <= 0 || R > 256 || (256 % R)) return -1;
   const size_t smem = sizeof(float) * 2 * Q * R;
