@@ -599,7 +599,12 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   p.stages = 3;
   const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + UM - 1) / UM);
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-  const size_t pipe = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
+  size_t pipe = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
+  // a fourth operand stage where the (8-warp) staging leaves room for it: fp16-only outputs
+  if (pipe + (UM * UK * 4 + BN * UK * 4) + staging_bytes(C != nullptr, aux != nullptr, C16 != nullptr, 2, 8) <= SMEM_OPTIN) {
+    p.stages = 4;
+    pipe += UM * UK * 4 + BN * UK * 4;
+  }
   pick_epilogue(pipe, C != nullptr, aux != nullptr, C16 != nullptr, p);
   const size_t smem = pipe + staging_bytes(C != nullptr, aux != nullptr, C16 != nullptr, p.nbuf, p.ewarps);
   return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p);
