@@ -621,12 +621,12 @@ block_bwd_dx_umma_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_
     mbar_expect_tx(&bar_w, IMG_DX);
     bulk_g2s(Wb, a.img, IMG_DX, &bar_w);
   }
+  // dx' (= dx of layer l+1) was written two launches ago: requested before the dependency wait (common.cuh invariant);
+  // dpre comes from the direct predecessor
+  if (tid == 0 && (int)blockIdx.x < n_tiles && have_dxn) issue_dxn(blockIdx.x);
   pdl_wait();
   if (a.pdl_next) pdl_trigger();
-  if (tid == 0 && (int)blockIdx.x < n_tiles) {
-    issue_loads(blockIdx.x);
-    if (have_dxn) issue_dxn(blockIdx.x);
-  }
+  if (tid == 0 && (int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
   mbar_wait(&bar_w, 0);
   tc_fence_before();
   __syncthreads();
