@@ -372,7 +372,7 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     prof_mark(st, PT_MISC);
   }
   RC(cond_bias_fwd(w.prebias, P(params, lo.filter_bias), P(params, lo.gate_bias), P(params, lo.gc_filter),
-                   P(params, lo.gc_gate), P(params, lo.gc_embedding), gc_ids, L, B, D, gc_ids ? G : 0, st));
+                   P(params, lo.gc_gate), P(params, lo.gc_embedding), gc_ids, L, B, D, gc_ids ? G : 0, c->gc_cardinality, st));
   prof_mark(st, PT_COND_BIAS);
   // (residual stream as fp16 split rows between the forward layers: the front end writes both forms of its output)
   RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, w.WimgH ? w.XS : nullptr, st));
@@ -453,6 +453,64 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     RC(gemm(0, p, 1, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stand-alone residual block entry points (wn_block_fwd / wn_block_bwd) on the PRODUCTION kernels: the same
+// block_fwd_chain_kernel / block_bwd_pre_umma<fp16 dz> / block_bwd_dx_umma / block_wgrad_all launches that
+// wn_loss_grad issues, driven as a one-layer network.  Scratch (split rows, weight images, tile flags, fp16 copy of the
+// skip-path gradient) comes from the stream-ordered allocator: these two entry points are test / integration surfaces,
+// the training step itself never allocates.
+// ---------------------------------------------------------------------------------------
+struct StreamScratch {
+  cudaStream_t st; char* base = nullptr; int64_t off = 0, cap = 0;
+  int init(int64_t bytes, cudaStream_t s) { st = s; cap = bytes; return (int)cudaMallocAsync((void**)&base, (size_t)bytes, s); }
+  void* take(int64_t bytes) { void* p = base + off; off = align_up(off + bytes, 1024); return off <= cap ? p : nullptr; }
+  ~StreamScratch() { if (base) cudaFreeAsync(base, st); }
+};
+
+static int block_fwd_production(const float* x, float* x_out, float* zcat, int ldz, const float* filter, const float* gate,
+                                const float* dense, const float* prebias, const float* dense_bias, int B, int T, int d,
+                                int is_last, cudaStream_t st) {
+  const int64_t M = (int64_t)B * T;
+  const int64_t n_tiles = (int64_t)B * ((T + 127) / 128);
+  StreamScratch sc;
+  RC(sc.init(2 * M * 128 + block_h_images_bytes(1) + (n_tiles + 1) * 4 + 2 * M * 32 * 4 + 8 * 1024, st));
+  void* ring = sc.take(2 * M * 128);
+  unsigned char* img = (unsigned char*)sc.take(block_h_images_bytes(1));
+  unsigned int* flags = (unsigned int*)sc.take((n_tiles + 1) * 4);
+  float* xall = (float*)sc.take(2 * M * 32 * 4);
+  if (!xall) return -5;
+  RC(split_rows(x, ring, M, st));
+  RC(block_h_images(img, filter, gate, dense ? dense : filter, 1, st));      // (the last layer's dense image is never read)
+  RC(block_fwd_chain(ring, is_last ? nullptr : xall, zcat, nullptr, ldz, img, prebias, dense_bias, &d, 1, B, T, flags, st,
+                     /*ring=*/2, /*last_dense=*/!is_last, /*zcols=*/32));
+  if (!is_last) RC((int)cudaMemcpyAsync(x_out, xall + M * 32, (size_t)M * 32 * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int block_bwd_production(const float* x, const float* dx_out, const float* dz_skip, int ldz, float* dx, float* dpre,
+                                const float* zcat, const float* filter, const float* gate, const float* dense,
+                                const float* prebias, float* gwf, float* gwg, float* gdense, float* gprebias,
+                                float* gdense_bias, int B, int T, int d, int is_last, cudaStream_t st) {
+  const int64_t M = (int64_t)B * T;
+  StreamScratch sc;
+  RC(sc.init(block_images_bytes(1) + M * 32 * 4 + M * 32 * 2 + 2 * M * 32 * 4 + 8 * 1024, st));
+  unsigned char* img = (unsigned char*)sc.take(block_images_bytes(1));
+  float* dzc = (float*)sc.take(M * 32 * 4);
+  void* dz16 = sc.take(M * 32 * 2);
+  float* dxall = (float*)sc.take(2 * M * 32 * 4);      // [dx of this layer | dx' = gradient wrt its output]
+  if (!dxall) return -5;
+  RC(block_images(img, filter, gate, dense ? dense : filter, 1, st));
+  RC((int)cudaMemcpy2DAsync(dzc, 32 * 4, dz_skip, (size_t)ldz * 4, 32 * 4, (size_t)M, cudaMemcpyDeviceToDevice, st));
+  RC(to_half(dzc, dz16, M * 32, st));
+  if (!is_last) RC((int)cudaMemcpyAsync(dxall + M * 32, dx_out, (size_t)M * 32 * 4, cudaMemcpyDeviceToDevice, st));
+  RC(block_bwd_pre_umma(x, is_last ? nullptr : dxall + M * 32, nullptr, dz16, 1.f, 32, 0, dpre, img + block_img_off_pre(), prebias,
+                        B, T, d, is_last, -1, st));
+  RC(block_bwd_dx_umma(is_last ? nullptr : dxall + M * 32, dpre, dxall, img + block_img_off_dx(), B, T, d, is_last, -1, st));
+  RC(block_wgrad_all(x, dxall, dpre, zcat, ldz, gwf, gwg, gdense, gprebias, gdense_bias, &d, 1, B, T, st, /*last_dense=*/!is_last));
+  RC((int)cudaMemcpyAsync(dx, dxall, (size_t)M * 32 * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -565,7 +623,10 @@ int wn_block_fwd(const float* x, float* x_out, float* zcat, int32_t ldz, const f
                  int32_t dilation, int32_t channels, int32_t is_last, wn_stream_t stream) {
   if (!x || !zcat || !filter || !gate || !prebias || batch < 1 || time < 1 || dilation < 1) return -1;
   if (!is_last && (!x_out || !dense)) return -1;
-  if ((ldz & 1) || ldz < channels) return -3;
+  if ((ldz & 3) || ldz < channels) return -3;
+  if (channels == 32 && block_umma_enabled() && fwd_h_enabled() && fwd_chain_enabled())
+    return block_fwd_production(x, x_out, zcat, ldz, filter, gate, dense, prebias, dense_bias, batch, time, dilation, is_last,
+                                (cudaStream_t)stream);
   return block_fwd(x, x_out, zcat, ldz, nullptr, filter, gate, dense, prebias, dense_bias,
                    batch * time, time, dilation, channels, is_last, (cudaStream_t)stream);
 }
@@ -580,6 +641,10 @@ int wn_block_bwd(const float* x, const float* dx_out, const float* dz_skip, int3
     return -1;
   if (!is_last && (!dx_out || !dense || !grad_dense)) return -1;
   if ((ldz & 3) || ldz < channels) return -3;
+  if (channels == 32 && block_umma_enabled())
+    return block_bwd_production(x, dx_out, dz_skip, ldz, dx, dpre_scratch, zcat, filter, gate, dense, prebias, grad_filter,
+                                grad_gate, grad_dense, grad_prebias, grad_dense_bias, batch, time, dilation, is_last,
+                                (cudaStream_t)stream);
   return block_bwd(x, dx_out, dz_skip, ldz, dx, dpre_scratch, zcat, filter, gate, dense, prebias, grad_filter,
                    grad_gate, grad_dense, grad_prebias, grad_dense_bias, batch * time, time, dilation, channels,
                    is_last, (cudaStream_t)stream);

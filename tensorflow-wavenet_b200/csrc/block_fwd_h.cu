@@ -428,7 +428,7 @@ int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, void*
 // The split rows travel through a ring of RING buffers [slot][B][T][hi|lo]; layer l reads slot l % RING and writes slot
 // (l+1) % RING.  Before overwriting rows of a slot the publisher checks the flags of the layer-(l+1-RING) tiles that
 // read them (write-after-read), which are RING-1 layers behind and practically always set.
-constexpr int RING = 4;
+constexpr int RING = 4;      // default ring depth (forward only); training keeps every layer's rows: ring = L + 1
 constexpr int CH_THREADS = 320;
 
 struct ChainArgs {
@@ -438,6 +438,8 @@ struct ChainArgs {
   unsigned int* flags;             // [L][n_tiles] tile flags, then the work counter; zeroed before the launch
   int L, B, T, n_tt;
   int has_xout, z16;
+  int ring;                        // slots of the split-row ring (>= 2; L + 1: nothing is ever overwritten)
+  int last_dense;                  // the last layer also computes its dense / residual output (stand-alone wn_block_fwd)
   long long* timeline;             // debug: cycles CTA 0 spent in each kind of wait (wn_debug_timeline)
   int dil[WN_MAX_LAYERS];
 };
@@ -552,7 +554,7 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
         // (acquire, then TMA loads issued by this thread -- the pattern of griddepcontrol.wait + TMA; a fence.proxy.async
         // here was measured at ~2500 cycles on the critical path of every tile)
         if (f0 && !ready) wait_flags(f0, f1, f2);
-        const int slot = l % RING;
+        const int slot = l % a.ring;
         mbar_expect_tx(&bar_tma, 2 * TILE);      // (release: publishes item_s to the waiters of this phase)
         tma_load_3d(Xc, &mapXS, &bar_tma, 0, t0, slot * a.B + b);
         tma_load_3d(Xp, &mapXS, &bar_tma, 0, t0 - d, slot * a.B + b);     // rows before the window start arrive as zeros
@@ -579,7 +581,7 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
       while (item >= 0) {
         const uint32_t par = i & 1;
         const int l = item / n_tiles;
-        const bool last = (l == a.L - 1);
+        const bool last = (l == a.L - 1) && !a.last_dense;
         // the next item is claimed and its producers' flags are looked at while the epilogue warps work on this one;
         // BLOCKING on flags has to wait until everything this tile needs has been issued (see the header)
         const int nx = claim();
@@ -593,8 +595,8 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
         // write-after-read: the ring slot this tile's x' goes to was read by layer l + 1 - RING (own rows and the
         // shifted tap of the tiles d later); those tiles are RING - 1 layers behind and practically always published
         const unsigned int *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
-        if (!last && l + 1 - RING >= 0) {
-          const int lr = l + 1 - RING, j = item - l * n_tiles;
+        if (!last && l + 1 - a.ring >= 0) {
+          const int lr = l + 1 - a.ring, j = item - l * n_tiles;
           const int b = j / a.n_tt, tt = j - b * a.n_tt, t0 = tt * TM, dr = a.dil[lr];
           const unsigned int* f = a.flags + (size_t)lr * n_tiles + (size_t)b * a.n_tt;
           const int ta = (t0 + dr) / TM, tb = (t0 + TM - 1 + dr) / TM;
@@ -685,7 +687,7 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
         const int item = item_s[i & 3];
         if (item < 0) break;
         const int l = item / n_tiles, j = item - l * n_tiles;
-        const bool last = (l == a.L - 1);
+        const bool last = (l == a.L - 1) && !a.last_dense;
         const int b = j / a.n_tt, tt = j - b * a.n_tt, t0 = tt * TM;
         tma_store_3d_hint(&mapZ, Sz, l * C, t0, b, pol_stream);      // rows past the end of the window are clipped by the tensor map
         if (a.z16) tma_store_3d_hint(&mapZ16, Zh, l * C, t0, b, pol_stream);
@@ -703,7 +705,7 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
           mbar_wait(&bar_o, par);                  // x' staged, and the issuer has seen the old readers of the slot finish
           p_o += clock64() - t_a;
           if (a.has_xout) tma_store_3d_hint(&mapXo, Sx, 0, t0, (l + 1) * a.B + b, pol_stream);      // fp32 x' (kept for the backward pass)
-          tma_store_3d_hint(&mapXS, Zs, 0, t0, ((l + 1) % RING) * a.B + b, pol_keep);             // split x' (next layer's operand rows)
+          tma_store_3d_hint(&mapXS, Zs, 0, t0, ((l + 1) % a.ring) * a.B + b, pol_keep);             // split x' (next layer's operand rows)
           bulk_commit();
         }
         t_a = clock64();
@@ -754,7 +756,7 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
         break;
       }
       const int l = item / n_tiles, j = item - l * n_tiles;
-      const bool last = (l == a.L - 1);
+      const bool last = (l == a.L - 1) && !a.last_dense;
       const int b = j / a.n_tt;
       if (l * a.B + b != key) {      // uniform over the epilogue warps: bias rows of this (layer, batch element)
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -852,16 +854,19 @@ block_fwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_c
 // xall[0] the input of layer 0 (layer l writes xall[l+1]; null: forward only); flags: L * B * ceil(T/128) + 1 words.
 int block_fwd_chain(void* xs_ring, float* xall, float* zcat, void* zcat16, int ldz, const unsigned char* img,
                     const float* prebias, const float* dense_bias, const int* dilations, int L, int B, int T,
-                    unsigned int* flags, cudaStream_t st) {
+                    unsigned int* flags, cudaStream_t st, int ring, int last_dense, int zcols) {
   if (L < 1 || L > WN_MAX_LAYERS) return -1;
+  if (ring <= 0) ring = RING;
+  if (ring < 2) return -1;
+  if (zcols <= 0) zcols = ldz;
   CUtensorMap mapXS, mapZ, mapXo, mapZ16;
-  int rc = make_map_split(&mapXS, (const __half*)xs_ring, (int64_t)RING * B, T);
+  int rc = make_map_split(&mapXS, (const __half*)xs_ring, (int64_t)ring * B, T);
   if (rc) return rc;
-  rc = make_map_3d(&mapZ, zcat, B, T, ldz, ldz, TM);
+  rc = make_map_3d(&mapZ, zcat, B, T, zcols, ldz, TM);
   if (rc) return rc;
   mapXo = mapZ;
   if (xall) {
-    rc = make_map_3d(&mapXo, xall, (int64_t)L * B, T, C, C, TM);
+    rc = make_map_3d(&mapXo, xall, (int64_t)(L + (last_dense ? 1 : 0)) * B, T, C, C, TM);
     if (rc) return rc;
   }
   mapZ16 = mapXS;
@@ -873,6 +878,7 @@ int block_fwd_chain(void* xs_ring, float* xall, float* zcat, void* zcat16, int l
   a.img = img; a.prebias = prebias; a.dense_bias = dense_bias; a.flags = flags;
   a.L = L; a.B = B; a.T = T; a.n_tt = (T + TM - 1) / TM;
   a.has_xout = xall ? 1 : 0; a.z16 = zcat16 ? 1 : 0;
+  a.ring = ring; a.last_dense = last_dense ? 1 : 0;
   a.timeline = g_timeline_h;
   for (int l = 0; l < WN_MAX_LAYERS; ++l) a.dil[l] = l < L ? dilations[l] : 0;
   const size_t smem = 1024 + 5 * TILE + IMG_H + TM * 64;
@@ -893,7 +899,7 @@ int block_fwd_chain(void* xs_ring, float* xall, float* zcat, void* zcat16, int l
   prof_mark(st, PT_BLOCK_FWD);
   return 0;
 }
-int64_t block_fwd_chain_ring_bytes(int64_t M) { return (int64_t)RING * M * 128; }
+int64_t block_fwd_chain_ring_bytes(int64_t M, int ring) { return (int64_t)(ring > 0 ? ring : RING) * M * 128; }
 
 int block_fwd_h_set_trap_info(unsigned int* p) { return umma::set_trap_info_tu(p); }
 

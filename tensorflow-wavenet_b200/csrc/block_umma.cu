@@ -846,6 +846,7 @@ block_wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
 struct WgAllArgs {
   float *gwf, *gwg, *gdense, *gprebias, *gdense_bias;   // bases of the per-layer gradient groups (gdense_bias may be null)
   int L, B, T;
+  int last_dense;      // the last layer has a dense output too (stand-alone wn_block_bwd): dx holds L + 1 slots
   int dil[WN_MAX_LAYERS];
 };
 
@@ -895,7 +896,7 @@ block_wgrad_all_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
       for (long long u = u0; u < u1; ++u, ++i) {
         const int lb = (int)(u / per_lb), kb = (int)(u - (long long)lb * per_lb);
         const int l = lb / a.B, b = lb - l * a.B;
-        const bool last = (l == a.L - 1);
+        const bool last = (l == a.L - 1) && !a.last_dense;
         const int s = i % STG;
         const uint32_t ph = (i / STG) & 1;
         const int t = kb * WG_ROWS;
@@ -948,7 +949,7 @@ block_wgrad_all_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
     while (u < u1) {
       const int lb = (int)(u / per_lb);
       const int l = lb / a.B, b = lb - l * a.B;
-      const bool last = (l == a.L - 1);
+      const bool last = (l == a.L - 1) && !a.last_dense;
       long long ue = (long long)(lb + 1) * per_lb;      // end of this (layer, batch element) inside the range
       if (ue > u1) ue = u1;
       mbar_wait(&done_bar, seg & 1);
@@ -991,7 +992,7 @@ block_wgrad_all_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_co
 // gradient group bases as in the parameter layout (per layer strides 2*C*C, 2*C*C, C*C, B*64, C)
 int block_wgrad_all(const float* x, const float* dx, const float* dpre, const float* Zcat, int ldz, float* gwf, float* gwg,
                     float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B, int T,
-                    cudaStream_t st) {
+                    cudaStream_t st, int last_dense) {
   if (L < 1 || L > WN_MAX_LAYERS) return -1;
   CUtensorMap mX, mZ, mP, mDn;
   int rc = make_map_3d_mn(&mX, x, (int64_t)L * B, T, C, C, WG_ROWS);
@@ -1000,9 +1001,10 @@ int block_wgrad_all(const float* x, const float* dx, const float* dpre, const fl
   if (rc) return rc;
   rc = make_map_4d_mn_blocks(&mP, dpre, (int64_t)L * B, T, 64, WG_ROWS, 2);
   if (rc) return rc;
-  rc = make_map_3d_mn(&mDn, dx, (int64_t)L * B, T, C, C, WG_ROWS);
+  rc = make_map_3d_mn(&mDn, dx, (int64_t)(L + (last_dense ? 1 : 0)) * B, T, C, C, WG_ROWS);
   if (rc) return rc;
   WgAllArgs a;
+  a.last_dense = last_dense ? 1 : 0;
   a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias;
   a.L = L; a.B = B; a.T = T;
   for (int l = 0; l < WN_MAX_LAYERS; ++l) a.dil[l] = l < L ? dilations[l] : 0;

@@ -341,7 +341,7 @@ int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float s
 __global__ void cond_bias_fwd_kernel(float* __restrict__ prebias, const float* __restrict__ filter_bias,
                                      const float* __restrict__ gate_bias, const float* __restrict__ gc_filter,
                                      const float* __restrict__ gc_gate, const float* __restrict__ emb_table,
-                                     const int32_t* __restrict__ gc_ids, int L, int B, int D, int G) {
+                                     const int32_t* __restrict__ gc_ids, int L, int B, int D, int G, int card) {
   const int total = L * B * 2 * D;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i % (2 * D), b = (i / (2 * D)) % B, l = i / (2 * D * B);
@@ -350,7 +350,8 @@ __global__ void cond_bias_fwd_kernel(float* __restrict__ prebias, const float* _
     float v = 0.f;
     const float* bias = is_g ? gate_bias : filter_bias;
     if (bias) v = bias[l * D + dd];
-    if (G > 0) {
+    // an id outside [0, card) contributes a zero embedding (tf.nn.embedding_lookup on the GPU) and never reads past the table
+    if (G > 0 && gc_ids[b] >= 0 && gc_ids[b] < card) {
       const float* w = (is_g ? gc_gate : gc_filter) + (size_t)l * G * D;
       const float* e = emb_table + (size_t)gc_ids[b] * G;
       for (int k = 0; k < G; ++k) v = fmaf(e[k], w[k * D + dd], v);
@@ -361,10 +362,10 @@ __global__ void cond_bias_fwd_kernel(float* __restrict__ prebias, const float* _
 
 int cond_bias_fwd(float* prebias, const float* filter_bias, const float* gate_bias, const float* gc_filter,
                   const float* gc_gate, const float* emb_table, const int32_t* gc_ids, int L, int B, int D,
-                  int G, cudaStream_t st) {
+                  int G, int card, cudaStream_t st) {
   const int total = L * B * 2 * D;
   cond_bias_fwd_kernel<<<(total + 255) / 256, 256, 0, st>>>(prebias, filter_bias, gate_bias, gc_filter, gc_gate,
-                                                             emb_table, gc_ids, L, B, D, G);
+                                                             emb_table, gc_ids, L, B, D, G, card);
   WN_CHECK_LAUNCH();
   return 0;
 }
@@ -374,7 +375,7 @@ __global__ void cond_bias_bwd_kernel(const float* __restrict__ gpre, float* __re
                                      const float* __restrict__ gc_gate, float* __restrict__ ggc_filter,
                                      float* __restrict__ ggc_gate, const float* __restrict__ emb_table,
                                      float* __restrict__ gemb_table, const int32_t* __restrict__ gc_ids, int L,
-                                     int B, int D, int G) {
+                                     int B, int D, int G, int card) {
   const int n_bias = L * 2 * D;
   const int n_w = L * G * 2 * D;
   const int n_e = B * G;
@@ -391,7 +392,8 @@ __global__ void cond_bias_bwd_kernel(const float* __restrict__ gpre, float* __re
       const int n = j % (2 * D), k = (j / (2 * D)) % G, l = j / (2 * D * G);
       float s = 0.f;
       for (int b = 0; b < B; ++b)
-        s = fmaf(emb_table[(size_t)gc_ids[b] * G + k], gpre[((size_t)l * B + b) * 2 * D + n], s);
+        if (gc_ids[b] >= 0 && gc_ids[b] < card)      // out-of-range id: zero embedding row, no gradient
+          s = fmaf(emb_table[(size_t)gc_ids[b] * G + k], gpre[((size_t)l * B + b) * 2 * D + n], s);
       if (n < D) ggc_filter[((size_t)l * G + k) * D + n] += s;
       else ggc_gate[((size_t)l * G + k) * D + (n - D)] += s;
     } else {
@@ -404,7 +406,7 @@ __global__ void cond_bias_bwd_kernel(const float* __restrict__ gpre, float* __re
         const float* wg = gc_gate + ((size_t)l * G + k) * D;
         for (int dd = 0; dd < D; ++dd) s += gp[dd] * wf[dd] + gp[D + dd] * wg[dd];
       }
-      if (gemb_table) atomicAdd(gemb_table + (size_t)gc_ids[b] * G + k, s);
+      if (gemb_table && gc_ids[b] >= 0 && gc_ids[b] < card) atomicAdd(gemb_table + (size_t)gc_ids[b] * G + k, s);
     }
   }
 }
@@ -413,11 +415,10 @@ int cond_bias_bwd(const float* gprebias, float* gfilter_bias, float* ggate_bias,
                   const float* gc_gate, float* ggc_filter, float* ggc_gate, const float* emb_table,
                   float* gemb_table, const int32_t* gc_ids, int L, int B, int D, int G, int card,
                   cudaStream_t st) {
-  (void)card;
   const int total = L * 2 * D + L * G * 2 * D + B * G;
   cond_bias_bwd_kernel<<<(total + 127) / 128, 128, 0, st>>>(gprebias, gfilter_bias, ggate_bias, gc_filter, gc_gate,
                                                              ggc_filter, ggc_gate, emb_table, gemb_table, gc_ids,
-                                                             L, B, D, G);
+                                                             L, B, D, G, card);
   WN_CHECK_LAUNCH();
   return 0;
 }

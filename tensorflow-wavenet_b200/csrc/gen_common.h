@@ -9,6 +9,7 @@ namespace wn {
 
 struct GenArgs {
   int L, C, S, Q, G, use_biases;
+  int gc_card;                     // rows of the embedding table; ids outside [0, gc_card) contribute nothing
   int sum_d;                       // sum of dilations (ring rows per stream)
   int streams, n_steps, commit;
   float temperature;

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) generator_kernel(GenArgs a) {
     const int dd = isg ? n - C : n;
     float v = 0.f;
     if (a.use_biases) v = (isg ? a.gate_bias : a.filter_bias)[l * C + dd];
-    if (a.G > 0 && a.gc_ids && s_base + s < a.streams) {
+    if (a.G > 0 && a.gc_ids && s_base + s < a.streams && a.gc_ids[s_base + s] >= 0 && a.gc_ids[s_base + s] < a.gc_card) {
       const float* e = a.gc_embedding + (size_t)a.gc_ids[s_base + s] * a.G;
       const float* w = (isg ? a.gc_gate : a.gc_filter) + (size_t)l * a.G * C;
       for (int k = 0; k < a.G; ++k) v = fmaf(e[k], w[k * C + dd], v);
@@ -455,6 +455,9 @@ int wn_debug_set_gen_impl(int32_t latency_kernel) {
 int64_t wn_gen_state_bytes(const wn_config* cfg, int32_t streams) {
   wn_layout lo;
   if (wn_param_layout(cfg, &lo) || streams < 1) return -1;
+  // both generator kernels index filter / gate as [2C][C] and dense as [C][C]: one channel width (the training path
+  // takes R != D through block_generic.cu, fast generation does not)
+  if (cfg->dilation_channels != cfg->residual_channels) return -2;
   return gen_hdr_bytes(cfg, streams) + gen_pending_bytes(cfg, streams) + gen_rings_bytes(cfg, streams) +
          gen_lat_comm_bytes(cfg);      // tagged-word scratch of the latency-mode kernel (generator_lat.cu)
 }
@@ -495,6 +498,7 @@ int wn_gen_run(const wn_config* cfg, const float* params, void* state, int32_t s
   wn_layout lo;
   int rc = wn_param_layout(cfg, &lo);
   if (rc) return rc;
+  if (cfg->dilation_channels != cfg->residual_channels) return -2;      // see wn_gen_state_bytes
   if (!params || !state || streams < 1 || n_steps < 1) return -1;
   if (!inputs && !forced) return -1;
   if (uniforms && !samples_out) return -1;
@@ -504,6 +508,7 @@ int wn_gen_run(const wn_config* cfg, const float* params, void* state, int32_t s
   memset(&a, 0, sizeof(a));
   a.L = cfg->n_layers; a.C = cfg->residual_channels; a.S = cfg->skip_channels; a.Q = cfg->quantization_channels;
   a.G = gc_ids ? cfg->gc_channels : 0;
+  a.gc_card = cfg->gc_cardinality;
   a.use_biases = cfg->use_biases;
   a.sum_d = sum_dil(cfg);
   a.streams = streams; a.n_steps = n_steps; a.commit = commit; a.temperature = temperature;

@@ -140,7 +140,7 @@ __device__ void chain_warp(const LatArgs& a, int c, int w, volatile u64* xbuf /*
     pbg = g.gate_bias[l * C + lane];
     bd = g.dense_bias[l * C + lane];
   }
-  if (g.G > 0 && g.gc_ids) {   // global conditioning: h . Wgc  (model.py:357-371)
+  if (g.G > 0 && g.gc_ids && g.gc_ids[0] >= 0 && g.gc_ids[0] < g.gc_card) {   // global conditioning: h . Wgc  (model.py:357-371)
     const float* e = g.gc_embedding + (size_t)g.gc_ids[0] * g.G;
     const float* wf = g.gc_filter + (size_t)l * g.G * C;
     const float* wg = g.gc_gate + (size_t)l * g.G * C;

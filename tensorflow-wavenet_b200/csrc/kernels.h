@@ -61,8 +61,10 @@ void set_fwd_h_timeline(long long* p);
 // all forward layers in one persistent kernel (block_fwd_h.cu, "chain")
 int block_fwd_chain(void* xs_ring, float* xall, float* zcat, void* zcat16, int ldz, const unsigned char* img,
                     const float* prebias, const float* dense_bias, const int* dilations, int L, int B, int T,
-                    unsigned int* flags, cudaStream_t st);
-int64_t block_fwd_chain_ring_bytes(int64_t M);
+                    unsigned int* flags, cudaStream_t st, int ring = 0, int last_dense = 0, int zcols = 0);
+// ring: slots of the split-row ring [ring][B][T][hi 32 | lo 32] (0: the default depth, forward only; L + 1: every layer's
+// rows are kept -- what the backward chain reads); last_dense: the last layer also writes x' (xall needs L + 1 slots)
+int64_t block_fwd_chain_ring_bytes(int64_t M, int ring = 0);
 bool block_umma_enabled();
 void set_block_timeline(long long* p);   // debug: clock64 stamps of block_fwd_umma CTA 0 (4 tiles x 8 phases)
 void set_block_impl(int mma);
@@ -74,7 +76,7 @@ int block_bwd_pre_umma(const float* x, const float* dxn, const float* dZcat, con
 // weight gradients of ALL layers in one persistent launch (after the pre / dx chain has finished)
 int block_wgrad_all(const float* x, const float* dx, const float* dpre, const float* Zcat, int ldz, float* gwf, float* gwg,
                     float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B, int T,
-                    cudaStream_t st);
+                    cudaStream_t st, int last_dense = 0);
 int block_wgrad_umma(const float* x, const float* dxn, const float* dpre, const float* Zcat, int ldz, int zcol,
                      float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, int B, int T, int d,
                      int is_last, int pdl, cudaStream_t st);
@@ -122,7 +124,7 @@ int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float s
 // prebias[l][b][2D] = [filter_bias_l | gate_bias_l] + emb[b] . [gc_filter_l | gc_gate_l]
 int cond_bias_fwd(float* prebias, const float* filter_bias, const float* gate_bias, const float* gc_filter,
                   const float* gc_gate, const float* emb_table, const int32_t* gc_ids, int L, int B, int D,
-                  int G, cudaStream_t st);
+                  int G, int card, cudaStream_t st);
 int cond_bias_bwd(const float* gprebias, float* gfilter_bias, float* ggate_bias, const float* gc_filter,
                   const float* gc_gate, float* ggc_filter, float* ggc_gate, const float* emb_table,
                   float* gemb_table, const int32_t* gc_ids, int L, int B, int D, int G, int card,

@@ -246,6 +246,10 @@ class WaveNetModel(object):
         if ids.numel() != count:
             raise ValueError('Shape of global_condition {} does not match batch size {}.'.format(
                 tuple(ids.shape), count))
+        # tf.nn.embedding_lookup raises on the CPU for an id outside the table (model.py:539-540); the kernels
+        # themselves treat such an id as a zero embedding and never touch memory outside the table
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.global_condition_cardinality):
+            raise ValueError('global_condition id outside [0, {})'.format(self.global_condition_cardinality))
         return ids
 
     # ------------------------------------------------------------------ training
@@ -305,6 +309,9 @@ class WaveNetModel(object):
 
     # ------------------------------------------------------------------ fast generation
     def _gen_state(self, streams):
+        if self.dilation_channels != self.residual_channels:
+            raise NotImplementedError('fast generation needs dilation_channels == residual_channels in this '
+                                      'build (training / predict_proba take any widths)')
         if self._gen is None or self._gen['streams'] != streams:
             nbytes = self._lib.wn_gen_state_bytes(C.byref(self._cfg), streams)
             if nbytes < 0:
@@ -365,7 +372,8 @@ class WaveNetModel(object):
             self._init_generator(streams)
         gc = self._gc_ids(global_condition, streams)
         if uniforms is None:
-            base = 0 if seed is None else int(seed)
+            # seed=None: like generate.py:237-238, draws come from the unseeded global np.random stream
+            base = int(np.random.randint(0, 2 ** 31 - 1 - streams)) if seed is None else int(seed)
             uniforms = np.stack([np.random.RandomState(base + s).random_sample(n_samples) for s in range(streams)])
         u = as_cuda(uniforms, torch.float64).reshape(streams, n_samples)
         out = torch.empty((streams, n_samples), dtype=torch.int32, device=self.device)

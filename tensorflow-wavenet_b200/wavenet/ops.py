@@ -27,8 +27,14 @@ def as_cuda(x, dtype):
     """numpy / python / torch -> contiguous CUDA tensor of `dtype`."""
     dev = _device()
     if isinstance(x, torch.Tensor):
-        return x.to(device=dev, dtype=dtype).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(np.asarray(x)), device=dev).to(dtype).contiguous()
+        t = x.to(device=dev, dtype=dtype).contiguous()
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(x)), device=dev).to(dtype).contiguous()
+    # the vectorised kernels want 16-byte aligned buffers: an offset view such as audio[1:] is contiguous
+    # but not aligned -- give it its own allocation instead of failing with "bad argument"
+    if t.numel() and t.data_ptr() % 16:
+        t = t.clone()
+    return t
 
 
 # --------------------------------------------------------------------------------------

@@ -161,8 +161,13 @@ def _block_oracle(x, wf, wg, wd, prebias, bd, d, is_last, gz, gx):
 
 @pytest.mark.parametrize('C_,B,T,d,is_last', [(32, 1, 1000, 1, 0), (32, 1, 1000, 64, 0), (32, 3, 333, 8, 0),
                                               (32, 2, 700, 512, 0), (32, 1, 999, 4, 1), (16, 2, 515, 16, 0),
-                                              (16, 1, 64, 256, 1), (32, 1, 16, 2, 0), (32, 2, 5, 1, 0)])
+                                              (16, 1, 64, 256, 1), (32, 1, 16, 2, 0), (32, 2, 5, 1, 0),
+                                              (32, 1, 100, 128, 0), (32, 3, 640, 512, 0), (32, 1, 257, 256, 1),
+                                              (32, 2, 1153, 127, 0), (16, 3, 300, 512, 0)])
 def test_block_fwd_bwd(lib, C_, B, T, d, is_last):
+    """wn_block_fwd / wn_block_bwd: for 32 channels these run the PRODUCTION kernels of the training step
+    (block_fwd_chain_kernel; block_bwd_pre_umma + block_bwd_dx_umma + block_wgrad_all) as a one-layer network.
+    Shapes cover T not a multiple of the 128-step tile, d >= T (no valid past tap), d = 512 with B = 3, 16 channels."""
     rng = np.random.default_rng(C_ + T + d)
     M = B * T
     lim = np.sqrt(6.0 / (4 * C_))
