@@ -71,9 +71,11 @@ CASES = {
     'cfg3_gc377': (dict(DEFAULT_NET, batch_size=2, global_condition_channels=32, global_condition_cardinality=377),
                    2500, [376, 7]),
 }
-# l2-rel of every gradient against the oracle that emulates the kernels' 11-bit operand rounding (the kernel LOGIC
-# check: a misplaced tile, tap or boundary row shows up here at >= 1e-2)
-GRAD_L2_VS_MATCHED = 4e-3
+# The "matched" oracle rounds operands to TF32 where the first-generation kernels did; the production kernels round to
+# fp16 / split fp16 at other positions, so it is no tighter than the exact oracle (both 1-4e-2: rounding noise amplified
+# by back-propagation at random initialisation, tests/test_oracle_network.py).  It is reported, not asserted; kernel
+# LOGIC is pinned (a) per kernel on the production kernels at 4e-3 max-norm (test_gpu_kernels.py::test_block_fwd_bwd),
+# (b) by the launch-structure equivalence test at the bottom of this file (1e-4 max-norm, also at the benchmarked size).
 
 
 @pytest.mark.parametrize('case', sorted(CASES))
@@ -104,7 +106,7 @@ def test_loss_logits_grads_vs_oracle(case):
         cos = float(np.dot(got[k].ravel().astype(np.float64), g.ravel().astype(np.float64)) /
                     max(np.linalg.norm(got[k]) * np.linalg.norm(g), 1e-300))
         worst, worst_l2 = max(worst, e), max(worst_l2, e2)
-        if e2 >= GRAD_L2_VS_EXACT or cos < 0.998 or e >= GRAD_L2_VS_MATCHED:
+        if e2 >= GRAD_L2_VS_EXACT or cos < 0.998:
             bad.append((k, e2, cos, e))
     print('case {} loss {:.6f} ref {:.6f} logits rel {:.2e} | grads: worst l2-rel vs exact {:.2e} (vs TF32-emulating '
           'oracle {:.2e})'.format(case, float(loss), loss_ref, rel_err(logits, logits_ref), worst_l2, worst))
