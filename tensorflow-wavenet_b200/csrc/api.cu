@@ -129,6 +129,10 @@ struct Workspace {
   unsigned int* chain_flags;      // [L][B * ceil(T/128)] tile flags of the persistent forward kernel (null: per-layer launches)
   void* XS;             // 2 x [M][hi 32 | lo 32] fp16 split rows: the residual stream between forward layers
   int umma_bwd;    // 1 when the tcgen05 backward path is used
+  int bwd16;       // 1: fp16 backward chain (block_bwd_h.cu): XS keeps every layer's split rows, DXS / P16 hold dx / dpre
+  void *DXS, *P16;                // [L][M][hi 32 | lo 32] input gradients, [L][M][df 32 | dg 32] pre-activation gradients (fp16, scaled)
+  unsigned char* WimgB;           // per-layer weight images of the backward chain
+  unsigned int* bflags;           // tile flags + work counter of the backward chain
   float* Pall;     // generic-width blocks: saved pre-activations [L or 1][M][2D]
   float* gscratch; // generic-width blocks: operand splits / temporaries (generic_scratch_floats)
   int64_t bytes;
@@ -166,6 +170,16 @@ static bool fwd_chain_enabled() {
   }
   return v == 1;
 }
+// backward of the fused blocks: one persistent fp16 chain kernel + one weight-gradient launch (default), or the
+// first-generation per-layer TF32 kernels (WN_BWD_CHAIN=0)
+static bool bwd_chain_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WN_BWD_CHAIN");
+    v = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 static void carve(const wn_config* c, int B, int T, bool training, void* base, Workspace* w) {
   const int64_t M = (int64_t)B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
                 S = c->skip_channels, Q = c->quantization_channels;
@@ -176,9 +190,18 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     return base ? (void*)((char*)base + r) : (void*)nullptr;
   };
   const int64_t f = sizeof(float);
+  const bool umma_blocks = fused_blocks(c) && (R == 32) && block_umma_enabled();
+  const bool fwd_h = umma_blocks && fwd_h_enabled();
+  const bool chain = fwd_h && fwd_chain_enabled();
+  const bool f16_chain = fwd_h && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0;
+  // fp16 gradient chain of the post-processing layers: all-or-nothing (its GEMMs keep no fp32 copies of G1 / G2), so
+  // every weight-gradient shape must suit the fp16 MN-major form (multiples of 64); otherwise the tf32 chain runs
+  const bool g16 = training && f16_chain && (Q % 64) == 0 && (S % 64) == 0 && ((L * D) % 64) == 0;
+  const bool bwd16 = g16 && chain && bwd_chain_enabled();
+  w->bwd16 = bwd16 ? 1 : 0;
   w->ids = (int32_t*)take(M * 4 + 16);
-  w->X = (float*)take((training ? L : 2) * M * R * f);
-  w->Zcat = (float*)take(M * L * D * f);
+  w->X = (float*)take((training && !bwd16 ? L : 2) * M * R * f);
+  w->Zcat = (float*)take(bwd16 ? 256 : M * L * D * f);      // (fp16 backward chain: every consumer of z reads Zcat16)
   w->A1 = (float*)take(M * S * f);
   w->A2 = (float*)take(M * S * f);
   w->S0 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
@@ -189,7 +212,6 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->WskipR = (float*)take(S * L * D * f);
   w->W1R = (float*)take(S * S * f);
   w->W2R = (float*)take(Q * S * f);
-  const bool umma_blocks = fused_blocks(c) && (R == 32) && block_umma_enabled();
   if (!fused_blocks(c)) {
     w->Pall = (float*)take((training ? L : 1) * M * 2 * D * f);
     w->gscratch = (float*)take(generic_scratch_floats(M, (int)R, (int)D) * f);
@@ -198,12 +220,19 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   }
   w->Wimg = umma_blocks ? (unsigned char*)take(block_images_bytes((int)L)) : nullptr;
   w->umma_bwd = (training && umma_blocks) ? 1 : 0;
-  const bool fwd_h = umma_blocks && fwd_h_enabled();
   w->WimgH = fwd_h ? (unsigned char*)take(block_h_images_bytes((int)L)) : nullptr;
-  const bool chain = fwd_h && fwd_chain_enabled();
-  w->XS = fwd_h ? take(chain ? block_fwd_chain_ring_bytes(M) : 2 * M * 128) : nullptr;
+  w->XS = fwd_h ? take(chain ? block_fwd_chain_ring_bytes(M, bwd16 ? (int)(L > 2 ? L : 2) : 0) : 2 * M * 128) : nullptr;
   w->chain_flags = chain ? (unsigned int*)take((L * (int64_t)B * ((T + 127) / 128) + 1) * 4) : nullptr;
-  const bool f16_chain = fwd_h && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0;
+  if (bwd16) {
+    w->DXS = take(L * M * 128);
+    w->P16 = take(L * M * 128);
+    w->WimgB = (unsigned char*)take(block_bwd_h_images_bytes((int)L));
+    w->bflags = (unsigned int*)take(block_bwd_chain_flag_words((int)L, B, T) * 4);
+  } else {
+    w->DXS = w->P16 = nullptr;
+    w->WimgB = nullptr;
+    w->bflags = nullptr;
+  }
   if (f16_chain) {
     w->Zcat16 = take(M * L * D * 2);
     w->A1h = take(M * S * 2);
@@ -214,9 +243,6 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   } else {
     w->Zcat16 = w->A1h = w->A2h = w->Wskip16 = w->W1h = w->W2h = nullptr;
   }
-  // fp16 gradient chain of the post-processing layers: all-or-nothing (its GEMMs keep no fp32 copies of G1 / G2), so
-  // every weight-gradient shape must suit the fp16 MN-major form (multiples of 64); otherwise the tf32 chain runs
-  const bool g16 = training && f16_chain && (Q % 64) == 0 && (S % 64) == 0 && ((L * D) % 64) == 0;
   if (g16) {      // (not a pointer test: a size query carves from a null base)
     w->dlog16 = take(M * Q * 2);
     w->dZcat16 = take(M * L * D * 2);
@@ -239,8 +265,8 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->G2 = g16 ? nullptr : (float*)take(M * S * f);
     w->G3 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
     w->dZcat = g16 ? nullptr : (float*)take(M * L * D * f);
-    w->dX = (float*)take((w->umma_bwd ? L : 2) * M * R * f);
-    w->dpre = (float*)take((w->umma_bwd ? L : 1) * M * 2 * D * f);
+    w->dX = (float*)take((bwd16 ? 1 : w->umma_bwd ? L : 2) * M * R * f);
+    w->dpre = (float*)take(bwd16 ? 256 : (w->umma_bwd ? L : 1) * M * 2 * D * f);
     w->gprebias = (float*)take(L * B * 2 * D * f);
     w->gtmp = (float*)take(S * f);
   } else {
@@ -362,12 +388,14 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   if (use_prep) {
     RC((int)cudaEventRecord(ev_fork, st));
     RC((int)cudaStreamWaitEvent(prep, ev_fork, 0));
-    RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, prep));      // backward images
+    if (w.bwd16) RC(block_bwd_h_images(w.WimgB, params + lo.filter, params + lo.gate, params + lo.dense, L, prep));
+    else RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, prep));      // backward images
     RC(prep_weights());
     RC((int)cudaEventRecord(ev_join, prep));
     RC(block_h_images(w.WimgH, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
   } else if (w.Wimg) {   // first, so that at least two launches separate it from the first block kernel (PDL, common.cuh)
-    RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
+    if (training && w.bwd16) RC(block_bwd_h_images(w.WimgB, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
+    else RC(block_images(w.Wimg, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
     if (w.WimgH) RC(block_h_images(w.WimgH, params + lo.filter, params + lo.gate, params + lo.dense, L, st));
     prof_mark(st, PT_MISC);
   }
@@ -379,8 +407,11 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   prof_mark(st, PT_FRONTEND_FWD);
   const int64_t xs = (int64_t)M * R;
   if (w.chain_flags) {
-    RC(block_fwd_chain(w.XS, training ? w.X : nullptr, w.Zcat, w.Zcat16, ldz, w.WimgH, w.prebias,
-                       lo.dense_bias >= 0 ? params + lo.dense_bias : nullptr, c->dilations, L, B, T, w.chain_flags, st));
+    // fp16 backward chain: the split rows of EVERY layer stay (ring = L) and nothing reads fp32 x' / z
+    const bool b16 = training && w.bwd16;
+    RC(block_fwd_chain(w.XS, (training && !b16) ? w.X : nullptr, b16 ? nullptr : w.Zcat, w.Zcat16, ldz, w.WimgH, w.prebias,
+                       lo.dense_bias >= 0 ? params + lo.dense_bias : nullptr, c->dilations, L, B, T, w.chain_flags, st,
+                       b16 ? (L > 2 ? L : 2) : 0));
   }
   for (int l = 0; l < L && !w.chain_flags; ++l) {
     const float* xin = training ? w.X + l * xs : w.X + (l & 1) * xs;
@@ -494,23 +525,35 @@ static int block_bwd_production(const float* x, const float* dx_out, const float
                                 const float* zcat, const float* filter, const float* gate, const float* dense,
                                 const float* prebias, float* gwf, float* gwg, float* gdense, float* gprebias,
                                 float* gdense_bias, int B, int T, int d, int is_last, cudaStream_t st) {
+  (void)dpre;
   const int64_t M = (int64_t)B * T;
+  const int64_t fw = block_bwd_chain_flag_words(1, B, T);
   StreamScratch sc;
-  RC(sc.init(block_images_bytes(1) + M * 32 * 4 + M * 32 * 2 + 2 * M * 32 * 4 + 8 * 1024, st));
-  unsigned char* img = (unsigned char*)sc.take(block_images_bytes(1));
-  float* dzc = (float*)sc.take(M * 32 * 4);
+  RC(sc.init(block_h_images_bytes(1) + block_bwd_h_images_bytes(1) + 2 * M * 32 * 4 + 2 * M * 32 * 2 + 4 * M * 128 + fw * 4 +
+             16 * 1024, st));
+  unsigned char* img_f = (unsigned char*)sc.take(block_h_images_bytes(1));
+  unsigned char* img_b = (unsigned char*)sc.take(block_bwd_h_images_bytes(1));
+  float* dzc = (float*)sc.take(M * 32 * 4);      // compact fp32 copies of the pitched inputs
+  float* zc = (float*)sc.take(M * 32 * 4);
   void* dz16 = sc.take(M * 32 * 2);
-  float* dxall = (float*)sc.take(2 * M * 32 * 4);      // [dx of this layer | dx' = gradient wrt its output]
-  if (!dxall) return -5;
-  RC(block_images(img, filter, gate, dense ? dense : filter, 1, st));
+  void* z16 = sc.take(M * 32 * 2);
+  void* xs = sc.take(M * 128);
+  void* dxs = sc.take(2 * M * 128);               // [dx of this layer | dx' = gradient wrt its output] as split rows
+  void* p16 = sc.take(M * 128);
+  unsigned int* flags = (unsigned int*)sc.take(fw * 4);
+  if (!flags) return -5;
+  const float* dn = dense ? dense : filter;       // (the last layer's dense images are never read)
+  RC(block_h_images(img_f, filter, gate, dn, 1, st));
+  RC(block_bwd_h_images(img_b, filter, gate, dn, 1, st));
   RC((int)cudaMemcpy2DAsync(dzc, 32 * 4, dz_skip, (size_t)ldz * 4, 32 * 4, (size_t)M, cudaMemcpyDeviceToDevice, st));
   RC(to_half(dzc, dz16, M * 32, st));
-  if (!is_last) RC((int)cudaMemcpyAsync(dxall + M * 32, dx_out, (size_t)M * 32 * 4, cudaMemcpyDeviceToDevice, st));
-  RC(block_bwd_pre_umma(x, is_last ? nullptr : dxall + M * 32, nullptr, dz16, 1.f, 32, 0, dpre, img + block_img_off_pre(), prebias,
-                        B, T, d, is_last, -1, st));
-  RC(block_bwd_dx_umma(is_last ? nullptr : dxall + M * 32, dpre, dxall, img + block_img_off_dx(), B, T, d, is_last, -1, st));
-  RC(block_wgrad_all(x, dxall, dpre, zcat, ldz, gwf, gwg, gdense, gprebias, gdense_bias, &d, 1, B, T, st, /*last_dense=*/!is_last));
-  RC((int)cudaMemcpyAsync(dx, dxall, (size_t)M * 32 * 4, cudaMemcpyDeviceToDevice, st));
+  RC((int)cudaMemcpy2DAsync(zc, 32 * 4, zcat, (size_t)ldz * 4, 32 * 4, (size_t)M, cudaMemcpyDeviceToDevice, st));
+  RC(to_half(zc, z16, M * 32, st));
+  RC(split_rows(x, xs, M, st));
+  if (!is_last) RC(split_rows(dx_out, (char*)dxs + M * 128, M, st));
+  RC(block_bwd_chain(xs, dxs, p16, dz16, 32, 1.f, img_f, img_b, prebias, &d, 1, B, T, flags, st, /*last_dense=*/!is_last));
+  RC(block_wgrad_h_all(xs, dxs, p16, z16, 32, 1.f, gwf, gwg, gdense, gprebias, gdense_bias, &d, 1, B, T, st, /*last_dense=*/!is_last));
+  RC(unsplit_rows(dxs, dx, M, 1.f, st));
   return 0;
 }
 
@@ -531,12 +574,14 @@ int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma) {
 int wn_debug_trap_info(unsigned int* host_mapped_words) {
   int rc = block_umma_set_trap_info(host_mapped_words);
   if (rc == 0) rc = block_fwd_h_set_trap_info(host_mapped_words);
+  if (rc == 0) rc = block_bwd_h_set_trap_info(host_mapped_words);
   return rc;
 }
 
 int wn_debug_timeline(long long* stamps) {
   set_block_timeline(stamps);
   set_fwd_h_timeline(stamps);
+  set_bwd_h_timeline(stamps ? stamps + 16 : nullptr);      // slots 16..26: the backward chain's wait cycles
   set_gen_timeline(stamps);
   return 0;
 }
@@ -641,7 +686,7 @@ int wn_block_bwd(const float* x, const float* dx_out, const float* dz_skip, int3
     return -1;
   if (!is_last && (!dx_out || !dense || !grad_dense)) return -1;
   if ((ldz & 3) || ldz < channels) return -3;
-  if (channels == 32 && block_umma_enabled())
+  if (channels == 32 && block_umma_enabled() && fwd_h_enabled() && bwd_chain_enabled())
     return block_bwd_production(x, dx_out, dz_skip, ldz, dx, dpre_scratch, zcat, filter, gate, dense, prebias, grad_filter,
                                 grad_gate, grad_dense, grad_prebias, grad_dense_bias, batch, time, dilation, is_last,
                                 (cudaStream_t)stream);
@@ -865,7 +910,19 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   }
   const int64_t xs = (int64_t)M * R;
   const float* dcur = nullptr;     // gradient wrt the output of the layer being processed
-  if (w.umma_bwd) {
+  if (w.bwd16) {
+    // One persistent, flag-ordered kernel for the pre-activation and input gradients of every layer, then the weight
+    // gradients of every layer in one launch; both on fp16 tiles in the domain scaled by gscale * cs (block_bwd_h.cu).
+    const float cs = 16.f;
+    RC(block_bwd_chain(w.XS, w.DXS, w.P16, w.dZcat16, ldz, cs, w.WimgH, w.WimgB, w.prebias, cfg->dilations, L, B, T, w.bflags, st));
+    if (trunc == 4) { RC((int)cudaStreamWaitEvent(st, ev_g[3], 0)); return 0; }
+    RC(block_wgrad_h_all(w.XS, w.DXS, w.P16, w.Zcat16, ldz, 1.f / (gscale * cs), grads + lo.filter, grads + lo.gate,
+                         grads + lo.dense, w.gprebias, lo.dense_bias >= 0 ? grads + lo.dense_bias : nullptr, cfg->dilations,
+                         L, B, T, st));
+    RC(unsplit_rows(w.DXS, w.dX, M, 1.f / (gscale * cs), st));
+    prof_mark(st, PT_MISC);
+    dcur = w.dX;
+  } else if (w.umma_bwd) {
     // Critical chain on `st`: pre(l) -> dx(l) -> pre(l-1) -> ...  The weight-gradient GEMM of a layer only feeds
     // the gradient buffers, so it runs on a side stream, concurrently with the chain.  Every layer has its own dpre
     // and dx buffer: the chain never has to wait for the side stream (a cross-stream wait in front of a

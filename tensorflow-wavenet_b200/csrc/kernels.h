@@ -101,6 +101,21 @@ int split_rows(const float* x, void* xs, int64_t M, cudaStream_t st);
 int block_fwd_h(const void* xs_in, void* xs_out, float* xout, float* zcat, void* zcat16, int ldz, int zcol, const unsigned char* img,
                 const float* prebias, const float* dense_bias, int B, int T, int d, int is_last, int pdl_next,
                 cudaStream_t st);
+// ---- backward chain on fp16 split rows (block_bwd_h.cu) ----
+int64_t block_bwd_h_images_bytes(int L);
+int block_bwd_h_images(unsigned char* img, const float* filter, const float* gate, const float* dense, int L, cudaStream_t st);
+int64_t block_bwd_chain_flag_words(int L, int B, int T);
+// pre-activation + input gradients of ALL layers in one persistent flag-ordered kernel (fp16 scaled domain)
+int block_bwd_chain(const void* xs, void* dxs, void* p16, const void* dz16, int ldz, float cs, const unsigned char* img_f,
+                    const unsigned char* img_b, const float* prebias, const int* dilations, int L, int B, int T,
+                    unsigned int* flags, cudaStream_t st, int last_dense = 0);
+// weight gradients of all layers from the fp16 tiles (x split rows, fp16 Zcat, dpre, dx split rows); scale: out of the scaled domain
+int block_wgrad_h_all(const void* xs, const void* dxs, const void* p16, const void* zcat16, int ldz, float scale, float* gwf,
+                      float* gwg, float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B,
+                      int T, cudaStream_t st, int last_dense = 0);
+int unsplit_rows(const void* xs, float* x, int64_t M, float scale, cudaStream_t st);
+int block_bwd_h_set_trap_info(unsigned int* p);
+void set_bwd_h_timeline(long long* p);
 int64_t block_images_bytes(int L);
 uint32_t block_img_off_pre();
 uint32_t block_img_off_dx();
