@@ -14,15 +14,15 @@
 // chain kept for every layer.  A row of 64 halfs is one 128-byte swizzle row, so the same shared-memory tile is
 //   * a K-major operand (contraction over channels: the products above), and
 //   * an MN-major operand (contraction over time: the weight gradients)        -- no transposed or re-swizzled copies.
-// Work item = (layer, batch element, 128-step tile), claimed from one global counter in (layer descending, time
-// descending) order; tile (l, t0) needs dx' of (l+1, t0) and dpre of the same layer at [t0+d, t0+d+128), i.e. tiles
-// later in time = earlier in the order, so the kernel is deadlock-free for any number of resident CTAs.
+// Work items (PRE and DX of a tile are separate items, see the chain kernel below) are claimed from one global counter.
 //   warps 0-7  epilogue (thread = one time step x 16 channels)
-//   warp  8    issuer: claims work, polls flags, TMA loads, tcgen05 MMAs, weight images
+//   warp  8    loader: claims work, polls flags, TMA loads, weight images
 //   warp  9    publisher: TMA stores of dpre and dx, then (stores complete) the tile's flags
-// The shifted operand dpre[t+d]: the tile's own dpre rows sit in shared memory (P), the rows of the tile(s) after it are
-// loaded right behind them (Pn), and the MMA reads [P | Pn] from row min(d, 128) on: a descriptor start address in the
-// middle of the swizzle pattern (matrix base offset = row & 7).  WN_BWD_SHIFT=global takes the own rows through L2 instead.
+//   warp 10    MMA issuer: tcgen05 MMAs of an item as soon as its operand tiles have landed
+// (tcgen05 finding kept for the record, probed with the first, fused version of this kernel: a K-major 128B-swizzled
+// operand may start at ANY row of a tile -- descriptor start address = tile + row * 128, matrix base offset field 0 --
+// because the swizzle is a function of the absolute shared-memory address bits, not of the row index relative to the
+// start address; with the base offset set to row & 7 the rows come out permuted.)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,10 +38,60 @@ namespace wn {
 using namespace umma;
 
 namespace {
-constexpr uint32_t IMG_B = 3 * 4096;          // WdT [32 c][hi r | lo r] | Bcur [32 r][df c | dg c] | Bpast
-constexpr uint32_t W_BYTES = 16384 + IMG_B;   // W0cat | W1cat (forward image) | backward image
-constexpr int BC_THREADS = 320;
+// per-layer weight image: W0h [64 n][32 k] | W1h (fp16, 64-byte rows, 64B swizzle: the recompute of the pre-activations is a
+// single fp16 product, like the TF32 recompute of the first-generation kernels) | WdT [32 c][hi r | lo r] | Bcur [32 r][df c | dg c] | Bpast
+constexpr uint32_t IMG_B = 5 * 4096;
+constexpr uint32_t IMG_PRE_BYTES = 3 * 4096, IMG_DX_OFF = 3 * 4096, IMG_DX_BYTES = 2 * 4096;
+constexpr uint32_t XH_TILE = TM * 64;         // [128 rows][32 halfs]
+constexpr int BC_THREADS = 352;      // 8 epilogue warps + loader + publisher + MMA issuer
 
+// byte offset of fp16 element (row, k) in a [rows][32 fp16] 64B-swizzled K-major tile
+__device__ __forceinline__ uint32_t swzh64(int row, int k) {
+  return (uint32_t)(row * 64 + ((((k >> 3) ^ ((row >> 1) & 3))) << 4) + ((k & 7) << 1));
+}
+// K-major operand, 64B swizzle: rows are 64 bytes, 8-row groups 512 bytes apart (SBO), layout type 4
+__device__ __forceinline__ uint64_t kmajor_desc64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// the hi halves of split rows [B][T][hi 32 | lo 32]: box = [TM rows][32 halfs], 64B swizzle
+static int make_map_xhi(CUtensorMap* m, const __half* ptr, int64_t B, int64_t T) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {32, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {128, (cuuint64_t)T * 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)TM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+// two floats -> packed fp16 pair, saturating at +-65504 (one F2FP.SATFINITE instruction); lo = the lower half
+__device__ __forceinline__ uint32_t pack_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// tanh(f) and sigmoid(g) for the backward recompute.  WN_BWD_TANH_APPROX: two MUFU.TANH (relative error 2^-11, the
+// precision of the fp16 operands of the recompute itself) instead of two ex2 + one rcp + the range clamps.
+#ifndef WN_BWD_TANH_APPROX
+#define WN_BWD_TANH_APPROX 1
+#endif
+__device__ __forceinline__ void gate_parts(float f, float g, float& tf, float& sg) {
+#if WN_BWD_TANH_APPROX
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tf) : "f"(f));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * g));
+  sg = fmaf(0.5f, t, 0.5f);
+#else
+  gated_parts_fast(f, g, tf, sg);
+#endif
+}
 __device__ __forceinline__ __half sat_half(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
 __device__ __forceinline__ void split_sat(float x, __half& h, __half& l) {
   x = fminf(fmaxf(x, -65504.f), 65504.f);
@@ -62,7 +112,7 @@ static int make_map_h64(CUtensorMap* m, const void* ptr, int64_t B, int64_t T, i
 }
 }  // namespace
 
-// ---- backward weight images: per layer  WdT | Bcur | Bpast  (fp16, swizzled K-major rows of 64 halfs) ----
+// ---- backward weight images: per layer  W0h | W1h | WdT | Bcur | Bpast  (fp16, swizzled K-major rows) ----
 __global__ void block_bwd_h_images_kernel(unsigned char* __restrict__ img, const float* __restrict__ filter,
                                           const float* __restrict__ gate, const float* __restrict__ dense) {
   const int l = blockIdx.x;
@@ -70,18 +120,23 @@ __global__ void block_bwd_h_images_kernel(unsigned char* __restrict__ img, const
   const float* wf = filter + (size_t)l * 2 * C * C;
   const float* wg = gate + (size_t)l * 2 * C * C;
   const float* wd = dense + (size_t)l * C * C;
+  for (int i = threadIdx.x; i < 2 * 64 * 32; i += blockDim.x) {  // W[tap]h: n = [filter | gate] output channel (fastest: coalesced), k = input channel
+    const int tap = i / (64 * 32), k = (i / 64) % 32, n = i % 64;
+    const float w = n < C ? wf[(tap * C + k) * C + n] : wg[(tap * C + k) * C + (n - C)];
+    *reinterpret_cast<__half*>(base + tap * 4096 + swzh64(n, k)) = __float2half_rn(w);
+  }
   for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {      // WdT: n = dilation channel c, k = residual channel r
     const int n = i / 32, k = i % 32;
     __half h, lo;
     split_h(wd[n * C + k], h, lo);
-    *reinterpret_cast<__half*>(base + swzh(n, k)) = h;
-    *reinterpret_cast<__half*>(base + swzh(n, 32 + k)) = lo;
+    *reinterpret_cast<__half*>(base + 8192 + swzh(n, k)) = h;
+    *reinterpret_cast<__half*>(base + 8192 + swzh(n, 32 + k)) = lo;
   }
   for (int i = threadIdx.x; i < 2 * 32 * 64; i += blockDim.x) {  // B[tap]: n = residual channel r, k = [df c | dg c]
     const int which = i / (32 * 64), n = (i / 64) % 32, k = i % 64;
     const int tap = which == 0 ? 1 : 0;      // Bcur multiplies dpre[t] (tap 1 = current sample), Bpast dpre[t+d] (tap 0)
     const float w = k < 32 ? wf[(tap * C + n) * C + k] : wg[(tap * C + n) * C + (k - 32)];
-    *reinterpret_cast<__half*>(base + 4096 + which * 4096 + swzh(n, k)) = __float2half_rn(w);
+    *reinterpret_cast<__half*>(base + IMG_DX_OFF + which * 4096 + swzh(n, k)) = __float2half_rn(w);
   }
 }
 int64_t block_bwd_h_images_bytes(int L) { return (int64_t)L * IMG_B; }
@@ -117,6 +172,26 @@ int unsplit_rows(const void* xs, float* x, int64_t M, float scale, cudaStream_t 
 // =====================================================================================================================
 // the chain kernel
 // =====================================================================================================================
+// Work items, claimed from one global counter, phase q = 0 .. L (n_tiles = B * ceil(T/128) items each):
+//   q = 0        PRE(L-1, tile)                       pre-activation gradient of the last layer (it has no output gradient)
+//   0 < q < L    DX(l, tile) + PRE(l-1, tile), l = L-q   input gradient of layer l, which IS the output gradient of layer
+//                                                     l-1 at the same time steps: it stays in shared memory as the A
+//                                                     operand of dx'.Wd^T and as the residual term of the next phase
+//   q = L        DX(0, tile)
+//   PRE(l): recompute pre-activations, dz = dz_skip + dx'.Wd^T, dpre -> P16[l]
+//   DX(l) : dx = dx' + dpre[t].W1^T + dpre[t+d].W0^T -> DXS[l]          (dpre of the tile and of the tiles d steps later)
+// An item only depends on items of the previous phase (deadlock-free for any number of resident CTAs), i.e. on items
+// >= n_tiles - 5 back in the order.  History of this structure (tools/timeline_bwd.py):
+//   * PRE and DX of the SAME layer fused per tile: a tile needs the dpre rows of the tile claimed right before it, the
+//     two run in lockstep on different CTAs and every tile stalled ~5,000 cycles on that flag;
+//   * PRE and DX as separate items (100 phases): no lockstep, but twice the dependent hops -- with 782 tiles per phase
+//     and 296 CTAs a phase lasts about as long as one item's latency (claim -> loads -> MMA -> epilogue -> store -> flag),
+//     so half of the items still found their flags unset;
+//   * this form: 51 phases, one L2 round trip per layer instead of two, dx never re-loaded by its own consumer.
+// Per CTA the items are pipelined: TMEM accumulators double buffered by item parity, a loader warp that prefetches the
+// next item's tiles as soon as the MMAs have read the current ones, a separate MMA-issuing warp, a publisher warp.
+enum { BC_W8 = 8, BC_W9 = 9, BC_W10 = 10 };
+
 struct BwdChainArgs {
   const unsigned char* img_f;      // [L] forward weight images (IMG_H bytes each; W0cat | W1cat are used)
   const unsigned char* img_b;      // [L] backward weight images (IMG_B bytes each)
@@ -124,346 +199,528 @@ struct BwdChainArgs {
   unsigned int* flags;             // [L][n_tiles] dpre published | [L][n_tiles] dx published | work counter; zeroed before the launch
   int L, B, T, n_tt;
   int last_dense;                  // the last layer has an output gradient too (stand-alone wn_block_bwd)
-  int base_off;                    // (probe) set the descriptor's matrix base offset field to the start row & 7
-  int shift_global;                // dilations that are not multiples of 8 (and < 128): own dpre rows through L2
   float cs;                        // the skip-path gradient is multiplied by cs on its way into the chain's scaled domain
-  long long* timeline;             // debug: cycles CTA 0 spent in each kind of wait
+  long long* timeline;             // debug: cycles CTA 0's warps spent in each kind of wait
   int dil[WN_MAX_LAYERS];
 };
 static long long* g_timeline_b = nullptr;
 void set_bwd_h_timeline(long long* p) { g_timeline_b = p; }
 
+// Bounded waits with role-specific bounds (loader / MMA issuer < epilogue < publisher): when the protocol hangs, the
+// trap info names what the LOADER was waiting for (tag = source line), which is what decides everything else.
+__device__ __forceinline__ void mbar_wait_n(uint64_t* b, uint32_t parity, uint32_t log2n, uint32_t tag) {
+  for (uint32_t i = 0; i < (1u << log2n); ++i) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
+    g_trap_info[0] = smem_u32(b); g_trap_info[1] = parity; g_trap_info[2] = blockDim.x; g_trap_info[3] = tag;
+    g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x; g_trap_info[6] = gridDim.y;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void spin_until(volatile int* cnt, int need, uint32_t tag) {
+  uint32_t spin = 0;
+  while (*cnt < need) {
+    if (++spin > (1u << 22)) {
+      if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
+        g_trap_info[0] = 0x5F4Eu; g_trap_info[1] = (unsigned int)need; g_trap_info[2] = blockDim.x; g_trap_info[3] = tag;
+        g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x; g_trap_info[6] = (unsigned int)*cnt;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+#define IWAIT(bar, par) mbar_wait_n(bar, par, 20, __LINE__)
+#define EWAIT(bar, par) mbar_wait_n(bar, par, 22, __LINE__)
+#define PWAIT(bar, par) mbar_wait_n(bar, par, 24, __LINE__)
+
 __global__ void __launch_bounds__(BC_THREADS, 2)
-block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXS, const __grid_constant__ CUtensorMap mapDX,
+block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_constant__ CUtensorMap mapDX,
                        const __grid_constant__ CUtensorMap mapDz, const __grid_constant__ CUtensorMap mapP,
                        const __grid_constant__ BwdChainArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* Xc = smem;                 // split rows x[t]
-  unsigned char* P = smem + TILE;           // dpre of this tile [128][df 32 | dg 32] fp16
-  unsigned char* Xp = smem + 2 * TILE;      // split rows x[t-d]; later Pn: the dpre rows that follow this tile's ([P | Pn] is contiguous)
-  unsigned char* Dn = smem + 3 * TILE;      // split rows dx' (A operand of dx'.Wd^T, residual term); later the dx rows on their way out
-  unsigned char* Dz = smem + 4 * TILE;      // skip-path gradient [128][32 halfs], 64B swizzle
-  unsigned char* W0 = Dz + TM * 64;         // [64][hi|lo] past tap (filter | gate)      } forward image
-  unsigned char* W1 = W0 + 8192;            // current tap                               }
-  unsigned char* WdT = W1 + 8192;           // [32 c][hi r | lo r]                        } backward image
-  unsigned char* Bc = WdT + 4096;           // [32 r][df c | dg c], tap 1
-  unsigned char* Bp = Bc + 4096;            // tap 0
-  __shared__ __align__(8) uint64_t bar_x, bar_d, bar_m1, bar_p, bar_pn, bar_m2, bar_o, bar_pfree, bar_sfree, bar_w;
+  unsigned char* X0 = smem;                 // dpre[t]      } operands of the DX products
+  unsigned char* X1 = smem + TILE;          // dpre[t+d]    }
+  unsigned char* Ob = smem + 2 * TILE;      // split rows dx' in -> dx out (in place): TMA store source AND A operand of dx.Wd^T
+  unsigned char* Pb = smem + 3 * TILE;      // dpre out [128][df 32 | dg 32]
+  unsigned char* Xh0 = smem + 4 * TILE;     // hi halves of x[t]   [128][32], 64B swizzle   } operands of the pre-activation recompute
+  unsigned char* Xh1 = Xh0 + XH_TILE;       // hi halves of x[t-d]                          }
+  unsigned char* Dz = Xh1 + XH_TILE;        // skip-path gradient [128][32 halfs], 64B swizzle
+  unsigned char* W0 = Dz + TM * 64;         // [64][32] past tap (filter | gate), 64B swizzle    } image of the PRE layer
+  unsigned char* W1 = W0 + 4096;            // current tap                                       }
+  unsigned char* WdT = W1 + 4096;           // [32 c][hi r | lo r]                               }
+  unsigned char* Bc = WdT + 4096;           // [32 r][df c | dg c], tap 1                 } image of the DX layer
+  unsigned char* Bp = Bc + 4096;            // tap 0                                      }
+  // Every barrier completes exactly once per item (parts an item does not have arrive without data): phase parity =
+  // item parity.  The accumulator / staging barriers exist once per item parity: an mbarrier whose phase is not looked
+  // at before it completes twice more aliases, and the MMAs / epilogue of item i+1 may finish before a slow waiter has
+  // looked at item i.
+  __shared__ __align__(8) uint64_t bar_xa, bar_da, bar_xb, bar_m1[2], bar_mx[2], bar_m2[2], bar_zr, bar_o1[2], bar_o2[2], bar_sfree, bar_w;
   __shared__ uint32_t tmem_slot;
-  __shared__ int item_s[4];                 // work item of tile i in item_s[i & 3] (-1: no more work), published through bar_x
-  __shared__ float pb_s[64];
+  __shared__ int item_s[6];                 // work item of tile i in item_s[i & 3] (-1: no more work), published through bar_xa / bar_da
+  __shared__ __align__(16) float pb_s[64];
+  // items whose dx store has read Ob (it may be re-loaded once the dx.Wd^T product has read it too): a monotonic counter,
+  // because the loader does not need it every time (see above)
+  __shared__ volatile int ob_cnt;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    mbar_init(&bar_x, 1);
-    mbar_init(&bar_d, 1);
-    mbar_init(&bar_m1, 1);
-    mbar_init(&bar_p, 256);
-    mbar_init(&bar_pn, 1);
-    mbar_init(&bar_m2, 1);
-    mbar_init(&bar_o, 256);
-    mbar_init(&bar_pfree, 1);
+    ob_cnt = 0;
+    mbar_init(&bar_xa, 1);
+    mbar_init(&bar_da, 1);
+    mbar_init(&bar_xb, 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&bar_m1[k], 1);
+      mbar_init(&bar_mx[k], 1);
+      mbar_init(&bar_m2[k], 1);
+      mbar_init(&bar_o1[k], 256);
+      mbar_init(&bar_o2[k], 256);
+    }
+    mbar_init(&bar_zr, 256);
     mbar_init(&bar_sfree, 1);
     mbar_init(&bar_w, 1);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, 128);
+  if (warp == BC_W8) tmem_alloc(&tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;          // columns 0-63 pre-activations (f | g), 64-95 dx'.Wd^T, 96-127 the dx products
+  // accumulators of item i at column 128 * (i & 1): 0-63 pre-activations (f | g), 64-95 dx.Wd^T, 96-127 the dx products
+  const uint32_t tmem = tmem_slot;
   const int n_tiles = a.B * a.n_tt;
-  const int n_items = a.L * n_tiles;
+  const int n_items = (a.L + 1) * n_tiles;
   unsigned int* flagP = a.flags;
-  unsigned int* flagX = a.flags + (size_t)n_items;
-  // item -> (layer, batch element, tile): layers descending, time descending
-  auto decode = [&](int item, int& l, int& b, int& tt) {
+  unsigned int* flagX = a.flags + (size_t)a.L * n_tiles;
+  // item -> (ld: layer of the DX part or -1, lp: layer of the PRE part or -1, batch element, tile)
+  auto decode = [&](int item, int& ld, int& lp, int& b, int& tt) {
     const int q = item / n_tiles, j = item - q * n_tiles;
-    l = a.L - 1 - q;
+    ld = q >= 1 ? a.L - q : -1;
+    lp = q <= a.L - 1 ? a.L - 1 - q : -1;
     b = j / a.n_tt;
-    tt = a.n_tt - 1 - (j - b * a.n_tt);
+    tt = j - b * a.n_tt;
   };
+  // does the PRE part / DX part of layer l have an output gradient dx' (the last layer of the network has none)
+  auto has_dn = [&](int l) { return l < a.L - 1 || a.last_dense; };
 
-  if (warp == 8) {
-    // ------------------------------------------------------------------------------------------------ issuer
+  if (warp == BC_W8) {
+    // ------------------------------------------------------------------------------------------------ loader
+    // claims items, reads their flags one item ahead (relaxed loads: the round trips overlap the barrier waits), issues
+    // the TMA loads of a part as soon as the MMAs of the part before it have read the operand tiles
     if (lane == 0) {
-      constexpr uint32_t ID64 = idesc_f16(128, 64), ID32 = idesc_f16(128, 32);
-      const uint64_t dXc = kmajor_desc(smem_u32(Xc)), dXp = kmajor_desc(smem_u32(Xp)), dDn = kmajor_desc(smem_u32(Dn));
-      const uint64_t dP = kmajor_desc(smem_u32(P));
-      const uint64_t dW0 = kmajor_desc(smem_u32(W0)), dW1 = kmajor_desc(smem_u32(W1)), dWdT = kmajor_desc(smem_u32(WdT));
-      const uint64_t dBc = kmajor_desc(smem_u32(Bc)), dBp = kmajor_desc(smem_u32(Bp));
-      unsigned int* counter = a.flags + 2 * (size_t)n_items;
+      unsigned int* counter = a.flags + 2 * (size_t)a.L * n_tiles;
       auto claim = [&]() -> int {
         const unsigned int w = atomicAdd(counter, 1u);
         return w < (unsigned int)n_items ? (int)w : -1;
       };
-      auto load_weights = [&](int l) {
-        mbar_expect_tx(&bar_w, W_BYTES);
-        bulk_g2s(W0, a.img_f + (size_t)l * IMG_H, 16384, &bar_w);
-        bulk_g2s(WdT, a.img_b + (size_t)l * IMG_B, IMG_B, &bar_w);
+      // weights of an item: Bc | Bp of the DX layer, W0 | W1 | WdT of the PRE layer (the same for every item of a phase)
+      auto load_weights = [&](int ld, int lp) {
+        mbar_expect_tx(&bar_w, (ld >= 0 ? IMG_DX_BYTES : 0u) + (lp >= 0 ? IMG_PRE_BYTES : 0u));
+        if (lp >= 0) bulk_g2s(W0, a.img_b + (size_t)lp * IMG_B, IMG_PRE_BYTES, &bar_w);
+        if (ld >= 0) bulk_g2s(Bc, a.img_b + (size_t)ld * IMG_B + IMG_DX_OFF, IMG_DX_BYTES, &bar_w);
       };
-      auto has_dn_of = [&](int l) { return l < a.L - 1 || a.last_dense; };
-      // x tiles: written by the forward pass, always ready
-      auto load_x = [&](int l, int b, int t0) {
-        mbar_expect_tx(&bar_x, 2 * TILE);      // (release: publishes item_s to the waiters of this phase)
-        tma_load_3d(Xc, &mapXS, &bar_x, 0, t0, l * a.B + b);
-        tma_load_3d(Xp, &mapXS, &bar_x, 0, t0 - a.dil[l], l * a.B + b);      // rows before the window start arrive as zeros
+      long long c_fl = 0, c_ob = 0, c_zr = 0, c_m1 = 0, c_m2 = 0, t_a, t_start = clock64();
+      long long n_slow = 0;
+      const unsigned int *fp0 = nullptr, *fp1 = nullptr, *fp2 = nullptr, *fp3 = nullptr;
+      unsigned int fv0 = 1u, fv1 = 1u, fv2 = 1u, fv3 = 1u;
+      auto flags_of = [&](int ld, int lp, int b, int tt) {
+        fp0 = fp1 = fp2 = fp3 = nullptr;
+        if (ld >= 0) {      // dpre of this tile and of the tile(s) d steps later, dx of the layer above: the previous phase
+          const unsigned int* f = flagP + (size_t)ld * n_tiles + (size_t)b * a.n_tt;
+          const int t0 = tt * TM, d = a.dil[ld];
+          const int ta = (t0 + d) / TM, tb = (t0 + d + TM - 1) / TM;
+          fp0 = f + tt;
+          if (ta < a.n_tt && ta != tt) fp1 = f + ta;
+          if (tb < a.n_tt && tb != ta) fp2 = f + tb;
+          if (ld < a.L - 1) fp3 = flagX + (size_t)(ld + 1) * n_tiles + (size_t)b * a.n_tt + tt;
+        }
+        // relaxed: an acquire load holds back every later memory operation of the thread until it has returned.  The
+        // consumer of a set flag is a TMA load issued behind a branch on the value, and it reads the L2, where the
+        // producer's stores had completed before it released the flag.
+        fv0 = fp0 ? ld_relaxed(fp0) : 1u;
+        fv1 = fp1 ? ld_relaxed(fp1) : 1u;
+        fv2 = fp2 ? ld_relaxed(fp2) : 1u;
+        fv3 = fp3 ? ld_relaxed(fp3) : 1u;
       };
-      // skip-path gradient (ready) and dx' of the layer above (needs that tile's flag)
-      auto load_d = [&](int l, int b, int tt) {
-        const bool hd = has_dn_of(l);
-        if (hd && l < a.L - 1) wait_flag(flagX + (size_t)(l + 1) * n_tiles + (size_t)b * a.n_tt + tt);      // (last_dense: dx' of the last layer is an input)
-        mbar_expect_tx(&bar_d, TM * 64 + (hd ? TILE : 0));
-        tma_load_3d(Dz, &mapDz, &bar_d, l * C, tt * TM, b);
-        if (hd) tma_load_3d(Dn, &mapDX, &bar_d, 0, tt * TM, (l + 1) * a.B + b);
+      auto flags_wait = [&]() {
+        if (fv0 & fv1 & fv2 & fv3) return;
+        t_a = clock64();
+        {   // one fresh look (the four loads overlap) before the acquire-polling slow path
+          const unsigned int v0 = fp0 ? ld_relaxed(fp0) : 1u, v1 = fp1 ? ld_relaxed(fp1) : 1u;
+          const unsigned int v2 = fp2 ? ld_relaxed(fp2) : 1u, v3 = fp3 ? ld_relaxed(fp3) : 1u;
+          if (v0 & v1 & v2 & v3) { c_fl += clock64() - t_a; return; }
+        }
+        ++n_slow;
+        if (fp0 && !fv0) wait_flag(fp0);
+        if (fp1 && !fv1) wait_flag(fp1);
+        if (fp2 && !fv2) wait_flag(fp2);
+        if (fp3 && !fv3) wait_flag(fp3);
+        c_fl += clock64() - t_a;
       };
-      long long c_x = 0, c_d = 0, c_fl = 0, c_p = 0, c_pn = 0, c_m2 = 0, c_sf = 0, c_w = 0, t_a, t_start = clock64();
+      // operand tiles of an item: dpre[t], dpre[t+d] for the DX products; hi(x[t]), hi(x[t-d]) for the recompute.  (arrive / expect_tx = release: publishes item_s to the waiters of these phases)
+      auto load_ops = [&](int ld, int lp, int b, int tt) {
+        const int t0 = tt * TM;
+        if (ld >= 0) {
+          mbar_expect_tx(&bar_xa, 2 * TILE);
+          tma_load_3d(X0, &mapP, &bar_xa, 0, t0, ld * a.B + b);
+          tma_load_3d(X1, &mapP, &bar_xa, 0, t0 + a.dil[ld], ld * a.B + b);      // rows at or past the window end arrive as zeros
+        } else {
+          mbar_arrive(&bar_xa);
+        }
+        if (lp >= 0) {
+          mbar_expect_tx(&bar_xb, 2 * XH_TILE);
+          tma_load_3d(Xh0, &mapXH, &bar_xb, 0, t0, lp * a.B + b);
+          tma_load_3d(Xh1, &mapXH, &bar_xb, 0, t0 - a.dil[lp], lp * a.B + b);     // rows before the window start arrive as zeros
+        } else {
+          mbar_arrive(&bar_xb);
+        }
+      };
+      // the tiles the epilogue threads read: dx' (the input gradient of the layer above) into Ob, the skip-path gradient into Dz
+      auto load_dn = [&](int ld, int lp, int b, int tt) {
+        const int lsrc = ld >= 0 ? ld : lp;
+        const bool hd = has_dn(lsrc);
+        const uint32_t bytes = (hd ? TILE : 0u) + (lp >= 0 ? (uint32_t)(TM * 64) : 0u);
+        if (bytes == 0) { mbar_arrive(&bar_da); return; }
+        mbar_expect_tx(&bar_da, bytes);
+        if (hd) tma_load_3d(Ob, &mapDX, &bar_da, 0, tt * TM, (lsrc + 1) * a.B + b);
+        if (lp >= 0) tma_load_3d(Dz, &mapDz, &bar_da, lp * C, tt * TM, b);
+      };
       int item = claim();
       item_s[0] = item;
-      uint32_t i = 0, wphase = 0;
-      int l = 0, b = 0, tt = 0;
+      uint32_t i = 0;
+      int ld = -1, lp = -1, b = 0, tt = 0, wq = -1;
+      int nx = -1, nld = -1, nlp = -1, nb = 0, ntt = 0;
       if (item < 0) {
-        mbar_arrive(&bar_x);
+        mbar_arrive(&bar_xa);
+        mbar_arrive(&bar_da);
       } else {
-        decode(item, l, b, tt);
-        load_weights(l);
-        load_x(l, b, tt * TM);
-        load_d(l, b, tt);
-        mbar_wait(&bar_w, 0);
+        decode(item, ld, lp, b, tt);
+        load_weights(ld, lp);
+        wq = item / n_tiles;
+        flags_of(ld, lp, b, tt);
+        flags_wait();
+        load_ops(ld, lp, b, tt);
+        load_dn(ld, lp, b, tt);
       }
       while (item >= 0) {
-        const uint32_t par = i & 1;
-        const int t0 = tt * TM, d = a.dil[l];
-        const bool hd = has_dn_of(l);
+        const uint32_t par = i & 1, ph = (i >> 1) & 1;
+        // every epilogue thread has left item i-1: the accumulators of the other parity are free for the MMAs of item i+1
         t_a = clock64();
-        mbar_wait(&bar_x, par);
-        c_x += clock64() - t_a;
-        tc_fence_after();
-        mma_split(tmem, dXp, dW0, ID64, true);      // x[t-d] . W[0]
-        mma_split(tmem, dXc, dW1, ID64, false);     // x[t]   . W[1]
+        if (i > 0) IWAIT(&bar_o2[par ^ 1u], ((i - 1) >> 1) & 1);
+        c_zr += clock64() - t_a;
         t_a = clock64();
-        mbar_wait(&bar_d, par);
-        c_d += clock64() - t_a;
-        tc_fence_after();
-        if (hd) mma_split(tmem + 64, dDn, dWdT, ID32, true);      // dx' . Wd^T
-        mma_commit(&bar_m1);
-        // the dpre rows behind this tile: [t0 + 128, ...) for d < 128 (the own rows are in P), [t0 + d, ...) otherwise
-        const bool via_l2 = a.shift_global && d < TM && (d & 7);
-        const int tpn = via_l2 ? t0 + d : t0 + (d > TM ? d : TM);
-        const int row0 = via_l2 ? TM : (d < TM ? d : TM);      // first row of [P | Pn] the shifted operand reads
-        mbar_wait(&bar_m1, par);      // the x tiles have been read: Xp becomes Pn
-        t_a = clock64();
-        {
-          const unsigned int* f = flagP + (size_t)l * n_tiles + (size_t)b * a.n_tt;
-          const int ta = tpn / TM, tb = (tpn + TM - 1) / TM;
-          if (ta < a.n_tt) wait_flag(f + ta);
-          if (tb < a.n_tt && tb != ta) wait_flag(f + tb);
+        IWAIT(&bar_mx[par], ph);      // the DX products and the recompute have read X0 / X1 / Xh0 / Xh1
+        c_m1 += clock64() - t_a;
+        // Item i+1 is claimed as LATE as the pipeline allows (here: the DX epilogue of item i is running): with 782 tiles
+        // per phase and 296 CTAs, every claimed-but-unstarted item shortens the distance (in time) to the items of the
+        // previous phase it depends on; claimed here, their flags are practically always set.
+        nx = claim();
+        if (nx >= 0) {
+          decode(nx, nld, nlp, nb, ntt);
+          flags_of(nld, nlp, nb, ntt);
         }
-        c_fl += clock64() - t_a;
-        mbar_expect_tx(&bar_pn, TILE);
-        tma_load_3d(Xp, &mapP, &bar_pn, 0, tpn, l * a.B + b);      // rows at or past the window end arrive as zeros
-        t_a = clock64();
-        mbar_wait(&bar_p, par);       // P staged by the epilogue threads
-        c_p += clock64() - t_a;
-        t_a = clock64();
-        mbar_wait(&bar_pn, par);
-        c_pn += clock64() - t_a;
-        tc_fence_after();
-        {
-          const uint32_t sh = smem_u32(P) + (uint32_t)row0 * 128u;
-          const uint64_t dSh = kmajor_desc(sh) | (a.base_off ? ((uint64_t)((sh >> 7) & 7u) << 49) : 0ull);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma_f16_ss(tmem + 96, dP + 2 * k, dBc + 2 * k, ID32, k > 0);      // dpre[t]   . W[1]^T
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma_f16_ss(tmem + 96, dSh + 2 * k, dBp + 2 * k, ID32, 1u);         // dpre[t+d] . W[0]^T
-        }
-        mma_commit(&bar_m2);
-        // ---- next item ----
-        const int nx = claim();
         item_s[(i + 1) & 3] = nx;
+        if (nx >= 0 && nx / n_tiles == wq) {      // (a new phase's weights: below, once every MMA of item i has completed)
+          flags_wait();
+          load_ops(nld, nlp, nb, ntt);
+        }
         t_a = clock64();
-        mbar_wait(&bar_m2, par);      // P / Pn / Bc / Bp have been read
+        IWAIT(&bar_zr, par);          // every epilogue thread has read Dz of item i (and is past its wait on bar_da of item i)
+        c_zr += clock64() - t_a;
+        t_a = clock64();
+        IWAIT(&bar_m2[par], ph);      // dx.Wd^T has read Ob (and every MMA of item i its weights)
         c_m2 += clock64() - t_a;
         if (nx < 0) {
-          mbar_arrive(&bar_x);        // completes the next phase without data: the other warps see "no more work"
+          mbar_arrive(&bar_xa);       // complete the next phases without data: the other warps see "no more work"
+          mbar_arrive(&bar_da);
           break;
         }
-        int nl, nb, ntt;
-        decode(nx, nl, nb, ntt);
-        if (nl != l) {
-          load_weights(nl);
-          wphase ^= 1;
+        if (nx / n_tiles != wq) {     // (the MMA warp waits for bar_w when it meets the first item of a phase)
+          load_weights(nld, nlp);
+          wq = nx / n_tiles;
+          flags_wait();
+          load_ops(nld, nlp, nb, ntt);
         }
-        load_x(nl, nb, ntt * TM);
-        t_a = clock64();
-        mbar_wait(&bar_sfree, par);   // the dx store has read Dn; every thread has read Dz
-        c_sf += clock64() - t_a;
-        load_d(nl, nb, ntt);
-        if (nl != l) {
+        if (ld >= 0 && ob_cnt < (int)i + 1) {      // the dx store of item i has left Ob
           t_a = clock64();
-          mbar_wait(&bar_w, wphase);
-          c_w += clock64() - t_a;
+          spin_until(&ob_cnt, (int)i + 1, __LINE__);
+          c_ob += clock64() - t_a;
         }
-        item = nx; l = nl; b = nb; tt = ntt;
+        load_dn(nld, nlp, nb, ntt);
+        item = nx; ld = nld; lp = nlp; b = nb; tt = ntt;
         ++i;
       }
       if (a.timeline && blockIdx.x == 0) {
-        a.timeline[0] = clock64() - t_start; a.timeline[1] = c_x; a.timeline[2] = c_d; a.timeline[3] = c_fl; a.timeline[4] = c_p;
-        a.timeline[5] = c_pn; a.timeline[6] = c_m2; a.timeline[7] = c_sf; a.timeline[8] = c_w; a.timeline[9] = i; a.timeline[10] = gridDim.x;
+        a.timeline[0] = clock64() - t_start; a.timeline[3] = c_fl; a.timeline[4] = c_ob; a.timeline[5] = c_zr; a.timeline[6] = c_m1;
+        a.timeline[8] = c_m2; a.timeline[9] = i; a.timeline[10] = gridDim.x; a.timeline[21] = n_slow;
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == BC_W10) {
+    // ------------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t ID64 = idesc_f16(128, 64), ID32 = idesc_f16(128, 32);
+      const uint64_t dX0 = kmajor_desc(smem_u32(X0)), dX1 = kmajor_desc(smem_u32(X1)), dOb = kmajor_desc(smem_u32(Ob));
+      const uint64_t dXh0 = kmajor_desc64(smem_u32(Xh0)), dXh1 = kmajor_desc64(smem_u32(Xh1));
+      const uint64_t dW0 = kmajor_desc64(smem_u32(W0)), dW1 = kmajor_desc64(smem_u32(W1)), dWdT = kmajor_desc(smem_u32(WdT));
+      const uint64_t dBc = kmajor_desc(smem_u32(Bc)), dBp = kmajor_desc(smem_u32(Bp));
+      long long c_xa = 0, c_xb = 0, c_o1 = 0, c_w = 0, b_mma = 0, t_a;
+      int wq = -1;
+      uint32_t wphase = 0;
+      for (uint32_t i = 0;; ++i) {
+        const uint32_t par = i & 1;
+        const uint32_t acc = tmem + 128 * par;      // (free: the loader armed bar_xa only after every epilogue thread had left item i-2)
+        t_a = clock64();
+        IWAIT(&bar_xa, par);
+        c_xa += clock64() - t_a;
+        const int item = item_s[i & 3];
+        if (item < 0) break;
+        int ld, lp, b, tt;
+        decode(item, ld, lp, b, tt);
+        if (item / n_tiles != wq) {      // first item of a phase: its weight images
+          t_a = clock64();
+          IWAIT(&bar_w, wphase);
+          c_w += clock64() - t_a;
+          wphase ^= 1;
+          wq = item / n_tiles;
+        }
+        tc_fence_after();
+        t_a = clock64();
+        if (ld >= 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_f16_ss(acc + 96, dX0 + 2 * k, dBc + 2 * k, ID32, k > 0);      // dpre[t]   . W[1]^T
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_f16_ss(acc + 96, dX1 + 2 * k, dBp + 2 * k, ID32, 1u);         // dpre[t+d] . W[0]^T
+          mma_commit(&bar_m1[par]);
+        } else {
+          mbar_arrive(&bar_m1[par]);
+        }
+        b_mma += clock64() - t_a;
+        if (lp >= 0) {
+          t_a = clock64();
+          IWAIT(&bar_xb, par);
+          c_xb += clock64() - t_a;
+          tc_fence_after();
+          t_a = clock64();
+          mma_f16_ss(acc, dXh1 + 0, dW0 + 0, ID64, 0u);       // hi(x[t-d]) . W[0]
+          mma_f16_ss(acc, dXh1 + 2, dW0 + 2, ID64, 1u);
+          mma_f16_ss(acc, dXh0 + 0, dW1 + 0, ID64, 1u);       // hi(x[t])   . W[1]
+          mma_f16_ss(acc, dXh0 + 2, dW1 + 2, ID64, 1u);
+          mma_commit(&bar_mx[par]);
+          b_mma += clock64() - t_a;
+          if (has_dn(lp)) {      // the output gradient of layer lp: this item's dx (staged by the epilogue threads), or the loaded dx'
+            t_a = clock64();
+            if (ld >= 0) IWAIT(&bar_o1[par], (i >> 1) & 1);
+            else IWAIT(&bar_da, par);
+            c_o1 += clock64() - t_a;
+            tc_fence_after();
+            t_a = clock64();
+            mma_split(acc + 64, dOb, dWdT, ID32, true);      // dx' . Wd^T
+            b_mma += clock64() - t_a;
+          }
+          mma_commit(&bar_m2[par]);
+        } else {
+          mma_commit(&bar_mx[par]);
+          mma_commit(&bar_m2[par]);
+        }
+      }
+      if (a.timeline && blockIdx.x == 0) {
+        a.timeline[1] = c_xa; a.timeline[2] = c_xb; a.timeline[7] = c_w; a.timeline[20] = b_mma; a.timeline[22] = c_o1;
+      }
+    }
+  } else if (warp == BC_W9) {
     // ------------------------------------------------------------------------------------------------ publisher
     if (lane == 0) {
       for (uint32_t i = 0;; ++i) {
-        const uint32_t par = i & 1;
-        mbar_wait(&bar_p, par);
+        const uint32_t par = i & 1, ph = (i >> 1) & 1;
+        PWAIT(&bar_o1[par], ph);
         const int item = item_s[i & 3];
         if (item < 0) break;
-        int l, b, tt;
-        decode(item, l, b, tt);
-        const size_t fidx = (size_t)l * n_tiles + (size_t)b * a.n_tt + tt;
-        tma_store_3d(&mapP, P, 0, tt * TM, l * a.B + b);      // rows past the end of the window are clipped by the tensor map
-        bulk_commit();
-        bulk_wait_read0();
-        mbar_arrive(&bar_pfree);
-        bulk_wait0();                 // the store has completed and is visible to this thread ...
-        __threadfence();
-        st_release(flagP + fidx, 1u);      // ... publish the tile's dpre
-        mbar_wait(&bar_o, par);
-        tma_store_3d(&mapDX, Dn, 0, tt * TM, l * a.B + b);
-        bulk_commit();
-        bulk_wait_read0();
-        mbar_arrive(&bar_sfree);
-        bulk_wait0();
-        __threadfence();
-        st_release(flagX + fidx, 1u);
+        int ld, lp, b, tt;
+        decode(item, ld, lp, b, tt);
+        const size_t tile = (size_t)b * a.n_tt + tt;
+        // rows past the end of the window are clipped by the tensor maps
+        if (ld >= 0) {
+          tma_store_3d(&mapDX, Ob, 0, tt * TM, ld * a.B + b);
+          bulk_commit();
+          bulk_wait_read0();
+          ob_cnt = (int)i + 1;        // Ob has been read (the loader may refill it once dx.Wd^T has read it too)
+          bulk_wait0();               // the store has completed and is visible to this thread ...
+          __threadfence();
+          st_release(flagX + (size_t)ld * n_tiles + tile, 1u);      // ... publish the tile's dx
+        }
+        PWAIT(&bar_o2[par], ph);
+        if (lp >= 0) {
+          tma_store_3d(&mapP, Pb, 0, tt * TM, lp * a.B + b);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+        mbar_arrive(&bar_sfree);      // Pb may be rewritten (and: this thread has looked at both staging barriers of item i)
+        if (lp >= 0) {
+          bulk_wait0();
+          __threadfence();
+          st_release(flagP + (size_t)lp * n_tiles + tile, 1u);
+        }
       }
     }
   } else {
     // ------------------------------------------------------------------------------------------------ epilogue
     const int r = tid & 127, half = tid >> 7;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 16 * half;
     const uint32_t row_off = (uint32_t)r * 128;
     const uint32_t ch0 = (uint32_t)((2 * half) ^ (r & 7)) << 4, ch1 = (uint32_t)((2 * half + 1) ^ (r & 7)) << 4;
     const uint32_t cl0 = (uint32_t)((4 + 2 * half) ^ (r & 7)) << 4, cl1 = (uint32_t)((5 + 2 * half) ^ (r & 7)) << 4;
     int key = -1;
+    const bool tl_on = a.timeline && blockIdx.x == 0 && tid == 0;
+    long long e_da = 0, e_m1 = 0, e_xb = 0, e_m2 = 0, e_sf = 0, e_t, e_start = clock64();
     for (uint32_t i = 0;; ++i) {
-      const uint32_t par = i & 1;
-      mbar_wait(&bar_x, par);
+      const uint32_t par = i & 1, ph = (i >> 1) & 1;
+      const uint32_t lane_addr = lane_base + 128 * par;
+      e_t = clock64();
+      EWAIT(&bar_da, par);
+      e_da += clock64() - e_t;
       const int item = item_s[i & 3];
       if (item < 0) {
-        // hand the end marker on to the publisher once it has consumed the previous phase of bar_p (its bar_pfree
-        // arrival follows its bar_p wait): a parity wait that falls two phases behind never returns
-        if (i > 0) mbar_wait(&bar_pfree, (i - 1) & 1);
-        mbar_arrive(&bar_p);
+        // hand the end marker on to the publisher (it has looked at every staging phase up to item i-1 once bar_sfree of
+        // item i-1 has completed; the barrier of this parity was last used by item i-2)
+        if (i > 0) EWAIT(&bar_sfree, par ^ 1u);
+        mbar_arrive(&bar_o1[par]);
+        if (tl_on) { a.timeline[11] = clock64() - e_start; a.timeline[12] = e_da; a.timeline[13] = e_m1; a.timeline[14] = e_xb; a.timeline[15] = e_m2; a.timeline[23] = e_sf; }
         break;
       }
-      int l, b, tt;
-      decode(item, l, b, tt);
-      const bool hd = l < a.L - 1 || a.last_dense;
-      if (l * a.B + b != key) {      // uniform over the epilogue warps: bias / conditioning row of this (layer, batch element)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid < 64) pb_s[tid] = a.prebias[((size_t)l * a.B + b) * 64 + tid];
-        key = l * a.B + b;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      mbar_wait(&bar_d, par);
-      float dz[16];
-      {
-        const unsigned char* zr = Dz + (uint32_t)r * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint4 v = *reinterpret_cast<const uint4*>(zr + ((uint32_t)((2 * half + c) ^ ((r >> 1) & 3)) << 4));
-          const __half2* h = reinterpret_cast<const __half2*>(&v);
+      int ld, lp, b, tt;
+      decode(item, ld, lp, b, tt);
+      // ---- DX part: dx = dx' + the two products, in place in Ob ----
+      if (ld >= 0) {
+        float dx[16];
+        if (has_dn(ld)) {
+          const uint4 h0 = *reinterpret_cast<const uint4*>(Ob + row_off + ch0), h1 = *reinterpret_cast<const uint4*>(Ob + row_off + ch1);
+          const uint4 l0 = *reinterpret_cast<const uint4*>(Ob + row_off + cl0), l1 = *reinterpret_cast<const uint4*>(Ob + row_off + cl1);
+          const __half2* hh0 = reinterpret_cast<const __half2*>(&h0);
+          const __half2* hh1 = reinterpret_cast<const __half2*>(&h1);
+          const __half2* ll0 = reinterpret_cast<const __half2*>(&l0);
+          const __half2* ll1 = reinterpret_cast<const __half2*>(&l1);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 f = __half22float2(h[q]);
-            dz[8 * c + 2 * q] = f.x * a.cs; dz[8 * c + 2 * q + 1] = f.y * a.cs;
+            const float2 a0 = __half22float2(hh0[q]), b0 = __half22float2(ll0[q]);
+            const float2 a1 = __half22float2(hh1[q]), b1 = __half22float2(ll1[q]);
+            dx[2 * q] = a0.x + b0.x; dx[2 * q + 1] = a0.y + b0.y;
+            dx[8 + 2 * q] = a1.x + b1.x; dx[8 + 2 * q + 1] = a1.y + b1.y;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) dx[q] = 0.f;
+        }
+        e_t = clock64();
+        EWAIT(&bar_m1[par], ph);
+        e_m1 += clock64() - e_t;
+        tc_fence_after();
+        {
+          uint32_t ov[16];
+          tmem_ld16(lane_addr + 96, ov);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) dx[q] += __uint_as_float(ov[q]);
+        }
+        uint32_t xh[8], xl[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {      // hi = fp16(dx) (saturating), lo = fp16(dx - hi)
+          xh[q] = pack_sat(dx[2 * q], dx[2 * q + 1]);
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&xh[q]));
+          xl[q] = pack_sat(dx[2 * q] - hf.x, dx[2 * q + 1] - hf.y);
+        }
+        *reinterpret_cast<uint4*>(Ob + row_off + ch0) = make_uint4(xh[0], xh[1], xh[2], xh[3]);
+        *reinterpret_cast<uint4*>(Ob + row_off + ch1) = make_uint4(xh[4], xh[5], xh[6], xh[7]);
+        *reinterpret_cast<uint4*>(Ob + row_off + cl0) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
+        *reinterpret_cast<uint4*>(Ob + row_off + cl1) = make_uint4(xl[4], xl[5], xl[6], xl[7]);
+        fence_async_smem();
+        tc_fence_before();
+      }
+      mbar_arrive(&bar_o1[par]);
+      // ---- PRE part: dpre of the layer below (its output gradient is the dx just staged) ----
+      if (lp >= 0) {
+        if (lp * a.B + b != key) {      // uniform over the epilogue warps: bias / conditioning row of this (layer, batch element)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tid < 64) pb_s[tid] = a.prebias[((size_t)lp * a.B + b) * 64 + tid];
+          key = lp * a.B + b;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        float dz[16];
+        {
+          const unsigned char* zr = Dz + (uint32_t)r * 64;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(zr + ((uint32_t)((2 * half + c) ^ ((r >> 1) & 3)) << 4));
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(h[q]);
+              dz[8 * c + 2 * q] = f.x * a.cs; dz[8 * c + 2 * q + 1] = f.y * a.cs;
+            }
           }
         }
-      }
-      mbar_wait(&bar_m1, par);
-      tc_fence_after();
-      if (hd) {
-        uint32_t av[16];
-        tmem_ld16(lane_addr + 64, av);
+        mbar_arrive(&bar_zr);
+        e_t = clock64();
+        EWAIT(&bar_m2[par], ph);
+        e_m2 += clock64() - e_t;
+        tc_fence_after();
+        if (has_dn(lp)) {
+          uint32_t av[16];
+          tmem_ld16(lane_addr + 64, av);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) dz[q] += __uint_as_float(av[q]);
-      }
-      const bool valid = (tt * TM + r) < a.T;
-      __align__(16) __half dfh[16], dgh[16];
-      {
-        uint32_t fv[16], gv[16];
-        tmem_ld16(lane_addr + 0, fv);
-        tmem_ld16(lane_addr + 32, gv);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          float tf, sg;
-          gated_parts_fast(__uint_as_float(fv[q]) + pb_s[16 * half + q], __uint_as_float(gv[q]) + pb_s[32 + 16 * half + q], tf, sg);
-          const float dzv = valid ? dz[q] : 0.f;      // rows past the window end act as the (zero) future of the rows before them
-          dfh[q] = sat_half(dzv * sg * (1.f - tf * tf));
-          dgh[q] = sat_half(dzv * tf * sg * (1.f - sg));
+          for (int q = 0; q < 16; ++q) dz[q] += __uint_as_float(av[q]);
         }
-      }
-      if (i > 0) mbar_wait(&bar_pfree, (i - 1) & 1);      // the previous tile's dpre store has left P
-      *reinterpret_cast<uint4*>(P + row_off + ch0) = *reinterpret_cast<const uint4*>(dfh);
-      *reinterpret_cast<uint4*>(P + row_off + ch1) = *reinterpret_cast<const uint4*>(dfh + 8);
-      *reinterpret_cast<uint4*>(P + row_off + cl0) = *reinterpret_cast<const uint4*>(dgh);
-      *reinterpret_cast<uint4*>(P + row_off + cl1) = *reinterpret_cast<const uint4*>(dgh + 8);
-      fence_async_smem();
-      tc_fence_before();
-      mbar_arrive(&bar_p);
-      // ---- dx = dx' + the two products ----
-      float dx[16];
-      if (hd) {
-        const uint4 h0 = *reinterpret_cast<const uint4*>(Dn + row_off + ch0), h1 = *reinterpret_cast<const uint4*>(Dn + row_off + ch1);
-        const uint4 l0 = *reinterpret_cast<const uint4*>(Dn + row_off + cl0), l1 = *reinterpret_cast<const uint4*>(Dn + row_off + cl1);
-        const __half2* hh0 = reinterpret_cast<const __half2*>(&h0);
-        const __half2* hh1 = reinterpret_cast<const __half2*>(&h1);
-        const __half2* ll0 = reinterpret_cast<const __half2*>(&l0);
-        const __half2* ll1 = reinterpret_cast<const __half2*>(&l1);
+        if ((tt * TM + r) >= a.T) {      // rows past the window end are the (zero) future of the rows before them
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 a0 = __half22float2(hh0[q]), b0 = __half22float2(ll0[q]);
-          const float2 a1 = __half22float2(hh1[q]), b1 = __half22float2(ll1[q]);
-          dx[2 * q] = a0.x + b0.x; dx[2 * q + 1] = a0.y + b0.y;
-          dx[8 + 2 * q] = a1.x + b1.x; dx[8 + 2 * q + 1] = a1.y + b1.y;
+          for (int q = 0; q < 16; ++q) dz[q] = 0.f;
         }
+        uint32_t dfh[8], dgh[8];
+        {
+          uint32_t fv[16], gv[16];
+          tmem_ld16(lane_addr + 0, fv);
+          tmem_ld16(lane_addr + 32, gv);
+          const float4* pbf = reinterpret_cast<const float4*>(pb_s + 16 * half);
+          const float4* pbg = reinterpret_cast<const float4*>(pb_s + 32 + 16 * half);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bf = pbf[q4], bg = pbg[q4];
+            const float bfa[4] = {bf.x, bf.y, bf.z, bf.w}, bga[4] = {bg.x, bg.y, bg.z, bg.w};
+            float df[4], dg[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int q = 4 * q4 + e;
+              float tf, sg;
+              gate_parts(__uint_as_float(fv[q]) + bfa[e], __uint_as_float(gv[q]) + bga[e], tf, sg);
+              const float zs = dz[q] * sg;
+              df[e] = zs * fmaf(-tf, tf, 1.f);
+              dg[e] = zs * tf * (1.f - sg);
+            }
+            dfh[2 * q4] = pack_sat(df[0], df[1]); dfh[2 * q4 + 1] = pack_sat(df[2], df[3]);
+            dgh[2 * q4] = pack_sat(dg[0], dg[1]); dgh[2 * q4 + 1] = pack_sat(dg[2], dg[3]);
+          }
+        }
+        e_t = clock64();
+        if (i > 0) EWAIT(&bar_sfree, par ^ 1u);      // the previous item's dpre store has left Pb
+        e_sf += clock64() - e_t;
+        *reinterpret_cast<uint4*>(Pb + row_off + ch0) = make_uint4(dfh[0], dfh[1], dfh[2], dfh[3]);
+        *reinterpret_cast<uint4*>(Pb + row_off + ch1) = make_uint4(dfh[4], dfh[5], dfh[6], dfh[7]);
+        *reinterpret_cast<uint4*>(Pb + row_off + cl0) = make_uint4(dgh[0], dgh[1], dgh[2], dgh[3]);
+        *reinterpret_cast<uint4*>(Pb + row_off + cl1) = make_uint4(dgh[4], dgh[5], dgh[6], dgh[7]);
+        fence_async_smem();
+        tc_fence_before();
       } else {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) dx[q] = 0.f;
+        mbar_arrive(&bar_zr);
+        if (i > 0) EWAIT(&bar_sfree, par ^ 1u);      // (every thread looks at every phase of this barrier)
       }
-      mbar_wait(&bar_m2, par);
-      tc_fence_after();
-      {
-        uint32_t ov[16];
-        tmem_ld16(lane_addr + 96, ov);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) dx[q] += __uint_as_float(ov[q]);
-      }
-      __align__(16) __half xh[16], xl[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) split_sat(dx[q], xh[q], xl[q]);
-      *reinterpret_cast<uint4*>(Dn + row_off + ch0) = *reinterpret_cast<const uint4*>(xh);
-      *reinterpret_cast<uint4*>(Dn + row_off + ch1) = *reinterpret_cast<const uint4*>(xh + 8);
-      *reinterpret_cast<uint4*>(Dn + row_off + cl0) = *reinterpret_cast<const uint4*>(xl);
-      *reinterpret_cast<uint4*>(Dn + row_off + cl1) = *reinterpret_cast<const uint4*>(xl + 8);
-      fence_async_smem();
-      tc_fence_before();
-      mbar_arrive(&bar_o);
+      mbar_arrive(&bar_o2[par]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 128);
-}
-
-static int bwd_shift_mode() {      // WN_BWD_SHIFT=global: dilations that are not multiples of 8 take the own dpre rows through L2; =baseoff: probe
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("WN_BWD_SHIFT"); v = (e && strcmp(e, "global") == 0) ? 1 : (e && strcmp(e, "baseoff") == 0) ? 2 : 0; }
-  return v;
+  if (warp == BC_W8) tmem_dealloc(tmem, 256);
 }
 
 // xs: [L][B][T][hi 32 | lo 32] layer inputs (the forward chain's ring with L slots); dxs: [L (+1)][B][T][hi | lo] input
@@ -473,8 +730,8 @@ int block_bwd_chain(const void* xs, void* dxs, void* p16, const void* dz16, int 
                     const unsigned char* img_b, const float* prebias, const int* dilations, int L, int B, int T,
                     unsigned int* flags, cudaStream_t st, int last_dense) {
   if (L < 1 || L > WN_MAX_LAYERS) return -1;
-  CUtensorMap mapXS, mapDX, mapDz, mapP;
-  int rc = make_map_split(&mapXS, (const __half*)xs, (int64_t)L * B, T);
+  CUtensorMap mapXH, mapDX, mapDz, mapP;
+  int rc = make_map_xhi(&mapXH, (const __half*)xs, (int64_t)L * B, T);
   if (rc) return rc;
   rc = make_map_split(&mapDX, (const __half*)dxs, (int64_t)(L + (last_dense ? 1 : 0)) * B, T);
   if (rc) return rc;
@@ -485,23 +742,23 @@ int block_bwd_chain(const void* xs, void* dxs, void* p16, const void* dz16, int 
   BwdChainArgs a;
   a.img_f = img_f; a.img_b = img_b; a.prebias = prebias; a.flags = flags;
   a.L = L; a.B = B; a.T = T; a.n_tt = (T + TM - 1) / TM;
-  a.last_dense = last_dense ? 1 : 0; a.shift_global = bwd_shift_mode() == 1 ? 1 : 0; a.base_off = bwd_shift_mode() == 2 ? 1 : 0; a.cs = cs;
+  a.last_dense = last_dense ? 1 : 0; a.cs = cs;
   a.timeline = g_timeline_b;
   for (int l = 0; l < WN_MAX_LAYERS; ++l) a.dil[l] = l < L ? dilations[l] : 0;
-  const size_t smem = 1024 + 4 * TILE + TM * 64 + W_BYTES;
+  const size_t smem = 1024 + 4 * TILE + 2 * XH_TILE + TM * 64 + IMG_B;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(block_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -5;
     cudaFuncSetAttribute(block_bwd_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
-  const int64_t n_items = (int64_t)L * B * a.n_tt;
-  if (n_items >= (1ll << 30)) return -1;
-  int grid = 2 * sm_count();
-  if (grid > B * a.n_tt) grid = B * a.n_tt;
-  cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(2 * n_items + 1) * sizeof(unsigned int), st);
+  const int64_t n_tiles = (int64_t)B * a.n_tt;
+  if ((L + 1) * n_tiles >= (1ll << 30)) return -1;
+  int grid = 2 * sm_count();      // two CTAs fit an SM (109 KB shared memory, 256 TMEM columns each)
+  if (grid > n_tiles) grid = (int)n_tiles;
+  cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(2 * L * n_tiles + 1) * sizeof(unsigned int), st);
   if (e != cudaSuccess) return (int)e;
-  block_bwd_chain_kernel<<<grid, BC_THREADS, smem, st>>>(mapXS, mapDX, mapDz, mapP, a);
+  block_bwd_chain_kernel<<<grid, BC_THREADS, smem, st>>>(mapXH, mapDX, mapDz, mapP, a);
   WN_CHECK_LAUNCH();
   prof_mark(st, PT_BLOCK_BWD_PRE);
   return 0;

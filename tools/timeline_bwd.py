@@ -16,7 +16,8 @@ float(net.loss(a))
 lib.wn_debug_timeline(None)
 t = tl.cpu().numpy()[16:]
 n = max(1, t[9])
-print('grid %d, CTA 0: %d tiles, %d cycles total (%.0f per tile)' % (t[10], t[9], t[0], t[0] / n))
-for k, nm in enumerate(['x tiles landed', "dz / dx' landed", 'neighbour dpre flags', 'dpre staged (epilogue 1)', 'shifted dpre rows landed',
-                        'dx products done', 'dx store read (staging free)', 'weight image']):
-    print('  issuer wait %-32s %9d  (%.0f per tile)' % (nm, t[1 + k], t[1 + k] / n))
+print('grid %d, CTA 0: %d items (item = DX of a layer + PRE of the layer below, one tile), %d cycles total (%.0f per item)' % (t[10], t[9], t[0], t[0] / n))
+print('  loader     waits: flags not set %.0f (%d items), dx store left Ob %.0f, epilogue started item %.0f, DX MMAs done %.0f, PRE MMAs done %.0f per item' % (t[3] / n, t[21], t[4] / n, t[5] / n, t[6] / n, t[8] / n))
+print('  MMA issuer waits: dpre tiles landed %.0f, x tiles landed %.0f, dx staged %.0f, weight image %.0f; MMA issue %.0f per item' % (t[1] / n, t[2] / n, t[22] / n, t[7] / n, t[20] / n))
+print('epilogue thread 0: %d cycles total (%.0f per item)' % (t[11], t[11] / n))
+print("  epilogue waits: dx' landed / next item (idle) %.0f, DX MMAs %.0f, dz landed %.0f, PRE MMAs %.0f, previous dpre store read %.0f per item" % (t[12] / n, t[13] / n, t[14] / n, t[15] / n, t[23] / n))
