@@ -310,94 +310,102 @@ block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_c
 
   if (warp == BC_W8) {
     // ------------------------------------------------------------------------------------------------ loader
-    // claims items, reads their flags one item ahead (relaxed loads: the round trips overlap the barrier waits), issues
-    // the TMA loads of a part as soon as the MMAs of the part before it have read the operand tiles
-    if (lane == 0) {
+    // The whole warp runs this loop (uniform control flow): lane 0 claims items and talks to the barriers, lanes 0-3 read
+    // the (at most four) flags of an item and issue its four operand loads, lanes 0-1 the two epilogue-facing loads --
+    // one thread issuing six TMA loads and polling four flags one after the other took ~2,000 cycles per item, on the
+    // critical path between "item claimed" and "tiles landed".
+    {
+      const unsigned FULL = 0xffffffffu;
       unsigned int* counter = a.flags + 2 * (size_t)a.L * n_tiles;
       auto claim = [&]() -> int {
-        const unsigned int w = atomicAdd(counter, 1u);
+        unsigned int w = 0;
+        if (lane == 0) w = atomicAdd(counter, 1u);
+        w = __shfl_sync(FULL, w, 0);
         return w < (unsigned int)n_items ? (int)w : -1;
+      };
+      auto lwait = [&](uint64_t* bar, uint32_t parity, uint32_t tag) {      // lane 0 polls, the warp follows
+        if (lane == 0) mbar_wait_n(bar, parity, 20, tag);
+        __syncwarp();
       };
       // weights of an item: Bc | Bp of the DX layer, W0 | W1 | WdT of the PRE layer (the same for every item of a phase)
       auto load_weights = [&](int ld, int lp) {
-        mbar_expect_tx(&bar_w, (ld >= 0 ? IMG_DX_BYTES : 0u) + (lp >= 0 ? IMG_PRE_BYTES : 0u));
-        if (lp >= 0) bulk_g2s(W0, a.img_b + (size_t)lp * IMG_B, IMG_PRE_BYTES, &bar_w);
-        if (ld >= 0) bulk_g2s(Bc, a.img_b + (size_t)ld * IMG_B + IMG_DX_OFF, IMG_DX_BYTES, &bar_w);
+        if (lane == 0) {
+          mbar_expect_tx(&bar_w, (ld >= 0 ? IMG_DX_BYTES : 0u) + (lp >= 0 ? IMG_PRE_BYTES : 0u));
+          if (lp >= 0) bulk_g2s(W0, a.img_b + (size_t)lp * IMG_B, IMG_PRE_BYTES, &bar_w);
+          if (ld >= 0) bulk_g2s(Bc, a.img_b + (size_t)ld * IMG_B + IMG_DX_OFF, IMG_DX_BYTES, &bar_w);
+        }
       };
       long long c_fl = 0, c_ob = 0, c_zr = 0, c_m1 = 0, c_m2 = 0, t_a, t_start = clock64();
       long long n_slow = 0;
-      const unsigned int *fp0 = nullptr, *fp1 = nullptr, *fp2 = nullptr, *fp3 = nullptr;
-      unsigned int fv0 = 1u, fv1 = 1u, fv2 = 1u, fv3 = 1u;
+      // flags of an item: dpre of its tile and of the tile(s) d steps later, dx of the layer above -- the previous phase.
+      // Lane k holds flag k.  Relaxed loads: an acquire load holds back every later memory operation of the thread until
+      // it has returned; the consumer of a set flag is a TMA load issued behind a branch on the value, and it reads the
+      // L2, where the producer's stores had completed before it released the flag.
+      const unsigned int* fmine = nullptr;
+      unsigned int fval = 1u;
       auto flags_of = [&](int ld, int lp, int b, int tt) {
-        fp0 = fp1 = fp2 = fp3 = nullptr;
-        if (ld >= 0) {      // dpre of this tile and of the tile(s) d steps later, dx of the layer above: the previous phase
+        fmine = nullptr;
+        if (ld >= 0) {
           const unsigned int* f = flagP + (size_t)ld * n_tiles + (size_t)b * a.n_tt;
           const int t0 = tt * TM, d = a.dil[ld];
           const int ta = (t0 + d) / TM, tb = (t0 + d + TM - 1) / TM;
-          fp0 = f + tt;
-          if (ta < a.n_tt && ta != tt) fp1 = f + ta;
-          if (tb < a.n_tt && tb != ta) fp2 = f + tb;
-          if (ld < a.L - 1) fp3 = flagX + (size_t)(ld + 1) * n_tiles + (size_t)b * a.n_tt + tt;
+          if (lane == 0) fmine = f + tt;
+          if (lane == 1 && ta < a.n_tt && ta != tt) fmine = f + ta;
+          if (lane == 2 && tb < a.n_tt && tb != ta) fmine = f + tb;
+          if (lane == 3 && ld < a.L - 1) fmine = flagX + (size_t)(ld + 1) * n_tiles + (size_t)b * a.n_tt + tt;
         }
-        // relaxed: an acquire load holds back every later memory operation of the thread until it has returned.  The
-        // consumer of a set flag is a TMA load issued behind a branch on the value, and it reads the L2, where the
-        // producer's stores had completed before it released the flag.
-        fv0 = fp0 ? ld_relaxed(fp0) : 1u;
-        fv1 = fp1 ? ld_relaxed(fp1) : 1u;
-        fv2 = fp2 ? ld_relaxed(fp2) : 1u;
-        fv3 = fp3 ? ld_relaxed(fp3) : 1u;
+        fval = fmine ? ld_relaxed(fmine) : 1u;
       };
       auto flags_wait = [&]() {
-        if (fv0 & fv1 & fv2 & fv3) return;
+        if (__all_sync(FULL, fval != 0u)) return;
         t_a = clock64();
-        {   // one fresh look (the four loads overlap) before the acquire-polling slow path
-          const unsigned int v0 = fp0 ? ld_relaxed(fp0) : 1u, v1 = fp1 ? ld_relaxed(fp1) : 1u;
-          const unsigned int v2 = fp2 ? ld_relaxed(fp2) : 1u, v3 = fp3 ? ld_relaxed(fp3) : 1u;
-          if (v0 & v1 & v2 & v3) { c_fl += clock64() - t_a; return; }
+        fval = fmine ? ld_relaxed(fmine) : 1u;      // one fresh look before the acquire-polling slow path
+        if (!__all_sync(FULL, fval != 0u)) {
+          ++n_slow;
+          if (fmine && !fval) wait_flag(fmine);
+          __syncwarp();
         }
-        ++n_slow;
-        if (fp0 && !fv0) wait_flag(fp0);
-        if (fp1 && !fv1) wait_flag(fp1);
-        if (fp2 && !fv2) wait_flag(fp2);
-        if (fp3 && !fv3) wait_flag(fp3);
         c_fl += clock64() - t_a;
       };
-      // operand tiles of an item: dpre[t], dpre[t+d] for the DX products; hi(x[t]), hi(x[t-d]) for the recompute.  (arrive / expect_tx = release: publishes item_s to the waiters of these phases)
+      // operand tiles of an item: dpre[t], dpre[t+d] for the DX products; hi(x[t]), hi(x[t-d]) for the recompute.
+      // (arrive / expect_tx = release: publishes item_s to the waiters of these phases)
       auto load_ops = [&](int ld, int lp, int b, int tt) {
         const int t0 = tt * TM;
-        if (ld >= 0) {
-          mbar_expect_tx(&bar_xa, 2 * TILE);
-          tma_load_3d(X0, &mapP, &bar_xa, 0, t0, ld * a.B + b);
-          tma_load_3d(X1, &mapP, &bar_xa, 0, t0 + a.dil[ld], ld * a.B + b);      // rows at or past the window end arrive as zeros
-        } else {
-          mbar_arrive(&bar_xa);
+        if (lane == 0) {
+          if (ld >= 0) mbar_expect_tx(&bar_xa, 2 * TILE);
+          else mbar_arrive(&bar_xa);
+          if (lp >= 0) mbar_expect_tx(&bar_xb, 2 * XH_TILE);
+          else mbar_arrive(&bar_xb);
         }
-        if (lp >= 0) {
-          mbar_expect_tx(&bar_xb, 2 * XH_TILE);
-          tma_load_3d(Xh0, &mapXH, &bar_xb, 0, t0, lp * a.B + b);
-          tma_load_3d(Xh1, &mapXH, &bar_xb, 0, t0 - a.dil[lp], lp * a.B + b);     // rows before the window start arrive as zeros
-        } else {
-          mbar_arrive(&bar_xb);
-        }
+        __syncwarp();
+        if (ld >= 0 && lane < 2)      // (rows at or past the window end arrive as zeros)
+          tma_load_3d(lane == 0 ? X0 : X1, &mapP, &bar_xa, 0, lane == 0 ? t0 : t0 + a.dil[ld], ld * a.B + b);
+        if (lp >= 0 && (lane == 2 || lane == 3))      // (rows before the window start arrive as zeros)
+          tma_load_3d(lane == 2 ? Xh0 : Xh1, &mapXH, &bar_xb, 0, lane == 2 ? t0 : t0 - a.dil[lp], lp * a.B + b);
       };
       // the tiles the epilogue threads read: dx' (the input gradient of the layer above) into Ob, the skip-path gradient into Dz
       auto load_dn = [&](int ld, int lp, int b, int tt) {
         const int lsrc = ld >= 0 ? ld : lp;
         const bool hd = has_dn(lsrc);
         const uint32_t bytes = (hd ? TILE : 0u) + (lp >= 0 ? (uint32_t)(TM * 64) : 0u);
-        if (bytes == 0) { mbar_arrive(&bar_da); return; }
-        mbar_expect_tx(&bar_da, bytes);
-        if (hd) tma_load_3d(Ob, &mapDX, &bar_da, 0, tt * TM, (lsrc + 1) * a.B + b);
-        if (lp >= 0) tma_load_3d(Dz, &mapDz, &bar_da, lp * C, tt * TM, b);
+        if (lane == 0) {
+          if (bytes == 0) mbar_arrive(&bar_da);
+          else mbar_expect_tx(&bar_da, bytes);
+        }
+        __syncwarp();
+        if (hd && lane == 0) tma_load_3d(Ob, &mapDX, &bar_da, 0, tt * TM, (lsrc + 1) * a.B + b);
+        if (lp >= 0 && lane == 1) tma_load_3d(Dz, &mapDz, &bar_da, lp * C, tt * TM, b);
       };
       int item = claim();
-      item_s[0] = item;
+      if (lane == 0) item_s[0] = item;
       uint32_t i = 0;
       int ld = -1, lp = -1, b = 0, tt = 0, wq = -1;
       int nx = -1, nld = -1, nlp = -1, nb = 0, ntt = 0;
       if (item < 0) {
-        mbar_arrive(&bar_xa);
-        mbar_arrive(&bar_da);
+        if (lane == 0) {
+          mbar_arrive(&bar_xa);
+          mbar_arrive(&bar_da);
+        }
       } else {
         decode(item, ld, lp, b, tt);
         load_weights(ld, lp);
@@ -412,7 +420,7 @@ block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_c
         // every epilogue thread has read Dz of item i: it has left item i-1 (the accumulators of the other parity are free
         // for the MMAs of item i+1) and is past its wait on bar_da of item i
         t_a = clock64();
-        IWAIT(&bar_zr, par);
+        lwait(&bar_zr, par, __LINE__);
         c_zr += clock64() - t_a;
         // Item i+1 is claimed as LATE as possible (the PRE epilogue of item i has started): with 782 tiles per phase and
         // 296 CTAs, every claimed-but-unstarted item shortens the distance (in time) to the items of the previous phase it
@@ -424,19 +432,22 @@ block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_c
           flags_of(nld, nlp, nb, ntt);
         }
         t_a = clock64();
-        IWAIT(&bar_mx[par], ph);      // the DX products and the recompute have read X0 / X1 / Xh0 / Xh1
+        lwait(&bar_mx[par], ph, __LINE__);      // the DX products and the recompute have read X0 / X1 / Xh0 / Xh1
         c_m1 += clock64() - t_a;
-        item_s[(i + 1) & 3] = nx;
+        if (lane == 0) item_s[(i + 1) & 3] = nx;
+        __syncwarp();
         if (nx >= 0 && nx / n_tiles == wq) {      // (a new phase's weights: below, once every MMA of item i has completed)
           flags_wait();
           load_ops(nld, nlp, nb, ntt);
         }
         t_a = clock64();
-        IWAIT(&bar_m2[par], ph);      // dx.Wd^T has read Ob (and every MMA of item i its weights)
+        lwait(&bar_m2[par], ph, __LINE__);      // dx.Wd^T has read Ob (and every MMA of item i its weights)
         c_m2 += clock64() - t_a;
         if (nx < 0) {
-          mbar_arrive(&bar_xa);       // complete the next phases without data: the other warps see "no more work"
-          mbar_arrive(&bar_da);
+          if (lane == 0) {
+            mbar_arrive(&bar_xa);       // complete the next phases without data: the other warps see "no more work"
+            mbar_arrive(&bar_da);
+          }
           break;
         }
         if (nx / n_tiles != wq) {     // (the MMA warp waits for bar_w when it meets the first item of a phase)
@@ -445,16 +456,17 @@ block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_c
           flags_wait();
           load_ops(nld, nlp, nb, ntt);
         }
-        if (ld >= 0 && ob_cnt < (int)i + 1) {      // the dx store of item i has left Ob
+        if (ld >= 0) {                // the dx store of item i has left Ob
           t_a = clock64();
-          spin_until(&ob_cnt, (int)i + 1, __LINE__);
+          if (lane == 0 && ob_cnt < (int)i + 1) spin_until(&ob_cnt, (int)i + 1, __LINE__);
+          __syncwarp();
           c_ob += clock64() - t_a;
         }
         load_dn(nld, nlp, nb, ntt);
         item = nx; ld = nld; lp = nlp; b = nb; tt = ntt;
         ++i;
       }
-      if (a.timeline && blockIdx.x == 0) {
+      if (a.timeline && blockIdx.x == 0 && lane == 0) {
         a.timeline[0] = clock64() - t_start; a.timeline[3] = c_fl; a.timeline[4] = c_ob; a.timeline[5] = c_zr; a.timeline[6] = c_m1;
         a.timeline[8] = c_m2; a.timeline[9] = i; a.timeline[10] = gridDim.x; a.timeline[21] = n_slow;
       }
