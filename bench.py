@@ -313,7 +313,7 @@ def main():
             kernels[buf.value.decode()] = {'launches_per_step': n_tag[i] // prof_steps,
                                            'ms_per_step': ms_tag[i] / prof_steps,
                                            'us_per_launch': 1e3 * ms_tag[i] / n_tag[i]}
-    launches_per_step = sum(k['launches_per_step'] for k in kernels.values()) + 1   # + optimizer kernel
+    launches_per_step = sum(k['launches_per_step'] for k in kernels.values() if not k.get('stage')) + 1   # + optimizer kernel
     peaks = measured_peaks()
     M = B * T
     p = DEFAULT_PARAMS
@@ -324,10 +324,10 @@ def main():
         # all forward layers (x in, x' and z out per layer; the last layer has no x'), divided by the launches that
         # cover them: one persistent kernel by default, L per-layer launches with WN_FWD_CHAIN=0
         'block_fwd': ('hbm', M * 4.0 * ((2 * R + D) * (L - 1) + (R + D)) / max(1, kernels.get('block_fwd', {}).get('launches_per_step', L))),
-        'block_bwd_pre': ('hbm', M * 4.0 * (2 * R + 3 * D)),     # x, dx', dz_skip in; dpre = [df | dg] out
-        'block_bwd_dx': ('hbm', M * 4.0 * (3 * R + D)),          # x, dx', dz_skip in; dx out
-        # x, dpre, z, dx' re-read per layer (not algorithmic: see DESIGN); one persistent launch covers all layers
-        'block_wgrad': ('hbm', M * 4.0 * (2 * R + 3 * D) * L / max(1, kernels.get('block_wgrad', {}).get('launches_per_step', L))),
+        # the WHOLE backward of the residual blocks (pre-activation + input gradients: one persistent kernel; weight
+        # gradients: one launch) against SURVEY section 8(d)'s figure for the stage, (3R + 2D) * 4 = 640 B per unit per
+        # layer -- every byte the two kernels move beyond that (dpre / dx round trips through L2 / HBM) counts against them
+        'block_bwd': ('hbm', M * 4.0 * (3 * R + 2 * D) * L),
         'softmax_xent': ('hbm', M * 4.0 * 2 * Q),
         'gemm_skip_fwd': ('tensor', 2.0 * M * L * D * S),
         'gemm_skip_wgrad': ('tensor', 2.0 * M * L * D * S),
@@ -339,6 +339,12 @@ def main():
         'gemm_post2_wgrad': ('tensor', 2.0 * M * S * Q),
         'gemm_post2_dgrad': ('tensor', 2.0 * M * S * Q),
     }
+    # stage entry: sum of the kernels that make up the block backward (tags block_bwd_pre [+ block_bwd_dx] + block_wgrad)
+    bwd_parts = [k for k in ('block_bwd_pre', 'block_bwd_dx', 'block_wgrad') if k in kernels]
+    if bwd_parts:
+        ms = sum(kernels[k]['ms_per_step'] for k in bwd_parts)
+        kernels['block_bwd'] = {'launches_per_step': 1, 'ms_per_step': ms, 'us_per_launch': 1e3 * ms,
+                                'kernels': {k: kernels[k]['ms_per_step'] for k in bwd_parts}, 'stage': True}
     rooflines = {}
     for name, (bound, work) in algo.items():
         if name not in kernels:
@@ -353,9 +359,9 @@ def main():
         rooflines[name] = {'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
                            'achieved_net_of_event_node': ach_net, 'frac_net_of_event_node': ach_net / peak,
                            'traffic': None, 'share_of_step': kernels[name]['ms_per_step'] /
-                           sum(k['ms_per_step'] for k in kernels.values())}
+                           sum(k['ms_per_step'] for k in kernels.values() if not k.get('stage'))}
     # measured DRAM traffic per launch of the dominant kernels (one `ncu --set full` capture, tools/ncu_summary.py traffic)
-    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     if os.path.exists(tpath):
         tr = json.load(open(tpath))
         for name in rooflines:

@@ -398,44 +398,64 @@ def test_default_params_full_size_properties():
     assert torch.equal(l_a, l_b)
 
 
-_VARIANT_SCRIPT = r'''
+_VARIANT_SCRIPT = r"""
 import json, os, sys
 sys.path.insert(0, os.path.join({root!r}, 'tensorflow-wavenet_b200'))
 import numpy as np, wavenet
 p = json.load(open(os.path.join({root!r}, 'tensorflow-wavenet_b200', 'wavenet_params.json')))
-net = wavenet.WaveNetModel(batch_size=2, dilations=p['dilations'], filter_width=2, residual_channels=32, dilation_channels=32,
+B, T = int(sys.argv[2]), int(sys.argv[3])
+net = wavenet.WaveNetModel(batch_size=B, dilations=p['dilations'], filter_width=2, residual_channels=32, dilation_channels=32,
                            quantization_channels=256, skip_channels=512, use_biases=True, global_condition_channels=16,
                            global_condition_cardinality=5, seed=3)
 rng = np.random.default_rng(5)
-T = 20011
-a = np.clip(0.5 * np.sin(np.arange(T) * 0.03)[None] + 0.2 * rng.standard_normal((2, T)), -1, 1).astype(np.float32)
-loss = float(net.loss(a, [1, 4]))
+a = np.clip(0.5 * np.sin(np.arange(T) * 0.03)[None] + 0.2 * rng.standard_normal((B, T)), -1, 1).astype(np.float32)
+loss = float(net.loss(a, [1, 4][:B]))
 np.savez(sys.argv[1], loss=loss, grads=net.flat_grads.cpu().numpy())
-'''
+"""
 
 
-def test_persistent_kernels_match_per_layer_launches(tmp_path):
-    """The default launch structure (all forward layers in one flag-ordered persistent kernel, the weight gradients of all
-    layers in one launch, fp16 post-processing GEMMs) against the per-layer / TF32 variants of the same arithmetic.
-    The switches are read once per process, hence the subprocesses."""
+def _run_variants(tmp_path, variants, B, T):
     import subprocess
     import sys
     script = tmp_path / 'variant.py'
     script.write_text(_VARIANT_SCRIPT.format(root=ROOT))
     out = {}
-    variants = {'default': {}, 'per_layer': {'WN_FWD_CHAIN': '0', 'WN_WGRAD_PER_LAYER': '1'}, 'tf32_gemms': {'WN_FWD_GEMM': 'tf32'}}
     for name, env in variants.items():
         path = str(tmp_path / (name + '.npz'))
         e = dict(os.environ)
         e.update(env)
-        r = subprocess.run([sys.executable, str(script), path], env=e, capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, str(script), path, str(B), str(T)], env=e, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         out[name] = np.load(path)
+    return out
+
+
+@pytest.mark.parametrize('B,T', [(2, 20011), (1, 100000)], ids=['b2_t20011', 'benchmark_shape'])
+def test_persistent_kernels_match_per_layer_launches(tmp_path, B, T):
+    """Launch structure and arithmetic variants of the training step on default params (the second case is the benchmarked
+    shape: 782 tiles per layer, every CTA of the persistent kernels busy).  The switches are read once per process, hence
+    the subprocesses.
+      * default twice: the persistent kernels claim their tiles dynamically, so two runs order their atomics differently
+        and nothing else -- a race (a tile read before it was published) would show up as a difference;
+      * first-generation backward (per-layer TF32 kernels) with the forward layers and weight gradients as per-layer
+        launches vs as persistent kernels: same arithmetic, different launch structure;
+      * fp16 backward chain (default) vs the first-generation TF32 backward, fp16 vs TF32 post-processing GEMMs: the same
+        11-bit operand precision with different roundings."""
+    variants = {'default': {}, 'default_again': {},
+                'bwd_tf32': {'WN_BWD_CHAIN': '0'},
+                'bwd_tf32_per_layer': {'WN_BWD_CHAIN': '0', 'WN_FWD_CHAIN': '0', 'WN_WGRAD_PER_LAYER': '1'},
+                'tf32_gemms': {'WN_FWD_GEMM': 'tf32'}}
+    out = _run_variants(tmp_path, variants, B, T)
     ref = out['default']
     assert math.isfinite(float(ref['loss'])) and np.isfinite(ref['grads']).all()
+    assert float(out['default_again']['loss']) == float(ref['loss'])
+    assert rel_err(out['default_again']['grads'], ref['grads']) < 2e-5
     # same arithmetic, different launch structure: only the order of the split-K / atomic accumulations differs
-    assert abs(float(out['per_layer']['loss']) - float(ref['loss'])) <= 1e-6 * abs(float(ref['loss']))
-    assert rel_err(out['per_layer']['grads'], ref['grads']) < 1e-4
-    # fp16 vs TF32 operand copies: both 11-bit mantissas, different roundings
+    old = out['bwd_tf32']
+    assert abs(float(out['bwd_tf32_per_layer']['loss']) - float(old['loss'])) <= 1e-6 * abs(float(old['loss']))
+    assert rel_err(out['bwd_tf32_per_layer']['grads'], old['grads']) < 1e-4
+    # fp16 split rows vs TF32 in the block backward, fp16 vs TF32 operand copies in the GEMMs: 11-bit mantissas, different roundings
+    assert float(old['loss']) == float(ref['loss'])
+    assert rel_err(old['grads'], ref['grads']) < 2e-2
     assert abs(float(out['tf32_gemms']['loss']) - float(ref['loss'])) <= LOSS_RTOL * abs(float(ref['loss']))
     assert rel_err(out['tf32_gemms']['grads'], ref['grads']) < 2e-2
