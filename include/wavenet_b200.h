@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define WN_MAX_LAYERS 128
-#define WN_ABI_VERSION 1
+#define WN_ABI_VERSION 2
 
 typedef void* wn_stream_t; /* cudaStream_t */
 
@@ -34,7 +34,7 @@ typedef void* wn_stream_t; /* cudaStream_t */
 typedef struct wn_config {
   int32_t n_layers;              /* len(dilations)                         */
   int32_t residual_channels;     /* R                                      */
-  int32_t dilation_channels;     /* D  (this build requires D == R)        */
+  int32_t dilation_channels;     /* D  (fast generation needs D == R)       */
   int32_t skip_channels;         /* S                                      */
   int32_t quantization_channels; /* Q                                      */
   int32_t gc_channels;           /* G, 0 = no global conditioning          */
@@ -42,13 +42,17 @@ typedef struct wn_config {
   int32_t use_biases;
   int32_t residual_postproc;
   int32_t dilations[WN_MAX_LAYERS];
+  /* ABI 2: scalar_input front end (model.py:143-153): the causal layer is a width-initial_filter_width convolution of the
+   * raw float waveform ([IFW, 1, R] filter) instead of a width-2 convolution of the one-hot encoding ([2, Q, R]) */
+  int32_t scalar_input;
+  int32_t initial_filter_width;
 } wn_config;
 
 /* Offsets (in floats) of each variable group inside the flat parameter / gradient buffer.
  * Groups are stored layer-major so that e.g. all skip weights form the [L*D, S] operand of
  * the skip-sum GEMM.  Shapes are the reference's (model.py:118-225). */
 typedef struct wn_layout {
-  int64_t causal;        /* [2, Q, R]            wavenet/causal_layer/filter             */
+  int64_t causal;        /* [2, Q, R] ([IFW, 1, R] with scalar_input)   wavenet/causal_layer/filter */
   int64_t filter;        /* [L][2, R, D]         .../layer{i}/filter                     */
   int64_t gate;          /* [L][2, R, D]         .../layer{i}/gate                       */
   int64_t dense;         /* [L][D, R]            .../layer{i}/dense                      */

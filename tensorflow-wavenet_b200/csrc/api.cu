@@ -61,6 +61,7 @@ static int check_cfg(const wn_config* c) {
   if (c->quantization_channels < 4 || (c->quantization_channels & 3) || c->quantization_channels > 1024) return -2;
   if (c->gc_channels < 0 || c->gc_channels > 1024) return -2;
   if (c->gc_channels > 0 && c->gc_cardinality < 0) return -2;
+  if (c->scalar_input && (c->initial_filter_width < 1 || c->initial_filter_width > 1024)) return -2;
   for (int i = 0; i < c->n_layers; ++i)
     if (c->dilations[i] < 1) return -1;
   return 0;
@@ -73,7 +74,7 @@ static int make_layout(const wn_config* c, wn_layout* o) {
                 Q = c->quantization_channels, G = c->gc_channels;
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t r = off; off = align_up(off + n, 64); return r; };
-  o->causal = take(2 * Q * R);
+  o->causal = take(c->scalar_input ? (int64_t)c->initial_filter_width * R : 2 * Q * R);
   o->filter = take(L * 2 * R * D);
   o->gate = take(L * 2 * R * D);
   o->dense = take(L * D * R);
@@ -341,7 +342,7 @@ static int truncate_stage() {
 
 static int run_forward(const wn_config* c, const wn_layout& lo, const float* params, Workspace& w,
                        const int32_t* ids, const int32_t* gc_ids, int B, int T, bool training, float* logits,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* scalar_in = nullptr) {
   const int M = B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
             S = c->skip_channels, Q = c->quantization_channels, G = c->gc_channels;
   const int ldz = L * D;
@@ -403,7 +404,13 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
                    P(params, lo.gc_gate), P(params, lo.gc_embedding), gc_ids, L, B, D, gc_ids ? G : 0, c->gc_cardinality, st));
   prof_mark(st, PT_COND_BIAS);
   // (residual stream as fp16 split rows between the forward layers: the front end writes both forms of its output)
-  RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, w.WimgH ? w.XS : nullptr, st));
+  if (c->scalar_input) {      // model.py:143-153: a width-IFW causal convolution of the raw waveform (1 input channel)
+    if (!scalar_in) return -1;
+    RC(causal_conv(scalar_in, params + lo.causal, w.X, M, T, 1, R, c->initial_filter_width, 1, st));
+    if (w.WimgH) RC(split_rows(w.X, w.XS, M, st));
+  } else {
+    RC(frontend_fwd(ids, params + lo.causal, w.X, M, T, Q, R, w.WimgH ? w.XS : nullptr, st));
+  }
   prof_mark(st, PT_FRONTEND_FWD);
   const int64_t xs = (int64_t)M * R;
   if (w.chain_flags) {
@@ -777,7 +784,9 @@ int wn_forward_logits(const wn_config* cfg, const float* params, void* workspace
   Workspace w;
   carve(cfg, batch, time, false, workspace, &w);
   if (w.bytes > workspace_bytes) return -5;
-  return run_forward(cfg, lo, params, w, ids, gc_ids, batch, time, false, logits, (cudaStream_t)stream);
+  // (scalar_input: `ids` carries the float32 waveform -- the mu-law decoded samples of predict_proba, model.py:570-576)
+  return run_forward(cfg, lo, params, w, ids, gc_ids, batch, time, false, logits, (cudaStream_t)stream,
+                     cfg->scalar_input ? reinterpret_cast<const float*>(ids) : nullptr);
 }
 
 int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* workspace, int64_t workspace_bytes,
@@ -802,7 +811,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   prof_mark(st, PT_MISC);
   RC(mulaw_encode(audio, M, mulaw_thresholds, Q, w.ids, st));            // model.py:639
   prof_mark(st, PT_MULAW);
-  RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, w.logits, st));
+  RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, w.logits, st, cfg->scalar_input ? audio : nullptr));      // model.py:645-648
   const int trunc = truncate_stage();
   if (trunc == 1) return 0;
   // fp16 input-gradient chain: gradients travel scaled by gscale = 2^ceil(log2 M), i.e. (softmax - onehot) * [1, 2)
@@ -1018,7 +1027,8 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
   }
   RC((int)cudaStreamWaitEvent(st, ev_g[3], 0));    // join the post-processing weight-gradient stream
-  RC(frontend_bwd(w.ids, dcur, grads + lo.causal, M, T, Q, R, st));
+  if (cfg->scalar_input) RC(scalar_frontend_bwd(audio, dcur, grads + lo.causal, M, T, R, cfg->initial_filter_width, st));
+  else RC(frontend_bwd(w.ids, dcur, grads + lo.causal, M, T, Q, R, st));
   prof_mark(st, PT_FRONTEND_BWD);
   if (lo.filter_bias >= 0 || G > 0) {
     RC(cond_bias_bwd(w.gprebias, P(grads, lo.filter_bias), P(grads, lo.gate_bias), P(params, lo.gc_filter),

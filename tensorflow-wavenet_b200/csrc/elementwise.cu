@@ -591,6 +591,32 @@ __global__ void causal_conv_kernel(const float* __restrict__ x, const float* __r
     y[i] = acc;
   }
 }
+// scalar_input front end (model.py:143-153, 227-234), gradient of the [width, 1, R] filter: one block per chunk of time
+// steps, thread = (tap, channel) pairs, partial sums added to the gradient with one atomic per pair and block
+__global__ void scalar_frontend_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dx0, float* __restrict__ gw,
+                                           int M, int T, int R, int width, int rows_per_block) {
+  const int m0 = blockIdx.x * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  const int left = (width - 1) / 2;
+  for (int pidx = threadIdx.x; pidx < width * R; pidx += blockDim.x) {
+    const int k = pidx / R, r = pidx % R;
+    const int lag = width - 1 + left - k;      // the tap's lag, dilation 1
+    float acc = 0.f;
+    for (int m = m0; m < m1; ++m) {
+      const int t = m % T;
+      if (t - lag >= 0) acc = fmaf(x[m - lag], dx0[(size_t)m * R + r], acc);
+    }
+    atomicAdd(gw + pidx, acc);
+  }
+}
+int scalar_frontend_bwd(const float* x, const float* dx0, float* gw, int M, int T, int R, int width, cudaStream_t st) {
+  if (M <= 0 || R < 1 || width < 1) return -1;
+  const int rows = 256;
+  scalar_frontend_bwd_kernel<<<(M + rows - 1) / rows, 256, 0, st>>>(x, dx0, gw, M, T, R, width, rows);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
 int causal_conv(const float* x, const float* w, float* y, int M, int T, int cin, int cout, int width, int d,
                 cudaStream_t st) {
   if (M <= 0 || cin < 1 || cout < 1 || width < 1 || d < 1) return -1;

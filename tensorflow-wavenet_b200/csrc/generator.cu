@@ -499,6 +499,7 @@ int wn_gen_run(const wn_config* cfg, const float* params, void* state, int32_t s
   int rc = wn_param_layout(cfg, &lo);
   if (rc) return rc;
   if (cfg->dilation_channels != cfg->residual_channels) return -2;      // see wn_gen_state_bytes
+  if (cfg->scalar_input) return -2;      // model.py:601-603: "Scalar input is not supported by fast generation"
   if (!params || !state || streams < 1 || n_steps < 1) return -1;
   if (!inputs && !forced) return -1;
   if (uniforms && !samples_out) return -1;

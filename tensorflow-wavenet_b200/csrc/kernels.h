@@ -131,6 +131,8 @@ int mulaw_decode(const int32_t* ids, int64_t n, const float* lut, int Q, float* 
 
 int frontend_fwd(const int32_t* ids, const float* wc, float* x0, int M, int T, int Q, int R, void* xs, cudaStream_t st);
 int frontend_bwd(const int32_t* ids, const float* dx0, float* gwc, int M, int T, int Q, int R, cudaStream_t st);
+// scalar_input front end, backward: gw[k][r] += sum_t x[t - lag_k] * dx0[t][r], lags as in causal_conv (width, dilation 1)
+int scalar_frontend_bwd(const float* x, const float* dx0, float* gw, int M, int T, int R, int width, cudaStream_t st);
 
 // g16 (optional): the gradient also as fp16 [M,Q], (softmax - onehot) * scale16
 int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float scale, float* row_loss_partials,

@@ -5,3 +5,5 @@ from .audio_reader import AudioReader
 from .ops import (mu_law_encode, mu_law_decode, time_to_batch,
                   batch_to_time, causal_conv, optimizer_factory)
 from .train_step import TrainStep
+from . import checkpoint, generation
+from .audio_reader import Coordinator

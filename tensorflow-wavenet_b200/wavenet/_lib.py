@@ -20,7 +20,8 @@ class WnConfig(C.Structure):
                 ('dilation_channels', C.c_int32), ('skip_channels', C.c_int32),
                 ('quantization_channels', C.c_int32), ('gc_channels', C.c_int32),
                 ('gc_cardinality', C.c_int32), ('use_biases', C.c_int32),
-                ('residual_postproc', C.c_int32), ('dilations', C.c_int32 * WN_MAX_LAYERS)]
+                ('residual_postproc', C.c_int32), ('dilations', C.c_int32 * WN_MAX_LAYERS),
+                ('scalar_input', C.c_int32), ('initial_filter_width', C.c_int32)]
 
 
 LAYOUT_FIELDS = ['causal', 'filter', 'gate', 'dense', 'skip', 'gc_filter', 'gc_gate', 'filter_bias',
@@ -131,7 +132,7 @@ def ptr(t):
 
 
 def make_config(dilations, residual_channels, dilation_channels, skip_channels, quantization_channels,
-                gc_channels, gc_cardinality, use_biases, residual_postproc):
+                gc_channels, gc_cardinality, use_biases, residual_postproc, scalar_input=False, initial_filter_width=32):
     if len(dilations) > WN_MAX_LAYERS:
         raise ValueError('at most {} layers are supported'.format(WN_MAX_LAYERS))
     cfg = WnConfig()
@@ -144,6 +145,8 @@ def make_config(dilations, residual_channels, dilation_channels, skip_channels, 
     cfg.gc_cardinality = gc_cardinality or 0
     cfg.use_biases = 1 if use_biases else 0
     cfg.residual_postproc = 1 if residual_postproc else 0
+    cfg.scalar_input = 1 if scalar_input else 0
+    cfg.initial_filter_width = int(initial_filter_width)
     for i, d in enumerate(dilations):
         cfg.dilations[i] = int(d)
     return cfg

@@ -65,7 +65,7 @@ class WaveNetModel(object):
         _lib.require_cuda()
         self._lib = _lib.load()
         self.device = torch.device('cuda', torch.cuda.current_device())
-        self._native = (filter_width == 2 and not scalar_input)
+        self._native = (filter_width == 2)      # (filter_width > 2 exists only as the ops.causal_conv op)
         self._workspaces = {}
         self._gen = None
         self.init_ops = [self._init_generator]
@@ -81,12 +81,12 @@ class WaveNetModel(object):
         S, Q, G = self.skip_channels, self.quantization_channels, self.global_condition_channels
         card = self.global_condition_cardinality
         if not self._native:
-            # scalar_input / filter_width > 2 have no sm_100a kernels yet: variables exist (so the
-            # object is constructible like the reference) but loss/predict raise.
+            # filter_width > 2 has no block kernels: the object is constructible like the reference, loss/predict raise.
             self._cfg = self._layout = None
             self.flat_params = self.flat_grads = None
             return None
-        self._cfg = _lib.make_config(self.dilations, R, D, S, Q, G, card, self.use_biases, self.residual_postproc)
+        self._cfg = _lib.make_config(self.dilations, R, D, S, Q, G, card, self.use_biases, self.residual_postproc,
+                                     self.scalar_input, self.initial_filter_width)
         self._layout = lo = _lib.param_layout(self._cfg)
         self.flat_params = torch.zeros(lo.total, dtype=torch.float32, device=self.device)
         self.flat_grads = torch.zeros(lo.total, dtype=torch.float32, device=self.device)
@@ -100,7 +100,8 @@ class WaveNetModel(object):
             if off >= 0:
                 self._groups[name] = (off, tuple(shape), layered)
 
-        group('causal', lo.causal, (2, Q, R), False)
+        # model.py:141-154: [2, Q, R] on the one-hot encoding, [initial_filter_width, 1, R] on the scalar waveform
+        group('causal', lo.causal, (self.initial_filter_width, 1, R) if self.scalar_input else (2, Q, R), False)
         group('filter', lo.filter, (2, R, D), True)
         group('gate', lo.gate, (2, R, D), True)
         group('dense', lo.dense, (1, D, R), True)
@@ -215,8 +216,8 @@ class WaveNetModel(object):
     # ------------------------------------------------------------------ helpers
     def _require_native(self):
         if not self._native:
-            raise NotImplementedError('scalar_input=True and filter_width > 2 have no sm_100a kernels in this '
-                                      'build (SURVEY section 8, row f4)')
+            raise NotImplementedError('filter_width > 2 has no sm_100a block kernels in this build (the causal_conv op '
+                                      'takes any width); SURVEY section 8, row f4')
 
     def _workspace(self, kind, batch, time):
         key = (kind, batch, time)
@@ -281,7 +282,41 @@ class WaveNetModel(object):
         out._wavenet_l2 = l2
         return out
 
+    # ------------------------------------------------------------------ summaries (model.py:314-325,668,682-683)
+    def summaries(self, loss=None, bins=30):
+        """What the reference hands to TensorBoard, as plain Python data: the scalar 'loss' (model.py:668) / 'total_loss'
+        (:682-683, when the loss tensor carries an L2 term) and, with `histograms=True`, one histogram per layer weight /
+        bias (:314-325: 'layer{i}_filter', '_gate', '_dense', '_skip', '_biases_filter', ...) as (counts, bin edges)."""
+        out = {}
+        if loss is not None:
+            l2 = getattr(loss, '_wavenet_l2', 0.0)
+            total = float(loss)
+            if l2:
+                out['total_loss'] = total
+                out['loss'] = total - l2 * 0.5 * float(torch.sum(self.flat_params * self.flat_params))
+            else:
+                out['loss'] = total
+        if self.histograms:
+            names = (('filter', 'filter'), ('gate', 'gate'), ('dense', 'dense'), ('skip', 'skip'),
+                     ('filter_bias', 'biases_filter'), ('gate_bias', 'biases_gate'), ('dense_bias', 'biases_dense'),
+                     ('skip_bias', 'biases_skip'))
+            for i, cur in enumerate(self.variables['dilated_stack']):
+                for key, tag in names:
+                    if key in cur:
+                        counts, edges = np.histogram(cur[key].detach().cpu().numpy().ravel(), bins=bins)
+                        out['layer{}_{}'.format(i, tag)] = (counts, edges)
+        return out
+
     # ------------------------------------------------------------------ naive prediction
+    def _net_input(self, waveform):
+        """Encoded ids [B, T] -> what the network reads: the ids themselves, or (scalar_input) their mu-law decoded
+        float values (model.py:570-576)."""
+        ids = as_cuda(waveform, torch.int32).reshape(self.batch_size, -1)
+        if self.scalar_input:
+            from .ops import mu_law_decode
+            return mu_law_decode(ids, self.quantization_channels)
+        return ids
+
     def _logits(self, ids, gc):
         B, T = ids.shape
         ws = self._workspace('fwd', B, T)
@@ -294,7 +329,7 @@ class WaveNetModel(object):
     def logits(self, waveform, global_condition=None):
         """Raw network output [B, T, Q] for encoded input ids (model.py:389-442)."""
         self._require_native()
-        ids = as_cuda(waveform, torch.int32).reshape(self.batch_size, -1)
+        ids = self._net_input(waveform)
         gc = self._gc_ids(global_condition, ids.shape[0])
         return self._logits(ids, gc).view(ids.shape[0], ids.shape[1], -1)
 
@@ -302,13 +337,15 @@ class WaveNetModel(object):
         '''Computes the probability distribution of the next sample based on all samples in the
         input waveform (model.py:564-590): float64 softmax of the last row, returned as float32.'''
         self._require_native()
-        ids = as_cuda(waveform, torch.int32).reshape(self.batch_size, -1)
+        ids = self._net_input(waveform)
         gc = self._gc_ids(global_condition, ids.shape[0])
         last = self._logits(ids, gc)[-1]
         return torch.softmax(last.to(torch.float64), dim=-1).to(torch.float32)
 
     # ------------------------------------------------------------------ fast generation
     def _gen_state(self, streams):
+        if self.scalar_input:
+            raise NotImplementedError("Scalar input is not supported by fast generation.")
         if self.dilation_channels != self.residual_channels:
             raise NotImplementedError('fast generation needs dilation_channels == residual_channels in this '
                                       'build (training / predict_proba take any widths)')

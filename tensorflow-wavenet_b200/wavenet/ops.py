@@ -211,6 +211,21 @@ class _Optimizer(object):
                                       self.learning_rate, 0.9, self.momentum, 1e-5, l2, grad_scale, st)
         _lib.check(rc, 'wn_optim_' + self.kind)
 
+    def state_dict(self):
+        """Step count and slot buffers (flat, in the layout of the model's flat parameter buffer) for checkpoints."""
+        out = {'step': np.int64(self.step), 'kind': np.array(self.kind)}
+        for i, t in enumerate(self._slots or ()):
+            out['slot{}'.format(i)] = t.detach().cpu().numpy()
+        return out
+
+    def load_state_dict(self, state):
+        if str(np.asarray(state.get('kind', self.kind))) != self.kind:
+            raise ValueError('optimizer kind mismatch: checkpoint has {}, this is {}'.format(state['kind'], self.kind))
+        self.step = int(state['step'])
+        slots = [state[k] for k in sorted(k for k in state if k.startswith('slot'))]
+        if slots:
+            self._slots = tuple(as_cuda(a, torch.float32) for a in slots)
+
     def minimize(self, loss, var_list=None):
         """tf.train.Optimizer.minimize: `loss` is the tensor returned by WaveNetModel.loss()."""
         net = getattr(loss, '_wavenet_model', None)

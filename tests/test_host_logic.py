@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), n
         assert n in _lib.SIGNATURES, 'ctypes signature missing for ' + n
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.wn_abi_version() == 1
+    assert lib.wn_abi_version() == 2
 
 
 def test_param_layout_matches_reference_shapes():
