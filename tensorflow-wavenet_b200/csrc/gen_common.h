@@ -32,5 +32,9 @@ int64_t gen_lat_comm_bytes(const wn_config* cfg);
 bool gen_lat_eligible(const GenArgs& a);
 void set_gen_timeline(long long* p);   // debug: 16 int64 %globaltimer stamps of one step
 int gen_lat_run(const GenArgs& a, void* comm, uint32_t launch_seq, cudaStream_t st);
+// pipelined form of the same kernel: 2 .. gen_pipe_max_streams() streams share the layer-per-warp chain
+bool gen_pipe_eligible(const GenArgs& a);
+int gen_pipe_max_streams();
+int gen_pipe_run(const GenArgs& a, void* comm, uint32_t launch_seq, cudaStream_t st);
 
 }  // namespace wn

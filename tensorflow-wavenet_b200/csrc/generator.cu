@@ -533,11 +533,11 @@ int wn_gen_run(const wn_config* cfg, const float* params, void* state, int32_t s
       const char* e = getenv("WN_GEN_IMPL");
       use_lat = (e && strcmp(e, "v1") == 0) ? 0 : 1;
     }
-    if (use_lat && g_gen_lat_enabled && gen_lat_eligible(a)) {
-      static uint32_t launch_seq = 0;
-      void* comm = (char*)state + gen_hdr_bytes(cfg, streams) + gen_pending_bytes(cfg, streams) + gen_rings_bytes(cfg, streams);
-      return gen_lat_run(a, comm, ++launch_seq, st);
-    }
+    static uint32_t launch_seq = 0;
+    void* comm = (char*)state + gen_hdr_bytes(cfg, streams) + gen_pending_bytes(cfg, streams) + gen_rings_bytes(cfg, streams);
+    if (use_lat && g_gen_lat_enabled && gen_lat_eligible(a)) return gen_lat_run(a, comm, ++launch_seq, st);
+    // 2 .. 32 streams: the same layer-per-warp chain, the streams pipelined through it
+    if (use_lat && g_gen_lat_enabled && gen_pipe_eligible(a)) return gen_pipe_run(a, comm, ++launch_seq, st);
   }
   const int nsm = sm_count();
   int spb = 1;
