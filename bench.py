@@ -416,7 +416,7 @@ def main():
         lo_s, hi_s = shard_streams(streams_total, rank, world)
         per_rank = hi_s - lo_s
         first = np.random.RandomState(rank).randint(0, 256, per_rank)
-        n2 = 1000
+        n2 = 16000          # BASELINE config 4: 16,000 samples per stream, also for the sharded streams
         u = np.random.RandomState(100 + rank).random_sample((per_rank, n2))
         gnet.generate(16, first, uniforms=u[:, :16])
         barrier()
@@ -430,8 +430,10 @@ def main():
                    'streams': streams_total, 'streams_per_gpu': per_rank,
                    'b256_samples_per_sec_per_stream': n2 / float(dt),
                    'b256_aggregate_samples_per_sec': streams_total * n2 / float(dt),
-                   'note': 'timed over {} (B=1, latency-mode kernel) / {} (256 streams, throughput-mode kernel) samples '
-                           'incl. launch + H2D of the uniforms'.format(n1, n2)}
+                   'kernel_256': ('pipelined layer-per-warp chain (2..32 streams per GPU)' if per_rank <= 32 else
+                                  'throughput-mode kernel (one CTA per 1-4 streams)'),
+                   'note': 'timed over {} (B=1, latency-mode kernel) / {} ({} streams per GPU) samples '
+                           'incl. launch + H2D of the uniforms'.format(n1, n2, per_rank)}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

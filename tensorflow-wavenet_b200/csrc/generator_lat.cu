@@ -674,11 +674,15 @@ __device__ void chain_warp_ms(const PipeArgs& pa, int c, int w, volatile u64* xb
     if (++p_s == NS) { p_s = 0; ++p_step; if (++p_mod == d) p_mod = 0; }
   };
   for (int k = 0; k < PD; ++k) prefetch_next();
-  // first warp of a chain CTA (input through L2) and the head (sampled id through L2): the word of the NEXT item is
-  // requested while this item is computed, so that a round trip is paid once per item only when the producer is late
+  // first warp of a chain CTA (input through L2) and the head (sampled id through L2): the words of the next FW items are
+  // requested while this item is computed (a ring of FW registers): a consumer that looks for item k+1 only when it is done
+  // with item k pays an L2 round trip per item, and the head then caps the whole chain at one item per round trip
+  constexpr int FW = 4;
   const bool l2_in = (w == 0);
-  u64 in_next = 0ull;
-  auto in_word = [&](int s, uint32_t T) -> const u64* {
+  u64 in_ring[FW];
+#pragma unroll
+  for (int j = 0; j < FW; ++j) in_ring[j] = 0ull;
+  auto in_word = [&](int s) -> const u64* {
     u64* comm = a.comm + (size_t)s * pa.wps;
     if (!head) return comm + off_xg() + c * 32 + lane;
     return comm + off_misc(a.NC, g.L, g.S, g.Q) + ((sampling && !g.forced) ? 0 : 2);
@@ -708,12 +712,17 @@ __device__ void chain_warp_ms(const PipeArgs& pa, int c, int w, volatile u64* xb
         ga = ffma2(make_float2(pv.z, pv.w), wgp[2 * j + 1], ga);
       }
       // ---- this layer's input ----
-      // (the L2 word of this item was requested during the previous item; the tag it must carry: T, or T-1 for the head's feedback words)
-      const u64 in_cur = in_next;
+      // (the L2 word of this item was requested up to FW items ago; the tag it must carry: T, or T-1 for the head's feedback
+      // words; a stale word just means polling as before)
+      const u64 in_cur = in_ring[0];
       if (l2_in) {
-        int ns = s + 1, nstep = step;
-        if (ns == NS) { ns = 0; ++nstep; }
-        if (nstep < g.n_steps) in_next = ld_gpu(in_word(ns, T));
+#pragma unroll
+        for (int j = 0; j + 1 < FW; ++j) in_ring[j] = in_ring[j + 1];
+        // the word FW items ahead; with fewer than FW + 1 streams it would be this stream's own NEXT step, whose word is
+        // still this step's: then the request is useless but harmless (tag mismatch -> polled when needed)
+        int fs = s + FW;
+        while (fs >= NS) fs -= NS;
+        in_ring[FW - 1] = ld_gpu(in_word(fs));
       }
       float x_own;
       if (head) {
@@ -794,78 +803,81 @@ __device__ void chain_warp_ms(const PipeArgs& pa, int c, int w, volatile u64* xb
   }
 }
 
-// One phase of the post-processing for a batch of up to SB streams: out_s[cols of p] = act(in_s . W[:, cols] + bias).
-// The streams' input words are polled together (their L2 round trips overlap), the weights are read from shared memory
-// once for the whole batch, and one block-wide reduction serves all SB x 4 sums: a (stream, phase) pair costs ~0.2 us
-// instead of the ~0.65 us of one stream at a time (which capped 32 streams at 81 us per step).
-constexpr int SB = 4;
+// Post-processing CTAs of the pipelined form.  With every CTA walking through ALL streams (4 columns each, like the
+// single-stream kernel) 32 streams cost 24 phase passes of ~2.3 us per step -- the bottleneck of the whole kernel (the
+// chain needs ~0.5 us per stream and step).  Here the NP = 128 CTAs form NG = 4 groups of 32; a group serves every fourth
+// batch of SB = 4 streams, and a CTA owns 16 columns of skip / postprocess1 (8 of postprocess2): six passes per step.
+// One pass (one phase, one batch): the batch's tagged input words are polled together and staged in shared memory; thread
+// (column c, k-slice j) multiplies its slice of the inputs of all SB streams with its weight column; the 16 k-slices are
+// summed with four shuffles.
+constexpr int SB = 4;            // streams per batch
+constexpr int NG = 4;            // groups of post CTAs (batches are dealt out round robin)
+constexpr int PCW = 16;          // columns of skip / postprocess1 per post CTA
+
 template <int MAXW>
-__device__ __forceinline__ void post_phase_b(const u64* in0, u64* out0, size_t wps, int nb, int n_in, const float4* wsm, const float* bias,
-                                             int col0, int ncols, int n_out, bool relu, uint32_t T, float4* red /*[2][8][SB]*/, int& flip) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float xv[SB][MAXW];
-  for (uint32_t it = 0;; ++it) {
-    bool ok = true;
-#pragma unroll
-    for (int b = 0; b < SB; ++b) {
-      if (b < nb) {
-#pragma unroll
-        for (int j = 0; j < MAXW; ++j) {
-          const int k = tid + j * THREADS;
-          const u64 w = (k < n_in) ? ld_gpu(in0 + (size_t)b * wps + k) : ((u64)T << 32);
-          ok = ok && ((uint32_t)(w >> 32) == T);
-          xv[b][j] = __uint_as_float((uint32_t)w);
-        }
-      }
-    }
-    if (ok) break;
-    if (it > (1u << 24)) __trap();
-  }
-  float4 acc[SB];
-#pragma unroll
-  for (int b = 0; b < SB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int j = 0; j < MAXW; ++j) {
-    const int k = tid + j * THREADS;
-    if (k < n_in) {
-      const float4 w = wsm[k];
+__device__ __forceinline__ void post_pass(const u64* in0, u64* out0, size_t wps, int nb, int n_in, const float* wsm /*[n_in][ncols]*/,
+                                          int ncols, const float* bias, int col0, int n_out, bool relu, uint32_t T, float* stage /*[SB][n_in]*/) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  {
+    float xv[SB][MAXW];
+    for (uint32_t it = 0;; ++it) {
+      bool ok = true;
 #pragma unroll
       for (int b = 0; b < SB; ++b) {
         if (b < nb) {
-          acc[b].x = fmaf(xv[b][j], w.x, acc[b].x); acc[b].y = fmaf(xv[b][j], w.y, acc[b].y);
-          acc[b].z = fmaf(xv[b][j], w.z, acc[b].z); acc[b].w = fmaf(xv[b][j], w.w, acc[b].w);
+#pragma unroll
+          for (int j = 0; j < MAXW; ++j) {
+            const int k = tid + j * THREADS;
+            const u64 w = (k < n_in) ? ld_gpu(in0 + (size_t)b * wps + k) : ((u64)T << 32);
+            ok = ok && ((uint32_t)(w >> 32) == T);
+            xv[b][j] = __uint_as_float((uint32_t)w);
+          }
         }
       }
+      if (ok) break;
+      if (it > (1u << 24)) __trap();
     }
-  }
+    __syncthreads();      // (the previous pass has finished reading the staging area)
 #pragma unroll
-  for (int b = 0; b < SB; ++b) {
+    for (int b = 0; b < SB; ++b) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      acc[b].x += __shfl_xor_sync(0xffffffffu, acc[b].x, o);
-      acc[b].y += __shfl_xor_sync(0xffffffffu, acc[b].y, o);
-      acc[b].z += __shfl_xor_sync(0xffffffffu, acc[b].z, o);
-      acc[b].w += __shfl_xor_sync(0xffffffffu, acc[b].w, o);
+      for (int j = 0; j < MAXW; ++j) {
+        const int k = tid + j * THREADS;
+        if (k < n_in) stage[b * n_in + k] = (b < nb) ? xv[b][j] : 0.f;
+      }
     }
-  }
-  float4* r = red + (size_t)flip * 8 * SB;      // alternating scratch: the barrier of call i+1 protects the buffer of call i
-  flip ^= 1;
-  if (lane == 0) {
-#pragma unroll
-    for (int b = 0; b < SB; ++b) r[warp * SB + b] = acc[b];
   }
   __syncthreads();
-  if (tid < SB * 4) {
-    const int b = tid >> 2, c = tid & 3;
-    if (b < nb && c < ncols && col0 + c < n_out) {
-      float v = bias[c];
+  // thread = (k-slice, column): lanes 0-15 and 16-31 of a warp hold two consecutive k-slices of the 16 columns
+  const int c = tid & 15, ks = tid >> 4;      // 16 k-slices
+  float acc[SB];
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const float4 t = r[w * SB + b];
-        v += (c == 0 ? t.x : c == 1 ? t.y : c == 2 ? t.z : t.w);
-      }
+  for (int b = 0; b < SB; ++b) acc[b] = 0.f;
+  if (c < ncols) {
+#pragma unroll 4
+    for (int k = ks; k < n_in; k += 16) {      // (unrolled: the shared-memory loads of four k in flight)
+      const float w = wsm[k * ncols + c];
+#pragma unroll
+      for (int b = 0; b < SB; ++b) acc[b] = fmaf(stage[b * n_in + k], w, acc[b]);
+    }
+  }
+  // sum over the 16 k-slices: lanes l and l ^ 16 (two slices of a warp), then the eight warps through shared memory
+#pragma unroll
+  for (int b = 0; b < SB; ++b) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 16);
+  __shared__ float part[8][SB][16];
+  if (lane < 16) {
+#pragma unroll
+    for (int b = 0; b < SB; ++b) part[tid >> 5][b][lane] = acc[b];
+  }
+  __syncthreads();
+  if (tid < SB * 16) {
+    const int b = tid >> 4, cc = tid & 15;
+    if (b < nb && cc < ncols && col0 + cc < n_out) {
+      float v = bias[cc];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w][b][cc];
       if (relu) v = fmaxf(v, 0.f);
-      st_gpu(out0 + (size_t)b * wps + col0 + c, pack(v, T));
+      st_gpu(out0 + (size_t)b * wps + col0 + cc, pack(v, T));
     }
   }
 }
@@ -874,82 +886,70 @@ __device__ void post_cta_ms(const PipeArgs& pa, int p, float* sm) {
   const LatArgs& a = pa.a;
   const GenArgs& g = a.g;
   const int tid = threadIdx.x;
-  const int LD = g.L * C, S = g.S, Q = g.Q, cq = a.cq;
-  float4* ws = reinterpret_cast<float4*>(sm);            // [LD]  skip weights, 4 columns
-  float4* w1 = ws + LD;                                   // [S]
-  float4* w2 = w1 + S;                                    // [S]   (cq <= 4 columns used)
-  float4* red = w2 + S;                                   // [2][8][SB]
-  __shared__ float bias_s[12];                            // skip-bias sum | post1 bias | post2 bias of my columns
-  for (int k = tid; k < LD; k += THREADS) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* src = g.skip + (size_t)k * S + CS * p;
-    if (CS * p + 0 < S) v.x = src[0];
-    if (CS * p + 1 < S) v.y = src[1];
-    if (CS * p + 2 < S) v.z = src[2];
-    if (CS * p + 3 < S) v.w = src[3];
-    ws[k] = v;
+  const int LD = g.L * C, S = g.S, Q = g.Q;
+  const int per_group = a.NP / NG;             // CTAs of a group
+  const int grp = p / per_group, pc = p % per_group;
+  const int ncq = (Q + per_group - 1) / per_group;      // postprocess2 columns per CTA (<= PCW)
+  float* ws = sm;                               // [LD][PCW] skip weights of my columns
+  float* w1 = ws + (size_t)LD * PCW;            // [S][PCW]
+  float* w2 = w1 + (size_t)S * PCW;             // [S][ncq]
+  float* stage = w2 + (size_t)S * ncq;          // [SB][max(LD, S)]
+  __shared__ float bias_s[3][PCW];              // skip-bias sum | post1 bias | post2 bias of my columns
+  for (int i = tid; i < LD * PCW; i += THREADS) {
+    const int k = i / PCW, c = i % PCW, col = PCW * pc + c;
+    ws[i] = col < S ? g.skip[(size_t)k * S + col] : 0.f;
   }
-  for (int k = tid; k < S; k += THREADS) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* src = g.post1 + (size_t)k * S + CS * p;
-    if (CS * p + 0 < S) v.x = src[0];
-    if (CS * p + 1 < S) v.y = src[1];
-    if (CS * p + 2 < S) v.z = src[2];
-    if (CS * p + 3 < S) v.w = src[3];
-    w1[k] = v;
-    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* s2 = g.post2 + (size_t)k * Q + cq * p;
-    if (0 < cq && cq * p + 0 < Q) u.x = s2[0];
-    if (1 < cq && cq * p + 1 < Q) u.y = s2[1];
-    if (2 < cq && cq * p + 2 < Q) u.z = s2[2];
-    if (3 < cq && cq * p + 3 < Q) u.w = s2[3];
-    w2[k] = u;
+  for (int i = tid; i < S * PCW; i += THREADS) {
+    const int k = i / PCW, c = i % PCW, col = PCW * pc + c;
+    w1[i] = col < S ? g.post1[(size_t)k * S + col] : 0.f;
   }
-  if (tid < 12) {
+  for (int i = tid; i < S * ncq; i += THREADS) {
+    const int k = i / ncq, c = i % ncq, col = ncq * pc + c;
+    w2[i] = col < Q ? g.post2[(size_t)k * Q + col] : 0.f;
+  }
+  if (tid < 3 * PCW) {
+    const int which = tid / PCW, c = tid % PCW;
     float v = 0.f;
     if (g.use_biases) {
-      const int j = tid & 3;
-      if (tid < 4) {
-        if (CS * p + j < S)
-          for (int l = 0; l < g.L; ++l) v += g.skip_bias[(size_t)l * S + CS * p + j];   // model.py:430 sum of skips
-      } else if (tid < 8) {
-        if (CS * p + j < S) v = g.post1_bias[CS * p + j];
+      if (which == 0) {
+        if (PCW * pc + c < S)
+          for (int l = 0; l < g.L; ++l) v += g.skip_bias[(size_t)l * S + PCW * pc + c];   // model.py:430 sum of skips
+      } else if (which == 1) {
+        if (PCW * pc + c < S) v = g.post1_bias[PCW * pc + c];
       } else {
-        if (j < cq && cq * p + j < Q) v = g.post2_bias[cq * p + j];
+        if (c < ncq && ncq * pc + c < Q) v = g.post2_bias[ncq * pc + c];
       }
     }
-    bias_s[tid] = v;
+    bias_s[which][c] = v;
   }
   __syncthreads();
   const bool sampling = g.uniforms != nullptr;
   const size_t wps = pa.wps;
-  int flip = 0;
+  const int nbatch = (pa.NS + SB - 1) / SB;
   for (int step = 0; step < g.n_steps; ++step) {
     if (!sampling && step != g.n_steps - 1) continue;       // priming: only the last distribution is needed
     const uint32_t T = a.tag_base + (uint32_t)step + 1u;
-    // Software pipeline over batches of SB streams: iteration k runs the skip sum of batch k, postprocess1 of batch k-1
-    // and postprocess2 of batch k-2 -- a batch leaves these CTAs three short iterations after it left the chain, and the
-    // L2 round trip between two phases of a batch (all NP CTAs publish their columns) is covered by the other batches.
-    // (Phase by phase over ALL streams, the first version, held every stream's logits back until the last stream of the
-    // round had left the chain: the step time became chain round + post + sampler instead of their maximum.)
-    const int nbatch = (pa.NS + SB - 1) / SB;
-    for (int k = 0; k < nbatch + 2; ++k) {
-      if (k < nbatch) {                        // skip sum -> relu            (model.py:505-507)
-        const int s0 = k * SB, nb = min(SB, pa.NS - s0);
+    // my batches: grp, grp + NG, ...  Software pipeline over them: iteration k runs the skip sum of my k-th batch,
+    // postprocess1 of the (k-1)-th and postprocess2 of the (k-2)-th -- the L2 round trip between two phases of a batch (all
+    // CTAs of the group publish their columns) is covered by the other batches.
+    const int mine = grp < nbatch ? (nbatch - grp + NG - 1) / NG : 0;
+    for (int k = 0; k < mine + 2; ++k) {
+      if (k < mine) {                          // skip sum -> relu            (model.py:505-507)
+        const int s0 = (grp + k * NG) * SB, nb = min(SB, pa.NS - s0);
         u64* comm = a.comm + (size_t)s0 * wps;
         if (tid == 0) wait_hint(comm + (size_t)(nb - 1) * wps + off_misc(a.NC, g.L, S, Q) + 1, T);      // (streams leave the chain in order)
         __syncthreads();
-        post_phase_b<8>(comm + off_zt(a.NC), comm + off_v0(a.NC, g.L), wps, nb, LD, ws, bias_s, CS * p, CS, S, true, T, red, flip);
+        post_pass<8>(comm + off_zt(a.NC), comm + off_v0(a.NC, g.L), wps, nb, LD, ws, PCW, bias_s[0], PCW * pc, S, true, T, stage);
       }
-      if (k >= 1 && k - 1 < nbatch) {          // postprocess1 -> relu        (model.py:508-511)
-        const int s0 = (k - 1) * SB, nb = min(SB, pa.NS - s0);
+      if (k >= 1 && k - 1 < mine) {            // postprocess1 -> relu        (model.py:508-511)
+        const int s0 = (grp + (k - 1) * NG) * SB, nb = min(SB, pa.NS - s0);
         u64* comm = a.comm + (size_t)s0 * wps;
-        post_phase_b<4>(comm + off_v0(a.NC, g.L), comm + off_v1(a.NC, g.L, S), wps, nb, S, w1, bias_s + 4, CS * p, CS, S, true, T, red, flip);
+        post_pass<4>(comm + off_v0(a.NC, g.L), comm + off_v1(a.NC, g.L, S), wps, nb, S, w1, PCW, bias_s[1], PCW * pc, S, true, T, stage);
       }
-      if (k >= 2 && k - 2 < nbatch) {          // postprocess2                (model.py:512-514)
-        const int s0 = (k - 2) * SB, nb = min(SB, pa.NS - s0);
+      if (k >= 2 && k - 2 < mine) {            // postprocess2                (model.py:512-514)
+        const int s0 = (grp + (k - 2) * NG) * SB, nb = min(SB, pa.NS - s0);
         u64* comm = a.comm + (size_t)s0 * wps;
-        post_phase_b<4>(comm + off_v1(a.NC, g.L, S), comm + off_lg(a.NC, g.L, S), wps, nb, S, w2, bias_s + 8, cq * p, cq, Q, false, T, red, flip);
+        post_pass<4>(comm + off_v1(a.NC, g.L, S), comm + off_lg(a.NC, g.L, S), wps, nb, S, w2, ncq, bias_s[2], ncq * pc, Q, false, T, stage);
       }
     }
   }
@@ -988,6 +988,11 @@ size_t chain_smem_ms(const GenArgs& g, int NS, int causal_in_smem, int pb_in_sme
                           (pb_in_smem ? (size_t)LPC * NS * 64 : 0));
 }
 
+size_t post_smem_ms(const GenArgs& g, int NP) {
+  const int per_group = NP / NG, ncq = (g.Q + per_group - 1) / per_group;
+  const size_t LD = (size_t)g.L * C, mx = LD > (size_t)g.S ? LD : (size_t)g.S;
+  return sizeof(float) * (LD * PCW + (size_t)g.S * PCW + (size_t)g.S * ncq + SB * mx);
+}
 size_t chain_smem(const GenArgs& g, int causal_in_smem) {
   return sizeof(float) * (2 * (LPC + 1) * 32 + LPC * 64 + (causal_in_smem ? 2 * g.Q * C : 0));
 }
@@ -1025,13 +1030,13 @@ bool gen_pipe_eligible(const GenArgs& a) {
   if (!a.forced && !a.uniforms && a.n_steps != 1) return false;
   const int NC = (a.L + LPC - 1) / LPC;
   const int NP = (a.S + CS - 1) / CS;
-  if ((a.Q + NP - 1) / NP > 4) return false;
+  if (NP % NG || (NP / NG) * PCW < a.S || ((a.Q + NP / NG - 1) / (NP / NG)) > PCW) return false;      // 16 columns per post CTA, NG groups
   if (a.L * C > 8 * THREADS || a.S > 4 * THREADS || a.Q > 4 * THREADS) return false;      // wait_batch<8> / <4>
   if (NC + NSAMP + NP > sm_count()) return false;
   const int causal_in_smem = (2 * a.Q * C * sizeof(float) <= 64 * 1024) ? 1 : 0;
   const int pb = (a.G > 0 && a.gc_ids) ? 1 : 0;
   if (chain_smem_ms(a, a.streams, causal_in_smem, pb) > 220 * 1024) return false;
-  if (post_smem(a) > 200 * 1024 || sampler_smem(a) > 200 * 1024) return false;
+  if (post_smem_ms(a, NP) > 220 * 1024 || sampler_smem(a) > 200 * 1024) return false;
   return true;
 }
 
@@ -1051,7 +1056,7 @@ int gen_pipe_run(const GenArgs& g, void* comm, uint32_t launch_seq, cudaStream_t
   pa.wps = comm_words_per_stream(g.L, g.S, g.Q);
   pa.pb_in_smem = (g.G > 0 && g.gc_ids) ? 1 : 0;
   size_t smem = chain_smem_ms(g, pa.NS, a.causal_in_smem, pa.pb_in_smem);
-  if (post_smem(g) > smem) smem = post_smem(g);
+  if (post_smem_ms(g, a.NP) > smem) smem = post_smem_ms(g, a.NP);
   if (sampler_smem(g) > smem) smem = sampler_smem(g);
   cudaError_t e = cudaFuncSetAttribute(generator_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
