@@ -152,6 +152,13 @@ int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t ti
                     float* partials, int32_t n_partials, float* loss_out, int32_t write_grad,
                     wn_stream_t stream);
 
+/* Data-parallel training (the reference is single-session, train.py:261): `cuda_event` (a cudaEvent_t,
+ * NULL = off) is recorded inside every following wn_loss_grad call at the point where the gradients of the TAIL of the flat
+ * buffer -- [layout.skip, layout.total): skip, skip_bias, postprocess1/2 and their biases, 80 % of the bytes -- are final,
+ * more than a millisecond before the call's last kernel.  A caller that all-reduces that range on another stream behind this
+ * event overlaps it with the residual-block backward (wavenet/train_step.py). */
+int wn_set_grad_ready_event(void* cuda_event);
+
 /* ---- whole training graph of WaveNetModel.loss: model.py:628-685 + train.py:252 gradients ----
  * audio [B,T] float32 -> loss (device scalar) and the flat gradient buffer (overwritten).
  * workspace: wn_train_workspace_bytes(cfg,batch,time) bytes, 256-byte aligned.               */

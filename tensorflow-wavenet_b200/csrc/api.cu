@@ -46,6 +46,8 @@ void prof_mark(cudaStream_t st, int tag) {
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+// wn_set_grad_ready_event: recorded when the gradients of the tail bucket [skip, total) are final (see make_layout)
+static cudaEvent_t g_tail_ready_event = nullptr;
 static inline bool fused_blocks(const wn_config* c) {
   return c->residual_channels == c->dilation_channels && (c->residual_channels == 16 || c->residual_channels == 32);
 }
@@ -74,22 +76,26 @@ static int make_layout(const wn_config* c, wn_layout* o) {
                 Q = c->quantization_channels, G = c->gc_channels;
   int64_t off = 0;
   auto take = [&](int64_t n) { int64_t r = off; off = align_up(off + n, 64); return r; };
+  // Group order = all-reduce buckets (wavenet/train_step.py): everything the residual-block backward produces comes first;
+  // the skip / post-processing weights and biases -- 80 % of the bytes, final more than a millisecond before the end of
+  // the step (their gradient GEMMs run first) -- form the contiguous tail [skip, total), which is reduced while the
+  // backward chain still runs.
   o->causal = take(c->scalar_input ? (int64_t)c->initial_filter_width * R : 2 * Q * R);
   o->filter = take(L * 2 * R * D);
   o->gate = take(L * 2 * R * D);
   o->dense = take(L * D * R);
-  o->skip = take(L * D * S);
   o->gc_filter = G > 0 ? take(L * G * D) : -1;
   o->gc_gate = G > 0 ? take(L * G * D) : -1;
   o->filter_bias = c->use_biases ? take(L * D) : -1;
   o->gate_bias = c->use_biases ? take(L * D) : -1;
   o->dense_bias = c->use_biases ? take(L * R) : -1;
+  o->gc_embedding = (G > 0 && c->gc_cardinality > 0) ? take((int64_t)c->gc_cardinality * G) : -1;
+  o->skip = take(L * D * S);
   o->skip_bias = c->use_biases ? take(L * S) : -1;
   o->post1 = take(S * S);
   o->post2 = take(S * Q);
   o->post1_bias = c->use_biases ? take(S) : -1;
   o->post2_bias = c->use_biases ? take(Q) : -1;
-  o->gc_embedding = (G > 0 && c->gc_cardinality > 0) ? take((int64_t)c->gc_cardinality * G) : -1;
   o->total = off;
   return 0;
 }
@@ -578,6 +584,11 @@ int wn_debug_set_impl(int32_t gemm_mma, int32_t block_mma) {
   return 0;
 }
 
+int wn_set_grad_ready_event(void* cuda_event) {
+  g_tail_ready_event = (cudaEvent_t)cuda_event;
+  return 0;
+}
+
 int wn_debug_trap_info(unsigned int* host_mapped_words) {
   int rc = block_umma_set_trap_info(host_mapped_words);
   if (rc == 0) rc = block_fwd_h_set_trap_info(host_mapped_words);
@@ -905,6 +916,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
   }
   RC((int)cudaEventRecord(ev_g[3], s2));
+  if (g_tail_ready_event) RC((int)cudaEventRecord(g_tail_ready_event, s2));      // the all-reduce of the tail bucket may start
   if (w.dlog16) {
     RC(gemm_f16_nt(w.G2h, S, w.Wskipg, S, nullptr, 0, w.dZcat16, ldz, M, ldz, S, nullptr, nullptr, 0, 1.f, 0, st));      // stays fp16 and scaled: block_bwd_pre rescales
     prof_mark(st, PT_GEMM_SKIP_DGRAD);

@@ -26,7 +26,7 @@ class WnConfig(C.Structure):
 
 LAYOUT_FIELDS = ['causal', 'filter', 'gate', 'dense', 'skip', 'gc_filter', 'gc_gate', 'filter_bias',
                  'gate_bias', 'dense_bias', 'skip_bias', 'post1', 'post2', 'post1_bias', 'post2_bias',
-                 'gc_embedding', 'total']
+                 'gc_embedding', 'total']      # (field order of the C struct, not the order of the groups in memory)
 
 
 class WnLayout(C.Structure):
@@ -79,6 +79,7 @@ SIGNATURES = {
     'wn_gen_commit': (C.c_int, [_CFG, _P, _I32, _P]),
     'wn_sample': (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
     'wn_debug_set_impl': (C.c_int, [_I32, _I32]),
+    'wn_set_grad_ready_event': (C.c_int, [_P]),
     'wn_profile_begin': (C.c_int, []),
     'wn_profile_end': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), _I32]),
     'wn_profile_tag_name': (C.c_int, [_I32, C.c_char_p, _I32]),

@@ -3,10 +3,18 @@
 Every rank runs the full model on its own [B_local, T] windows (the reference is single-device;
 data parallelism is this build's addition).  The only exchange is a sum
 all-reduce of the flat fp32 gradient buffer over NCCL, followed by the same optimizer update on
-every rank (weights stay replicated).  The loss/gradient launch sequence (~170 kernels for the
-default network) is captured once into a CUDA graph and replayed.
+every rank (weights stay replicated).
+
+The all-reduce is split into two buckets and lives INSIDE the captured CUDA graph of the step:
+  * tail bucket [layout.skip, layout.total): skip / postprocess1 / postprocess2 weights and biases, 80 % of the bytes.
+    Their gradients are final when the post-processing gradient GEMMs are done -- more than a millisecond before the
+    end of the step; the library records an event there (wn_set_grad_ready_event) and the bucket is reduced on a
+    communication stream while the residual-block backward still runs;
+  * head bucket [0, layout.skip): everything the residual-block backward produces, reduced at the end.
+WN_DP_OVERLAP=0 restores one all-reduce of the whole buffer after the graph replay.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -55,15 +63,42 @@ class TrainStep(object):
         self._thr, _ = device_tables(net.quantization_channels)
         self._graph = None
         self.kernel_launches = None
+        # bucketed all-reduce inside the step (world > 1, NCCL): see the module docstring
+        self.overlap = (self.world > 1 and os.environ.get('WN_DP_OVERLAP', '1') != '0' and
+                        torch.distributed.get_backend(process_group) == 'nccl')
+        self._reduced_in_step = False
+        if self.overlap:
+            self._comm = torch.cuda.Stream(device=dev)
+            self._ev_tail = torch.cuda.Event()
+            self._ev_comm = torch.cuda.Event()
+            self._ev_tail.record()                      # (creates the CUDA event: its handle goes to the library)
+            self._tail_off = int(net._layout.skip)
+            torch.distributed.all_reduce(torch.zeros(8, device=dev), group=process_group)   # communicator up before any capture
         if use_cuda_graph:
             self._capture()
 
     def _launch(self):
         n = self.net
-        rc = n._lib.wn_loss_grad(C.byref(n._cfg), _lib.ptr(n.flat_params), _lib.ptr(n.flat_grads),
-                                 _lib.ptr(self._ws), self._ws.numel(), _lib.ptr(self.audio), _lib.ptr(self.gc),
-                                 _lib.ptr(self._thr), self.batch, self.time, _lib.ptr(self.loss), _lib.stream_ptr())
+        if self.overlap:
+            _lib.check(n._lib.wn_set_grad_ready_event(C.c_void_p(self._ev_tail.cuda_event)), 'wn_set_grad_ready_event')
+        try:
+            rc = n._lib.wn_loss_grad(C.byref(n._cfg), _lib.ptr(n.flat_params), _lib.ptr(n.flat_grads),
+                                     _lib.ptr(self._ws), self._ws.numel(), _lib.ptr(self.audio), _lib.ptr(self.gc),
+                                     _lib.ptr(self._thr), self.batch, self.time, _lib.ptr(self.loss), _lib.stream_ptr())
+        finally:
+            if self.overlap:
+                n._lib.wn_set_grad_ready_event(None)
         _lib.check(rc, 'wn_loss_grad')
+        if self.overlap:
+            cur = torch.cuda.current_stream()
+            g = n.flat_grads
+            self._comm.wait_event(self._ev_tail)        # recorded by the library where the tail bucket's gradients are final
+            with torch.cuda.stream(self._comm):
+                torch.distributed.all_reduce(g[self._tail_off:], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+                self._ev_comm.record(self._comm)
+            torch.distributed.all_reduce(g[:self._tail_off], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            cur.wait_event(self._ev_comm)
+            self._reduced_in_step = True
 
     def _capture(self):
         s = torch.cuda.Stream()
@@ -90,6 +125,9 @@ class TrainStep(object):
             self._graph.replay()
         else:
             self._launch()
-        scale = allreduce_gradients(self.net.flat_grads, self.pg) if self.world > 1 else 1.0
+        if self._reduced_in_step:
+            scale = 1.0 / self.world
+        else:
+            scale = allreduce_gradients(self.net.flat_grads, self.pg) if self.world > 1 else 1.0
         self.opt.apply(self.net.flat_params, self.net.flat_grads, l2=self.l2, grad_scale=scale)
         return self.loss

@@ -33,11 +33,19 @@ def main():
     g_one = big.flat_grads.cpu().numpy()
     err = float(np.abs(g_dp - g_one).max() / np.abs(g_one).max())
     assert err < 1e-5, err
-    # 2) replicas stay bit-identical: 5 graph-replayed steps with the NCCL all-reduce in between
+    # 2) replicas stay bit-identical: 5 graph-replayed steps, the bucketed all-reduce captured INSIDE the graph (the tail
+    #    bucket reduced while the backward chain runs) -- and they equal the plain schedule (one all-reduce after the replay)
     opt = wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9)
     step = wavenet.TrainStep(net, opt, 1, T)
+    assert step.overlap, 'the bucketed all-reduce should be on with NCCL'
+    os.environ['WN_DP_OVERLAP'] = '0'
+    net_plain = wavenet.WaveNetModel(batch_size=1, seed=5, **kw)
+    step_plain = wavenet.TrainStep(net_plain, wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9), 1, T)
+    del os.environ['WN_DP_OVERLAP']
+    assert not step_plain.overlap
     for i in range(5):
         step(np.roll(audio[rank], 17 * i))
+        step_plain(np.roll(audio[rank], 17 * i))
     torch.cuda.synchronize()
     mine = net.flat_params.clone()
     gathered = [torch.empty_like(mine) for _ in range(world)]
@@ -46,9 +54,11 @@ def main():
         assert torch.equal(other, mine), 'replicas diverged'
     moved = float((mine - big.flat_params).abs().max())
     assert moved > 0
+    sched = float((mine - net_plain.flat_params).abs().max())
+    assert sched <= 1e-6 * max(1.0, float(mine.abs().max())), sched      # same sums, possibly another NCCL reduction order
     dist.barrier()
     if rank == 0:
-        print('DP_OK grad max-norm rel err {:.2e}; params moved by {:.2e}'.format(err, moved))
+        print('DP_OK grad max-norm rel err {:.2e}; params moved by {:.2e}; overlapped vs plain schedule {:.1e}'.format(err, moved, sched))
     dist.destroy_process_group()
 
 
