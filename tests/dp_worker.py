@@ -36,26 +36,27 @@ def main():
     # 2) replicas stay bit-identical: 5 graph-replayed steps, the bucketed all-reduce captured INSIDE the graph (the tail
     #    bucket reduced while the backward chain runs) -- and they equal the plain schedule (one all-reduce after the replay)
     opt = wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9)
+    os.environ['WN_DP_OVERLAP'] = '1'
     step = wavenet.TrainStep(net, opt, 1, T)
-    assert step.overlap, 'the bucketed all-reduce should be on with NCCL'
-    os.environ['WN_DP_OVERLAP'] = '0'
+    assert step.overlap, 'WN_DP_OVERLAP=1 should turn the bucketed all-reduce on with NCCL'
+    del os.environ['WN_DP_OVERLAP']
     net_plain = wavenet.WaveNetModel(batch_size=1, seed=5, **kw)
     step_plain = wavenet.TrainStep(net_plain, wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9), 1, T)
-    del os.environ['WN_DP_OVERLAP']
-    assert not step_plain.overlap
+    assert not step_plain.overlap      # the default: one all-reduce of the whole buffer after the graph replay
     for i in range(5):
         step(np.roll(audio[rank], 17 * i))
         step_plain(np.roll(audio[rank], 17 * i))
     torch.cuda.synchronize()
     mine = net.flat_params.clone()
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    for other in gathered:
-        assert torch.equal(other, mine), 'replicas diverged'
+    for params in (mine, net_plain.flat_params.clone()):      # both schedules keep the replicas bit-identical
+        gathered = [torch.empty_like(params) for _ in range(world)]
+        dist.all_gather(gathered, params)
+        for other in gathered:
+            assert torch.equal(other, params), 'replicas diverged'
     moved = float((mine - big.flat_params).abs().max())
     assert moved > 0
     sched = float((mine - net_plain.flat_params).abs().max())
-    assert sched <= 1e-6 * max(1.0, float(mine.abs().max())), sched      # same sums, possibly another NCCL reduction order
+    assert sched <= 2e-4, sched      # (two runs order their fp32 atomics differently, and Adam normalises tiny gradients)
     dist.barrier()
     if rank == 0:
         print('DP_OK grad max-norm rel err {:.2e}; params moved by {:.2e}; overlapped vs plain schedule {:.1e}'.format(err, moved, sched))
