@@ -152,6 +152,15 @@ int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t ti
                     float* partials, int32_t n_partials, float* loss_out, int32_t write_grad,
                     wn_stream_t stream);
 
+/* WaveNetModel.predict_proba (model.py:564-590): the network over the whole window, post-processing on its LAST row only,
+ * float64 softmax cast to float32.  proba: [Q].  ids as in wn_forward_logits; workspace: wn_forward_workspace_bytes. */
+int wn_predict_last(const wn_config* cfg, const float* params, void* workspace, int64_t workspace_bytes, const int32_t* ids,
+                    const int32_t* gc_ids, int32_t batch, int32_t time, float* proba, wn_stream_t stream);
+
+/* model.py:670-680: *loss += coef * sum_v tf.nn.l2_loss(v) = coef * sum(params^2) / 2 over the flat parameter buffer (its
+ * alignment gaps are zero; in this snapshot of the reference the biases are NOT excluded). */
+int wn_add_l2(float* loss, const float* params, int64_t n, float coef, wn_stream_t stream);
+
 /* Data-parallel training (the reference is single-session, train.py:261): `cuda_event` (a cudaEvent_t,
  * NULL = off) is recorded inside every following wn_loss_grad call at the point where the gradients of the TAIL of the flat
  * buffer -- [layout.skip, layout.total): skip, skip_bias, postprocess1/2 and their biases, 80 % of the bytes -- are final,

@@ -348,7 +348,7 @@ static int truncate_stage() {
 
 static int run_forward(const wn_config* c, const wn_layout& lo, const float* params, Workspace& w,
                        const int32_t* ids, const int32_t* gc_ids, int B, int T, bool training, float* logits,
-                       cudaStream_t st, const float* scalar_in = nullptr) {
+                       cudaStream_t st, const float* scalar_in = nullptr, bool last_only = false) {
   const int M = B * T, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels,
             S = c->skip_channels, Q = c->quantization_channels, G = c->gc_channels;
   const int ldz = L * D;
@@ -456,22 +456,26 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   if (use_prep) RC((int)cudaStreamWaitEvent(st, ev_join, 0));      // join the parameter-conversion branch
   else RC(prep_weights());
   if (training && truncate_stage() == 1) return 0;
+  // predict_proba (model.py:564-590) needs the LAST row of the logits only: the post-processing runs on that one row
+  const int Mg = last_only ? 1 : M;
+  const int64_t r0 = last_only ? (int64_t)M - 1 : 0;
   if (w.Zcat16) {
     // fp32 copies of the two hidden activations only where something reads them: the tf32 gradient chain
     float* a1_32 = (training && !w.dlog16) ? w.A1 : nullptr;
     float* a2_32 = (training && !w.dlog16) ? w.A2 : nullptr;
-    RC(gemm_f16_nt(w.Zcat16, ldz, w.Wskip16, ldz, a1_32, S, w.A1h, S, M, S, ldz, bsum, nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
+    const char* z16 = (const char*)w.Zcat16 + r0 * ldz * 2;
+    RC(gemm_f16_nt(z16, ldz, w.Wskip16, ldz, a1_32, S, w.A1h, S, Mg, S, ldz, bsum, nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
                    training ? w.maskA1 : nullptr, nullptr, S / 32));
     prof_mark(st, PT_GEMM_SKIP_FWD);
-    RC(gemm_f16_nt(w.A1h, S, w.W1h, S, a2_32, S, w.A2h, S, M, S, S, P(params, lo.post1_bias), nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
+    RC(gemm_f16_nt(w.A1h, S, w.W1h, S, a2_32, S, w.A2h, S, Mg, S, S, P(params, lo.post1_bias), nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
                    training ? w.maskA2 : nullptr, nullptr, S / 32));
     prof_mark(st, PT_GEMM_POST1_FWD);
-    RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, M, Q, S, P(params, lo.post2_bias), nullptr, 0, 1.f, 0, st));
+    RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, Mg, Q, S, P(params, lo.post2_bias), nullptr, 0, 1.f, 0, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
     return 0;
   }
   {  // total = sum_l skip_l  ->  relu            (model.py:430-431)
-    GemmParams p = gp(w.Zcat, ldz, w.WskipR, S, w.A1, S, M, S, ldz);
+    GemmParams p = gp(w.Zcat + r0 * ldz, ldz, w.WskipR, S, w.A1, S, Mg, S, ldz);
     p.bias = bsum;
     p.flags = GEMM_RELU | GEMM_ROUND;
     if (c->residual_postproc) { p.C2 = w.S0; p.ldc2 = S; }
@@ -479,7 +483,7 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     prof_mark(st, PT_GEMM_SKIP_FWD);
   }
   {  // conv1 -> relu                             (model.py:432-435)
-    GemmParams p = gp(w.A1, S, w.W1R, S, w.A2, S, M, S, S);
+    GemmParams p = gp(w.A1, S, w.W1R, S, w.A2, S, Mg, S, S);
     p.bias = P(params, lo.post1_bias);
     p.flags = GEMM_RELU | GEMM_ROUND;
     RC(gemm(0, p, 1, st));
@@ -487,12 +491,12 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   }
   const float* x2 = w.A2;
   if (c->residual_postproc) {  // transformed2 += total   (model.py:436-437)
-    RC((int)cudaMemcpyAsync(w.T2, w.A2, (size_t)M * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    RC(add_inplace(w.T2, w.S0, (int64_t)M * S, 1, st));
+    RC((int)cudaMemcpyAsync(w.T2, w.A2, (size_t)Mg * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    RC(add_inplace(w.T2, w.S0, (int64_t)Mg * S, 1, st));
     x2 = w.T2;
   }
   {  // conv2                                      (model.py:438-440)
-    GemmParams p = gp(x2, S, w.W2R, Q, logits, Q, M, Q, S);
+    GemmParams p = gp(x2, S, w.W2R, Q, logits, Q, Mg, Q, S);
     p.bias = P(params, lo.post2_bias);
     RC(gemm(0, p, 1, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
@@ -798,6 +802,28 @@ int wn_forward_logits(const wn_config* cfg, const float* params, void* workspace
   // (scalar_input: `ids` carries the float32 waveform -- the mu-law decoded samples of predict_proba, model.py:570-576)
   return run_forward(cfg, lo, params, w, ids, gc_ids, batch, time, false, logits, (cudaStream_t)stream,
                      cfg->scalar_input ? reinterpret_cast<const float*>(ids) : nullptr);
+}
+
+int wn_predict_last(const wn_config* cfg, const float* params, void* workspace, int64_t workspace_bytes, const int32_t* ids,
+                    const int32_t* gc_ids, int32_t batch, int32_t time, float* proba, wn_stream_t stream) {
+  wn_layout lo;
+  RC(make_layout(cfg, &lo));
+  if (!params || !workspace || !ids || !proba || batch < 1 || time < 1) return -1;
+  if ((uintptr_t)workspace & 255) return -4;
+  Workspace w;
+  carve(cfg, batch, time, false, workspace, &w);
+  if (w.bytes > workspace_bytes) return -5;
+  // the layers run over the whole window, skip sum / postprocess1 / postprocess2 on its last row only; the row of logits
+  // goes through the partials scratch (4096 floats)
+  if (cfg->quantization_channels > 4096) return -2;
+  RC(run_forward(cfg, lo, params, w, ids, gc_ids, batch, time, false, w.partials, (cudaStream_t)stream,
+                 cfg->scalar_input ? reinterpret_cast<const float*>(ids) : nullptr, /*last_only=*/true));
+  return softmax_f64(w.partials, cfg->quantization_channels, proba, (cudaStream_t)stream);
+}
+
+int wn_add_l2(float* loss, const float* params, int64_t n, float coef, wn_stream_t stream) {
+  if (!loss || !params || n < 0) return -1;
+  return add_l2(loss, params, n, coef, (cudaStream_t)stream);
 }
 
 int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* workspace, int64_t workspace_bytes,

@@ -423,6 +423,56 @@ int cond_bias_bwd(const float* gprebias, float* gfilter_bias, float* ggate_bias,
   return 0;
 }
 
+// float64 softmax of one row of logits, cast to float32 (model.py:584-585, 620-621)
+__global__ void softmax_f64_kernel(const float* __restrict__ logits, int Q, float* __restrict__ proba) {
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  double mx = -1e300;
+  for (int i = tid; i < Q; i += blockDim.x) mx = fmax(mx, (double)logits[i]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < nw; ++w) mx = fmax(mx, red[w]);
+  __syncthreads();
+  double sum = 0.0;
+  for (int i = tid; i < Q; i += blockDim.x) sum += exp((double)logits[i] - mx);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.0;
+  for (int w = 0; w < nw; ++w) sum += red[w];
+  for (int i = tid; i < Q; i += blockDim.x) proba[i] = (float)(exp((double)logits[i] - mx) / sum);
+}
+int softmax_f64(const float* logits, int Q, float* proba, cudaStream_t st) {
+  softmax_f64_kernel<<<1, 256, 0, st>>>(logits, Q, proba);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void add_l2_kernel(float* __restrict__ loss, const float* __restrict__ p, int64_t n, float coef) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s = fmaf(p[i], p[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(loss, 0.5f * coef * t);
+  }
+}
+int add_l2(float* loss, const float* params, int64_t n, float coef, cudaStream_t st) {
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  add_l2_kernel<<<(int)blocks, 256, 0, st>>>(loss, params, n, coef);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
 __global__ void skip_bias_sum_kernel(const float* __restrict__ skip_bias, int L, int S, float* __restrict__ out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;

@@ -149,6 +149,10 @@ int cond_bias_bwd(const float* gprebias, float* gfilter_bias, float* ggate_bias,
 int causal_conv(const float* x, const float* w, float* y, int M, int T, int cin, int cout, int width, int d,
                 cudaStream_t st);
 int skip_bias_sum(const float* skip_bias, int L, int S, float* out, cudaStream_t st);
+// proba[q] = float(softmax(double(logits))[q])   (model.py:584-585: float64 softmax, cast back to float32), one row
+int softmax_f64(const float* logits, int Q, float* proba, cudaStream_t st);
+// *loss += coef * sum(params^2) / 2   (model.py:670-680: l2_regularization_strength * sum of tf.nn.l2_loss)
+int add_l2(float* loss, const float* params, int64_t n, float coef, cudaStream_t st);
 int bcast_rows(const float* src, int n, float* dst, int rows, cudaStream_t st);
 int add_inplace(float* dst, const float* src, int64_t n, int round_out, cudaStream_t st);
 int relu_mask_add(float* dst, const float* grad, const float* act, int64_t n, int round_out, cudaStream_t st);

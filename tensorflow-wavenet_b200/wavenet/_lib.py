@@ -80,6 +80,8 @@ SIGNATURES = {
     'wn_sample': (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
     'wn_debug_set_impl': (C.c_int, [_I32, _I32]),
     'wn_set_grad_ready_event': (C.c_int, [_P]),
+    'wn_predict_last': (C.c_int, [_CFG, _P, _P, _I64, _P, _P, _I32, _I32, _P, _P]),
+    'wn_add_l2': (C.c_int, [_P, _P, _I64, _F, _P]),
     'wn_profile_begin': (C.c_int, []),
     'wn_profile_end': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), _I32]),
     'wn_profile_tag_name': (C.c_int, [_I32, C.c_char_p, _I32]),

@@ -277,7 +277,8 @@ class WaveNetModel(object):
             # model.py:670-680: sum of tf.nn.l2_loss over ALL trainables in this snapshot (App. A10);
             # alignment gaps of the flat buffer are zero.  The gradient term is added by the optimizer.
             l2 = float(l2_regularization_strength)
-            out = out + l2 * 0.5 * torch.sum(self.flat_params * self.flat_params)
+            _lib.check(self._lib.wn_add_l2(_lib.ptr(out), _lib.ptr(self.flat_params), self.flat_params.numel(), l2,
+                                           _lib.stream_ptr()), 'wn_add_l2')
         out._wavenet_model = self
         out._wavenet_l2 = l2
         return out
@@ -293,7 +294,7 @@ class WaveNetModel(object):
             total = float(loss)
             if l2:
                 out['total_loss'] = total
-                out['loss'] = total - l2 * 0.5 * float(torch.sum(self.flat_params * self.flat_params))
+                out['loss'] = total - l2 * 0.5 * float((self.flat_params.double() ** 2).sum())
             else:
                 out['loss'] = total
         if self.histograms:
@@ -338,9 +339,14 @@ class WaveNetModel(object):
         input waveform (model.py:564-590): float64 softmax of the last row, returned as float32.'''
         self._require_native()
         ids = self._net_input(waveform)
-        gc = self._gc_ids(global_condition, ids.shape[0])
-        last = self._logits(ids, gc)[-1]
-        return torch.softmax(last.to(torch.float64), dim=-1).to(torch.float32)
+        B, T = ids.shape
+        gc = self._gc_ids(global_condition, B)
+        ws = self._workspace('fwd', B, T)
+        proba = torch.empty((self.quantization_channels,), dtype=torch.float32, device=self.device)
+        rc = self._lib.wn_predict_last(C.byref(self._cfg), _lib.ptr(self.flat_params), _lib.ptr(ws), ws.numel(),
+                                       _lib.ptr(ids), _lib.ptr(gc), B, T, _lib.ptr(proba), _lib.stream_ptr())
+        _lib.check(rc, 'wn_predict_last')
+        return proba
 
     # ------------------------------------------------------------------ fast generation
     def _gen_state(self, streams):
