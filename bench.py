@@ -367,6 +367,10 @@ def main():
         for name in rooflines:
             if name in tr and args.batch == B_PER_GPU and args.time == T_WINDOW:
                 rooflines[name]['traffic'] = tr[name]['dram_bytes_per_launch']
+        if 'block_bwd' in rooflines and args.batch == B_PER_GPU and args.time == T_WINDOW and \
+                'block_bwd_chain' in tr and 'block_wgrad' in tr:      # the stage = its two launches
+            rooflines['block_bwd']['traffic'] = (tr['block_bwd_chain']['dram_bytes_per_launch'] +
+                                                 tr['block_wgrad']['dram_bytes_per_launch'])
     dominant = max(rooflines, key=lambda n: kernels[n]['ms_per_step']) if rooflines else None
     roofline = dict(rooflines[dominant], kernel=dominant, peak_source=peaks['source'] +
                     (' (bf16 dense GEMM; the post-processing GEMMs run fp16 operands with fp32 accumulation, same nominal rate)'

@@ -982,11 +982,18 @@ block_wgrad_h_all_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
+static int block_wgrad_h32_all(const void* xs, const void* dxs, const void* p16, const void* zcat16, int ldz, float scale,
+                               float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias,
+                               const int* dilations, int L, int B, int T, cudaStream_t st, int last_dense);
 // xs / dxs / p16 as in block_bwd_chain; zcat16: [B][T][ldz] fp16 (ldz = L * 32 in the training step)
 int block_wgrad_h_all(const void* xs, const void* dxs, const void* p16, const void* zcat16, int ldz, float scale, float* gwf,
                       float* gwg, float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B,
                       int T, cudaStream_t st, int last_dense) {
   if (L < 1 || L > WN_MAX_LAYERS) return -1;
+  static const bool full = [] { const char* e = getenv("WN_WGRAD_FULL"); return e && e[0] == '1'; }();
+  if (!full)
+    return block_wgrad_h32_all(xs, dxs, p16, zcat16, ldz, scale, gwf, gwg, gdense, gprebias, gdense_bias, dilations, L, B, T,
+                               st, last_dense);
   CUtensorMap mX, mZ, mP, mDn;
   int rc = make_map_h64(&mX, xs, (int64_t)L * B, T, 64, 64, WGH_ROWS);
   if (rc) return rc;
@@ -1007,6 +1014,225 @@ int block_wgrad_h_all(const void* xs, const void* dxs, const void* p16, const vo
   int grid = sm_count();
   if (grid > n_units) grid = (int)n_units;
   block_wgrad_h_all_kernel<<<grid, 192, smem, st>>>(mX, mZ, mP, mDn, a);
+  WN_CHECK_LAUNCH();
+  prof_mark(st, PT_BLOCK_WGRAD);
+  return 0;
+}
+
+// =====================================================================================================================
+// The same weight gradients from HALF the bytes: only the hi halves of x and dx' are read (64 B of each 128 B row; dpre is
+// fp16 anyway, so every product already carries an 11-bit factor) and z comes as a 32-column box instead of 64.  Per
+// (layer, time step) the kernel reads 64 (x) + 64 (z) + 128 (dpre) + 64 (dx') = 320 B from HBM (x[t-d] hits L2) instead of
+// 512.  All operands are MN-major blocks of [64 time steps][32 halfs] (64-byte rows, 64B swizzle, LBO = distance between
+// blocks, SBO 512, 1024 B per K = 16 step) and ONE accumulator serves everything:
+//   D[i][j] = sum_t [x | x[t-d] | z | 1,0..][t][i] * [df | dg | dx'][t][j]       (M = 128, N = 96)
+//   lanes 0-31 x (tap 1), 32-63 x[t-d] (tap 0): columns 0-63 -> filter / gate gradients
+//   lanes 64-95 z: columns 64-95 -> dense;   lane 96 (ones): columns 0-63 -> bias / conditioning sums, 64-95 -> dense bias
+// =====================================================================================================================
+constexpr int WG3_STAGES = 7;
+constexpr uint32_t WG3_BLK = WGH_ROWS * 64;       // one [64 steps][32 halfs] block
+constexpr uint32_t WG3_STAGE = 7 * WG3_BLK;       // x | x[t-d] | z | ones | df | dg | dx'
+
+__device__ __forceinline__ uint64_t mn16_desc64(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// [rows][32 halfs] boxes (64B swizzle) out of rows of `ld` halfs; no L2 promotion: the other half of a 128 B line is not wanted
+static int make_map_h32(CUtensorMap* m, const void* ptr, int64_t B, int64_t T, int64_t cols, int64_t ld, int rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -8;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -9;
+}
+
+__global__ void __launch_bounds__(192, 1)
+block_wgrad_h32_all_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
+                           const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapDn,
+                           const __grid_constant__ WgHArgs a) {
+  constexpr int STG = WG3_STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full_bar[STG], empty_bar[STG], done_bar, free_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = (a.T + WGH_ROWS - 1) / WGH_ROWS;
+  const long long n_units = (long long)a.L * a.B * nkb;
+  const long long per = (n_units + gridDim.x - 1) / gridDim.x;
+  const long long u0 = (long long)blockIdx.x * per;
+  long long u1 = u0 + per;
+  if (u1 > n_units) u1 = n_units;
+  if (u0 >= u1) return;
+
+  // per stage: the constant block (column 0 = 1, i.e. the first half of every 64-byte row; the 64B swizzle moves 16-byte
+  // chunk 0 of row r to chunk (r >> 1) & 3) and a defined (zero) dx' block
+  for (int i = tid; i < STG * (int)(WG3_BLK / 16); i += blockDim.x) {
+    const int s = i / (WG3_BLK / 16), o = i % (WG3_BLK / 16);
+    const int rr = o >> 2, ch = o & 3;
+    const bool one = ch == ((rr >> 1) & 3);
+    *reinterpret_cast<uint4*>(smem + s * WG3_STAGE + 3 * WG3_BLK + o * 16) = make_uint4(one ? 0x3C00u : 0u, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + s * WG3_STAGE + 6 * WG3_BLK + o * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STG; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    mbar_init(&free_bar, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 128);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int per_lb = nkb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t i = 0;
+      for (long long u = u0; u < u1; ++u, ++i) {
+        const int lb = (int)(u / per_lb), kb = (int)(u - (long long)lb * per_lb);
+        const int l = lb / a.B, b = lb - l * a.B;
+        const bool hd = (l < a.L - 1) || a.last_dense;
+        const int s = i % STG;
+        const uint32_t ph = (i / STG) & 1;
+        const int t = kb * WGH_ROWS;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], (hd ? 6 : 5) * WG3_BLK);
+        unsigned char* sa = smem + s * WG3_STAGE;
+        tma_load_3d(sa, &mapX, &full_bar[s], 0, t, lb);                          // x[t] of layer l (hi)
+        tma_load_3d(sa + WG3_BLK, &mapX, &full_bar[s], 0, t - a.dil[l], lb);     // x[t-d]  (zeros for t < d)
+        tma_load_3d(sa + 2 * WG3_BLK, &mapZ, &full_bar[s], l * C, t, b);         // z_l
+        tma_load_3d(sa + 4 * WG3_BLK, &mapP, &full_bar[s], 0, t, lb);            // df
+        tma_load_3d(sa + 5 * WG3_BLK, &mapP, &full_bar[s], 32, t, lb);           // dg
+        if (hd) tma_load_3d(sa + 6 * WG3_BLK, &mapDn, &full_bar[s], 0, t, lb + a.B);   // dx' = dx of layer l+1 (hi)
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t ID = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t i = 0, seg = 0;
+      int cur_lb = -1;
+      for (long long u = u0; u < u1; ++u, ++i) {
+        const int lb = (int)(u / per_lb);
+        const bool first = (lb != cur_lb);
+        if (first) {
+          if (cur_lb >= 0) {
+            mma_commit(&done_bar);
+            mbar_wait(&free_bar, seg & 1);
+            tc_fence_after();
+            ++seg;
+          }
+          cur_lb = lb;
+        }
+        const int s = i % STG;
+        const uint32_t ph = (i / STG) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * WG3_STAGE);
+        const uint64_t dA = mn16_desc64(sa, WG3_BLK);
+        const uint64_t dB = mn16_desc64(sa + 4 * WG3_BLK, WG3_BLK);
+#pragma unroll
+        for (int k = 0; k < WGH_ROWS / 16; ++k)      // +1024 B per K = 16 time steps
+          mma_f16_ss(tmem, dA + 64 * k, dB + 64 * k, ID, (first && k == 0) ? 0u : 1u);
+        mma_commit(&empty_bar[s]);
+      }
+      mma_commit(&done_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    uint32_t seg = 0;
+    long long u = u0;
+    while (u < u1) {
+      const int lb = (int)(u / per_lb);
+      const int l = lb / a.B, b = lb - l * a.B;
+      const bool hd = (l < a.L - 1) || a.last_dense;
+      long long ue = (long long)(lb + 1) * per_lb;
+      if (ue > u1) ue = u1;
+      mbar_wait(&done_bar, seg & 1);
+      tc_fence_after();
+      const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+      uint32_t v[32];
+      if (quad < 2) {      // x (tap 1) / x[t-d] (tap 0): columns = df | dg
+        const int tap = quad == 0 ? 1 : 0;
+        float* gf = a.gwf + (size_t)l * 2 * C * C + (size_t)(tap * C + lane) * C;
+        float* gg = a.gwg + (size_t)l * 2 * C * C + (size_t)(tap * C + lane) * C;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          tmem_ld32(lane_base + c0, v);
+          float* dst = c0 == 0 ? gf : gg;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4h(dst + j, __uint_as_float(v[j]) * a.scale, __uint_as_float(v[j + 1]) * a.scale,
+                        __uint_as_float(v[j + 2]) * a.scale, __uint_as_float(v[j + 3]) * a.scale);
+        }
+      } else if (quad == 2) {      // z: dense[c][r], c = lane
+        if (hd) {
+          tmem_ld32(lane_base + 64, v);
+          float* dst = a.gdense + (size_t)l * C * C + (size_t)lane * C;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4h(dst + j, __uint_as_float(v[j]) * a.scale, __uint_as_float(v[j + 1]) * a.scale,
+                        __uint_as_float(v[j + 2]) * a.scale, __uint_as_float(v[j + 3]) * a.scale);
+        }
+      } else {                     // the ones row (lane 0 of this quadrant): column sums
+#pragma unroll 1
+        for (int c0 = 0; c0 < 96; c0 += 32) {
+          if (c0 == 64 && !(hd && a.gdense_bias)) break;      // (warp-uniform)
+          tmem_ld32(lane_base + c0, v);
+          if (lane == 0) {
+            float* dst = c0 < 64 ? a.gprebias + ((size_t)l * a.B + b) * 64 + c0 : a.gdense_bias + (size_t)l * C;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4h(dst + j, __uint_as_float(v[j]) * a.scale, __uint_as_float(v[j + 1]) * a.scale,
+                          __uint_as_float(v[j + 2]) * a.scale, __uint_as_float(v[j + 3]) * a.scale);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&free_bar);
+      ++seg;
+      u = ue;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+static int block_wgrad_h32_all(const void* xs, const void* dxs, const void* p16, const void* zcat16, int ldz, float scale,
+                               float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias,
+                               const int* dilations, int L, int B, int T, cudaStream_t st, int last_dense) {
+  CUtensorMap mX, mZ, mP, mDn;
+  int rc = make_map_h32(&mX, xs, (int64_t)L * B, T, 32, 64, WGH_ROWS);      // the hi halves only
+  if (rc) return rc;
+  rc = make_map_h32(&mZ, zcat16, B, T, ldz, ldz, WGH_ROWS);
+  if (rc) return rc;
+  rc = make_map_h32(&mP, p16, (int64_t)L * B, T, 64, 64, WGH_ROWS);
+  if (rc) return rc;
+  rc = make_map_h32(&mDn, dxs, (int64_t)(L + (last_dense ? 1 : 0)) * B, T, 32, 64, WGH_ROWS);
+  if (rc) return rc;
+  WgHArgs a;
+  a.gwf = gwf; a.gwg = gwg; a.gdense = gdense; a.gprebias = gprebias; a.gdense_bias = gdense_bias;
+  a.L = L; a.B = B; a.T = T; a.last_dense = last_dense ? 1 : 0; a.scale = scale;
+  for (int l = 0; l < WN_MAX_LAYERS; ++l) a.dil[l] = l < L ? dilations[l] : 0;
+  const size_t smem = 1024 + WG3_STAGES * WG3_STAGE;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(block_wgrad_h32_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const long long n_units = (long long)L * B * ((T + WGH_ROWS - 1) / WGH_ROWS);
+  int grid = sm_count();
+  if (grid > n_units) grid = (int)n_units;
+  block_wgrad_h32_all_kernel<<<grid, 192, smem, st>>>(mX, mZ, mP, mDn, a);
   WN_CHECK_LAUNCH();
   prof_mark(st, PT_BLOCK_WGRAD);
   return 0;
