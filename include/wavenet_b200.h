@@ -152,6 +152,15 @@ int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t ti
                     float* partials, int32_t n_partials, float* loss_out, int32_t write_grad,
                     wn_stream_t stream);
 
+/* postprocess2 + softmax cross entropy in one kernel (model.py:438-440 + 654-666), the form the training step runs when
+ * quantization_channels == 256: a16 [B*T, k] fp16 (relu(conv1) rows), w16 [256, k] fp16 (postprocess2 transposed),
+ * bias [256] fp32 or null.  Writes loss (mean over B*T rows), g16 [B*T, 256] fp16 = (softmax - onehot) * grad_scale and,
+ * when bias_grad is given, ADDS colsum_scale * column sums of g16 to bias_grad[256].  partials: >= 148 floats.
+ * The logits themselves are never stored.  Returns -2 unless q == 256 and k is a multiple of 64. */
+int wn_post2_xent(const void* a16, int32_t lda, const void* w16, int32_t ldw, const float* bias, const int32_t* ids,
+                  int32_t batch, int32_t time, int32_t k, int32_t q, float* partials, float* loss_out, void* g16,
+                  float grad_scale, float* bias_grad, float colsum_scale, wn_stream_t stream);
+
 /* WaveNetModel.predict_proba (model.py:564-590): the network over the whole window, post-processing on its LAST row only,
  * float64 softmax cast to float32.  proba: [Q].  ids as in wn_forward_logits; workspace: wn_forward_workspace_bytes. */
 int wn_predict_last(const wn_config* cfg, const float* params, void* workspace, int64_t workspace_bytes, const int32_t* ids,

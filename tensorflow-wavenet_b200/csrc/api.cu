@@ -179,6 +179,10 @@ static bool fwd_chain_enabled() {
 }
 // backward of the fused blocks: one persistent fp16 chain kernel + one weight-gradient launch (default), or the
 // first-generation per-layer TF32 kernels (WN_BWD_CHAIN=0)
+static bool fused_xent_enabled() {      // WN_FUSED_XENT=0: postprocess2 GEMM, cross-entropy kernel and column sums as separate launches
+  static const bool on = [] { const char* e = getenv("WN_FUSED_XENT"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static bool bwd_chain_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -470,6 +474,7 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
     RC(gemm_f16_nt(w.A1h, S, w.W1h, S, a2_32, S, w.A2h, S, Mg, S, S, P(params, lo.post1_bias), nullptr, 0, 1.f, GEMM_RELU | GEMM_ROUND, st,
                    training ? w.maskA2 : nullptr, nullptr, S / 32));
     prof_mark(st, PT_GEMM_POST1_FWD);
+    if (!logits) return 0;      // training with the fused postprocess2 + cross-entropy kernel: the caller runs it
     RC(gemm_f16_nt(w.A2h, S, w.W2h, S, logits, Q, nullptr, 0, Mg, Q, S, P(params, lo.post2_bias), nullptr, 0, 1.f, 0, st));
     prof_mark(st, PT_GEMM_POST2_FWD);
     return 0;
@@ -776,6 +781,16 @@ int wn_softmax_xent(float* logits, const int32_t* ids, int32_t batch, int32_t ti
                       (cudaStream_t)stream);
 }
 
+int wn_post2_xent(const void* a16, int32_t lda, const void* w16, int32_t ldw, const float* bias, const int32_t* ids,
+                  int32_t batch, int32_t time, int32_t k, int32_t q, float* partials, float* loss_out, void* g16,
+                  float grad_scale, float* bias_grad, float colsum_scale, wn_stream_t stream) {
+  if (!a16 || !w16 || !ids || !partials || !loss_out || !g16 || batch < 1 || time < 1 || lda < k || ldw < k || (lda & 7) || (ldw & 7))
+    return -1;
+  const int M = batch * time;
+  return post2_xent(a16, lda, w16, ldw, bias, ids, M, time, k, q, 1.0f / (float)M, partials, loss_out, g16, grad_scale, bias_grad,
+                    colsum_scale, (cudaStream_t)stream);
+}
+
 int64_t wn_train_workspace_bytes(const wn_config* cfg, int32_t batch, int32_t time) {
   if (check_cfg(cfg) || batch < 1 || time < 1 || (int64_t)batch * time > (1 << 30)) return -1;
   Workspace w;
@@ -848,13 +863,20 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   prof_mark(st, PT_MISC);
   RC(mulaw_encode(audio, M, mulaw_thresholds, Q, w.ids, st));            // model.py:639
   prof_mark(st, PT_MULAW);
-  RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, w.logits, st, cfg->scalar_input ? audio : nullptr));      // model.py:645-648
+  // postprocess2 + loss + d logits (+ the bias column sums) as one kernel when a logits row fits one accumulator
+  const bool fused_xent = w.dlog16 && w.Zcat16 && Q == 256 && (S % 64) == 0 && fused_xent_enabled();
+  RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, fused_xent ? nullptr : w.logits, st,
+                 cfg->scalar_input ? audio : nullptr));      // model.py:645-648
   const int trunc = truncate_stage();
   if (trunc == 1) return 0;
   // fp16 input-gradient chain: gradients travel scaled by gscale = 2^ceil(log2 M), i.e. (softmax - onehot) * [1, 2)
   float gscale = 1.f;
   while (gscale < (float)M) gscale *= 2.f;
-  RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, w.dlog16 ? 0 : 1, w.dlog16, gscale / (float)M, st));      // (fp16 chain: nobody reads the fp32 gradient)
+  if (fused_xent)
+    RC(post2_xent(w.A2h, S, w.W2h, S, P(params, lo.post2_bias), w.ids, M, T, S, Q, 1.0f / (float)M, w.partials, loss_out, w.dlog16,
+                  gscale / (float)M, lo.post2_bias >= 0 ? grads + lo.post2_bias : nullptr, 1.f / gscale, st));
+  else
+    RC(softmax_xent(w.logits, w.ids, M, T, Q, 1.0f / (float)M, w.partials, 4096, loss_out, w.dlog16 ? 0 : 1, w.dlog16, gscale / (float)M, st));      // (fp16 chain: nobody reads the fp32 gradient)
   prof_mark(st, PT_XENT);
   if (trunc == 2) return 0;
 
@@ -877,7 +899,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     else
       RC(gemm(2, p, split_for(S, Q, M), s2));
     prof_mark(s2, PT_GEMM_POST2_WGRAD);
-    if (lo.post2_bias >= 0) {
+    if (lo.post2_bias >= 0 && !fused_xent) {
       if (w.dlog16) RC(colsum16(w.dlog16, Q, M, Q, 1.f / gscale, grads + lo.post2_bias, w.cs_scratch, s2));
       else RC(colsum(w.logits, Q, M, Q, grads + lo.post2_bias, s2));
       prof_mark(s2, PT_COLSUM);

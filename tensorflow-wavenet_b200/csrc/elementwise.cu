@@ -319,6 +319,12 @@ __global__ void xent_finalize_kernel(const float* __restrict__ partials, int n, 
   if (threadIdx.x == 0) loss_out[0] = (float)(red[0] * (double)scale);
 }
 
+int xent_finalize(const float* partials, int n, float scale, float* loss_out, cudaStream_t st) {
+  xent_finalize_kernel<<<1, 256, 0, st>>>(partials, n, scale, loss_out);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
 int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float scale, float* partials,
                  int n_partials, float* loss_out, int write_grad, void* g16v, float scale16, cudaStream_t st) {
   __half* g16 = (__half*)g16v;

@@ -138,6 +138,13 @@ int scalar_frontend_bwd(const float* x, const float* dx0, float* gw, int M, int 
 int softmax_xent(float* logits, const int32_t* ids, int M, int T, int Q, float scale, float* row_loss_partials,
                  int n_partials, float* loss_out, int write_grad, void* g16, float scale16, cudaStream_t st);
 
+int xent_finalize(const float* partials, int n, float scale, float* loss_out, cudaStream_t st);
+// postprocess2 GEMM + softmax cross entropy + fp16 gradient + bias-gradient column sums in one kernel (post_xent.cu);
+// -2: shape not supported (needs Q == 256, K % 64 == 0)
+int post2_xent(const void* A16, int lda, const void* W16, int ldw, const float* bias, const int32_t* ids, int M, int T, int K,
+               int Q, float loss_scale, float* partials, float* loss_out, void* g16, float scale16, float* bias_grad,
+               float colsum_scale, cudaStream_t st);
+
 // prebias[l][b][2D] = [filter_bias_l | gate_bias_l] + emb[b] . [gc_filter_l | gc_gate_l]
 int cond_bias_fwd(float* prebias, const float* filter_bias, const float* gate_bias, const float* gc_filter,
                   const float* gc_gate, const float* emb_table, const int32_t* gc_ids, int L, int B, int D,

@@ -404,6 +404,44 @@ def test_softmax_xent(lib, B, T, Q):
     assert rel_err(dl.cpu().numpy(), L64.grad.numpy()) < 1e-3      # gradient is stored tf32-rounded
 
 
+@pytest.mark.parametrize('B,T,K,with_bias', [(1, 1000, 512, True), (3, 77, 128, True), (2, 4099, 64, False), (1, 1, 512, True),
+                                             (1, 40000, 512, True)])
+def test_post2_xent_fused(lib, B, T, K, with_bias):
+    """postprocess2 GEMM + TF softmax cross entropy + fp16 gradient + bias column sums in one kernel (csrc/post_xent.cu)
+    against the oracle's xent on the logits of the same fp16-rounded operands: loss 1e-5, gradient 1e-3 (it is fp16),
+    bias gradient 1e-3.  model.py:438-440, 654-666."""
+    Q = 256
+    rng = np.random.default_rng(K + T)
+    M = B * T
+    a16 = torch.tensor(np.maximum(rng.standard_normal((M, K)), 0).astype(np.float32)).half()
+    w16 = torch.tensor((rng.standard_normal((Q, K)) * (2.0 / np.sqrt(K))).astype(np.float32)).half()
+    bias = (0.5 * rng.standard_normal(Q)).astype(np.float32) if with_bias else None
+    ids = rng.integers(0, Q, (B, T)).astype(np.int32)
+    logits = a16.double() @ w16.double().T + (torch.tensor(bias, dtype=torch.float64) if with_bias else 0.0)
+    L64 = logits.clone().requires_grad_(True)
+    oh = torch.nn.functional.one_hot(torch.tensor(ids, dtype=torch.int64), Q).to(torch.float64)
+    shifted = torch.nn.functional.pad(oh[:, 1:, :], (0, 0, 0, 1)).reshape(M, Q)
+    loss_ref = O._TFSoftmaxXent.apply(L64, shifted).mean()
+    loss_ref.backward()
+    grad_ref = L64.grad.numpy() * M                      # (softmax - onehot), unscaled
+    da, dw = a16.cuda().contiguous(), w16.cuda().contiguous()
+    partials = torch.zeros(4096, device='cuda')
+    out = torch.zeros((), device='cuda')
+    g16 = torch.zeros(M, Q, dtype=torch.float16, device='cuda')
+    bgrad = torch.full((Q,), 0.25, device='cuda')
+    gs = 1.5
+    dbias, dids = (dev(bias) if with_bias else None), dev(ids, torch.int32)      # (kept alive across the launch)
+    rc = lib.wn_post2_xent(p(da), K, p(dw), K, p(dbias) if with_bias else None, p(dids), B, T, K, Q,
+                           p(partials), p(out), p(g16), gs, p(bgrad), 1.0 / gs, stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert abs(float(out) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel_err(g16.float().cpu().numpy() / gs, grad_ref) < 1e-3
+    assert rel_err(bgrad.cpu().numpy() - 0.25, grad_ref.sum(0)) < 2e-3      # sums of the fp16-rounded gradient
+    assert lib.wn_post2_xent(p(da), K, p(dw), K, None, p(dids), B, T, K, 128, p(partials), p(out), p(g16), gs,
+                             None, 0.0, stream()) == -2
+
+
 # ----------------------------------------------------------------------------- optimizers
 @pytest.mark.parametrize('kind', ['adam', 'sgd', 'rmsprop'])
 def test_optimizers_bit_exact(kind):
