@@ -140,6 +140,13 @@ int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, f
                    int32_t ldc16, int32_t m, int32_t n, int32_t k, const float* bias, const float* relu_mask,
                    int32_t ldmask, float c_scale, int32_t flags, wn_stream_t stream);
 
+/* The same product where only the fp16 copy is wanted (c may be null) and the epilogue also ADDS colsum_scale * (column
+ * sums of c16 over all m rows) to colsum[n]: how the training step gets the bias gradient of the layer below out of the
+ * input-gradient GEMM that produces the matrix (autodiff of model.py:432-440).  No bias argument in this form. */
+int wn_gemm_f16_nt_colsum(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, void* c16,
+                          int32_t ldc16, int32_t m, int32_t n, int32_t k, float c_scale, float* colsum, float colsum_scale,
+                          wn_stream_t stream);
+
 /* Weight-gradient form on fp16 operands: c[m,n] += c_scale * sum_k a16[k,m] * b16[k,n]  (a16 [k][lda], b16 [k][ldb] as
  * they lie in memory: time is the row index; fp32 accumulation, split over k, red.global.add into c).
  * m, n multiples of 64, lda/ldb multiples of 8; returns -3 otherwise. */

@@ -755,6 +755,14 @@ int wn_gemm_f16_nt(const void* a16, int32_t lda, const void* b16, int32_t ldb, f
                      (cudaStream_t)stream);
 }
 
+int wn_gemm_f16_nt_colsum(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, void* c16,
+                          int32_t ldc16, int32_t m, int32_t n, int32_t k, float c_scale, float* colsum, float colsum_scale,
+                          wn_stream_t stream) {
+  if (!a16 || !b16 || !c16 || !colsum) return -1;
+  return gemm_f16_nt(a16, lda, b16, ldb, c, ldc, c16, ldc16, m, n, k, nullptr, nullptr, 0, c_scale, 0, (cudaStream_t)stream,
+                     nullptr, nullptr, 0, colsum, colsum_scale);
+}
+
 int wn_gemm_f16_tn(const void* a16, int32_t lda, const void* b16, int32_t ldb, float* c, int32_t ldc, int32_t m, int32_t n,
                    int32_t k, float c_scale, int32_t split_k, wn_stream_t stream) {
   return gemm_f16_tn(a16, lda, b16, ldb, c, ldc, m, n, k, c_scale, split_k, (cudaStream_t)stream);
@@ -864,6 +872,9 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
   RC(mulaw_encode(audio, M, mulaw_thresholds, Q, w.ids, st));            // model.py:639
   prof_mark(st, PT_MULAW);
   // postprocess2 + loss + d logits (+ the bias column sums) as one kernel when a logits row fits one accumulator
+  // bias gradients (column sums of G1 / G2) collected by the epilogue of the GEMM that produces the matrix (WN_FOLD_COLSUM=0: own launches)
+  static const bool fold_env = [] { const char* e = getenv("WN_FOLD_COLSUM"); return !(e && e[0] == '0'); }();
+  const bool fold_cs = w.dlog16 && fold_env;
   const bool fused_xent = w.dlog16 && w.Zcat16 && Q == 256 && (S % 64) == 0 && fused_xent_enabled();
   RC(run_forward(cfg, lo, params, w, w.ids, gc_ids, B, T, true, fused_xent ? nullptr : w.logits, st,
                  cfg->scalar_input ? audio : nullptr));      // model.py:645-648
@@ -906,7 +917,9 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     }
   }
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.dlog16, Q, w.W2g, Q, nullptr, 0, w.G1h, S, M, S, Q, nullptr, nullptr, 0, 1.f, 0, st, nullptr, w.maskA2, S / 32));      // (fp16 only: every consumer of G1 reads the scaled copy)
+    // (fp16 only: every consumer of G1 reads the scaled copy; its column sums = the postprocess1 bias gradient)
+    RC(gemm_f16_nt(w.dlog16, Q, w.W2g, Q, nullptr, 0, w.G1h, S, M, S, Q, nullptr, nullptr, 0, 1.f, 0, st, nullptr, w.maskA2, S / 32,
+                   fold_cs && lo.post1_bias >= 0 ? grads + lo.post1_bias : nullptr, 1.f / gscale));
     prof_mark(st, PT_GEMM_POST2_DGRAD);
   } else {  // d transformed2 -> d conv1 (relu mask from A2):  G1 = (dlogits . W2^T) * (A2 > 0)
     GemmParams p = gp(w.logits, Q, w.W2R, Q, w.G1, S, M, S, Q);
@@ -925,14 +938,16 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     else
       RC(gemm(2, p, split_for(S, S, M), s2));
     prof_mark(s2, PT_GEMM_POST1_WGRAD);
-    if (lo.post1_bias >= 0) {
+    if (lo.post1_bias >= 0 && !fold_cs) {
       if (w.dlog16) RC(colsum16(w.G1h, S, M, S, 1.f / gscale, grads + lo.post1_bias, w.cs_scratch, s2));
       else RC(colsum(w.G1, S, M, S, grads + lo.post1_bias, s2));
       prof_mark(s2, PT_COLSUM);
     }
   }
   if (w.dlog16) {
-    RC(gemm_f16_nt(w.G1h, S, w.W1g, S, nullptr, 0, w.G2h, S, M, S, S, nullptr, nullptr, 0, 1.f, 0, st, nullptr, w.maskA1, S / 32));
+    if (fold_cs && lo.skip_bias >= 0) RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), st));
+    RC(gemm_f16_nt(w.G1h, S, w.W1g, S, nullptr, 0, w.G2h, S, M, S, S, nullptr, nullptr, 0, 1.f, 0, st, nullptr, w.maskA1, S / 32,
+                   fold_cs && lo.skip_bias >= 0 ? w.gtmp : nullptr, 1.f / gscale));      // column sums of G2 = every skip bias gradient
     prof_mark(st, PT_GEMM_POST1_DGRAD);
   } else {  // d transformed1 -> d total (relu mask from A1) [+ residual_postproc path]
     GemmParams p = gp(w.G1, S, w.W1R, S, w.G2, S, M, S, S);
@@ -955,10 +970,12 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       RC(gemm(2, p, split_for(ldz, S, M), s2));
     prof_mark(s2, PT_GEMM_SKIP_WGRAD);
     if (lo.skip_bias >= 0) {
-      RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), s2));
-      if (w.dlog16) RC(colsum16(w.G2h, S, M, S, 1.f / gscale, w.gtmp, w.cs_scratch, s2));
-      else RC(colsum(w.G2, S, M, S, w.gtmp, s2));
-      prof_mark(s2, PT_COLSUM);
+      if (!fold_cs) {
+        RC((int)cudaMemsetAsync(w.gtmp, 0, S * sizeof(float), s2));
+        if (w.dlog16) RC(colsum16(w.G2h, S, M, S, 1.f / gscale, w.gtmp, w.cs_scratch, s2));
+        else RC(colsum(w.G2, S, M, S, w.gtmp, s2));
+        prof_mark(s2, PT_COLSUM);
+      }
       RC(bcast_rows(w.gtmp, S, grads + lo.skip_bias, L, s2));
       prof_mark(s2, PT_MISC);
     }

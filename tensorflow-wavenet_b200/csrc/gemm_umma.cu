@@ -132,6 +132,8 @@ struct UmmaParams {
   int ewarps;                     // epilogue warps: 4 (a warp takes all BN columns of its 32 rows) or 8 (two warps per row quadrant, BN/2 columns each)
   int nbuf;                       // depth of the per-warp output staging rings (2..4 TMA stores in flight per warp)
   float c_scale;                  // C = c_scale * (accumulator, bias, relu, mask); the fp16 copy stays unscaled (0: no scaling)
+  float* colsum;                  // [N] += colsum_scale * column sums of the fp16 copy (needs has_c16 and no bias: the sums
+  float colsum_scale;             // collect in the bias row of shared memory); the bias gradient of the layer below
 };
 
 template <int BN>
@@ -280,9 +282,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     unsigned char* my_c16 = c16_stage + ew * p.nbuf * (STG_BYTES / 2);
     const bool staged = !(p.flags & GEMM_ATOMIC) && (p.C != nullptr || p.has_c16);
     uint32_t local = 0, out_cnt = 0, aux_cnt = 0;
+    int cs_n0 = -1;      // column range whose sums bias_s currently holds
+    auto colsum_flush = [&](int next_n0) {      // all epilogue warps: add the collected sums to global memory, start over
+      asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
+      for (int i = etid; i < BN; i += ethreads) {
+        if (cs_n0 >= 0 && cs_n0 + i < p.N) atomicAdd(p.colsum + cs_n0 + i, bias_s[i] * p.colsum_scale);
+        bias_s[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
+      cs_n0 = next_n0;
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
       int m0, n0, k_begin, nk;
       decode(item, m0, n0, k_begin, nk);
+      if (p.colsum && n0 != cs_n0) colsum_flush(n0);      // (warp-uniform, CTA-uniform)
       const uint32_t acc = p.m2 ? 0u : (local & 1), aph = p.m2 ? (local & 1) : ((local >> 1) & 1);
       const int row0 = m0 + quad * 32;
       const int row = row0 + lane;
@@ -449,6 +462,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                            ::"l"(&mapC16), "r"(smem_u32(my_c16 + buf * (STG_BYTES / 2))), "r"(nb), "r"(row0) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (p.colsum) {      // lane j: column j of the fp16 block over its 32 rows (rows past M and columns past N hold zeros)
+            const unsigned char* hb = my_c16 + buf * (STG_BYTES / 2);
+            float sacc = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              sacc += __half2float(*reinterpret_cast<const __half*>(hb + rr * 64 + ((uint32_t)((lane >> 3) ^ ((rr >> 1) & 3)) << 4) + (lane & 7) * 2));
+            atomicAdd(&bias_s[c0 + lane], sacc);
+          }
           ++out_cnt;
         }
         if (p.CT && row_ok) {   // transposed copy: for a fixed column the 32 lanes write 32 consecutive floats
@@ -463,6 +484,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
+    if (p.colsum) colsum_flush(-1);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -533,6 +555,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
     if (rc) return rc;
   }
   UmmaParams p;
+  p.colsum = nullptr; p.colsum_scale = 0.f;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
   p.m2 = 0;
@@ -561,8 +584,9 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
 // travel as fp16 in a domain scaled by a power of two (c_scale undoes it for the fp32 copies).
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
                 int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st,
-                uint32_t* mask_out, const uint32_t* mask_in, int ldmw) {
+                uint32_t* mask_out, const uint32_t* mask_in, int ldmw, float* colsum, float colsum_scale) {
   if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || (!C && !C16)) return -1;
+  if (colsum && (!C16 || bias)) return -1;
   if ((lda & 7) || (ldb & 7) || (C && (ldc & 3)) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
       ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & 3) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
     return -3;
@@ -588,12 +612,14 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
     if (rc) return rc;
   }
   UmmaParams p;
+  p.colsum = nullptr; p.colsum_scale = 0.f;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
   p.aux = aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
   p.m2 = 0;
   p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
   p.mask_out = mask_out; p.mask_in = mask_in; p.ldmw = ldmw;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
+  p.colsum = colsum; p.colsum_scale = colsum_scale;
   p.k_per_split = (K + 63) / 64 * 64;
   p.splits = 1;
   p.stages = 3;
@@ -648,6 +674,7 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
   if (rc) return rc;
   UmmaParams p;
+  p.colsum = nullptr; p.colsum_scale = 0.f;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
   p.nbuf = 2; p.ewarps = 8; p.m2 = m2;

@@ -40,7 +40,8 @@ bool gemm_umma_supported(int mode, const GemmParams& p);
 // forward chain in fp16 (operands K-major fp16, fp32 accumulate / output, optional fp16 copy of the output)
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
                 int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st,
-                uint32_t* mask_out = nullptr, const uint32_t* mask_in = nullptr, int ldmw = 0);
+                uint32_t* mask_out = nullptr, const uint32_t* mask_in = nullptr, int ldmw = 0, float* colsum = nullptr,
+                float colsum_scale = 0.f);      // colsum[N] += colsum_scale * column sums of C16 (no bias allowed then)
 // C[M,N] += c_scale * A16[K,M]^T . B16[K,N]: fp16 operands as they lie in memory (M, N multiples of 64), split-K atomics
 bool gemm_f16_tn_supported(int lda, int ldb, int M, int N);
 int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, int M, int N, int K, float c_scale,

@@ -66,6 +66,7 @@ SIGNATURES = {
                                  _I32, _P]),
     'wn_gemm_f16_tn': (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, C.c_float, _I32, _P]),
     'wn_softmax_xent': (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _P, _I32, _P]),
+    'wn_gemm_f16_nt_colsum': (C.c_int, [_P, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _F, _P, _F, _P]),
     'wn_post2_xent': (C.c_int, [_P, _I32, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _F, _P, _F, _P]),
     'wn_train_workspace_bytes': (_I64, [_CFG, _I32, _I32]),
     'wn_loss_grad': (C.c_int, [_CFG, _P, _P, _P, _I64, _P, _P, _P, _I32, _I32, _P, _P]),

@@ -338,6 +338,14 @@ def test_gemm_f16_nt(lib, M, N, K):
     ref = (a.astype(np.float64) @ b.astype(np.float64).T) * (mask > 0)
     assert rel_err(c.cpu().numpy(), 0.25 * ref) < LOGIT_RTOL
     assert rel_err(c16.cpu().numpy().astype(np.float64), ref) < 1e-3
+    # input-gradient form of the training step: fp16 copy only, bias gradient (column sums) collected by the epilogue
+    cs = torch.full((N,), 3.0, device='cuda')
+    c16.fill_(-7.0)
+    assert lib.wn_gemm_f16_nt_colsum(p(da), K, p(db), K, None, 0, p(c16), N, M, N, K, 1.0, p(cs), 0.5, stream()) == 0
+    torch.cuda.synchronize()
+    got16 = c16.cpu().numpy().astype(np.float64)
+    assert rel_err(got16, a.astype(np.float64) @ b.astype(np.float64).T) < 1e-3
+    np.testing.assert_allclose(cs.cpu().numpy() - 3.0, 0.5 * got16.sum(0), rtol=2e-4, atol=2e-4 * np.abs(got16).sum(0).max())
 
 
 @pytest.mark.parametrize('M,N,K,split', [(128, 256, 64, 1), (512, 256, 5000, 6), (1600, 512, 3333, 3), (64, 64, 200, 2),
