@@ -183,6 +183,10 @@ static bool fused_xent_enabled() {      // WN_FUSED_XENT=0: postprocess2 GEMM, c
   static const bool on = [] { const char* e = getenv("WN_FUSED_XENT"); return !(e && e[0] == '0'); }();
   return on;
 }
+static bool bwd_fused_enabled() {      // WN_BWD_FUSED=0: weight gradients of the residual blocks as their own launch
+  static const bool on = [] { const char* e = getenv("WN_BWD_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static bool bwd_chain_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -573,8 +577,13 @@ static int block_bwd_production(const float* x, const float* dx_out, const float
   RC(to_half(zc, z16, M * 32, st));
   RC(split_rows(x, xs, M, st));
   if (!is_last) RC(split_rows(dx_out, (char*)dxs + M * 128, M, st));
-  RC(block_bwd_chain(xs, dxs, p16, dz16, 32, 1.f, img_f, img_b, prebias, &d, 1, B, T, flags, st, /*last_dense=*/!is_last));
-  RC(block_wgrad_h_all(xs, dxs, p16, z16, 32, 1.f, gwf, gwg, gdense, gprebias, gdense_bias, &d, 1, B, T, st, /*last_dense=*/!is_last));
+  if (bwd_fused_enabled()) {
+    RC(block_bwd_chain_fused(xs, dxs, p16, dz16, 32, 1.f, img_f, img_b, prebias, &d, 1, B, T, flags, 1.f, gwf, gwg, gdense, gprebias,
+                             gdense_bias, st, /*last_dense=*/!is_last));
+  } else {
+    RC(block_bwd_chain(xs, dxs, p16, dz16, 32, 1.f, img_f, img_b, prebias, &d, 1, B, T, flags, st, /*last_dense=*/!is_last));
+    RC(block_wgrad_h_all(xs, dxs, p16, z16, 32, 1.f, gwf, gwg, gdense, gprebias, gdense_bias, &d, 1, B, T, st, /*last_dense=*/!is_last));
+  }
   RC(unsplit_rows(dxs, dx, M, 1.f, st));
   return 0;
 }
@@ -1000,11 +1009,18 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     // One persistent, flag-ordered kernel for the pre-activation and input gradients of every layer, then the weight
     // gradients of every layer in one launch; both on fp16 tiles in the domain scaled by gscale * cs (block_bwd_h.cu).
     const float cs = 16.f;
-    RC(block_bwd_chain(w.XS, w.DXS, w.P16, w.dZcat16, ldz, cs, w.WimgH, w.WimgB, w.prebias, cfg->dilations, L, B, T, w.bflags, st));
-    if (trunc == 4) { RC((int)cudaStreamWaitEvent(st, ev_g[3], 0)); return 0; }
-    RC(block_wgrad_h_all(w.XS, w.DXS, w.P16, w.Zcat16, ldz, 1.f / (gscale * cs), grads + lo.filter, grads + lo.gate,
-                         grads + lo.dense, w.gprebias, lo.dense_bias >= 0 ? grads + lo.dense_bias : nullptr, cfg->dilations,
-                         L, B, T, st));
+    if (bwd_fused_enabled()) {      // ... or both in ONE launch: the weight gradients from the tiles the chain has in shared memory
+      RC(block_bwd_chain_fused(w.XS, w.DXS, w.P16, w.dZcat16, ldz, cs, w.WimgH, w.WimgB, w.prebias, cfg->dilations, L, B, T, w.bflags,
+                               1.f / (gscale * cs), grads + lo.filter, grads + lo.gate, grads + lo.dense, w.gprebias,
+                               lo.dense_bias >= 0 ? grads + lo.dense_bias : nullptr, st));
+      if (trunc == 4) { RC((int)cudaStreamWaitEvent(st, ev_g[3], 0)); return 0; }
+    } else {
+      RC(block_bwd_chain(w.XS, w.DXS, w.P16, w.dZcat16, ldz, cs, w.WimgH, w.WimgB, w.prebias, cfg->dilations, L, B, T, w.bflags, st));
+      if (trunc == 4) { RC((int)cudaStreamWaitEvent(st, ev_g[3], 0)); return 0; }
+      RC(block_wgrad_h_all(w.XS, w.DXS, w.P16, w.Zcat16, ldz, 1.f / (gscale * cs), grads + lo.filter, grads + lo.gate,
+                           grads + lo.dense, w.gprebias, lo.dense_bias >= 0 ? grads + lo.dense_bias : nullptr, cfg->dilations,
+                           L, B, T, st));
+    }
     RC(unsplit_rows(w.DXS, w.dX, M, 1.f / (gscale * cs), st));
     prof_mark(st, PT_MISC);
     dcur = w.dX;

@@ -199,6 +199,7 @@ struct BwdChainArgs {
   unsigned int* flags;             // [L][n_tiles] dpre published | [L][n_tiles] dx published | work counter; zeroed before the launch
   int L, B, T, n_tt;
   int last_dense;                  // the last layer has an output gradient too (stand-alone wn_block_bwd)
+  int late;                        // (experiment) reload Xh / Ob / Dz only after the PRE epilogue of the previous item
   float cs;                        // the skip-path gradient is multiplied by cs on its way into the chain's scaled domain
   long long* timeline;             // debug: cycles CTA 0's warps spent in each kind of wait
   int dil[WN_MAX_LAYERS];
@@ -369,19 +370,29 @@ block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_c
       };
       // operand tiles of an item: dpre[t], dpre[t+d] for the DX products; hi(x[t]), hi(x[t-d]) for the recompute.
       // (arrive / expect_tx = release: publishes item_s to the waiters of these phases)
-      auto load_ops = [&](int ld, int lp, int b, int tt) {
+      auto load_ops_a = [&](int ld, int lp, int b, int tt) {
         const int t0 = tt * TM;
         if (lane == 0) {
           if (ld >= 0) mbar_expect_tx(&bar_xa, 2 * TILE);
           else mbar_arrive(&bar_xa);
-          if (lp >= 0) mbar_expect_tx(&bar_xb, 2 * XH_TILE);
-          else mbar_arrive(&bar_xb);
         }
         __syncwarp();
         if (ld >= 0 && lane < 2)      // (rows at or past the window end arrive as zeros)
           tma_load_3d(lane == 0 ? X0 : X1, &mapP, &bar_xa, 0, lane == 0 ? t0 : t0 + a.dil[ld], ld * a.B + b);
+      };
+      auto load_ops_b = [&](int ld, int lp, int b, int tt) {
+        const int t0 = tt * TM;
+        if (lane == 0) {
+          if (lp >= 0) mbar_expect_tx(&bar_xb, 2 * XH_TILE);
+          else mbar_arrive(&bar_xb);
+        }
+        __syncwarp();
         if (lp >= 0 && (lane == 2 || lane == 3))      // (rows before the window start arrive as zeros)
           tma_load_3d(lane == 2 ? Xh0 : Xh1, &mapXH, &bar_xb, 0, lane == 2 ? t0 : t0 - a.dil[lp], lp * a.B + b);
+      };
+      auto load_ops = [&](int ld, int lp, int b, int tt) {
+        load_ops_a(ld, lp, b, tt);
+        load_ops_b(ld, lp, b, tt);
       };
       // the tiles the epilogue threads read: dx' (the input gradient of the layer above) into Ob, the skip-path gradient into Dz
       auto load_dn = [&](int ld, int lp, int b, int tt) {
@@ -438,7 +449,8 @@ block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_c
         __syncwarp();
         if (nx >= 0 && nx / n_tiles == wq) {      // (a new phase's weights: below, once every MMA of item i has completed)
           flags_wait();
-          load_ops(nld, nlp, nb, ntt);
+          load_ops_a(nld, nlp, nb, ntt);
+          if (!a.late) load_ops_b(nld, nlp, nb, ntt);
         }
         t_a = clock64();
         lwait(&bar_m2[par], ph, __LINE__);      // dx.Wd^T has read Ob (and every MMA of item i its weights)
@@ -454,7 +466,12 @@ block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_c
           load_weights(nld, nlp);
           wq = nx / n_tiles;
           flags_wait();
-          load_ops(nld, nlp, nb, ntt);
+          load_ops_a(nld, nlp, nb, ntt);
+          if (!a.late) load_ops_b(nld, nlp, nb, ntt);
+        }
+        if (a.late) {
+          lwait(&bar_o2[par], ph, __LINE__);
+          load_ops_b(nld, nlp, nb, ntt);
         }
         if (ld >= 0) {                // the dx store of item i has left Ob
           t_a = clock64();
@@ -754,6 +771,7 @@ int block_bwd_chain(const void* xs, void* dxs, void* p16, const void* dz16, int 
   a.img_f = img_f; a.img_b = img_b; a.prebias = prebias; a.flags = flags;
   a.L = L; a.B = B; a.T = T; a.n_tt = (T + TM - 1) / TM;
   a.last_dense = last_dense ? 1 : 0; a.cs = cs;
+  { static const int late = [] { const char* e = getenv("WN_BWD_LATE"); return (e && e[0] == '1') ? 1 : 0; }(); a.late = late; }
   a.timeline = g_timeline_b;
   for (int l = 0; l < WN_MAX_LAYERS; ++l) a.dil[l] = l < L ? dilations[l] : 0;
   const size_t smem = 1024 + 4 * TILE + 2 * XH_TILE + TM * 64 + IMG_B;
@@ -1237,6 +1255,8 @@ static int block_wgrad_h32_all(const void* xs, const void* dxs, const void* p16,
   prof_mark(st, PT_BLOCK_WGRAD);
   return 0;
 }
+
+#include "block_bwd_fused.inc"
 
 int block_bwd_h_set_trap_info(unsigned int* p) { return umma::set_trap_info_tu(p); }
 

@@ -111,6 +111,11 @@ int block_bwd_chain(const void* xs, void* dxs, void* p16, const void* dz16, int 
                     const unsigned char* img_b, const float* prebias, const int* dilations, int L, int B, int T,
                     unsigned int* flags, cudaStream_t st, int last_dense = 0);
 // weight gradients of all layers from the fp16 tiles (x split rows, fp16 Zcat, dpre, dx split rows); scale: out of the scaled domain
+// block_bwd_chain + block_wgrad_h_all as ONE launch (z is recomputed, nothing is re-read from HBM for the weight gradients)
+int block_bwd_chain_fused(const void* xs, void* dxs, void* p16, const void* dz16, int ldz, float cs, const unsigned char* img_f,
+                          const unsigned char* img_b, const float* prebias, const int* dilations, int L, int B, int T,
+                          unsigned int* flags, float wscale, float* gwf, float* gwg, float* gdense, float* gprebias,
+                          float* gdense_bias, cudaStream_t st, int last_dense = 0);
 int block_wgrad_h_all(const void* xs, const void* dxs, const void* p16, const void* zcat16, int ldz, float scale, float* gwf,
                       float* gwg, float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B,
                       int T, cudaStream_t st, int last_dense = 0);
