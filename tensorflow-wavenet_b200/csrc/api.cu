@@ -140,6 +140,7 @@ struct Workspace {
   void *DXS, *P16;                // [L][M][hi 32 | lo 32] input gradients, [L][M][df 32 | dg 32] pre-activation gradients (fp16, scaled)
   unsigned char* WimgB;           // per-layer weight images of the backward chain
   unsigned int* bflags;           // tile flags + work counter of the backward chain
+  void* bpart;                    // per-CTA weight-gradient partial sums of the fused backward chain
   float* Pall;     // generic-width blocks: saved pre-activations [L or 1][M][2D]
   float* gscratch; // generic-width blocks: operand splits / temporaries (generic_scratch_floats)
   int64_t bytes;
@@ -243,10 +244,12 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->P16 = take(L * M * 128);
     w->WimgB = (unsigned char*)take(block_bwd_h_images_bytes((int)L));
     w->bflags = (unsigned int*)take(block_bwd_chain_flag_words((int)L, B, T) * 4);
+    w->bpart = bwd_fused_enabled() ? take(block_bwd_fused_scratch_bytes((int)L, B, T)) : nullptr;
   } else {
     w->DXS = w->P16 = nullptr;
     w->WimgB = nullptr;
     w->bflags = nullptr;
+    w->bpart = nullptr;
   }
   if (f16_chain) {
     w->Zcat16 = take(M * L * D * 2);
@@ -555,7 +558,8 @@ static int block_bwd_production(const float* x, const float* dx_out, const float
   const int64_t M = (int64_t)B * T;
   const int64_t fw = block_bwd_chain_flag_words(1, B, T);
   StreamScratch sc;
-  RC(sc.init(block_h_images_bytes(1) + block_bwd_h_images_bytes(1) + 2 * M * 32 * 4 + 2 * M * 32 * 2 + 4 * M * 128 + fw * 4 +
+  const int64_t pb = bwd_fused_enabled() ? block_bwd_fused_scratch_bytes(1, B, T) : 0;
+  RC(sc.init(block_h_images_bytes(1) + block_bwd_h_images_bytes(1) + 2 * M * 32 * 4 + 2 * M * 32 * 2 + 4 * M * 128 + fw * 4 + pb +
              16 * 1024, st));
   unsigned char* img_f = (unsigned char*)sc.take(block_h_images_bytes(1));
   unsigned char* img_b = (unsigned char*)sc.take(block_bwd_h_images_bytes(1));
@@ -567,7 +571,8 @@ static int block_bwd_production(const float* x, const float* dx_out, const float
   void* dxs = sc.take(2 * M * 128);               // [dx of this layer | dx' = gradient wrt its output] as split rows
   void* p16 = sc.take(M * 128);
   unsigned int* flags = (unsigned int*)sc.take(fw * 4);
-  if (!flags) return -5;
+  void* part = pb ? sc.take(pb) : nullptr;
+  if (!flags || (pb && !part)) return -5;
   const float* dn = dense ? dense : filter;       // (the last layer's dense images are never read)
   RC(block_h_images(img_f, filter, gate, dn, 1, st));
   RC(block_bwd_h_images(img_b, filter, gate, dn, 1, st));
@@ -579,7 +584,7 @@ static int block_bwd_production(const float* x, const float* dx_out, const float
   if (!is_last) RC(split_rows(dx_out, (char*)dxs + M * 128, M, st));
   if (bwd_fused_enabled()) {
     RC(block_bwd_chain_fused(xs, dxs, p16, dz16, 32, 1.f, img_f, img_b, prebias, &d, 1, B, T, flags, 1.f, gwf, gwg, gdense, gprebias,
-                             gdense_bias, st, /*last_dense=*/!is_last));
+                             gdense_bias, part, st, /*last_dense=*/!is_last));
   } else {
     RC(block_bwd_chain(xs, dxs, p16, dz16, 32, 1.f, img_f, img_b, prebias, &d, 1, B, T, flags, st, /*last_dense=*/!is_last));
     RC(block_wgrad_h_all(xs, dxs, p16, z16, 32, 1.f, gwf, gwg, gdense, gprebias, gdense_bias, &d, 1, B, T, st, /*last_dense=*/!is_last));
@@ -1012,7 +1017,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     if (bwd_fused_enabled()) {      // ... or both in ONE launch: the weight gradients from the tiles the chain has in shared memory
       RC(block_bwd_chain_fused(w.XS, w.DXS, w.P16, w.dZcat16, ldz, cs, w.WimgH, w.WimgB, w.prebias, cfg->dilations, L, B, T, w.bflags,
                                1.f / (gscale * cs), grads + lo.filter, grads + lo.gate, grads + lo.dense, w.gprebias,
-                               lo.dense_bias >= 0 ? grads + lo.dense_bias : nullptr, st));
+                               lo.dense_bias >= 0 ? grads + lo.dense_bias : nullptr, w.bpart, st));
       if (trunc == 4) { RC((int)cudaStreamWaitEvent(st, ev_g[3], 0)); return 0; }
     } else {
       RC(block_bwd_chain(w.XS, w.DXS, w.P16, w.dZcat16, ldz, cs, w.WimgH, w.WimgB, w.prebias, cfg->dilations, L, B, T, w.bflags, st));

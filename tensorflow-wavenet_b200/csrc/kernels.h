@@ -115,7 +115,8 @@ int block_bwd_chain(const void* xs, void* dxs, void* p16, const void* dz16, int 
 int block_bwd_chain_fused(const void* xs, void* dxs, void* p16, const void* dz16, int ldz, float cs, const unsigned char* img_f,
                           const unsigned char* img_b, const float* prebias, const int* dilations, int L, int B, int T,
                           unsigned int* flags, float wscale, float* gwf, float* gwg, float* gdense, float* gprebias,
-                          float* gdense_bias, cudaStream_t st, int last_dense = 0);
+                          float* gdense_bias, void* scratch, cudaStream_t st, int last_dense = 0);
+int64_t block_bwd_fused_scratch_bytes(int L, int B, int T);      // bytes of `scratch`
 int block_wgrad_h_all(const void* xs, const void* dxs, const void* p16, const void* zcat16, int ldz, float scale, float* gwf,
                       float* gwg, float* gdense, float* gprebias, float* gdense_bias, const int* dilations, int L, int B,
                       int T, cudaStream_t st, int last_dense = 0);
