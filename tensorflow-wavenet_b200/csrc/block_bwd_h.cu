@@ -216,24 +216,13 @@ __device__ __forceinline__ void mbar_wait_n(uint64_t* b, uint32_t parity, uint32
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
     if (ok) return;
   }
-  if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
-    g_trap_info[0] = smem_u32(b); g_trap_info[1] = parity; g_trap_info[2] = blockDim.x; g_trap_info[3] = tag;
-    g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x; g_trap_info[6] = gridDim.y;
-    __threadfence_system();
-  }
-  __trap();
+  wait_timed_out(smem_u32(b), parity, tag, gridDim.y);
 }
 __device__ __forceinline__ void spin_until(volatile int* cnt, int need, uint32_t tag) {
   uint32_t spin = 0;
+#pragma unroll 1
   while (*cnt < need) {
-    if (++spin > (1u << 22)) {
-      if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
-        g_trap_info[0] = 0x5F4Eu; g_trap_info[1] = (unsigned int)need; g_trap_info[2] = blockDim.x; g_trap_info[3] = tag;
-        g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x; g_trap_info[6] = (unsigned int)*cnt;
-        __threadfence_system();
-      }
-      __trap();
-    }
+    if (++spin > (1u << 22)) wait_timed_out(0x5F4Eu, (unsigned int)need, tag, (unsigned int)*cnt);
   }
 }
 #define IWAIT(bar, par) mbar_wait_n(bar, par, 20, __LINE__)

@@ -85,6 +85,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 }
 // Bounded wait: a protocol bug must fail loudly (trap -> launch error), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 24); ++i) {
     uint32_t ok;
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"

@@ -109,16 +109,12 @@ __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void wait_flag(const unsigned int* p) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 22); ++i) {
     if (ld_acquire(p)) return;
     __nanosleep(32);
   }
-  if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
-    g_trap_info[0] = 0xF1A6u; g_trap_info[1] = (unsigned int)(uintptr_t)p; g_trap_info[2] = blockDim.x;
-    g_trap_info[3] = gridDim.x; g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x;
-    __threadfence_system();
-  }
-  __trap();
+  wait_timed_out(0xF1A6u, (unsigned int)(uintptr_t)p, gridDim.x, 0u);
 }
 // three flags at once (the loads overlap): all set?
 __device__ __forceinline__ bool flags_set(const unsigned int* f0, const unsigned int* f1, const unsigned int* f2) {

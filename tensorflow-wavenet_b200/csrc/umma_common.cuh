@@ -136,19 +136,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
 // of the first wait that times out (wn_debug_trap_info)
 static __device__ unsigned int* g_trap_info = nullptr;      // one copy per translation unit (no -rdc)
 static inline int set_trap_info_tu(unsigned int* p) { return (int)cudaMemcpyToSymbol(g_trap_info, &p, sizeof(p)); }
+// the diagnostics of a timed-out wait live out of line: inlined into every wait they were a third of the persistent
+// kernels' code (those kernels are sensitive to instruction fetch: four warp roles per CTA run four different loops)
+static __device__ __noinline__ void wait_timed_out(uint32_t w0, uint32_t w1, uint32_t w3, uint32_t w6) {
+  if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
+    g_trap_info[0] = w0; g_trap_info[1] = w1; g_trap_info[2] = blockDim.x; g_trap_info[3] = w3;
+    g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x; g_trap_info[6] = w6;
+    __threadfence_system();
+  }
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 24); ++i) {
     uint32_t ok;
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
     if (ok) return;
   }
-  if (g_trap_info && atomicCAS(g_trap_info + 7, 0u, 1u) == 0u) {
-    g_trap_info[0] = smem_u32(b); g_trap_info[1] = parity; g_trap_info[2] = blockDim.x; g_trap_info[3] = gridDim.x;
-    g_trap_info[4] = blockIdx.x; g_trap_info[5] = threadIdx.x; g_trap_info[6] = gridDim.y;
-    __threadfence_system();
-  }
-  __trap();
+  wait_timed_out(smem_u32(b), parity, gridDim.x, gridDim.y);
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

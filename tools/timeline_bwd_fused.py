@@ -20,3 +20,5 @@ print('grid %d, CTA 0: %d items, %d cycles (%.0f per item)' % (t[10], n, t[0], t
 print('  waits per item: tiles landed (idle) %.0f, DX MMAs %.0f, PRE MMAs %.0f' % (t[12] / n, t[13] / n, t[15] / n))
 print('  flushes %d: %.0f cycles each; PRE part after a flush %.0f, otherwise %.0f cycles' %
       (t[25], t[24] / max(1, t[25]), t[26] / max(1, t[25]), t[27] / max(1, t[28])))
+print('  loader waits per item: flags not set %.0f (%d items), epilogue inside PRE %.0f, DX+PRE MMAs read their tiles %.0f, dz MMA %.0f, weight-gradient MMAs %.0f, dx store left Ob %.0f'
+      % (t[3] / n, t[21], t[5] / n, t[6] / n, t[8] / n, t[7] / n, t[4] / n))
