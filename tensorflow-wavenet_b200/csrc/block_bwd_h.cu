@@ -212,8 +212,13 @@ void set_bwd_h_timeline(long long* p) { g_timeline_b = p; }
 __device__ __forceinline__ void mbar_wait_n(uint64_t* b, uint32_t parity, uint32_t log2n, uint32_t tag) {
   for (uint32_t i = 0; i < (1u << log2n); ++i) {
     uint32_t ok;
+#ifdef WN_BWD_WAIT_HINT
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)WN_BWD_WAIT_HINT) : "memory");
+#else
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+#endif
     if (ok) return;
   }
   wait_timed_out(smem_u32(b), parity, tag, gridDim.y);
@@ -225,9 +230,20 @@ __device__ __forceinline__ void spin_until(volatile int* cnt, int need, uint32_t
     if (++spin > (1u << 22)) wait_timed_out(0x5F4Eu, (unsigned int)need, tag, (unsigned int)*cnt);
   }
 }
-#define IWAIT(bar, par) mbar_wait_n(bar, par, 20, __LINE__)
+// single-lane roles (loader, MMA issuer, publisher): poll without suspending first -- their wake-up latency is on the
+// critical path of every item, and one polling lane costs next to nothing (WN_BWD_SPIN polls before the suspending waits)
+#ifndef WN_BWD_SPIN
+#define WN_BWD_SPIN 0
+#endif
+__device__ __forceinline__ void mbar_spin_n(uint64_t* b, uint32_t parity, uint32_t log2n, uint32_t tag) {
+#pragma unroll 1
+  for (int i = 0; i < WN_BWD_SPIN; ++i)
+    if (mbar_test(b, parity)) return;
+  mbar_wait_n(b, parity, log2n, tag);
+}
+#define IWAIT(bar, par) mbar_spin_n(bar, par, 20, __LINE__)
 #define EWAIT(bar, par) mbar_wait_n(bar, par, 22, __LINE__)
-#define PWAIT(bar, par) mbar_wait_n(bar, par, 24, __LINE__)
+#define PWAIT(bar, par) mbar_spin_n(bar, par, 24, __LINE__)
 
 __global__ void __launch_bounds__(BC_THREADS, 2)
 block_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapXH, const __grid_constant__ CUtensorMap mapDX,
