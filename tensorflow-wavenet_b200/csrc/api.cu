@@ -141,6 +141,10 @@ struct Workspace {
   unsigned char* WimgB;           // per-layer weight images of the backward chain
   unsigned int* bflags;           // tile flags + work counter of the backward chain
   void* bpart;                    // per-CTA weight-gradient partial sums of the fused backward chain
+  int wide16;      // 1: wide residual blocks in 16-bit storage (block_wide16.cu: R, D multiples of 64)
+  void *X16, *P16w, *Wimg16;      // [L or 2][M][R] layer inputs, [L or 1][M][2D] pre-activations (fp16), per-layer weight images
+  void *dz16w, *dpre16w, *dx16w;  // backward temporaries: [M][D], [M][2D], 2 x [M][R] (fp16, scaled domain)
+  float *wtmp16, *cs_scratch2;    // [L][2][R][2D] filter | gate gradients before unpacking; column-sum partials
   float* Pall;     // generic-width blocks: saved pre-activations [L or 1][M][2D]
   float* gscratch; // generic-width blocks: operand splits / temporaries (generic_scratch_floats)
   int64_t bytes;
@@ -188,6 +192,10 @@ static bool bwd_fused_enabled() {      // WN_BWD_FUSED=0: weight gradients of th
   static const bool on = [] { const char* e = getenv("WN_BWD_FUSED"); return !(e && e[0] == '0'); }();
   return on;
 }
+static bool wide16_enabled() {      // WN_WIDE16=0: wide blocks through the fp32 / TF32 GEMM-built path (block_generic.cu)
+  static const bool on = [] { const char* e = getenv("WN_WIDE16"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static bool bwd_chain_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -209,15 +217,18 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   const bool umma_blocks = fused_blocks(c) && (R == 32) && block_umma_enabled();
   const bool fwd_h = umma_blocks && fwd_h_enabled();
   const bool chain = fwd_h && fwd_chain_enabled();
-  const bool f16_chain = fwd_h && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0;
+  const bool wide16 = !fused_blocks(c) && wide16_supported((int)R, (int)D) && wide16_enabled() && fwd16_enabled() &&
+                      !c->residual_postproc && (S % 8) == 0 && (!training || ((Q % 64) == 0 && (S % 64) == 0));
+  w->wide16 = wide16 ? 1 : 0;
+  const bool f16_chain = (fwd_h || wide16) && fwd16_enabled() && !c->residual_postproc && ((L * D) % 8) == 0 && (S % 8) == 0;
   // fp16 gradient chain of the post-processing layers: all-or-nothing (its GEMMs keep no fp32 copies of G1 / G2), so
   // every weight-gradient shape must suit the fp16 MN-major form (multiples of 64); otherwise the tf32 chain runs
   const bool g16 = training && f16_chain && (Q % 64) == 0 && (S % 64) == 0 && ((L * D) % 64) == 0;
   const bool bwd16 = g16 && chain && bwd_chain_enabled();
   w->bwd16 = bwd16 ? 1 : 0;
   w->ids = (int32_t*)take(M * 4 + 16);
-  w->X = (float*)take((training && !bwd16 ? L : 2) * M * R * f);
-  w->Zcat = (float*)take(bwd16 ? 256 : M * L * D * f);      // (fp16 backward chain: every consumer of z reads Zcat16)
+  w->X = (float*)take((training && !bwd16 && !wide16 ? L : 2) * M * R * f);
+  w->Zcat = (float*)take((bwd16 || wide16) ? 256 : M * L * D * f);      // (fp16 backward chain: every consumer of z reads Zcat16)
   w->A1 = (float*)take(M * S * f);
   w->A2 = (float*)take(M * S * f);
   w->S0 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
@@ -228,7 +239,21 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
   w->WskipR = (float*)take(S * L * D * f);
   w->W1R = (float*)take(S * S * f);
   w->W2R = (float*)take(Q * S * f);
-  if (!fused_blocks(c)) {
+  w->X16 = w->P16w = w->Wimg16 = w->dz16w = w->dpre16w = w->dx16w = nullptr;
+  w->wtmp16 = w->cs_scratch2 = nullptr;
+  if (wide16) {
+    w->X16 = take((training ? L : 2) * M * R * 2);
+    w->P16w = take((training ? L : 1) * M * 2 * D * 2);
+    w->Wimg16 = take(wide16_images_bytes((int)L, (int)R, (int)D));
+    if (training) {
+      w->dz16w = take(M * D * 2);
+      w->dpre16w = take(M * 2 * D * 2);
+      w->dx16w = take(2 * M * R * 2);
+      w->wtmp16 = (float*)take(wide16_wgrad_tmp_floats((int)L, (int)R, (int)D) * f);
+      w->cs_scratch2 = (float*)take(colsum16_scratch_floats((int)(2 * D > R ? 2 * D : R)) * f);
+    }
+  }
+  if (!fused_blocks(c) && !wide16) {
     w->Pall = (float*)take((training ? L : 1) * M * 2 * D * f);
     w->gscratch = (float*)take(generic_scratch_floats(M, (int)R, (int)D) * f);
   } else {
@@ -284,7 +309,7 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
     w->G3 = c->residual_postproc ? (float*)take(M * S * f) : nullptr;
     w->dZcat = g16 ? nullptr : (float*)take(M * L * D * f);
     w->dX = (float*)take((bwd16 ? 1 : w->umma_bwd ? L : 2) * M * R * f);
-    w->dpre = (float*)take(bwd16 ? 256 : (w->umma_bwd ? L : 1) * M * 2 * D * f);
+    w->dpre = (float*)take((bwd16 || wide16) ? 256 : (w->umma_bwd ? L : 1) * M * 2 * D * f);
     w->gprebias = (float*)take(L * B * 2 * D * f);
     w->gtmp = (float*)take(S * f);
   } else {
@@ -430,6 +455,11 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
   }
   prof_mark(st, PT_FRONTEND_FWD);
   const int64_t xs = (int64_t)M * R;
+  if (w.wide16) {      // 16-bit storage between the layers; weight images of every layer (forward and backward forms)
+    RC(wide16_images(w.Wimg16, params + lo.filter, params + lo.gate, params + lo.dense, L, R, D, st));
+    RC(to_half(w.X, w.X16, xs, st));
+    prof_mark(st, PT_MISC);
+  }
   if (w.chain_flags) {
     // fp16 backward chain: the split rows of EVERY layer stay (ring = L) and nothing reads fp32 x' / z
     const bool b16 = training && w.bwd16;
@@ -448,6 +478,14 @@ static int run_forward(const wn_config* c, const wn_layout& lo, const float* par
                      w.WimgH + (size_t)l * block_h_img_stride(), w.prebias + (int64_t)l * B * 2 * D,
                      lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, B, T, c->dilations[l], last,
                      /*pdl_next=*/!last, st));
+      continue;
+    }
+    if (w.wide16) {
+      char* x16_in = (char*)w.X16 + (training ? (int64_t)l : (int64_t)(l & 1)) * xs * 2;
+      char* x16_out = (char*)w.X16 + (training ? (int64_t)(l + 1) : (int64_t)((l + 1) & 1)) * xs * 2;
+      RC(wide16_block_fwd(x16_in, last ? nullptr : x16_out, (char*)w.P16w + (training ? (int64_t)l : 0) * M * 2 * D * 2, w.Zcat16, ldz,
+                          l * D, (char*)w.Wimg16 + (int64_t)l * (wide16_images_bytes(1, R, D)), w.prebias + (int64_t)l * B * 2 * D,
+                          lo.dense_bias >= 0 ? params + lo.dense_bias + (int64_t)l * R : nullptr, B, T, c->dilations[l], R, D, st));
       continue;
     }
     if (w.gscratch) {
@@ -1090,6 +1128,23 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
     // join: the bias / conditioning gradients below read what the weight-gradient kernels accumulated
     if (ws != st)
       for (int i = 0; i < 3 && i < L; ++i) RC((int)cudaStreamWaitEvent(st, ev_wg[i], 0));
+  } else if (w.wide16) {
+    const float cs = 16.f, inv = 1.f / (gscale * cs);
+    RC((int)cudaMemsetAsync(w.wtmp16, 0, (size_t)wide16_wgrad_tmp_floats(L, R, D) * sizeof(float), st));
+    const char* dcur16 = nullptr;
+    for (int l = L - 1; l >= 0; --l) {
+      char* dx_out = (char*)w.dx16w + (int64_t)(l & 1) * xs * 2;
+      RC(wide16_block_bwd((char*)w.X16 + (int64_t)l * xs * 2, dcur16, w.dZcat16, ldz, l * D, cs, (char*)w.P16w + (int64_t)l * M * 2 * D * 2,
+                          w.Zcat16, w.dz16w, w.dpre16w, dx_out, (char*)w.Wimg16 + (int64_t)l * wide16_images_bytes(1, R, D), inv,
+                          w.wtmp16 + (int64_t)l * 2 * R * 2 * D, grads + lo.dense + (int64_t)l * D * R,
+                          w.gprebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr,
+                          w.cs_scratch2, B, T, cfg->dilations[l], R, D, st));
+      dcur16 = dx_out;
+    }
+    RC(wide16_unpack_wgrad(w.wtmp16, grads + lo.filter, grads + lo.gate, L, R, D, st));
+    RC(wide16_to_float(dcur16, w.dX, inv, xs, st));
+    prof_mark(st, PT_MISC);
+    dcur = w.dX;
   } else if (w.gscratch) {
     float* bufs[2] = {w.dX, w.dX + xs};
     int cur_i = 0;

@@ -1,0 +1,249 @@
+// Gated residual blocks for WIDE channel counts (R, D multiples of 64: BASELINE config 5, R = D = 128) in 16-bit
+// storage: wavenet/model.py:236-330 and its autodiff.  Every product runs on the tcgen05 fp16 GEMM (gemm_umma.cu,
+// fp32 accumulation in TMEM); dilation is a second TMA box of the SAME activation matrix at row t - d (forward) /
+// t + d (backward), zero-filled outside the batch element -- no [x[t-d] | x[t]] concatenation, padding or time_to_batch
+// tensor exists.  Residual add, skip-path gradient add and biases are fused into the GEMM epilogues:
+//   forward   P16 = [x[t-d] | x[t]] . [W0 ; W1] + b                 two-tap GEMM (K = 2R, N = 2D), fp16 out
+//             z   = tanh(Pf) * sigmoid(Pg) -> Zcat16 columns          gate kernel (HBM bound)
+//             x'  = x + bd + z . Wd                                   GEMM (K = D, N = R), residual added in the epilogue
+//   backward  dz  = cs * dz_skip + dx' . Wd^T                         GEMM (K = R, N = D), skip-path term added in the epilogue
+//             dpre = [dz s (1 - t^2) | dz t s (1 - s)]                kernel, from the saved pre-activations P16
+//             dW0 = x[t-d]^T . dpre, dW1 = x^T . dpre, dWd = z^T . dx'   fp16 TN GEMMs over time (operands as they lie), biases = column sums
+//             dx  = dx' + [dpre[t+d] | dpre[t]] . [W0^T ; W1^T]       two-tap GEMM (K = 4D, N = R), dx' added in the epilogue
+// Gradients travel as fp16 in the domain scaled by gscale * cs (see api.cu: gscale = 2^ceil(log2 M) / M).
+// The activations between layers are fp16 (north_star config 5 asks for 16-bit storage; fp16 has the bytes of bf16 and
+// three more mantissa bits, the values are O(1)); accumulation, biases, parameters and gradients are fp32.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wn {
+
+namespace {
+
+// per-layer weight image (halfs): Wc [2D][2R] | Wdt [R][D] | Wdg [D][R] | Wdx [R][4D]
+__host__ __device__ inline int64_t img_halfs(int R, int D) { return (int64_t)10 * R * D; }
+
+// filter / gate: [tap][R][D] (tap 0 multiplies x[t-d]);  dense: [D][R]
+__global__ void w16_weights_kernel(const float* __restrict__ filter, const float* __restrict__ gate,
+                                   const float* __restrict__ dense, __half* __restrict__ img, int L, int R, int D) {
+  const int64_t per = img_halfs(R, D);
+  const int64_t n = per * L, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int l = (int)(i / per);
+    int64_t j = i % per;
+    const float* wf = filter + (int64_t)l * 2 * R * D;
+    const float* wg = gate + (int64_t)l * 2 * R * D;
+    const float* wd = dense + (int64_t)l * D * R;
+    float v;
+    if (j < (int64_t)4 * R * D) {              // Wc[n][k]: n over [filter D | gate D], k over [past R | current R]
+      const int n_ = (int)(j / (2 * R)), k = (int)(j % (2 * R));
+      const int tap = k / R, r = k % R;
+      v = n_ < D ? wf[((int64_t)tap * R + r) * D + n_] : wg[((int64_t)tap * R + r) * D + (n_ - D)];
+    } else if ((j -= (int64_t)4 * R * D) < (int64_t)R * D) {      // Wdt[r][dch] = dense[dch][r]
+      const int r = (int)(j / D), dc = (int)(j % D);
+      v = wd[(int64_t)dc * R + r];
+    } else if ((j -= (int64_t)R * D) < (int64_t)R * D) {          // Wdg = dense as stored
+      v = wd[j];
+    } else {                                                      // Wdx[r][tap * 2D + n]
+      j -= (int64_t)R * D;
+      const int r = (int)(j / (4 * D)), c = (int)(j % (4 * D));
+      const int tap = c / (2 * D), n_ = c % (2 * D);
+      v = n_ < D ? wf[((int64_t)tap * R + r) * D + n_] : wg[((int64_t)tap * R + r) * D + (n_ - D)];
+    }
+    img[i] = __float2half_rn(v);
+  }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float2 a = __half22float2(h[u]);
+    f[2 * u] = a.x; f[2 * u + 1] = a.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    h[u] = __floats2half2_rn(fminf(fmaxf(f[2 * u], -65504.f), 65504.f), fminf(fmaxf(f[2 * u + 1], -65504.f), 65504.f));
+  return q;
+}
+
+// z = tanh(f) sigmoid(g) from P16 = [f D | g D] (biases already added) -> a D-column block of Zcat16; 8 channels per thread
+__global__ void w16_gate_kernel(const __half* __restrict__ P, __half* __restrict__ z, int ldz, int64_t M, int D) {
+  const int d8 = D >> 3;
+  const int64_t n = M * d8, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t m = i / d8;
+    const int c = (int)(i % d8) * 8;
+    float f[8], g[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + c)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + D + c)), g);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o[u] = tanh_f(f[u]) * sigmoid_f(g[u]);
+    *reinterpret_cast<uint4*>(z + m * ldz + c) = pack8(o);
+  }
+}
+
+// dpre = [df | dg] from dz (src, times src_scale) and the saved pre-activations
+__global__ void w16_dpre_kernel(const __half* __restrict__ src, int lds, float src_scale, const __half* __restrict__ P,
+                                __half* __restrict__ dpre, int64_t M, int D) {
+  const int d8 = D >> 3;
+  const int64_t n = M * d8, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t m = i / d8;
+    const int c = (int)(i % d8) * 8;
+    float f[8], g[8], dz[8], df[8], dg[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + c)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + D + c)), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + m * lds + c)), dz);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float t = tanh_f(f[u]), s = sigmoid_f(g[u]), q = dz[u] * src_scale;
+      df[u] = q * s * (1.f - t * t);
+      dg[u] = q * t * s * (1.f - s);
+    }
+    *reinterpret_cast<uint4*>(dpre + m * 2 * D + c) = pack8(df);
+    *reinterpret_cast<uint4*>(dpre + m * 2 * D + D + c) = pack8(dg);
+  }
+}
+
+__global__ void w16_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, float scale, int64_t n8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in) + i), f);
+    reinterpret_cast<float4*>(out)[2 * i] = make_float4(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+    reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+  }
+}
+
+// tmp [L][tap][R][2D] (filter | gate columns) -> the reference layout filter / gate [L][tap][R][D]
+__global__ void w16_unpack_wgrad_kernel(const float* __restrict__ tmp, float* __restrict__ gwf, float* __restrict__ gwg,
+                                        int64_t rows, int D) {
+  const int64_t n = rows * 2 * D, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / (2 * D);
+    const int c = (int)(i % (2 * D));
+    if (c < D) gwf[r * D + c] += tmp[i];
+    else gwg[r * D + (c - D)] += tmp[i];
+  }
+}
+
+inline int nblk(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = 16LL * sm_count();
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+#define WRC(x)             \
+  do {                     \
+    int rc__ = (x);        \
+    if (rc__) return rc__; \
+  } while (0)
+
+}  // namespace
+
+bool wide16_supported(int R, int D) { return R >= 64 && D >= 64 && !(R & 63) && !(D & 63) && R <= 256 && D <= 256; }
+int64_t wide16_images_bytes(int L, int R, int D) { return img_halfs(R, D) * L * 2; }
+int64_t wide16_wgrad_tmp_floats(int L, int R, int D) { return (int64_t)L * 2 * R * 2 * D; }
+
+int wide16_images(void* img, const float* filter, const float* gate, const float* dense, int L, int R, int D, cudaStream_t st) {
+  w16_weights_kernel<<<nblk(img_halfs(R, D) * L), 256, 0, st>>>(filter, gate, dense, (__half*)img, L, R, D);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+int wide16_to_float(const void* in, float* out, float scale, int64_t n, cudaStream_t st) {
+  if (n & 7) return -3;
+  w16_to_float_kernel<<<nblk(n / 8), 256, 0, st>>>((const __half*)in, out, scale, n / 8);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+// one layer forward: x16 [B*T][R] -> P16 [B*T][2D] (kept for the backward pass), z into Zcat16 columns [zcol, zcol + D),
+// x16_out (null for the last layer)
+int wide16_block_fwd(const void* x16, void* x16_out, void* P16, void* zcat16, int ldz, int zcol, const void* img_l,
+                     const float* prebias, const float* dense_bias, int B, int T, int d, int R, int D, cudaStream_t st) {
+  const int64_t M = (int64_t)B * T;
+  const __half* img = (const __half*)img_l;
+  const __half* Wc = img;
+  const __half* Wdt = img + (int64_t)4 * R * D;
+  for (int b = 0; b < B; ++b) {      // (per batch element: rows t - d < 0 must read zeros, not the previous element)
+    F16Extra ex;
+    ex.a_split = R; ex.a_shift = -d;
+    WRC(gemm_f16_nt((const __half*)x16 + (int64_t)b * T * R, R, Wc, 2 * R, nullptr, 0, (__half*)P16 + (int64_t)b * T * 2 * D, 2 * D, T,
+                    2 * D, 2 * R, prebias + (int64_t)b * 2 * D, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, nullptr, 0.f, &ex));
+  }
+  w16_gate_kernel<<<nblk(M * (D >> 3)), 256, 0, st>>>((const __half*)P16, (__half*)zcat16 + zcol, ldz, M, D);
+  WN_CHECK_LAUNCH();
+  if (x16_out) {
+    F16Extra ex;
+    ex.aux16 = x16; ex.ldaux16 = R; ex.aux_scale = 1.f;
+    WRC(gemm_f16_nt((const __half*)zcat16 + zcol, ldz, Wdt, D, nullptr, 0, x16_out, R, (int)M, R, D, dense_bias, nullptr, 0, 1.f, 0, st,
+                    nullptr, nullptr, 0, nullptr, 0.f, &ex));
+  }
+  prof_mark(st, PT_BLOCK_FWD);
+  return 0;
+}
+
+// one layer backward.  dxn16: gradient wrt the layer's output (null for the last layer), dz16_skip: the layer's column
+// block of dZcat16 (scaled by gscale; cs brings it to the block domain), dx16_out: gradient wrt the layer's input.
+// inv_scale = 1 / (gscale * cs).  wtmp: this layer's [2][R][2D] fp32 scratch (zeroed by the caller).
+int wide16_block_bwd(const void* x16, const void* dxn16, const void* dzcat16, int ldz, int zcol, float cs, const void* P16,
+                     const void* zcat16, void* dz16, void* dpre16, void* dx16_out, const void* img_l, float inv_scale,
+                     float* wtmp, float* gdense, float* gprebias, float* gdense_bias, float* cs_scratch, int B, int T, int d,
+                     int R, int D, cudaStream_t st) {
+  const int64_t M = (int64_t)B * T;
+  const __half* img = (const __half*)img_l;
+  const __half* Wdg = img + (int64_t)5 * R * D;
+  const __half* Wdx = img + (int64_t)6 * R * D;
+  const __half* dzs = (const __half*)dzcat16 + zcol;
+  if (dxn16) {
+    F16Extra ex;
+    ex.aux16 = dzs; ex.ldaux16 = ldz; ex.aux_scale = cs;
+    WRC(gemm_f16_nt(dxn16, R, Wdg, R, nullptr, 0, dz16, D, (int)M, D, R, nullptr, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, nullptr,
+                    0.f, &ex));
+    w16_dpre_kernel<<<nblk(M * (D >> 3)), 256, 0, st>>>((const __half*)dz16, D, 1.f, (const __half*)P16, (__half*)dpre16, M, D);
+  } else {
+    w16_dpre_kernel<<<nblk(M * (D >> 3)), 256, 0, st>>>(dzs, ldz, cs, (const __half*)P16, (__half*)dpre16, M, D);
+  }
+  WN_CHECK_LAUNCH();
+  prof_mark(st, PT_BLOCK_BWD_PRE);
+  // weight gradients: contraction over time on the operands as they lie in memory
+  const int split = sm_count();
+  for (int b = 0; b < B; ++b) {
+    const __half* xb = (const __half*)x16 + (int64_t)b * T * R;
+    const __half* pb = (const __half*)dpre16 + (int64_t)b * T * 2 * D;
+    if (d < T) WRC(gemm_f16_tn(xb, R, pb + (int64_t)d * 2 * D, 2 * D, wtmp, 2 * D, R, 2 * D, T - d, inv_scale, split, st));      // x[t-d]^T . dpre[t]
+    WRC(gemm_f16_tn(xb, R, pb, 2 * D, wtmp + (int64_t)R * 2 * D, 2 * D, R, 2 * D, T, inv_scale, split, st));
+    WRC(colsum16(pb, 2 * D, T, 2 * D, inv_scale, gprebias + (int64_t)b * 2 * D, cs_scratch, st));
+  }
+  if (dxn16) {
+    WRC(gemm_f16_tn((const __half*)zcat16 + zcol, ldz, dxn16, R, gdense, R, D, R, (int)M, inv_scale, split, st));
+    if (gdense_bias) WRC(colsum16(dxn16, R, (int)M, R, inv_scale, gdense_bias, cs_scratch, st));
+  }
+  prof_mark(st, PT_BLOCK_WGRAD);
+  for (int b = 0; b < B; ++b) {
+    F16Extra ex;
+    ex.a_split = 2 * D; ex.a_shift = d;
+    if (dxn16) { ex.aux16 = (const __half*)dxn16 + (int64_t)b * T * R; ex.ldaux16 = R; ex.aux_scale = 1.f; }
+    WRC(gemm_f16_nt((const __half*)dpre16 + (int64_t)b * T * 2 * D, 2 * D, Wdx, 4 * D, nullptr, 0, (__half*)dx16_out + (int64_t)b * T * R, R,
+                    T, R, 4 * D, nullptr, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, nullptr, 0.f, &ex));
+  }
+  prof_mark(st, PT_BLOCK_BWD_DX);
+  return 0;
+}
+
+int wide16_unpack_wgrad(const float* tmp, float* gwf, float* gwg, int L, int R, int D, cudaStream_t st) {
+  const int64_t rows = (int64_t)L * 2 * R;
+  w16_unpack_wgrad_kernel<<<nblk(rows * 2 * D), 256, 0, st>>>(tmp, gwf, gwg, rows, D);
+  WN_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace wn

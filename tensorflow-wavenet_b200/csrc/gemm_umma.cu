@@ -135,6 +135,12 @@ struct UmmaParams {
   float c_scale;                  // C = c_scale * (accumulator, bias, relu, mask); the fp16 copy stays unscaled (0: no scaling)
   float* colsum;                  // [N] += colsum_scale * column sums of the fp16 copy (needs has_c16 and no bias: the sums
   float colsum_scale;             // collect in the bias row of shared memory); the bias gradient of the layer below
+  // dilated (two-tap) A operand of the wide residual blocks (block_wide16.cu): K chunks below a_split come from rows
+  // m + a_shift of the SAME [rows][a_split] matrix, chunks from a_split on from rows m (columns k - a_split); rows outside
+  // the matrix are zero-filled by the TMA unit = the causal padding.  0: plain A[M][K]
+  int a_split, a_shift;
+  int aux_add;                    // aux is an fp16 matrix ADDED (times aux_scale) to the accumulator (residual / skip-path term)
+  float aux_scale;
 };
 
 template <int BN>
@@ -208,7 +214,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int kc = k_begin + i * ukk;
           const int bsh = p.f16 ? 6 : 5;      // MN-major blocks: 32 floats / 64 halfs wide
           if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> bsh);     // [blocks][k rows][128 B of m]
-          else tma_load_2d(sa, &mapA, &full_bar[s], kc, m0);
+          else if (p.a_split && kc < p.a_split) tma_load_2d(sa, &mapA, &full_bar[s], kc, m0 + p.a_shift);
+          else tma_load_2d(sa, &mapA, &full_bar[s], kc - p.a_split, m0);
           if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> bsh);
           else tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kc, n0);
         }
@@ -308,7 +315,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       auto issue_aux = [&](int c0) {   // lane 0: mask chunk [32 rows][32 cols] -> staging buffer (aux_cnt parity)
         const uint32_t buf = (aux_cnt + (c0 > col_lo ? 1u : 0u)) & 1u;
-        mbar_expect_tx(&aux_bar[ew][buf], STG_BYTES);
+        mbar_expect_tx(&aux_bar[ew][buf], p.aux_add ? STG_BYTES / 2 : STG_BYTES);
         tma_load_2d(my_aux + buf * STG_BYTES, &mapAux, &aux_bar[ew][buf], n0 + c0, row0);
       };
       if (p.aux && lane == 0 && n0 + col_lo < p.N) issue_aux(col_lo);
@@ -404,7 +411,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           if (lane == 0 && c0 + 32 < col_hi && nb + 32 < p.N) issue_aux(c0 + 32);   // next chunk, other buffer
           mbar_wait(&aux_bar[ew][buf], (aux_cnt >> 1) & 1u);
           const unsigned char* ms = my_aux + buf * STG_BYTES + lane * 128;
+          if (p.aux_add) {      // [32 rows][32 halfs], 64-byte rows, 64B swizzle (as the fp16 output staging blocks)
+            const unsigned char* hs = my_aux + buf * STG_BYTES + lane * 64;
 #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(hs + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 a = __half22float2(h2[u]);
+                f[8 * j + 2 * u] = fmaf(p.aux_scale, a.x, f[8 * j + 2 * u]);
+                f[8 * j + 2 * u + 1] = fmaf(p.aux_scale, a.y, f[8 * j + 2 * u + 1]);
+              }
+            }
+          } else
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 mk = *reinterpret_cast<const float4*>(ms + ((uint32_t)(j ^ (lane & 7)) << 4));
@@ -556,7 +576,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
     if (rc) return rc;
   }
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
   p.m2 = 0;
@@ -585,15 +605,19 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
 // travel as fp16 in a domain scaled by a power of two (c_scale undoes it for the fp32 copies).
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
                 int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st,
-                uint32_t* mask_out, const uint32_t* mask_in, int ldmw, float* colsum, float colsum_scale) {
+                uint32_t* mask_out, const uint32_t* mask_in, int ldmw, float* colsum, float colsum_scale, const F16Extra* ex) {
   if (M <= 0 || N <= 0 || K <= 0 || !A16 || !B16 || (!C && !C16)) return -1;
   if (colsum && (!C16 || bias)) return -1;
+  const int a_split = ex ? ex->a_split : 0;
+  const void* aux16 = ex ? ex->aux16 : nullptr;
+  if (a_split && (K != 2 * a_split || (a_split & 63))) return -1;
+  if (aux16 && (aux || (ex->ldaux16 & 7) || ((uintptr_t)aux16 & 15))) return -3;
   if ((lda & 7) || (ldb & 7) || (C && (ldc & 3)) || (C16 && (ldc16 & 7)) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) ||
       ((uintptr_t)C & 15) || ((uintptr_t)C16 & 15) || (aux && ((ldaux & 3) || ((uintptr_t)aux & 15))) || (flags & GEMM_ATOMIC))
     return -3;
   const int BN = N > 128 ? 256 : 128;
   CUtensorMap mA, mB, mC, mAux, mC16;
-  int rc = make_map16(&mA, A16, M, K, lda, UM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_map16(&mA, A16, M, a_split ? a_split : K, lda, UM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   rc = make_map16(&mB, B16, N, K, ldb, BN, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
@@ -607,6 +631,10 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
     rc = make_map(&mAux, aux, M, N, ldaux, 32);
     if (rc) return rc;
   }
+  if (aux16) {
+    rc = make_map16(&mAux, aux16, M, N, ex->ldaux16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
   mC16 = mA;
   if (C16) {
     rc = make_map16(&mC16, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -615,8 +643,9 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   UmmaParams p;
   p.colsum = nullptr; p.colsum_scale = 0.f;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
-  p.aux = aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
+  p.aux = aux16 ? (const float*)aux16 : aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
   p.m2 = 0;
+  p.a_split = a_split; p.a_shift = ex ? ex->a_shift : 0; p.aux_add = aux16 ? 1 : 0; p.aux_scale = ex ? ex->aux_scale : 1.f;
   p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
   p.mask_out = mask_out; p.mask_in = mask_in; p.ldmw = ldmw;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
@@ -628,12 +657,13 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
   size_t pipe = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
   // a fourth operand stage where the (8-warp) staging leaves room for it: fp16-only outputs
-  if (pipe + (UM * UK * 4 + BN * UK * 4) + staging_bytes(C != nullptr, aux != nullptr, C16 != nullptr, 2, 8) <= SMEM_OPTIN) {
+  const bool has_aux = aux != nullptr || aux16 != nullptr;
+  if (pipe + (UM * UK * 4 + BN * UK * 4) + staging_bytes(C != nullptr, has_aux, C16 != nullptr, 2, 8) <= SMEM_OPTIN) {
     p.stages = 4;
     pipe += UM * UK * 4 + BN * UK * 4;
   }
-  pick_epilogue(pipe, C != nullptr, aux != nullptr, C16 != nullptr, p);
-  const size_t smem = pipe + staging_bytes(C != nullptr, aux != nullptr, C16 != nullptr, p.nbuf, p.ewarps);
+  pick_epilogue(pipe, C != nullptr, has_aux, C16 != nullptr, p);
+  const size_t smem = pipe + staging_bytes(C != nullptr, has_aux, C16 != nullptr, p.nbuf, p.ewarps);
   return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p);
 }
 
@@ -675,7 +705,7 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
   if (rc) return rc;
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
   p.nbuf = 2; p.ewarps = 8; p.m2 = m2;

@@ -37,11 +37,19 @@ int gemm_nt_umma(const GemmParams& p, float* CT, int ldct, int split_k, cudaStre
 // tcgen05 path, mode 0 NN (p.B = [K,N]) / 1 NT (p.B = [N,K]) / 2 TN (p.A = [K,M], p.B = [K,N]; GEMM_ATOMIC)
 int gemm_umma(int mode, const GemmParams& p, float* CT, int ldct, int split_k, cudaStream_t st);
 bool gemm_umma_supported(int mode, const GemmParams& p);
+// extras of gemm_f16_nt for the wide residual blocks (block_wide16.cu)
+struct F16Extra {
+  int a_split = 0, a_shift = 0;      // two-tap A: k < a_split reads rows m + a_shift, k >= a_split rows m of A16[M][a_split] (K = 2 a_split)
+  const void* aux16 = nullptr;       // fp16 [M][N] matrix added (times aux_scale) to the product
+  int ldaux16 = 0;
+  float aux_scale = 1.f;
+};
 // forward chain in fp16 (operands K-major fp16, fp32 accumulate / output, optional fp16 copy of the output)
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
                 int K, const float* bias, const float* aux, int ldaux, float c_scale, int flags, cudaStream_t st,
                 uint32_t* mask_out = nullptr, const uint32_t* mask_in = nullptr, int ldmw = 0, float* colsum = nullptr,
-                float colsum_scale = 0.f);      // colsum[N] += colsum_scale * column sums of C16 (no bias allowed then)
+                float colsum_scale = 0.f,      // colsum[N] += colsum_scale * column sums of C16 (no bias allowed then)
+                const F16Extra* ex = nullptr);
 // C[M,N] += c_scale * A16[K,M]^T . B16[K,N]: fp16 operands as they lie in memory (M, N multiples of 64), split-K atomics
 bool gemm_f16_tn_supported(int lda, int ldb, int M, int N);
 int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, int M, int N, int K, float c_scale,
@@ -94,6 +102,19 @@ int generic_block_bwd(const float* x, const float* dxn, const float* dZcat, cons
                       const float* P, float* dx, float* dpre, const float* wf, const float* wg, const float* dense,
                       float* gwf, float* gwg, float* gdense, float* gprebias, float* gdense_bias, float* scratch,
                       int B, int T, int d, int R, int D, int is_last, cudaStream_t st);
+// wide residual blocks (R, D multiples of 64) in 16-bit storage, built from the fp16 tcgen05 GEMM (block_wide16.cu)
+bool wide16_supported(int R, int D);
+int64_t wide16_images_bytes(int L, int R, int D);
+int64_t wide16_wgrad_tmp_floats(int L, int R, int D);
+int wide16_images(void* img, const float* filter, const float* gate, const float* dense, int L, int R, int D, cudaStream_t st);
+int wide16_to_float(const void* in, float* out, float scale, int64_t n, cudaStream_t st);
+int wide16_block_fwd(const void* x16, void* x16_out, void* P16, void* zcat16, int ldz, int zcol, const void* img_l,
+                     const float* prebias, const float* dense_bias, int B, int T, int d, int R, int D, cudaStream_t st);
+int wide16_block_bwd(const void* x16, const void* dxn16, const void* dzcat16, int ldz, int zcol, float cs, const void* P16,
+                     const void* zcat16, void* dz16, void* dpre16, void* dx16_out, const void* img_l, float inv_scale,
+                     float* wtmp, float* gdense, float* gprebias, float* gdense_bias, float* cs_scratch, int B, int T, int d,
+                     int R, int D, cudaStream_t st);
+int wide16_unpack_wgrad(const float* tmp, float* gwf, float* gwg, int L, int R, int D, cudaStream_t st);
 // second-generation forward block (block_fwd_h.cu): fp16 split rows [hi 32 | lo 32] between layers
 int64_t block_h_images_bytes(int L);
 uint32_t block_h_img_stride();

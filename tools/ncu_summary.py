@@ -93,7 +93,7 @@ def traffic(paths):
     """JSON: kernel tag -> mean (dram__bytes_read + dram__bytes_write) per launch, from `ncu --set full` reports."""
     import json
     import re
-    tags = [('block_bwd_chain', 'block_bwd_chain'), ('block_wgrad_h_all', 'block_wgrad'), ('generator_pipe', 'generator_pipe'), ('block_fwd_chain', 'block_fwd'), ('block_fwd_h', 'block_fwd'), ('block_fwd_umma', 'block_fwd'), ('block_bwd_pre_umma', 'block_bwd_pre'), ('block_bwd_dx_umma', 'block_bwd_dx'),
+    tags = [('block_bwd_fused_reduce', 'block_wgrad'), ('post2_xent', 'softmax_xent'), ('block_bwd_chain', 'block_bwd_chain'), ('block_wgrad_h_all', 'block_wgrad'), ('generator_pipe', 'generator_pipe'), ('block_fwd_chain', 'block_fwd'), ('block_fwd_h', 'block_fwd'), ('block_fwd_umma', 'block_fwd'), ('block_bwd_pre_umma', 'block_bwd_pre'), ('block_bwd_dx_umma', 'block_bwd_dx'),
             ('block_wgrad_all', 'block_wgrad'), ('block_wgrad_umma', 'block_wgrad'), ('gemm_umma_kernel', 'gemm_umma'), ('generator_lat', 'generator_lat'),
             ('generator_kernel', 'generator')]
     acc = {}

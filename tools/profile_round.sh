@@ -7,9 +7,7 @@ timeout 300 python bench.py --steps 2 --warmup 3 --no-batch4 --no-fastgen --no-c
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --no-batch4 --no-fastgen --no-cpu-baseline > gpurun_out/${R}_ncu0.log 2>&1
 timeout 100 python tools/one_step.py 2 > /dev/null 2>&1 || exit 1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:block_fwd_chain --launch-skip 1 --launch-count 1 -o gpurun_out/${R}_fwd_chain python tools/one_step.py 2 > gpurun_out/${R}_ncu1.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:block_bwd_chain --launch-skip 1 --launch-count 1 -o gpurun_out/${R}_bwd_chain python tools/one_step.py 2 > gpurun_out/${R}_ncu2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:block_wgrad_h_all --launch-skip 1 --launch-count 1 -o gpurun_out/${R}_wgrad python tools/one_step.py 2 > gpurun_out/${R}_ncu4.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_umma_kernel --launch-skip 9 --launch-count 9 -o gpurun_out/${R}_gemm python tools/one_step.py 2 > gpurun_out/${R}_ncu3.log 2>&1
-timeout 100 python tools/bench_gen.py 32 300 > /dev/null 2>&1 || exit 1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:generator_pipe --launch-skip 1 --launch-count 1 -o gpurun_out/${R}_genpipe python tools/bench_gen.py 32 300 > gpurun_out/${R}_ncu5.log 2>&1
-for f in gpurun_out/${R}_ncu1.log gpurun_out/${R}_ncu2.log gpurun_out/${R}_ncu3.log gpurun_out/${R}_ncu4.log gpurun_out/${R}_ncu5.log; do tail -n 2 $f; done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:block_bwd_chain_f --launch-skip 1 --launch-count 1 -o gpurun_out/${R}_bwd_chain python tools/one_step.py 2 > gpurun_out/${R}_ncu2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"block_bwd_fused_reduce|post2_xent" --launch-skip 2 --launch-count 2 -o gpurun_out/${R}_wgrad python tools/one_step.py 2 > gpurun_out/${R}_ncu4.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_umma_kernel --launch-skip 8 --launch-count 8 -o gpurun_out/${R}_gemm python tools/one_step.py 2 > gpurun_out/${R}_ncu3.log 2>&1
+for f in gpurun_out/${R}_ncu1.log gpurun_out/${R}_ncu2.log gpurun_out/${R}_ncu3.log gpurun_out/${R}_ncu4.log; do tail -n 2 $f; done
