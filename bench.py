@@ -183,6 +183,82 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+def run_cfg5(args):
+    """BASELINE config 5: scaled net (res/dil 128, skip 512, 4 x dilations 1..512), 16-bit activation storage, 64k windows.
+    Same contract as the default line (one JSON line, device-timed graph replays + an end-to-end leg); the roofline block
+    is the tensor bound of the whole step: SURVEY 8(d) FLOPs per unit x units / step time against the measured bf16 peak."""
+    import wavenet
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.distributed.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    B, T = 1, 65536
+    R = D = 128
+    S, Q = 512, 256
+    dil = [2 ** i for i in range(10)] * 4
+    L = len(dil)
+    net = wavenet.WaveNetModel(batch_size=B, dilations=dil, filter_width=2, residual_channels=R, dilation_channels=D,
+                               quantization_channels=Q, skip_channels=S, use_biases=True, seed=0)
+    opt = wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9)
+    step = wavenet.TrainStep(net, opt, B, T)
+    host_audio = torch.as_tensor(synthetic_audio(B, T, rank)).pin_memory()
+    step.audio.copy_(host_audio)
+    W, K = max(3, args.warmup), max(1, args.steps)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_per_step = float(ms) / K
+    value = world * B * T / (ms_per_step * 1e-3)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss_host = float(step(host_audio))
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    # forward + input-gradient + weight-gradient products: 3 x 2 x (2R.2D + D.R) per layer, 3 x 2 x (L.D.S + S.S + S.Q) post-processing
+    flop_per_unit = 6.0 * (L * (2 * R * 2 * D + D * R) - D * R + L * D * S + S * S + S * Q)
+    ach = flop_per_unit * B * T / (ms_per_step * 1e-3) / 1e12
+    print(json.dumps({
+        'metric': 'training audio samples/sec (scaled net, BASELINE config 5)', 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': K, 'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'fp16 activation / gradient storage and tensor-core operands, fp32 accumulation, parameters and optimizer',
+        'data': 'synthetic',
+        'config': {'workload': 'scaled net (L=%d, R=D=%d, S=%d, Q=%d, biases) training step (fwd+bwd+allreduce+Adam), B=%d x T=%d per GPU' % (L, R, S, Q, B, T),
+                   'parallelism': 'dp%d' % world, 'l2_between_iterations': 'per-step working set (~4 GB) exceeds the 126 MB L2; no explicit flush'},
+        'clocks': clocks,
+        'e2e': {'value': world * B * T * K / float(e2e_s), 'unit': UNIT, 'h2d_bytes_per_step': B * T * 4, 'd2h_bytes_per_step': 4},
+        'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'],
+                     'traffic': None, 'kernel': 'whole step (fp16 tcgen05 GEMMs of the wide residual blocks + post-processing)',
+                     'flop_per_unit': flop_per_unit, 'peak_source': peaks['source']},
+        'final_loss': loss_host}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -194,9 +270,13 @@ def main():
     ap.add_argument('--no-batch4', action='store_true')
     ap.add_argument('--batch', type=int, default=B_PER_GPU)
     ap.add_argument('--time', type=int, default=T_WINDOW)
+    ap.add_argument('--config', default='default', choices=['default', 'cfg5'],
+                    help='cfg5: BASELINE config 5, the scaled net (R = D = 128, 4 x dilations 1..512, 64k windows, 16-bit storage)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.config == 'cfg5':
+        return run_cfg5(args)
 
     import wavenet
     from wavenet import _lib

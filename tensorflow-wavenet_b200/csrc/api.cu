@@ -250,7 +250,7 @@ static void carve(const wn_config* c, int B, int T, bool training, void* base, W
       w->dpre16w = take(M * 2 * D * 2);
       w->dx16w = take(2 * M * R * 2);
       w->wtmp16 = (float*)take(wide16_wgrad_tmp_floats((int)L, (int)R, (int)D) * f);
-      w->cs_scratch2 = (float*)take(colsum16_scratch_floats((int)(2 * D > R ? 2 * D : R)) * f);
+      w->cs_scratch2 = (float*)take((int64_t)B * wide16_colsum_chunks() * 2 * D * f);
     }
   }
   if (!fused_blocks(c) && !wide16) {
@@ -1137,7 +1137,7 @@ int wn_loss_grad(const wn_config* cfg, const float* params, float* grads, void* 
       RC(wide16_block_bwd((char*)w.X16 + (int64_t)l * xs * 2, dcur16, w.dZcat16, ldz, l * D, cs, (char*)w.P16w + (int64_t)l * M * 2 * D * 2,
                           w.Zcat16, w.dz16w, w.dpre16w, dx_out, (char*)w.Wimg16 + (int64_t)l * wide16_images_bytes(1, R, D), inv,
                           w.wtmp16 + (int64_t)l * 2 * R * 2 * D, grads + lo.dense + (int64_t)l * D * R,
-                          w.gprebias + (int64_t)l * B * 2 * D, lo.dense_bias >= 0 ? grads + lo.dense_bias + (int64_t)l * R : nullptr,
+                          w.gprebias + (int64_t)l * B * 2 * D, (lo.dense_bias >= 0 && l > 0) ? grads + lo.dense_bias + (int64_t)(l - 1) * R : nullptr,
                           w.cs_scratch2, B, T, cfg->dilations[l], R, D, st));
       dcur16 = dx_out;
     }

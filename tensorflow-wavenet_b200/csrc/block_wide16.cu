@@ -89,26 +89,69 @@ __global__ void w16_gate_kernel(const __half* __restrict__ P, __half* __restrict
   }
 }
 
-// dpre = [df | dg] from dz (src, times src_scale) and the saved pre-activations
-__global__ void w16_dpre_kernel(const __half* __restrict__ src, int lds, float src_scale, const __half* __restrict__ P,
-                                __half* __restrict__ dpre, int64_t M, int D) {
-  const int d8 = D >> 3;
-  const int64_t n = M * d8, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t m = i / d8;
-    const int c = (int)(i % d8) * 8;
-    float f[8], g[8], dz[8], df[8], dg[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + c)), f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + D + c)), g);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(src + m * lds + c)), dz);
+// dpre = [df | dg] from dz (src, times src_scale) and the saved pre-activations; the column sums of dpre (= the gradients
+// of the filter / gate biases and of the conditioning projections, per batch element) are collected on the way:
+// block (x, b) walks rows x*RS + rsub + k*gridDim.x*RS of batch element b (RS = 256 / (D/8) rows per pass) and writes its
+// partial sums to partials[b][x][2D]; w16_colsum_finish_kernel adds them up (atomics on one address serialise).
+__global__ void __launch_bounds__(256)
+w16_dpre_kernel(const __half* __restrict__ src, int lds, float src_scale, const __half* __restrict__ P,
+                __half* __restrict__ dpre, int T, int D, float* __restrict__ partials) {
+  extern __shared__ float red[];      // [RS][2D]
+  const int d8 = D >> 3, RS = 256 / d8;
+  const int cg = threadIdx.x % d8, rsub = threadIdx.x / d8, c = cg * 8;
+  const int64_t base = (int64_t)blockIdx.y * T;
+  float sf[8], sg[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) sf[u] = sg[u] = 0.f;
+  if (rsub < RS)
+    for (int t = blockIdx.x * RS + rsub; t < T; t += gridDim.x * RS) {
+      const int64_t m = base + t;
+      float f[8], g[8], dz[8], df[8], dg[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + c)), f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(P + m * 2 * D + D + c)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + m * lds + c)), dz);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float t_ = tanh_f(f[u]), s_ = sigmoid_f(g[u]), q = dz[u] * src_scale;
+        df[u] = q * s_ * (1.f - t_ * t_);
+        dg[u] = q * t_ * s_ * (1.f - s_);
+      }
+      const uint4 qf = pack8(df), qg = pack8(dg);
+      *reinterpret_cast<uint4*>(dpre + m * 2 * D + c) = qf;
+      *reinterpret_cast<uint4*>(dpre + m * 2 * D + D + c) = qg;
+      unpack8(qf, df);      // the sums are those of the ROUNDED values (what the weight-gradient GEMMs read)
+      unpack8(qg, dg);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { sf[u] += df[u]; sg[u] += dg[u]; }
+    }
+  if (rsub < RS) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float t = tanh_f(f[u]), s = sigmoid_f(g[u]), q = dz[u] * src_scale;
-      df[u] = q * s * (1.f - t * t);
-      dg[u] = q * t * s * (1.f - s);
+      red[rsub * 2 * D + c + u] = sf[u];
+      red[rsub * 2 * D + D + c + u] = sg[u];
     }
-    *reinterpret_cast<uint4*>(dpre + m * 2 * D + c) = pack8(df);
-    *reinterpret_cast<uint4*>(dpre + m * 2 * D + D + c) = pack8(dg);
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < 2 * D; n += 256) {
+    float t = 0.f;
+    for (int r = 0; r < RS; ++r) t += red[r * 2 * D + n];
+    partials[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * D + n] = t;
+  }
+}
+// out[b][n] += scale * sum_x partials[b][x][n];  grid (N / 32, B), block (32, 8)
+__global__ void w16_colsum_finish_kernel(const float* __restrict__ partials, int chunks, int N, float scale, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const float* pb = partials + (int64_t)blockIdx.y * chunks * N;
+  float t = 0.f;
+  if (n < N)
+    for (int x = threadIdx.y; x < chunks; x += 8) t += pb[(int64_t)x * N + n];
+  red[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][threadIdx.x];
+    out[(int64_t)blockIdx.y * N + n] += t * scale;
   }
 }
 
@@ -151,6 +194,7 @@ inline int nblk(int64_t n) {
 bool wide16_supported(int R, int D) { return R >= 64 && D >= 64 && !(R & 63) && !(D & 63) && R <= 256 && D <= 256; }
 int64_t wide16_images_bytes(int L, int R, int D) { return img_halfs(R, D) * L * 2; }
 int64_t wide16_wgrad_tmp_floats(int L, int R, int D) { return (int64_t)L * 2 * R * 2 * D; }
+int wide16_colsum_chunks() { return 4 * sm_count(); }      // row chunks per batch element of the dpre kernel (partials: [B][chunks][2D])
 
 int wide16_images(void* img, const float* filter, const float* gate, const float* dense, int L, int R, int D, cudaStream_t st) {
   w16_weights_kernel<<<nblk(img_halfs(R, D) * L), 256, 0, st>>>(filter, gate, dense, (__half*)img, L, R, D);
@@ -193,10 +237,11 @@ int wide16_block_fwd(const void* x16, void* x16_out, void* P16, void* zcat16, in
 
 // one layer backward.  dxn16: gradient wrt the layer's output (null for the last layer), dz16_skip: the layer's column
 // block of dZcat16 (scaled by gscale; cs brings it to the block domain), dx16_out: gradient wrt the layer's input.
-// inv_scale = 1 / (gscale * cs).  wtmp: this layer's [2][R][2D] fp32 scratch (zeroed by the caller).
+// inv_scale = 1 / (gscale * cs).  wtmp: this layer's [2][R][2D] fp32 scratch (zeroed by the caller).  gdense_bias_below: the
+// dense-bias gradient of layer l - 1 (column sums of dx; null for layer 0 / no biases).  cs_scratch: B * chunks * 2D floats.
 int wide16_block_bwd(const void* x16, const void* dxn16, const void* dzcat16, int ldz, int zcol, float cs, const void* P16,
                      const void* zcat16, void* dz16, void* dpre16, void* dx16_out, const void* img_l, float inv_scale,
-                     float* wtmp, float* gdense, float* gprebias, float* gdense_bias, float* cs_scratch, int B, int T, int d,
+                     float* wtmp, float* gdense, float* gprebias, float* gdense_bias_below, float* cs_scratch, int B, int T, int d,
                      int R, int D, cudaStream_t st) {
   const int64_t M = (int64_t)B * T;
   const __half* img = (const __half*)img_l;
@@ -208,32 +253,42 @@ int wide16_block_bwd(const void* x16, const void* dxn16, const void* dzcat16, in
     ex.aux16 = dzs; ex.ldaux16 = ldz; ex.aux_scale = cs;
     WRC(gemm_f16_nt(dxn16, R, Wdg, R, nullptr, 0, dz16, D, (int)M, D, R, nullptr, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, nullptr,
                     0.f, &ex));
-    w16_dpre_kernel<<<nblk(M * (D >> 3)), 256, 0, st>>>((const __half*)dz16, D, 1.f, (const __half*)P16, (__half*)dpre16, M, D);
-  } else {
-    w16_dpre_kernel<<<nblk(M * (D >> 3)), 256, 0, st>>>(dzs, ldz, cs, (const __half*)P16, (__half*)dpre16, M, D);
   }
-  WN_CHECK_LAUNCH();
+  {
+    const int RS = 256 / (D >> 3);
+    int chunks = (4 * sm_count() + B - 1) / B;
+    if (chunks > (T + RS - 1) / RS) chunks = (T + RS - 1) / RS;
+    if (chunks > wide16_colsum_chunks()) chunks = wide16_colsum_chunks();
+    const size_t sh = (size_t)RS * 2 * D * sizeof(float);
+    if (dxn16) w16_dpre_kernel<<<dim3(chunks, B), 256, sh, st>>>((const __half*)dz16, D, 1.f, (const __half*)P16, (__half*)dpre16, T, D, cs_scratch);
+    else w16_dpre_kernel<<<dim3(chunks, B), 256, sh, st>>>(dzs, ldz, cs, (const __half*)P16, (__half*)dpre16, T, D, cs_scratch);
+    WN_CHECK_LAUNCH();
+    w16_colsum_finish_kernel<<<dim3((2 * D + 31) / 32, B), dim3(32, 8), 0, st>>>(cs_scratch, chunks, 2 * D, inv_scale, gprebias);
+    WN_CHECK_LAUNCH();
+  }
   prof_mark(st, PT_BLOCK_BWD_PRE);
   // weight gradients: contraction over time on the operands as they lie in memory
   const int split = sm_count();
   for (int b = 0; b < B; ++b) {
     const __half* xb = (const __half*)x16 + (int64_t)b * T * R;
     const __half* pb = (const __half*)dpre16 + (int64_t)b * T * 2 * D;
-    if (d < T) WRC(gemm_f16_tn(xb, R, pb + (int64_t)d * 2 * D, 2 * D, wtmp, 2 * D, R, 2 * D, T - d, inv_scale, split, st));      // x[t-d]^T . dpre[t]
-    WRC(gemm_f16_tn(xb, R, pb, 2 * D, wtmp + (int64_t)R * 2 * D, 2 * D, R, 2 * D, T, inv_scale, split, st));
-    WRC(colsum16(pb, 2 * D, T, 2 * D, inv_scale, gprebias + (int64_t)b * 2 * D, cs_scratch, st));
+    if ((R & 127) == 0) {      // both taps in one launch: rows [0, R) of wtmp = x[t-d]^T . dpre[t], rows [R, 2R) = x[t]^T . dpre[t]
+      WRC(gemm_f16_tn(xb, R, pb, 2 * D, wtmp, 2 * D, 2 * R, 2 * D, T, inv_scale, split / 2, st, R, d));
+    } else {
+      if (d < T) WRC(gemm_f16_tn(xb, R, pb + (int64_t)d * 2 * D, 2 * D, wtmp, 2 * D, R, 2 * D, T - d, inv_scale, split, st));
+      WRC(gemm_f16_tn(xb, R, pb, 2 * D, wtmp + (int64_t)R * 2 * D, 2 * D, R, 2 * D, T, inv_scale, split, st));
+    }
   }
-  if (dxn16) {
-    WRC(gemm_f16_tn((const __half*)zcat16 + zcol, ldz, dxn16, R, gdense, R, D, R, (int)M, inv_scale, split, st));
-    if (gdense_bias) WRC(colsum16(dxn16, R, (int)M, R, inv_scale, gdense_bias, cs_scratch, st));
-  }
+  if (dxn16) WRC(gemm_f16_tn((const __half*)zcat16 + zcol, ldz, dxn16, R, gdense, R, D, R, (int)M, inv_scale, split, st));
   prof_mark(st, PT_BLOCK_WGRAD);
   for (int b = 0; b < B; ++b) {
     F16Extra ex;
     ex.a_split = 2 * D; ex.a_shift = d;
     if (dxn16) { ex.aux16 = (const __half*)dxn16 + (int64_t)b * T * R; ex.ldaux16 = R; ex.aux_scale = 1.f; }
+    // (the column sums of dx = the dense-bias gradient of the layer below, collected by the epilogue)
     WRC(gemm_f16_nt((const __half*)dpre16 + (int64_t)b * T * 2 * D, 2 * D, Wdx, 4 * D, nullptr, 0, (__half*)dx16_out + (int64_t)b * T * R, R,
-                    T, R, 4 * D, nullptr, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, nullptr, 0.f, &ex));
+                    T, R, 4 * D, nullptr, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, gdense_bias_below, gdense_bias_below ? inv_scale : 0.f,
+                    &ex));
   }
   prof_mark(st, PT_BLOCK_BWD_DX);
   return 0;

@@ -139,6 +139,8 @@ struct UmmaParams {
   // m + a_shift of the SAME [rows][a_split] matrix, chunks from a_split on from rows m (columns k - a_split); rows outside
   // the matrix are zero-filled by the TMA unit = the causal padding.  0: plain A[M][K]
   int a_split, a_shift;
+  int tn_R, tn_shift;             // two-tap weight-gradient form: output rows [0, tn_R) pair A row k with B row k + tn_shift, rows
+                                  // [tn_R, 2 tn_R) (A columns m - tn_R) pair row k with row k:  [x[t-d] | x[t]]^T . dpre in one launch
   int aux_add;                    // aux is an fp16 matrix ADDED (times aux_scale) to the accumulator (residual / skip-path term)
   float aux_scale;
 };
@@ -213,10 +215,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           unsigned char* sa = smem + s * STAGE_BYTES;
           const int kc = k_begin + i * ukk;
           const int bsh = p.f16 ? 6 : 5;      // MN-major blocks: 32 floats / 64 halfs wide
-          if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, m0 >> bsh);     // [blocks][k rows][128 B of m]
+          const int tap1 = (p.tn_R && m0 >= p.tn_R) ? 1 : 0;
+          const int kb = kc + ((p.tn_R && !tap1) ? p.tn_shift : 0);
+          if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, (m0 - tap1 * p.tn_R) >> bsh);     // [blocks][k rows][128 B of m]
           else if (p.a_split && kc < p.a_split) tma_load_2d(sa, &mapA, &full_bar[s], kc, m0 + p.a_shift);
           else tma_load_2d(sa, &mapA, &full_bar[s], kc - p.a_split, m0);
-          if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kc, n0 >> bsh);
+          if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kb, n0 >> bsh);
           else tma_load_2d(sa + A_BYTES, &mapB, &full_bar[s], kc, n0);
         }
       }
@@ -438,16 +442,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         uint4 hq[4];      // fp16 copy of the (unscaled) values
         if (p.has_c16) {
-          __half2* h2 = reinterpret_cast<__half2*>(hq);
+          uint32_t* hw = reinterpret_cast<uint32_t*>(hq);      // (one saturating conversion per pair: +-65504 instead of inf)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            h2[j] = __floats2half2_rn(fminf(fmaxf(f[2 * j], -65504.f), 65504.f), fminf(fmaxf(f[2 * j + 1], -65504.f), 65504.f));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw[j]) : "f"(f[2 * j + 1]), "f"(f[2 * j]));
         }
-        if (p.c_scale != 0.f) {
+        // (scaling and tf32 rounding only concern the fp32 output)
+        if ((p.C || p.CT) && p.c_scale != 0.f) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= p.c_scale;
         }
-        if (p.flags & GEMM_ROUND) {
+        if ((p.C || p.CT) && (p.flags & GEMM_ROUND)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
         }
@@ -576,7 +581,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
     if (rc) return rc;
   }
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
   p.m2 = 0;
@@ -645,6 +650,7 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = bias;
   p.aux = aux16 ? (const float*)aux16 : aux; p.ldaux = ldaux; p.M = M; p.N = N; p.K = K; p.flags = flags;
   p.m2 = 0;
+  p.tn_R = 0; p.tn_shift = 0;
   p.a_split = a_split; p.a_shift = ex ? ex->a_shift : 0; p.aux_add = aux16 ? 1 : 0; p.aux_scale = ex ? ex->aux_scale : 1.f;
   p.a_mn = 0; p.b_mn = 0; p.f16 = 1; p.has_c16 = C16 ? 1 : 0;
   p.mask_out = mask_out; p.mask_in = mask_in; p.ldmw = ldmw;
@@ -688,8 +694,9 @@ bool gemm_f16_tn_supported(int lda, int ldb, int M, int N) {
 // Weight-gradient form on fp16 operands:  C[M,N] += c_scale * A16[K,M]^T . B16[K,N]  (both operands as they lie in
 // memory: the contracted dimension -- time -- is the row index), split over K, accumulated with red.global.add.
 int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, int M, int N, int K, float c_scale,
-                int split_k, cudaStream_t st) {
+                int split_k, cudaStream_t st, int tn_R, int tn_shift) {
   if (K <= 0 || !A16 || !B16 || !C) return -1;
+  if (tn_R && (M != 2 * tn_R || (tn_R & 127) || tn_shift < 0)) return -1;
   if (!gemm_f16_tn_supported(lda, ldb, M, N) || ((uintptr_t)A16 & 15) || ((uintptr_t)B16 & 15) || (ldc & 3) || ((uintptr_t)C & 15))
     return -3;
   const int BN = N > 128 ? 256 : 128;
@@ -697,18 +704,18 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   // 256 x 256 tile moves 64 KB per k-step where two 128 x 256 tiles move 96 KB (WN_GEMM_M2=0 switches it off)
   static int m2_on = -1;
   if (m2_on < 0) m2_on = (getenv("WN_GEMM_M2") && atoi(getenv("WN_GEMM_M2")) == 0) ? 0 : 1;
-  const int m2 = (m2_on && M >= 1024 && BN == 256) ? 1 : 0;      // (few output tiles -> many K splits -> the atomics of the bigger tiles cost more than the operand traffic saved: measured on the 512-row products)
+  const int m2 = (m2_on && M >= 1024 && BN == 256 && !tn_R) ? 1 : 0;      // (few output tiles -> many K splits -> the atomics of the bigger tiles cost more than the operand traffic saved: measured on the 512-row products)
   const int TMR = m2 ? 2 * UM : UM;
   CUtensorMap mA, mB;
-  int rc = make_map16_blocks_mn(&mA, A16, K, M, lda, TMR / 64);
+  int rc = make_map16_blocks_mn(&mA, A16, K, tn_R ? tn_R : M, lda, TMR / 64);
   if (rc) return rc;
   rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
   if (rc) return rc;
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
-  p.nbuf = 2; p.ewarps = 8; p.m2 = m2;
+  p.nbuf = 2; p.ewarps = 8; p.m2 = m2; p.tn_R = tn_R; p.tn_shift = tn_shift;
   p.a_mn = 1; p.b_mn = 1; p.f16 = 1; p.has_c16 = 0; p.mask_out = nullptr; p.mask_in = nullptr; p.ldmw = 0;
   p.c_scale = (c_scale == 1.f) ? 0.f : c_scale;
   int splits = split_k > 0 ? split_k : 1;

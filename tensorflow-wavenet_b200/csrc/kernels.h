@@ -52,8 +52,10 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
                 const F16Extra* ex = nullptr);
 // C[M,N] += c_scale * A16[K,M]^T . B16[K,N]: fp16 operands as they lie in memory (M, N multiples of 64), split-K atomics
 bool gemm_f16_tn_supported(int lda, int ldb, int M, int N);
+// tn_R > 0 (multiple of 128, M = 2 tn_R): two-tap form, C rows [0, tn_R) = A16[k][m]^T . B16[k + tn_shift], rows [tn_R, 2 tn_R) =
+// A16[k][m - tn_R]^T . B16[k]  (A16 has tn_R columns; B16 rows past K are zero-filled)
 int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, int M, int N, int K, float c_scale,
-                int split_k, cudaStream_t st);
+                int split_k, cudaStream_t st, int tn_R = 0, int tn_shift = 0);
 // out[i] = half(in[i])
 int to_half(const float* in, void* out, int64_t n, cudaStream_t st);
 int transpose_half(const float* in, int K, int N, void* out, int ldo, cudaStream_t st);
@@ -112,8 +114,9 @@ int wide16_block_fwd(const void* x16, void* x16_out, void* P16, void* zcat16, in
                      const float* prebias, const float* dense_bias, int B, int T, int d, int R, int D, cudaStream_t st);
 int wide16_block_bwd(const void* x16, const void* dxn16, const void* dzcat16, int ldz, int zcol, float cs, const void* P16,
                      const void* zcat16, void* dz16, void* dpre16, void* dx16_out, const void* img_l, float inv_scale,
-                     float* wtmp, float* gdense, float* gprebias, float* gdense_bias, float* cs_scratch, int B, int T, int d,
+                     float* wtmp, float* gdense, float* gprebias, float* gdense_bias_below, float* cs_scratch, int B, int T, int d,
                      int R, int D, cudaStream_t st);
+int wide16_colsum_chunks();
 int wide16_unpack_wgrad(const float* tmp, float* gwf, float* gwg, int L, int R, int D, cudaStream_t st);
 // second-generation forward block (block_fwd_h.cu): fp16 split rows [hi 32 | lo 32] between layers
 int64_t block_h_images_bytes(int L);

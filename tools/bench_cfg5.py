@@ -21,3 +21,21 @@ for _ in range(10): step()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print('cfg5 (R=D=128, L=40, S=512) B=%d T=%d: %.2f ms/step, %.3e samples/s, loss %.4f' % (B, T, ms, B * T / ms * 1e3, float(step.loss)))
+# per-stage times: events recorded after every launch of an eager step (serialises the side streams)
+import ctypes as C
+from wavenet import _lib
+lib = _lib.load()
+n_tags = 23
+ms_tag, n_tag = (C.c_float * n_tags)(), (C.c_int32 * n_tags)()
+torch.cuda.synchronize()
+assert lib.wn_profile_begin() == 0
+step._launch()
+assert lib.wn_profile_end(ms_tag, n_tag, n_tags) == 0
+buf = C.create_string_buffer(64)
+tot = 0.0
+for i in range(n_tags):
+    lib.wn_profile_tag_name(i, buf, 64)
+    if n_tag[i]:
+        print('  %-18s %4d launches %8.3f ms' % (buf.value.decode(), n_tag[i], ms_tag[i]))
+        tot += ms_tag[i]
+print('  total %.3f ms (eager, serialised)' % tot)
