@@ -141,6 +141,8 @@ struct UmmaParams {
   int a_split, a_shift;
   int tn_R, tn_shift;             // two-tap weight-gradient form: output rows [0, tn_R) pair A row k with B row k + tn_shift, rows
                                   // [tn_R, 2 tn_R) (A columns m - tn_R) pair row k with row k:  [x[t-d] | x[t]]^T . dpre in one launch
+  int wstage;                     // fp16-only outputs, 8 epilogue warps: a warp stages ALL its columns of a tile ([32 rows][64 halfs] blocks,
+                                  // 128B swizzle) and issues its TMA stores once per tile; the accumulator is released before the stores
   int aux_add;                    // aux is an fp16 matrix ADDED (times aux_scale) to the accumulator (residual / skip-path term)
   float aux_scale;
 };
@@ -322,7 +324,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_expect_tx(&aux_bar[ew][buf], p.aux_add ? STG_BYTES / 2 : STG_BYTES);
         tma_load_2d(my_aux + buf * STG_BYTES, &mapAux, &aux_bar[ew][buf], n0 + c0, row0);
       };
-      if (p.aux && lane == 0 && n0 + col_lo < p.N) issue_aux(col_lo);
+      if (p.aux && !p.wstage && lane == 0 && n0 + col_lo < p.N) issue_aux(col_lo);
       uint32_t mw[8];      // this row's mask words of the tile, fetched before the accumulator is waited for
 #pragma unroll
       for (int q = 0; q < 8; ++q) mw[q] = 0xFFFFFFFFu;
@@ -330,6 +332,131 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
         for (int q = 0; q < BN / 32; ++q)
           if (n0 + 32 * q < p.N) mw[q] = __ldg(p.mask_in + (size_t)row * p.ldmw + (n0 >> 5) + q);
+      }
+      if (p.wstage) {
+        // ---- wide staging (see UmmaParams::wstage): per tile ONE staging pass, one fence, one store group per warp ----
+        constexpr int NBW = BN / 128;                         // 64-column blocks per warp (its BN / 2 columns)
+        constexpr uint32_t WS = NBW * 4096;                   // bytes per warp
+        unsigned char* ws_out = out_stage + ew * WS;
+        unsigned char* ws_aux = out_stage + 8 * WS + ew * WS;
+        if (p.aux && lane == 0) {                             // fp16 addend blocks of this warp's columns: in flight while the MMAs run
+          int nblk = 0;
+#pragma unroll
+          for (int b = 0; b < NBW; ++b) nblk += (n0 + col_lo + 64 * b < p.N) ? 1 : 0;
+          if (nblk) {
+            mbar_expect_tx(&aux_bar[ew][0], nblk * 4096);
+#pragma unroll
+            for (int b = 0; b < NBW; ++b)
+              if (n0 + col_lo + 64 * b < p.N) tma_load_2d(ws_aux + b * 4096, &mapAux, &aux_bar[ew][0], n0 + col_lo + 64 * b, row0);
+          }
+        }
+        mbar_wait(&tmem_full_bar[acc], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's stores have left the blocks
+        __syncwarp();
+        if (p.aux && n0 + col_lo < p.N) { mbar_wait(&aux_bar[ew][0], aux_cnt & 1u); ++aux_cnt; }
+        auto tld = [&](uint32_t (&v)[32], int c0) {
+          const uint32_t taddr = tmem + acc * BN + ((uint32_t)(quad * 32) << 16) + c0;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr));
+        };
+        auto chunk = [&](uint32_t (&v)[32], int c0, int b, int sub) {      // 32 columns [c0, c0 + 32): block b, half sub
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          const int nb = n0 + c0;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+            }
+          }
+          if (p.flags & GEMM_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            if (p.mask_out && row_ok && nb < p.N) {
+              uint32_t word = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) word |= (f[j] > 0.f ? 1u : 0u) << j;
+              p.mask_out[(size_t)row * p.ldmw + (nb >> 5)] = word;
+            }
+          }
+          if (p.mask_in) {
+            uint32_t word = mw[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) word = (c0 >> 5) == q ? mw[q] : word;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = ((word >> j) & 1u) ? f[j] : 0.f;
+          }
+          if (p.aux) {
+            const unsigned char* as = ws_aux + b * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(as + ((uint32_t)((sub * 4 + j) ^ (lane & 7)) << 4));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 a = __half22float2(h2[u]);
+                f[8 * j + 2 * u] = fmaf(p.aux_scale, a.x, f[8 * j + 2 * u]);
+                f[8 * j + 2 * u + 1] = fmaf(p.aux_scale, a.y, f[8 * j + 2 * u + 1]);
+              }
+            }
+          }
+          uint4 hq[4];
+          uint32_t* hw = reinterpret_cast<uint32_t*>(hq);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw[j]) : "f"(f[2 * j + 1]), "f"(f[2 * j]));
+          unsigned char* os = ws_out + b * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(os + ((uint32_t)((sub * 4 + j) ^ (lane & 7)) << 4)) = hq[j];
+        };
+#pragma unroll 1
+        for (int b = 0; b < NBW; ++b) {
+          const int c0 = col_lo + 64 * b;
+          if (n0 + c0 >= p.N) break;                          // warp-uniform
+          uint32_t va[32], vb[32];
+          tld(va, c0);
+          tld(vb, c0 + 32);                                   // (columns past N: the accumulator holds zeros / stale data, the store clips them)
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          chunk(va, c0, b, 0);
+          chunk(vb, c0 + 32, b, 1);
+        }
+        // the accumulator is free as soon as it has been read: the MMAs of the tile after next start while the stores drain
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+#pragma unroll
+          for (int b = 0; b < NBW; ++b)
+            if (n0 + col_lo + 64 * b < p.N)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&mapC16), "r"(smem_u32(ws_out + b * 4096)), "r"(n0 + col_lo + 64 * b), "r"(row0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.colsum) {      // lane: columns lane, lane + 32 of every 64-column block over the warp's 32 rows (rows past M hold zeros)
+#pragma unroll 1
+          for (int b = 0; b < NBW; ++b) {
+            if (n0 + col_lo + 64 * b >= p.N) break;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = lane + 32 * cc;
+              float sacc = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                sacc += __half2float(*reinterpret_cast<const __half*>(ws_out + b * 4096 + rr * 128 + ((uint32_t)((c >> 3) ^ (rr & 7)) << 4) + (c & 7) * 2));
+              atomicAdd(&bias_s[col_lo + 64 * b + c], sacc);
+            }
+          }
+        }
+        continue;
       }
       mbar_wait(&tmem_full_bar[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -581,7 +708,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
     if (rc) return rc;
   }
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0; p.wstage = 0;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
   p.m2 = 0;
@@ -636,13 +763,33 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
     rc = make_map(&mAux, aux, M, N, ldaux, 32);
     if (rc) return rc;
   }
+  // wide staging (UmmaParams::wstage): fp16-only outputs; needs room for 8 warps x BN/2 columns (x 2 with an fp16 addend)
+  static const bool ws_env = [] { const char* e = getenv("WN_GEMM_WSTAGE"); return !(e && e[0] == '0'); }();
+  const size_t ws_bytes = (size_t)8 * (BN / 128) * 4096 * (aux16 ? 2 : 1);
+  const size_t stage_bytes = UM * UK * 4 + BN * UK * 4;
+  int ws_stages = 0;
+  if (ws_env && !C && C16 && !aux)
+    for (int sg = 4; sg >= 2 && !ws_stages; --sg)
+      if (1024 + sg * stage_bytes + ws_bytes <= SMEM_OPTIN) ws_stages = sg;
+  if (ws_stages < 3 && K > 128) ws_stages = 0;      // (two stages only for the shortest K loops)
+  // Measured: the wide staging wins where the epilogue sets the pace (K <= 256, relu-gradient masks, column sums, fp16
+  // addends: post2_dgrad 80 -> 59 us, post1_dgrad 88 -> 79) and loses where it costs the operand ring its fourth stage
+  // on a product that is bound by the L2 -> SM operand traffic (skip_fwd 176 -> 186, skip_dgrad 203 -> 213)
+  {
+    const bool has_aux_ = aux != nullptr || aux16 != nullptr;
+    const int base_stages = (1024 + 4 * stage_bytes + staging_bytes(C != nullptr, has_aux_, C16 != nullptr, 2, 8) <= SMEM_OPTIN) ? 4 : 3;
+    if (ws_stages < base_stages && K > 256 && !mask_in && !colsum) ws_stages = 0;
+  }
+  const bool wstage = ws_stages > 0;
   if (aux16) {
-    rc = make_map16(&mAux, aux16, M, N, ex->ldaux16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = wstage ? make_map16(&mAux, aux16, M, N, ex->ldaux16, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map16(&mAux, aux16, M, N, ex->ldaux16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   mC16 = mA;
   if (C16) {
-    rc = make_map16(&mC16, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = wstage ? make_map16(&mC16, C16, M, N, ldc16, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map16(&mC16, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   UmmaParams p;
@@ -669,7 +816,13 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
     pipe += UM * UK * 4 + BN * UK * 4;
   }
   pick_epilogue(pipe, C != nullptr, has_aux, C16 != nullptr, p);
-  const size_t smem = pipe + staging_bytes(C != nullptr, has_aux, C16 != nullptr, p.nbuf, p.ewarps);
+  size_t smem = pipe + staging_bytes(C != nullptr, has_aux, C16 != nullptr, p.nbuf, p.ewarps);
+  p.wstage = wstage ? 1 : 0;
+  if (wstage) {
+    p.stages = ws_stages;
+    p.ewarps = 8;
+    smem = 1024 + ws_stages * stage_bytes + ws_bytes;
+  }
   return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p);
 }
 
@@ -712,7 +865,7 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
   if (rc) return rc;
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0; p.wstage = 0;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
   p.nbuf = 2; p.ewarps = 8; p.m2 = m2; p.tn_R = tn_R; p.tn_shift = tn_shift;
