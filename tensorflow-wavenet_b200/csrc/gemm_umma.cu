@@ -30,7 +30,7 @@ namespace {
 
 constexpr int UM = 128;        // UMMA M (rows of A per tile)
 constexpr int UK = 32;         // floats per stage along K (= one 128-byte swizzle row)
-constexpr int MAX_STAGES = 4;        // 4 for the split-K weight-gradient form (no staging buffers), else 3
+constexpr int MAX_STAGES = 6;        // ring depth: 3-4 (48 KB stages), up to 6 for CTA pairs (32 KB stages)
 constexpr uint32_t STG_BYTES = 4096;   // one [32 rows][32 floats] epilogue staging block (128B-swizzled)
 constexpr int THREADS = 320;      // TMA warp, MMA warp, up to 8 epilogue warps (p.ewarps = 4 or 8)
 
@@ -147,15 +147,24 @@ struct UmmaParams {
   float aux_scale;
 };
 
-template <int BN>
+// PAIR = 1: CTA pairs (clusters of 2, tcgen05 cta_group::2): one M = 256 MMA per k-step spans both CTAs of a pair; a CTA
+// loads its own 128 rows of A and HALF of the B tile, so an SM receives 32 KB instead of 48 KB per k-step (BN = 256) -- the
+// long-K products are bound by exactly that L2 -> SM traffic.  The even CTA (leader) issues the MMAs and commits to the
+// barriers of both; TMA loads of both CTAs complete on the leader's "full" barrier; each CTA runs the epilogue of its own
+// 128 rows out of its own TMEM.  fp16 NT form only.
+template <int BN, int PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapAux, const __grid_constant__ CUtensorMap mapC16,
                  UmmaParams p) {
   const uint32_t A_BYTES = (p.m2 ? 2 : 1) * UM * UK * 4;       // 16 KB (32 KB for 256-row tiles)
-  constexpr uint32_t B_BYTES = BN * UK * 4;                    // 16 / 32 KB
+  constexpr uint32_t B_BYTES = BN * UK * 4 / (PAIR ? 2 : 1);   // 16 / 32 KB (a pair: each CTA holds half of the B tile)
   const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  const int TM_ROWS = p.m2 ? 2 * UM : UM;                      // rows of an output tile
+  const int TM_ROWS = PAIR ? 2 * UM : (p.m2 ? 2 * UM : UM);    // rows of an output tile (a pair: 128 per CTA)
+  uint32_t cta_rank = 0;
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // persistent loop over items: per CTA / per pair
+  const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[8][2];
@@ -177,16 +186,25 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], p.ewarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 2 * p.ewarps : p.ewarps); }
     for (int s = 0; s < 16; ++s) mbar_init(&aux_bar[s >> 1][s & 1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * BN));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) {      // both CTAs' barriers exist before either signals the other
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
@@ -195,7 +213,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int nt = item % n_nt;
     const int rest = item / n_nt;
     const int mt = rest % n_mt, sp = rest / n_mt;
-    m0 = mt * TM_ROWS;
+    m0 = mt * TM_ROWS + (PAIR ? (int)cta_rank * UM : 0);      // (a pair: this CTA's 128 rows)
     n0 = nt * BN;
     k_begin = sp * p.k_per_split;
     int k_end = k_begin + p.k_per_split;
@@ -206,16 +224,30 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      uint32_t lead_full[MAX_STAGES];      // a pair: the leader's "full" barriers (cluster addresses)
+      if (PAIR)
+        for (int s = 0; s < MAX_STAGES; ++s)
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lead_full[s]) : "r"(smem_u32(&full_bar[s])), "r"(0));
+      for (int item = item0; item < n_items; item += item_step) {
         int m0, n0, k_begin, nk;
         decode(item, m0, n0, k_begin, nk);
         for (int i = 0; i < nk; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           unsigned char* sa = smem + s * STAGE_BYTES;
           const int kc = k_begin + i * ukk;
+          if (PAIR) {      // both CTAs' boxes complete on the leader's barrier, which expects the bytes of both
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            const int ka = (p.a_split && kc < p.a_split) ? kc : kc - p.a_split;
+            const int ma = (p.a_split && kc < p.a_split) ? m0 + p.a_shift : m0;
+            asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(smem_u32(sa)), "l"(&mapA), "r"(lead_full[s]), "r"(ka), "r"(ma) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(smem_u32(sa + A_BYTES)), "l"(&mapB), "r"(lead_full[s]), "r"(kc), "r"(n0 + (int)cta_rank * (BN / 2)) : "memory");
+            continue;
+          }
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int bsh = p.f16 ? 6 : 5;      // MN-major blocks: 32 floats / 64 halfs wide
           const int tap1 = (p.tn_R && m0 >= p.tn_R) ? 1 : 0;
           const int kb = kc + ((p.tn_R && !tap1) ? p.tn_shift : 0);
@@ -228,9 +260,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       const uint32_t idesc = p.f16 ? ((1u << 4) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                                      ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24))
+                                      ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * UM : UM) >> 4) << 24))
                                    : umma::idesc_tf32(UM, BN, p.a_mn, p.b_mn);
       // descriptor start-address step per MMA (>> 4): K-major 32 B; MN-major tf32 8 rows x 128 B, fp16 16 rows x 128 B
       const uint32_t mnstep = p.f16 ? 128 : 64;
@@ -247,11 +279,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         return d;
       };
       uint32_t it = 0, local = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+      for (int item = item0; item < n_items; item += item_step, ++local) {
         int m0, n0, k_begin, nk;
         decode(item, m0, n0, k_begin, nk);
         const uint32_t acc = p.m2 ? 0u : (local & 1), aph = p.m2 ? (local & 1) : ((local >> 1) & 1);
-        mbar_wait(&tmem_empty_bar[acc], aph ^ 1);      // the epilogue has drained this accumulator
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1);      // the epilogue (a pair: of both CTAs) has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem + acc * BN;
         for (int i = 0; i < nk; ++i, ++it) {
@@ -265,7 +297,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < UK / 8; ++k) {
             const uint32_t accum = (i > 0 || k > 0) ? 1u : 0u;
-            if (p.f16) {
+            if (PAIR) {
+              asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                           ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
+            } else if (p.f16) {
               asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                            ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
               if (p.m2)      // rows 128..255 of the tile: the second half of the A stage (+16 KB), second accumulator
@@ -275,9 +310,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                            ::"r"(d_tmem), "l"(da + astep * k), "l"(db + bstep * k), "r"(idesc), "r"(accum) : "memory");
           }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+          if (PAIR) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(smem_u32(&empty_bar[s])), "h"((uint16_t)3) : "memory");      // the stage is free in BOTH CTAs
+          else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tmem_full_bar[acc])) : "memory");
+        if (PAIR) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                               ::"r"(smem_u32(&tmem_full_bar[acc])), "h"((uint16_t)3) : "memory");
+        else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tmem_full_bar[acc])) : "memory");
       }
     }
   } else if (warp - 2 < p.ewarps) {
@@ -306,7 +345,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
       cs_n0 = next_n0;
     };
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+    // (a pair: every epilogue warp of both CTAs arrives on the LEADER's "accumulator drained" barrier)
+    auto release_acc = [&](uint32_t acc_) {
+      if (PAIR) {
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(&tmem_empty_bar[acc_])), "r"(0));
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc_])) : "memory");
+      }
+    };
+    for (int item = item0; item < n_items; item += item_step, ++local) {
       int m0, n0, k_begin, nk;
       decode(item, m0, n0, k_begin, nk);
       if (p.colsum && n0 != cs_n0) colsum_flush(n0);      // (warp-uniform, CTA-uniform)
@@ -433,7 +482,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+          release_acc(acc);
 #pragma unroll
           for (int b = 0; b < NBW; ++b)
             if (n0 + col_lo + 64 * b < p.N)
@@ -634,14 +683,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       // this warp has read everything it needs from the accumulator: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+      if (lane == 0) release_acc(acc);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores have landed
     if (p.colsum) colsum_flush(-1);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN));
+  if (PAIR) {      // neither CTA leaves (or frees its TMEM) while the other may still touch its shared memory / barriers / TMEM
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN));
+  } else {
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * BN));
+  }
 }
 
 // shared memory of the epilogue staging regions, and the deepest output ring that fits
@@ -657,21 +712,35 @@ static void pick_epilogue(size_t pipeline_bytes, bool has_c, bool has_aux, bool 
   p.ewarps = (pipeline_bytes + staging_bytes(has_c, has_aux, has_c16, 2, 8) <= SMEM_OPTIN) ? 8 : 4;
 }
 
-static int launch_umma(int BN, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB,
-                       const CUtensorMap& mC, const CUtensorMap& mAux, const CUtensorMap& mC16, const UmmaParams& p) {
-  constexpr int MAX_SMEM = (int)SMEM_OPTIN;
-  if (smem > (size_t)MAX_SMEM) return -5;
-  if (BN == 256) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM); attr = true; }
-    gemm_umma_kernel<256><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, mC16, p);
+template <int BN, int PAIR>
+static int launch_umma_t(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC,
+                         const CUtensorMap& mAux, const CUtensorMap& mC16, const UmmaParams& p) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm_umma_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_OPTIN);
+    attr = true;
+  }
+  if (!PAIR) {
+    gemm_umma_kernel<BN, PAIR><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, mC16, p);
   } else {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM); attr = true; }
-    gemm_umma_kernel<128><<<grid, THREADS, smem, st>>>(mA, mB, mC, mAux, mC16, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_umma_kernel<BN, PAIR>, mA, mB, mC, mAux, mC16, p);
+    if (e != cudaSuccess) return (int)e;
   }
   WN_CHECK_LAUNCH();
   return 0;
+}
+static int launch_umma(int BN, dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mB,
+                       const CUtensorMap& mC, const CUtensorMap& mAux, const CUtensorMap& mC16, const UmmaParams& p, bool pair = false) {
+  if (smem > SMEM_OPTIN) return -5;
+  if (pair) return BN == 256 ? launch_umma_t<256, 1>(grid, smem, st, mA, mB, mC, mAux, mC16, p) : -1;
+  return BN == 256 ? launch_umma_t<256, 0>(grid, smem, st, mA, mB, mC, mAux, mC16, p)
+                   : launch_umma_t<128, 0>(grid, smem, st, mA, mB, mC, mAux, mC16, p);
 }
 
 // mode 0 NN / 1 NT / 2 TN (see the file header).  Returns -3 for shapes the tcgen05 path does not take
@@ -751,7 +820,10 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   CUtensorMap mA, mB, mC, mAux, mC16;
   int rc = make_map16(&mA, A16, M, a_split ? a_split : K, lda, UM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_map16(&mB, B16, N, K, ldb, BN, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  // CTA pairs (gemm_umma_kernel<BN, 1>): 256-row tiles, each CTA loads half of the B tile (WN_GEMM_PAIR=0: off)
+  static const bool pair_env = [] { const char* e = getenv("WN_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  const bool pair = pair_env && BN == 256 && M >= 4 * UM && sm_count() >= 2;
+  rc = make_map16(&mB, B16, N, K, ldb, pair ? BN / 2 : BN, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   mC = mA;
   if (C) {
@@ -766,10 +838,11 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   // wide staging (UmmaParams::wstage): fp16-only outputs; needs room for 8 warps x BN/2 columns (x 2 with an fp16 addend)
   static const bool ws_env = [] { const char* e = getenv("WN_GEMM_WSTAGE"); return !(e && e[0] == '0'); }();
   const size_t ws_bytes = (size_t)8 * (BN / 128) * 4096 * (aux16 ? 2 : 1);
-  const size_t stage_bytes = UM * UK * 4 + BN * UK * 4;
+  const size_t stage_bytes = UM * UK * 4 + BN * UK * 4 / (pair ? 2 : 1);
+  const int max_stages = pair ? MAX_STAGES : 4;
   int ws_stages = 0;
   if (ws_env && !C && C16 && !aux)
-    for (int sg = 4; sg >= 2 && !ws_stages; --sg)
+    for (int sg = max_stages; sg >= 2 && !ws_stages; --sg)
       if (1024 + sg * stage_bytes + ws_bytes <= SMEM_OPTIN) ws_stages = sg;
   if (ws_stages < 3 && K > 128) ws_stages = 0;      // (two stages only for the shortest K loops)
   // Measured: the wide staging wins where the epilogue sets the pace (K <= 256, relu-gradient masks, column sums, fp16
@@ -778,7 +851,7 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   {
     const bool has_aux_ = aux != nullptr || aux16 != nullptr;
     const int base_stages = (1024 + 4 * stage_bytes + staging_bytes(C != nullptr, has_aux_, C16 != nullptr, 2, 8) <= SMEM_OPTIN) ? 4 : 3;
-    if (ws_stages < base_stages && K > 256 && !mask_in && !colsum) ws_stages = 0;
+    if (ws_stages < base_stages && K > 256 && !mask_in && !colsum) ws_stages = 0;      // (never with pairs: their 32 KB stages leave room)
   }
   const bool wstage = ws_stages > 0;
   if (aux16) {
@@ -806,14 +879,17 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
   p.k_per_split = (K + 63) / 64 * 64;
   p.splits = 1;
   p.stages = 3;
-  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + UM - 1) / UM);
-  dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-  size_t pipe = 1024 + (size_t)p.stages * (UM * UK * 4 + BN * UK * 4);
-  // a fourth operand stage where the (8-warp) staging leaves room for it: fp16-only outputs
+  const int tm_rows = pair ? 2 * UM : UM;
+  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + tm_rows - 1) / tm_rows);
+  unsigned gx = (unsigned)(items < sm_count() ? items : sm_count());
+  if (pair) { gx = (unsigned)(2 * items < sm_count() ? 2 * items : sm_count()); gx &= ~1u; }      // whole pairs
+  dim3 grid(gx);
+  size_t pipe = 1024 + (size_t)p.stages * stage_bytes;
+  // more operand stages where the (8-warp) staging leaves room for them: fp16-only outputs, CTA pairs
   const bool has_aux = aux != nullptr || aux16 != nullptr;
-  if (pipe + (UM * UK * 4 + BN * UK * 4) + staging_bytes(C != nullptr, has_aux, C16 != nullptr, 2, 8) <= SMEM_OPTIN) {
-    p.stages = 4;
-    pipe += UM * UK * 4 + BN * UK * 4;
+  while (p.stages < max_stages && pipe + stage_bytes + staging_bytes(C != nullptr, has_aux, C16 != nullptr, 2, 8) <= SMEM_OPTIN) {
+    ++p.stages;
+    pipe += stage_bytes;
   }
   pick_epilogue(pipe, C != nullptr, has_aux, C16 != nullptr, p);
   size_t smem = pipe + staging_bytes(C != nullptr, has_aux, C16 != nullptr, p.nbuf, p.ewarps);
@@ -823,7 +899,7 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
     p.ewarps = 8;
     smem = 1024 + ws_stages * stage_bytes + ws_bytes;
   }
-  return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p);
+  return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p, pair);
 }
 
 // fp16 [rows][cols] row-major viewed as [cols/64][rows][64]: one box {64, 64 rows, n_blocks} lands as n_blocks
