@@ -14,6 +14,7 @@
 // The activations between layers are fp16 (north_star config 5 asks for 16-bit storage; fp16 has the bytes of bf16 and
 // three more mantissa bits, the values are O(1)); accumulation, biases, parameters and gradients are fp32.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -217,14 +218,20 @@ int wide16_block_fwd(const void* x16, void* x16_out, void* P16, void* zcat16, in
   const __half* img = (const __half*)img_l;
   const __half* Wc = img;
   const __half* Wdt = img + (int64_t)4 * R * D;
+  // D = 128: one 128 x 256 accumulator holds [f | g] of 128 steps, the gate runs in the GEMM epilogue (WN_WIDE16_GATE=0: own kernel)
+  static const bool gate_env = [] { const char* e = getenv("WN_WIDE16_GATE"); return !(e && e[0] == '0'); }();
+  const bool gate_fused = gate_env && D == 128;
   for (int b = 0; b < B; ++b) {      // (per batch element: rows t - d < 0 must read zeros, not the previous element)
     F16Extra ex;
     ex.a_split = R; ex.a_shift = -d;
+    if (gate_fused) { ex.gate_z16 = (__half*)zcat16 + zcol + (int64_t)b * T * ldz; ex.ldz = ldz; }      // z from the epilogue
     WRC(gemm_f16_nt((const __half*)x16 + (int64_t)b * T * R, R, Wc, 2 * R, nullptr, 0, (__half*)P16 + (int64_t)b * T * 2 * D, 2 * D, T,
                     2 * D, 2 * R, prebias + (int64_t)b * 2 * D, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, nullptr, 0.f, &ex));
   }
-  w16_gate_kernel<<<nblk(M * (D >> 3)), 256, 0, st>>>((const __half*)P16, (__half*)zcat16 + zcol, ldz, M, D);
-  WN_CHECK_LAUNCH();
+  if (!gate_fused) {
+    w16_gate_kernel<<<nblk(M * (D >> 3)), 256, 0, st>>>((const __half*)P16, (__half*)zcat16 + zcol, ldz, M, D);
+    WN_CHECK_LAUNCH();
+  }
   if (x16_out) {
     F16Extra ex;
     ex.aux16 = x16; ex.ldaux16 = R; ex.aux_scale = 1.f;
@@ -248,13 +255,24 @@ int wide16_block_bwd(const void* x16, const void* dxn16, const void* dzcat16, in
   const __half* Wdg = img + (int64_t)5 * R * D;
   const __half* Wdx = img + (int64_t)6 * R * D;
   const __half* dzs = (const __half*)dzcat16 + zcol;
-  if (dxn16) {
+  // D = 128: dpre and its column sums come out of the epilogue of the dz GEMM (WN_WIDE16_DPRE=0: own kernels)
+  static const bool dpre_env = [] { const char* e = getenv("WN_WIDE16_DPRE"); return !(e && e[0] == '0'); }();
+  const bool dpre_fused = dpre_env && dxn16 && D == 128;
+  if (dpre_fused) {
+    for (int b = 0; b < B; ++b) {      // (per batch element: the column sums are per element)
+      F16Extra ex;
+      ex.aux16 = dzs + (int64_t)b * T * ldz; ex.ldaux16 = ldz; ex.aux_scale = cs;
+      ex.dpre_P16 = (const __half*)P16 + (int64_t)b * T * 2 * D; ex.ldp = 2 * D;
+      WRC(gemm_f16_nt((const __half*)dxn16 + (int64_t)b * T * R, R, Wdg, R, nullptr, 0, (__half*)dpre16 + (int64_t)b * T * 2 * D, 2 * D, T, D, R,
+                      nullptr, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, gprebias + (int64_t)b * 2 * D, inv_scale, &ex));
+    }
+  } else if (dxn16) {
     F16Extra ex;
     ex.aux16 = dzs; ex.ldaux16 = ldz; ex.aux_scale = cs;
     WRC(gemm_f16_nt(dxn16, R, Wdg, R, nullptr, 0, dz16, D, (int)M, D, R, nullptr, nullptr, 0, 1.f, 0, st, nullptr, nullptr, 0, nullptr,
                     0.f, &ex));
   }
-  {
+  if (!dpre_fused) {
     const int RS = 256 / (D >> 3);
     int chunks = (4 * sm_count() + B - 1) / B;
     if (chunks > (T + RS - 1) / RS) chunks = (T + RS - 1) / RS;

@@ -143,6 +143,9 @@ struct UmmaParams {
                                   // [tn_R, 2 tn_R) (A columns m - tn_R) pair row k with row k:  [x[t-d] | x[t]]^T . dpre in one launch
   int wstage;                     // fp16-only outputs, 8 epilogue warps: a warp stages ALL its columns of a tile ([32 rows][64 halfs] blocks,
                                   // 128B swizzle) and issues its TMA stores once per tile; the accumulator is released before the stores
+  int dpre;                       // N = BN = 128 (block_wide16.cu backward): the product + aux is dz; the epilogue loads the saved
+                                  // pre-activations [f 128 | g 128] through mapC and stores dpre = [df | dg] ([M][256]) through mapC16
+  int gate;                       // N = BN = 256 = [f | g]: z = tanh(f + b) sigmoid(g + b) stored through mapC (fp16), f / g through mapC16
   int aux_add;                    // aux is an fp16 matrix ADDED (times aux_scale) to the accumulator (residual / skip-path term)
   float aux_scale;
 };
@@ -169,7 +172,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2], aux_bar[8][2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[BN];
+  __shared__ __align__(16) float bias_s[256];      // bias of the tile's columns / collected column sums (dpre mode: 256 of them)
   // epilogue staging (per epilogue warp, double buffered): output chunks leave through TMA stores, the
   // relu-gradient mask chunks arrive through TMA loads -- no scattered 16-byte global accesses
   const int STAGES = p.stages;
@@ -338,8 +341,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int cs_n0 = -1;      // column range whose sums bias_s currently holds
     auto colsum_flush = [&](int next_n0) {      // all epilogue warps: add the collected sums to global memory, start over
       asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
-      for (int i = etid; i < BN; i += ethreads) {
-        if (cs_n0 >= 0 && cs_n0 + i < p.N) atomicAdd(p.colsum + cs_n0 + i, bias_s[i] * p.colsum_scale);
+      for (int i = etid; i < (p.dpre ? 256 : BN); i += ethreads) {
+        if (cs_n0 >= 0 && cs_n0 + i < (p.dpre ? 256 : p.N)) atomicAdd(p.colsum + cs_n0 + i, bias_s[i] * p.colsum_scale);
         bias_s[i] = 0.f;
       }
       asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
@@ -373,7 +376,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_expect_tx(&aux_bar[ew][buf], p.aux_add ? STG_BYTES / 2 : STG_BYTES);
         tma_load_2d(my_aux + buf * STG_BYTES, &mapAux, &aux_bar[ew][buf], n0 + c0, row0);
       };
-      if (p.aux && !p.wstage && lane == 0 && n0 + col_lo < p.N) issue_aux(col_lo);
+      if (p.aux && !p.wstage && !p.dpre && lane == 0 && n0 + col_lo < p.N) issue_aux(col_lo);
       uint32_t mw[8];      // this row's mask words of the tile, fetched before the accumulator is waited for
 #pragma unroll
       for (int q = 0; q < 8; ++q) mw[q] = 0xFFFFFFFFu;
@@ -381,6 +384,167 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
         for (int q = 0; q < BN / 32; ++q)
           if (n0 + 32 * q < p.N) mw[q] = __ldg(p.mask_in + (size_t)row * p.ldmw + (n0 >> 5) + q);
+      }
+      auto tld = [&](uint32_t (&v)[32], int c0) {
+        const uint32_t taddr = tmem + acc * BN + ((uint32_t)(quad * 32) << 16) + c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+      };
+      if (BN == 128 && p.dpre) {
+        // ---- dz -> dpre in the epilogue: a warp takes 64 dz columns of its 32 rows, the matching saved f and g blocks and
+        // the skip-path gradient block arrive by TMA while the MMAs run; df / dg leave as two blocks, their column sums
+        // (bias / conditioning gradients) are collected on the way ----
+        unsigned char* ds = out_stage + ew * 5 * 4096;        // blocks: dz_skip, f, g (in), df, dg (out)
+        const int cf = (ew >> 2) * 64;
+        if (lane == 0) {
+          mbar_expect_tx(&aux_bar[ew][0], 3 * 4096);
+          tma_load_2d(ds, &mapAux, &aux_bar[ew][0], cf, row0);
+          tma_load_2d(ds + 4096, &mapC, &aux_bar[ew][0], cf, row0);
+          tma_load_2d(ds + 8192, &mapC, &aux_bar[ew][0], 128 + cf, row0);
+        }
+        mbar_wait(&tmem_full_bar[acc], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        mbar_wait(&aux_bar[ew][0], aux_cnt & 1u);
+        ++aux_cnt;
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t va[32];
+          tld(va, cf + 32 * sub);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const unsigned char* is = ds + lane * 128;
+          uint4 qf[4], qg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t off = (uint32_t)((sub * 4 + j) ^ (lane & 7)) << 4;
+            const uint4 qs = *reinterpret_cast<const uint4*>(is + off);
+            const uint4 pf = *reinterpret_cast<const uint4*>(is + 4096 + off);
+            const uint4 pg = *reinterpret_cast<const uint4*>(is + 8192 + off);
+            const __half2* hs = reinterpret_cast<const __half2*>(&qs);
+            const __half2* hf = reinterpret_cast<const __half2*>(&pf);
+            const __half2* hg = reinterpret_cast<const __half2*>(&pg);
+            uint32_t* of = reinterpret_cast<uint32_t*>(&qf[j]);
+            uint32_t* og = reinterpret_cast<uint32_t*>(&qg[j]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 sk = __half22float2(hs[u]), ff = __half22float2(hf[u]), gg = __half22float2(hg[u]);
+              const float dz0 = fmaf(p.aux_scale, sk.x, __uint_as_float(va[8 * j + 2 * u]));
+              const float dz1 = fmaf(p.aux_scale, sk.y, __uint_as_float(va[8 * j + 2 * u + 1]));
+              float t0, s0, t1, s1;
+              gated_parts_fast(ff.x, gg.x, t0, s0);
+              gated_parts_fast(ff.y, gg.y, t1, s1);
+              const float df0 = dz0 * s0 * (1.f - t0 * t0), df1 = dz1 * s1 * (1.f - t1 * t1);
+              const float dg0 = dz0 * t0 * s0 * (1.f - s0), dg1 = dz1 * t1 * s1 * (1.f - s1);
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(of[u]) : "f"(df1), "f"(df0));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(og[u]) : "f"(dg1), "f"(dg0));
+            }
+          }
+          unsigned char* os = ds + 12288 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t off = (uint32_t)((sub * 4 + j) ^ (lane & 7)) << 4;
+            *reinterpret_cast<uint4*>(os + off) = qf[j];
+            *reinterpret_cast<uint4*>(os + 4096 + off) = qg[j];
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          release_acc(acc);
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&mapC16), "r"(smem_u32(ds + 12288)), "r"(cf), "r"(row0) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&mapC16), "r"(smem_u32(ds + 16384)), "r"(128 + cf), "r"(row0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.colsum) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = lane + 32 * cc;
+              float sacc = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                sacc += __half2float(*reinterpret_cast<const __half*>(ds + 12288 + b * 4096 + rr * 128 + ((uint32_t)((c >> 3) ^ (rr & 7)) << 4) + (c & 7) * 2));
+              atomicAdd(&bias_s[128 * b + cf + c], sacc);
+            }
+        }
+        continue;
+      }
+      if (BN == 256 && p.gate) {
+        // ---- gated activation in the epilogue (block_wide16.cu): the tile is [f 128 | g 128]; a warp takes 64 f columns and
+        // the matching 64 g columns of its 32 rows, stores both (the saved pre-activations) and z = tanh(f) sigmoid(g) ----
+        unsigned char* gs = out_stage + ew * 3 * 4096;        // blocks: f, g, z ([32 rows][64 halfs], 128B swizzle)
+        const int cf = (ew >> 2) * 64, cg = 128 + cf;
+        mbar_wait(&tmem_full_bar[acc], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t va[32], vb[32];
+          tld(va, cf + 32 * sub);
+          tld(vb, cg + 32 * sub);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float f[32], g[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(va[j]); g[j] = __uint_as_float(vb[j]); }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bf = *reinterpret_cast<const float4*>(bias_s + cf + 32 * sub + j);
+              const float4 bg = *reinterpret_cast<const float4*>(bias_s + cg + 32 * sub + j);
+              f[j] += bf.x; f[j + 1] += bf.y; f[j + 2] += bf.z; f[j + 3] += bf.w;
+              g[j] += bg.x; g[j + 1] += bg.y; g[j + 2] += bg.z; g[j + 3] += bg.w;
+            }
+          }
+          uint4 hq[4];
+          uint32_t* hw = reinterpret_cast<uint32_t*>(hq);
+          unsigned char* os = gs + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw[j]) : "f"(f[2 * j + 1]), "f"(f[2 * j]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(os + ((uint32_t)((sub * 4 + j) ^ (lane & 7)) << 4)) = hq[j];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw[j]) : "f"(g[2 * j + 1]), "f"(g[2 * j]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(os + 4096 + ((uint32_t)((sub * 4 + j) ^ (lane & 7)) << 4)) = hq[j];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {      // two MUFU.TANH per element: sigmoid(g) = 0.5 tanh(g / 2) + 0.5  (2^-11 relative, the
+            float t, u;                       // precision z is stored with; ex2 / rcp forms measured: +6 us per layer, same logits error)
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(f[j]));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(u) : "f"(0.5f * g[j]));
+            f[j] = t * fmaf(0.5f, u, 0.5f);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hw[j]) : "f"(f[2 * j + 1]), "f"(f[2 * j]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(os + 8192 + ((uint32_t)((sub * 4 + j) ^ (lane & 7)) << 4)) = hq[j];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          release_acc(acc);
+          if (p.has_c16) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&mapC16), "r"(smem_u32(gs)), "r"(n0 + cf), "r"(row0) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&mapC16), "r"(smem_u32(gs + 4096)), "r"(n0 + cg), "r"(row0) : "memory");
+          }
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&mapC), "r"(smem_u32(gs + 8192)), "r"(cf), "r"(row0) : "memory");      // z: mapC is the layer's column block of Zcat16
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        continue;
       }
       if (p.wstage) {
         // ---- wide staging (see UmmaParams::wstage): per tile ONE staging pass, one fence, one store group per warp ----
@@ -404,16 +568,6 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's stores have left the blocks
         __syncwarp();
         if (p.aux && n0 + col_lo < p.N) { mbar_wait(&aux_bar[ew][0], aux_cnt & 1u); ++aux_cnt; }
-        auto tld = [&](uint32_t (&v)[32], int c0) {
-          const uint32_t taddr = tmem + acc * BN + ((uint32_t)(quad * 32) << 16) + c0;
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr));
-        };
         auto chunk = [&](uint32_t (&v)[32], int c0, int b, int sub) {      // 32 columns [c0, c0 + 32): block b, half sub
           float f[32];
 #pragma unroll
@@ -777,7 +931,7 @@ int gemm_umma(int mode, const GemmParams& g, float* CT, int ldct, int split_k, c
     if (rc) return rc;
   }
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0; p.wstage = 0;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0; p.wstage = 0; p.gate = 0; p.dpre = 0;
   p.C = g.C; p.ldc = g.ldc; p.CT = CT; p.ldct = ldct; p.C2 = g.C2; p.ldc2 = g.ldc2; p.bias = g.bias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.M = g.M; p.N = g.N; p.K = g.K; p.flags = g.flags;
   p.m2 = 0;
@@ -853,15 +1007,29 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
     const int base_stages = (1024 + 4 * stage_bytes + staging_bytes(C != nullptr, has_aux_, C16 != nullptr, 2, 8) <= SMEM_OPTIN) ? 4 : 3;
     if (ws_stages < base_stages && K > 256 && !mask_in && !colsum) ws_stages = 0;      // (never with pairs: their 32 KB stages leave room)
   }
+  const void* dpre_P16 = ex ? ex->dpre_P16 : nullptr;
+  if (dpre_P16 && (N != 128 || C || aux || !aux16 || !C16 || bias || a_split || (ex->ldp & 7) || ((uintptr_t)dpre_P16 & 15))) return -3;
+  if (dpre_P16) {
+    ws_stages = 0;
+    rc = make_map16(&mC, dpre_P16, M, 256, ex->ldp, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  void* gate_z16 = ex ? ex->gate_z16 : nullptr;
+  if (gate_z16 && (N != 256 || C || aux || aux16 || !C16 || (ex->ldz & 7) || ((uintptr_t)gate_z16 & 15))) return -3;
+  if (gate_z16) ws_stages = 0;
   const bool wstage = ws_stages > 0;
+  if (gate_z16) {      // z block map in the mapC slot: [M][128] halfs at the layer's columns of Zcat16
+    rc = make_map16(&mC, gate_z16, M, N / 2, ex->ldz, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
   if (aux16) {
-    rc = wstage ? make_map16(&mAux, aux16, M, N, ex->ldaux16, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+    rc = (wstage || dpre_P16) ? make_map16(&mAux, aux16, M, N, ex->ldaux16, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)
                 : make_map16(&mAux, aux16, M, N, ex->ldaux16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   mC16 = mA;
   if (C16) {
-    rc = wstage ? make_map16(&mC16, C16, M, N, ldc16, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)
+    rc = (wstage || gate_z16 || dpre_P16) ? make_map16(&mC16, C16, M, dpre_P16 ? 256 : N, ldc16, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)
                 : make_map16(&mC16, C16, M, N, ldc16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
@@ -898,6 +1066,21 @@ int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, in
     p.stages = ws_stages;
     p.ewarps = 8;
     smem = 1024 + ws_stages * stage_bytes + ws_bytes;
+  }
+  p.dpre = dpre_P16 ? 1 : 0;
+  if (dpre_P16) {      // five blocks per warp (dz_skip, f, g in; df, dg out) beside a two-stage ring (K = 128: two k-steps per tile)
+    p.stages = 2;
+    p.ewarps = 8;
+    smem = 1024 + 2 * stage_bytes + (size_t)8 * 5 * 4096;
+  }
+  p.gate = gate_z16 ? 1 : 0;
+  if (gate_z16) {      // three staging blocks per warp (f, g, z); as many operand stages as fit beside them
+    const size_t gs_bytes = (size_t)8 * 3 * 4096;
+    int sg = max_stages;
+    while (sg > 2 && 1024 + sg * stage_bytes + gs_bytes > SMEM_OPTIN) --sg;
+    p.stages = sg;
+    p.ewarps = 8;
+    smem = 1024 + sg * stage_bytes + gs_bytes;
   }
   return launch_umma(BN, grid, smem, st, mA, mB, mC, mAux, mC16, p, pair);
 }
@@ -941,7 +1124,7 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
   if (rc) return rc;
   UmmaParams p;
-  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0; p.wstage = 0;
+  p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0; p.wstage = 0; p.gate = 0; p.dpre = 0;
   p.C = C; p.ldc = ldc; p.CT = nullptr; p.ldct = 0; p.C2 = nullptr; p.ldc2 = 0; p.bias = nullptr;
   p.aux = nullptr; p.ldaux = 0; p.M = M; p.N = N; p.K = K; p.flags = GEMM_ATOMIC;
   p.nbuf = 2; p.ewarps = 8; p.m2 = m2; p.tn_R = tn_R; p.tn_shift = tn_shift;

@@ -43,6 +43,10 @@ struct F16Extra {
   const void* aux16 = nullptr;       // fp16 [M][N] matrix added (times aux_scale) to the product
   int ldaux16 = 0;
   float aux_scale = 1.f;
+  void* gate_z16 = nullptr;          // N = 256 = [f 128 | g 128]: also store z = tanh(f) sigmoid(g) as fp16 [M][128] (row pitch ldz); C16 keeps f | g
+  int ldz = 0;
+  const void* dpre_P16 = nullptr;    // N = 128: product + aux16 is dz; with the saved [f 128 | g 128] (fp16, row pitch ldp) the epilogue stores
+  int ldp = 0;                       // dpre = [df | dg] into C16 ([M][256]); colsum then has 256 entries
 };
 // forward chain in fp16 (operands K-major fp16, fp32 accumulate / output, optional fp16 copy of the output)
 int gemm_f16_nt(const void* A16, int lda, const void* B16, int ldb, float* C, int ldc, void* C16, int ldc16, int M, int N,
