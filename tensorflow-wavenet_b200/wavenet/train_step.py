@@ -14,8 +14,9 @@ The all-reduce is split into two buckets and lives INSIDE the captured CUDA grap
 Measured on 2 x B200 (gpurun_out/r2_dp_bench_*.log): 2.805 ms / step with the bucketed in-graph all-reduce against
 2.767 ms with ONE all-reduce of the whole buffer after the graph replay -- the persistent backward kernels occupy every
 SM with two CTAs, so the NCCL kernel of the tail bucket does not get an SM before they are done, and the second
-collective only adds launch latency.  The bucketed form is therefore OFF by default (WN_DP_OVERLAP=1 turns it on; the
-2-rank test runs both and checks that they agree).
+collective only adds launch latency.  The bucketed form is therefore OFF by default (WN_DP_OVERLAP=1 turns it on).  It runs
+two collectives of one communicator on two streams of one graph, which NCCL does not guarantee to be deadlock-free next to
+other in-flight collectives: the 2-rank test exercises it only with WN_TEST_DP_OVERLAP=1.
 """
 import ctypes as C
 import os
