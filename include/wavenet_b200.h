@@ -13,7 +13,9 @@
  *     row-major [B*T, C] (time-major within a batch element, channels contiguous), float32;
  *   - every call is asynchronous on `stream` (a cudaStream_t) and allocates nothing;
  *   - return value: 0 ok, < 0 bad argument / unsupported shape, > 0 a cudaError_t;
- *   - not thread-safe per stream, no global state besides cached function attributes.
+ *   - ONE DEVICE PER PROCESS (the deployment model: one process per GPU, torch.distributed / NCCL between them): the
+ *     library's side streams, fork / join events, cached function attributes and SM count are process-global and
+ *     belong to the device that was current at the first call; calls are not thread-safe.
  */
 #ifndef WAVENET_B200_H_
 #define WAVENET_B200_H_
@@ -34,7 +36,7 @@ typedef void* wn_stream_t; /* cudaStream_t */
 typedef struct wn_config {
   int32_t n_layers;              /* len(dilations)                         */
   int32_t residual_channels;     /* R                                      */
-  int32_t dilation_channels;     /* D  (fast generation needs D == R)       */
+  int32_t dilation_channels;     /* D  (fast generation needs D == R in {16, 32}; training takes any widths) */
   int32_t skip_channels;         /* S                                      */
   int32_t quantization_channels; /* Q                                      */
   int32_t gc_channels;           /* G, 0 = no global conditioning          */
