@@ -482,6 +482,40 @@ def main():
         except Exception as e:      # noqa: BLE001  (an optional extra must not take the headline down)
             batch4 = {'error': repr(e)[:200]}
 
+    # ---------------- BASELINE config 5 (scaled net, 16-bit storage) next to the headline: `--config cfg5` gives the full line ----
+    cfg5 = None
+    if not args.no_batch4 and args.batch == B_PER_GPU and args.time == T_WINDOW:
+        try:
+            T5, R5, S5, Q5 = 65536, 128, 512, 256
+            dil5 = [2 ** i for i in range(10)] * 4
+            net5 = wavenet.WaveNetModel(batch_size=1, dilations=dil5, filter_width=2, residual_channels=R5, dilation_channels=R5,
+                                        quantization_channels=Q5, skip_channels=S5, use_biases=True, seed=0)
+            step5 = wavenet.TrainStep(net5, wavenet.optimizer_factory['adam'](learning_rate=1e-3, momentum=0.9), 1, T5)
+            step5.audio.copy_(torch.as_tensor(synthetic_audio(1, T5, 200 + rank)))
+            for _ in range(3):
+                step5()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(10):
+                step5()
+            f1.record()
+            barrier()
+            ms5 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(ms5, op=torch.distributed.ReduceOp.MAX)
+            L5 = len(dil5)
+            flop5 = 6.0 * (L5 * (2 * R5 * 2 * R5 + R5 * R5) - R5 * R5 + L5 * R5 * S5 + S5 * S5 + S5 * Q5)
+            tf5 = flop5 * T5 / (float(ms5) / 10 * 1e-3) / 1e12
+            cfg5 = {'value': world * T5 / (float(ms5) / 10 * 1e-3), 'unit': UNIT, 'ms_per_step': float(ms5) / 10,
+                    'workload': 'scaled net (L=40, R=D=128, S=512), fp16 activation storage, B=1 x T=65536 per GPU',
+                    'roofline': {'bound': 'tensor', 'achieved': tf5, 'peak': measured_peaks()['tflops'], 'unit': 'TFLOP/s',
+                                 'frac': tf5 / measured_peaks()['tflops']}}
+            del step5, net5
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001
+            cfg5 = {'error': repr(e)[:200]}
+
     # ---------------- fast generation (second half of the BASELINE metric) ----------------
     fastgen = None
     if not args.no_fastgen:
@@ -555,6 +589,7 @@ def main():
             'cpu_baseline': cpu,
             'fastgen': fastgen,
             'batch4': batch4,
+            'cfg5': cfg5,
             'loss': {'after_timed_steps': final_loss, 'e2e_last': loss_host},
         }
         print(json.dumps(line))

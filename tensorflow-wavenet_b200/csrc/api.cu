@@ -631,6 +631,67 @@ static int block_bwd_production(const float* x, const float* dx_out, const float
   return 0;
 }
 
+// Stand-alone wide block (channels a multiple of 64, R = D): the production kernels of block_wide16.cu as a one-layer
+// network.  fp32 in / out at the boundary; inside, the 16-bit storage of the training step (unscaled gradient domain).
+static int pitched_to_half(const float* src, int ld, void* dst16, float* tmp, int64_t M, int C_, cudaStream_t st) {
+  RC((int)cudaMemcpy2DAsync(tmp, (size_t)C_ * 4, src, (size_t)ld * 4, (size_t)C_ * 4, (size_t)M, cudaMemcpyDeviceToDevice, st));
+  return to_half(tmp, dst16, M * C_, st);
+}
+static int block_fwd_wide(const float* x, float* x_out, float* zcat, int ldz, const float* filter, const float* gate,
+                          const float* dense, const float* prebias, const float* dense_bias, int B, int T, int d, int Cw,
+                          int is_last, cudaStream_t st) {
+  const int64_t M = (int64_t)B * T, n = M * Cw;
+  StreamScratch sc;
+  RC(sc.init(5 * n * 2 + n * 4 + wide16_images_bytes(1, Cw, Cw) + 16 * 1024, st));
+  void* x16 = sc.take(n * 2);
+  void* xo16 = sc.take(n * 2);
+  void* P16 = sc.take(2 * n * 2);
+  void* z16 = sc.take(n * 2);
+  float* tmp = (float*)sc.take(n * 4);
+  void* img = sc.take(wide16_images_bytes(1, Cw, Cw));
+  if (!img) return -5;
+  RC(to_half(x, x16, n, st));
+  RC(wide16_images(img, filter, gate, dense ? dense : filter, 1, Cw, Cw, st));      // (the last layer's dense images are never read)
+  RC(wide16_block_fwd(x16, is_last ? nullptr : xo16, P16, z16, Cw, 0, img, prebias, dense_bias, B, T, d, Cw, Cw, st));
+  RC(wide16_to_float(z16, tmp, 1.f, n, st));
+  RC((int)cudaMemcpy2DAsync(zcat, (size_t)ldz * 4, tmp, (size_t)Cw * 4, (size_t)Cw * 4, (size_t)M, cudaMemcpyDeviceToDevice, st));
+  if (!is_last) RC(wide16_to_float(xo16, x_out, 1.f, n, st));
+  return 0;
+}
+static int block_bwd_wide(const float* x, const float* dx_out, const float* dz_skip, int ldz, float* dx, const float* filter,
+                          const float* gate, const float* dense, const float* prebias, float* gwf, float* gwg, float* gdense,
+                          float* gprebias, float* gdense_bias, int B, int T, int d, int Cw, int is_last, cudaStream_t st) {
+  const int64_t M = (int64_t)B * T, n = M * Cw;
+  const int64_t wt = wide16_wgrad_tmp_floats(1, Cw, Cw), csn = (int64_t)B * wide16_colsum_chunks() * 2 * Cw;
+  StreamScratch sc;
+  RC(sc.init(10 * n * 2 + n * 4 + (wt + csn) * 4 + wide16_images_bytes(1, Cw, Cw) + 32 * 1024, st));
+  void* x16 = sc.take(n * 2);
+  void* P16 = sc.take(2 * n * 2);
+  void* z16 = sc.take(n * 2);
+  void* dxn16 = sc.take(n * 2);
+  void* dzs16 = sc.take(n * 2);
+  void* dz16 = sc.take(n * 2);
+  void* dpre16 = sc.take(2 * n * 2);
+  void* dxo16 = sc.take(n * 2);
+  float* tmp = (float*)sc.take(n * 4);
+  float* wtmp = (float*)sc.take(wt * 4);
+  float* css = (float*)sc.take(csn * 4);
+  void* img = sc.take(wide16_images_bytes(1, Cw, Cw));
+  if (!img) return -5;
+  RC(to_half(x, x16, n, st));
+  RC(wide16_images(img, filter, gate, dense ? dense : filter, 1, Cw, Cw, st));
+  // the saved pre-activations (and z) of the forward pass: recomputed here, the entry point is stateless
+  RC(wide16_block_fwd(x16, nullptr, P16, z16, Cw, 0, img, prebias, nullptr, B, T, d, Cw, Cw, st));
+  RC(pitched_to_half(dz_skip, ldz, dzs16, tmp, M, Cw, st));
+  if (!is_last) RC(to_half(dx_out, dxn16, n, st));
+  RC((int)cudaMemsetAsync(wtmp, 0, (size_t)wt * 4, st));
+  RC(wide16_block_bwd(x16, is_last ? nullptr : dxn16, dzs16, Cw, 0, 1.f, P16, z16, dz16, dpre16, dxo16, img, 1.f, wtmp, gdense,
+                      gprebias, nullptr, css, B, T, d, Cw, Cw, st));
+  RC(wide16_unpack_wgrad(wtmp, gwf, gwg, 1, Cw, Cw, st));
+  if (!is_last && gdense_bias) RC(colsum(dx_out, Cw, (int)M, Cw, gdense_bias, st));      // (in the network: the epilogue of the layer above's dx GEMM)
+  return wide16_to_float(dxo16, dx, 1.f, n, st);
+}
+
 }  // namespace wn
 
 using namespace wn;
@@ -748,6 +809,9 @@ int wn_block_fwd(const float* x, float* x_out, float* zcat, int32_t ldz, const f
   if (!x || !zcat || !filter || !gate || !prebias || batch < 1 || time < 1 || dilation < 1) return -1;
   if (!is_last && (!x_out || !dense)) return -1;
   if ((ldz & 3) || ldz < channels) return -3;
+  if (wide16_supported(channels, channels) && wide16_enabled() && fwd16_enabled())
+    return block_fwd_wide(x, x_out, zcat, ldz, filter, gate, dense, prebias, dense_bias, batch, time, dilation, channels, is_last,
+                          (cudaStream_t)stream);
   if (channels == 32 && block_umma_enabled() && fwd_h_enabled() && fwd_chain_enabled())
     return block_fwd_production(x, x_out, zcat, ldz, filter, gate, dense, prebias, dense_bias, batch, time, dilation, is_last,
                                 (cudaStream_t)stream);
@@ -765,6 +829,9 @@ int wn_block_bwd(const float* x, const float* dx_out, const float* dz_skip, int3
     return -1;
   if (!is_last && (!dx_out || !dense || !grad_dense)) return -1;
   if ((ldz & 3) || ldz < channels) return -3;
+  if (wide16_supported(channels, channels) && wide16_enabled() && fwd16_enabled())
+    return block_bwd_wide(x, dx_out, dz_skip, ldz, dx, filter, gate, dense, prebias, grad_filter, grad_gate, grad_dense, grad_prebias,
+                          grad_dense_bias, batch, time, dilation, channels, is_last, (cudaStream_t)stream);
   if (channels == 32 && block_umma_enabled() && fwd_h_enabled() && bwd_chain_enabled())
     return block_bwd_production(x, dx_out, dz_skip, ldz, dx, dpre_scratch, zcat, filter, gate, dense, prebias, grad_filter,
                                 grad_gate, grad_dense, grad_prebias, grad_dense_bias, batch, time, dilation, is_last,

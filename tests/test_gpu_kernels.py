@@ -163,11 +163,18 @@ def _block_oracle(x, wf, wg, wd, prebias, bd, d, is_last, gz, gx):
                                               (32, 2, 700, 512, 0), (32, 1, 999, 4, 1), (16, 2, 515, 16, 0),
                                               (16, 1, 64, 256, 1), (32, 1, 16, 2, 0), (32, 2, 5, 1, 0),
                                               (32, 1, 100, 128, 0), (32, 3, 640, 512, 0), (32, 1, 257, 256, 1),
-                                              (32, 2, 1153, 127, 0), (16, 3, 300, 512, 0)])
+                                              (32, 2, 1153, 127, 0), (16, 3, 300, 512, 0),
+                                              # wide blocks (block_wide16.cu: two-tap GEMM, gate / dpre in the epilogues, 16-bit storage)
+                                              (128, 1, 1000, 1, 0), (128, 2, 700, 512, 0), (128, 3, 333, 8, 0),
+                                              (128, 1, 999, 4, 1), (128, 2, 130, 256, 0), (64, 2, 515, 16, 0),
+                                              (64, 1, 300, 2, 1), (192, 2, 257, 64, 0)])
 def test_block_fwd_bwd(lib, C_, B, T, d, is_last):
     """wn_block_fwd / wn_block_bwd: for 32 channels these run the PRODUCTION kernels of the training step
-    (block_fwd_chain_kernel; block_bwd_pre_umma + block_bwd_dx_umma + block_wgrad_all) as a one-layer network.
-    Shapes cover T not a multiple of the 128-step tile, d >= T (no valid past tap), d = 512 with B = 3, 16 channels."""
+    (block_fwd_chain_kernel; block_bwd_chain_f + reduce) as a one-layer network, for multiples of 64 channels the wide
+    blocks in 16-bit storage.  Shapes cover T not a multiple of the 128-step tile, d >= T (no valid past tap), d = 512
+    with B = 3, 16 channels.  Tolerances of the 16-bit path: every stored activation / gradient is rounded to fp16 (2^-11)."""
+    wide = C_ % 64 == 0
+    tol_z, tol_x, tol_g = (3e-3, 2e-3, 8e-3) if wide else (6e-4, 2e-5, GRAD_RTOL)
     rng = np.random.default_rng(C_ + T + d)
     M = B * T
     lim = np.sqrt(6.0 / (4 * C_))
@@ -190,10 +197,10 @@ def test_block_fwd_bwd(lib, C_, B, T, d, is_last):
     assert rc == 0
     z = zc[:, C_:2 * C_].cpu().numpy().reshape(B, T, C_)
     # forward block = split-precision (3xTF32) products; only the stored z is tf32-rounded (2^-11)
-    assert rel_err(z, ref['z']) < 6e-4
+    assert rel_err(z, ref['z']) < tol_z
     assert float(zc[:, :C_].abs().max()) == 0.0 and float(zc[:, 2 * C_:].abs().max()) == 0.0
     if not is_last:
-        assert rel_err(xo.cpu().numpy().reshape(B, T, C_), ref['xo']) < 2e-5
+        assert rel_err(xo.cpu().numpy().reshape(B, T, C_), ref['xo']) < tol_x
 
     dzs = torch.zeros(M, ldz, device='cuda')
     dzs[:, C_:2 * C_] = dev(gz).reshape(M, C_)
@@ -207,13 +214,13 @@ def test_block_fwd_bwd(lib, C_, B, T, d, is_last):
                           p(gwd), p(gpb), p(gbd), B, T, d, C_, is_last, stream())
     assert rc == 0
     torch.cuda.synchronize()
-    assert rel_err(dx.cpu().numpy().reshape(B, T, C_), ref['dx']) < GRAD_RTOL
-    assert rel_err(gwf.cpu().numpy(), ref['dwf']) < GRAD_RTOL
-    assert rel_err(gwg.cpu().numpy(), ref['dwg']) < GRAD_RTOL
-    assert rel_err(gpb.cpu().numpy(), ref['dpb']) < GRAD_RTOL
+    assert rel_err(dx.cpu().numpy().reshape(B, T, C_), ref['dx']) < tol_g
+    assert rel_err(gwf.cpu().numpy(), ref['dwf']) < tol_g
+    assert rel_err(gwg.cpu().numpy(), ref['dwg']) < tol_g
+    assert rel_err(gpb.cpu().numpy(), ref['dpb']) < tol_g
     if not is_last:
-        assert rel_err(gwd.cpu().numpy(), ref['dwd'][0]) < GRAD_RTOL
-        assert rel_err(gbd.cpu().numpy(), ref['dbd']) < GRAD_RTOL
+        assert rel_err(gwd.cpu().numpy(), ref['dwd'][0]) < tol_g
+        assert rel_err(gbd.cpu().numpy(), ref['dbd']) < tol_g
 
 
 # ----------------------------------------------------------------------------- GEMM
