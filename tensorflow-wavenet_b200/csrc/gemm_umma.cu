@@ -242,6 +242,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int kc = k_begin + i * ukk;
           if (PAIR) {      // both CTAs' boxes complete on the leader's barrier, which expects the bytes of both
             if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            if (p.a_mn) {      // weight-gradient form: MN-major blocks of this CTA's 128 A columns and its half of the B columns
+              const int tap1 = (p.tn_R && m0 >= p.tn_R) ? 1 : 0;
+              const int kr = kc - ((p.tn_R && !tap1) ? p.tn_shift : 0);      // two-tap: the past tap reads A rows k - d (B rows are shared)
+              asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                           ::"r"(smem_u32(sa)), "l"(&mapA), "r"(lead_full[s]), "r"(0), "r"(kr), "r"((m0 - tap1 * p.tn_R) >> 6) : "memory");
+              asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                           ::"r"(smem_u32(sa + A_BYTES)), "l"(&mapB), "r"(lead_full[s]), "r"(0), "r"(kc), "r"((n0 + (int)cta_rank * (BN / 2)) >> 6) : "memory");
+              continue;
+            }
             const int ka = (p.a_split && kc < p.a_split) ? kc : kc - p.a_split;
             const int ma = (p.a_split && kc < p.a_split) ? m0 + p.a_shift : m0;
             asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -253,8 +262,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int bsh = p.f16 ? 6 : 5;      // MN-major blocks: 32 floats / 64 halfs wide
           const int tap1 = (p.tn_R && m0 >= p.tn_R) ? 1 : 0;
-          const int kb = kc + ((p.tn_R && !tap1) ? p.tn_shift : 0);
-          if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kc, (m0 - tap1 * p.tn_R) >> bsh);     // [blocks][k rows][128 B of m]
+          const int kr = kc - ((p.tn_R && !tap1) ? p.tn_shift : 0);      // two-tap: the past tap pairs A row k - d with B row k
+          const int kb = kc;
+          if (p.a_mn) umma::tma_load_3d(sa, &mapA, &full_bar[s], 0, kr, (m0 - tap1 * p.tn_R) >> bsh);     // [blocks][k rows][128 B of m]
           else if (p.a_split && kc < p.a_split) tma_load_2d(sa, &mapA, &full_bar[s], kc, m0 + p.a_shift);
           else tma_load_2d(sa, &mapA, &full_bar[s], kc - p.a_split, m0);
           if (p.b_mn) umma::tma_load_3d(sa + A_BYTES, &mapB, &full_bar[s], 0, kb, n0 >> bsh);
@@ -1118,10 +1128,16 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   if (m2_on < 0) m2_on = (getenv("WN_GEMM_M2") && atoi(getenv("WN_GEMM_M2")) == 0) ? 0 : 1;
   const int m2 = (m2_on && M >= 1024 && BN == 256 && !tn_R) ? 1 : 0;      // (few output tiles -> many K splits -> the atomics of the bigger tiles cost more than the operand traffic saved: measured on the 512-row products)
   const int TMR = m2 ? 2 * UM : UM;
+  // CTA pairs for the 256-column products that do not use the 256-row tiles: each CTA loads its 128 A columns and half of B.
+  // Correct (tests pass with it on) but measured without gain -- post1_wgrad 71.7 us either way, post2_wgrad 55 vs 51, the
+  // two-tap weight gradient of the wide blocks unchanged: these split-K products are paced by their red.add flushes, not by
+  // the operand traffic -- so it is OFF unless WN_GEMM_PAIR_TN=1.
+  static const bool pair_env = [] { const char* e = getenv("WN_GEMM_PAIR_TN"); return e && e[0] == '1'; }();
+  const bool pair = pair_env && !m2 && BN == 256 && M >= 2 * UM && (M % (2 * UM)) == 0 && sm_count() >= 2;
   CUtensorMap mA, mB;
   int rc = make_map16_blocks_mn(&mA, A16, K, tn_R ? tn_R : M, lda, TMR / 64);
   if (rc) return rc;
-  rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, BN / 64);
+  rc = make_map16_blocks_mn(&mB, B16, K, N, ldb, (pair ? BN / 2 : BN) / 64);
   if (rc) return rc;
   UmmaParams p;
   p.colsum = nullptr; p.colsum_scale = 0.f; p.a_split = 0; p.a_shift = 0; p.aux_add = 0; p.aux_scale = 0.f; p.tn_R = 0; p.tn_shift = 0; p.wstage = 0; p.gate = 0; p.dpre = 0;
@@ -1140,12 +1156,15 @@ int gemm_f16_tn(const void* A16, int lda, const void* B16, int ldb, float* C, in
   splits = (K + kps - 1) / kps;
   p.k_per_split = kps;
   p.splits = splits;
-  p.stages = m2 ? 3 : 4;
-  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + TMR - 1) / TMR) * splits;
+  p.stages = m2 ? 3 : (pair ? 6 : 4);
+  const int tile_rows = pair ? 2 * UM : TMR;
+  const int64_t items = (int64_t)((N + BN - 1) / BN) * ((M + tile_rows - 1) / tile_rows) * splits;
   if (items > (1 << 30)) return -1;
-  dim3 grid((unsigned)(items < sm_count() ? items : sm_count()));
-  const size_t smem = 1024 + (size_t)p.stages * (TMR * UK * 4 + BN * UK * 4);
-  return launch_umma(BN, grid, smem, st, mA, mB, mA, mA, mA, p);
+  unsigned gx = (unsigned)(items < sm_count() ? items : sm_count());
+  if (pair) { gx = (unsigned)(2 * items < sm_count() ? 2 * items : sm_count()); gx &= ~1u; }
+  dim3 grid(gx);
+  const size_t smem = 1024 + (size_t)p.stages * (TMR * UK * 4 + BN * UK * 4 / (pair ? 2 : 1));
+  return launch_umma(BN, grid, smem, st, mA, mB, mA, mA, mA, p, pair);
 }
 
 // out16[n][k] = half(in[k][n])   (fp16 K-major weight copies for gemm_f16_nt; [K][N] fp32 row-major in)
