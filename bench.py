@@ -484,7 +484,7 @@ def main():
 
     # ---------------- BASELINE config 5 (scaled net, 16-bit storage) next to the headline: `--config cfg5` gives the full line ----
     cfg5 = None
-    if not args.no_batch4 and args.batch == B_PER_GPU and args.time == T_WINDOW:
+    if world == 1 and not args.no_batch4 and args.batch == B_PER_GPU and args.time == T_WINDOW:      # (N > 1: `--config cfg5` under torchrun)
         try:
             T5, R5, S5, Q5 = 65536, 128, 512, 256
             dil5 = [2 ** i for i in range(10)] * 4
