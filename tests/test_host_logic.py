@@ -173,3 +173,19 @@ def test_single_process_allreduce_is_identity():
     g = torch.ones(8)
     assert allreduce_gradients(g) == 1.0 and float(g.sum()) == 8.0
     assert shard_streams(256, 3, 8) == (96, 128)
+
+
+def test_workspace_of_the_benchmark_configs_fits_one_gpu():
+    """Workspace sizes (host arithmetic only): BASELINE config 2 (default params, T = 100000) and config 5 (scaled net in
+    16-bit storage, T = 65536) need a few GB of the 180 GB of a B200; forward-only needs less than training."""
+    from wavenet import _lib
+    lib = _lib.load()
+    cfg2 = _lib.make_config([2 ** i for i in range(10)] * 5, 32, 32, 512, 256, None, None, True, False)
+    cfg5 = _lib.make_config([2 ** i for i in range(10)] * 4, 128, 128, 512, 256, None, None, True, False)
+    for cfg, t in ((cfg2, 100000), (cfg5, 65536)):
+        train = lib.wn_train_workspace_bytes(C.byref(cfg), 1, t)
+        fwd = lib.wn_forward_workspace_bytes(C.byref(cfg), 1, t)
+        assert 1e9 < train < 8e9, train
+        assert 0 < fwd < train
+    # four windows per GPU scale the activation part
+    assert lib.wn_train_workspace_bytes(C.byref(cfg2), 4, 100000) > 3 * lib.wn_train_workspace_bytes(C.byref(cfg2), 1, 100000)
