@@ -192,7 +192,8 @@ inline int nblk(int64_t n) {
 
 }  // namespace
 
-bool wide16_supported(int R, int D) { return R >= 64 && D >= 64 && !(R & 63) && !(D & 63) && R <= 256 && D <= 256; }
+// (R != D is written for but has no GPU parity case yet: those widths stay on the fp32 GEMM-built blocks, which do)
+bool wide16_supported(int R, int D) { return R == D && R >= 64 && !(R & 63) && R <= 256; }
 int64_t wide16_images_bytes(int L, int R, int D) { return img_halfs(R, D) * L * 2; }
 int64_t wide16_wgrad_tmp_floats(int L, int R, int D) { return (int64_t)L * 2 * R * 2 * D; }
 int wide16_colsum_chunks() { return 4 * sm_count(); }      // row chunks per batch element of the dpre kernel (partials: [B][chunks][2D])
